@@ -1,0 +1,282 @@
+// Separable Lanczos-2 (4x4x4 taps) voxel feature query + backward (sm_100a).
+//
+// Replaces csrc/grid_feature/lanczos_voxel_feature_cuda.cu (5 exports, :822-834); window functions from
+// csrc/grid_feature/common.cuh:54-97.  xyz0 = floor(xyz) is NOT clamped, the tap coordinates are
+// (duplicated border taps, :61-76); M_PI*x is a double product narrowed at sinc(float) (q6).
+// Thread mapping: one thread per point.  The 12 window weights (and 12 derivative weights) are evaluated
+// ONCE per point - the reference re-evaluates them per channel and inside the j/k loops (192 sinf per
+// thread) - then the 64 taps are gathered with one 16/8/4-byte load per tap for all channels.
+// Roofline: L2-gather-bound at bench size (G=256,D=4: 268 MB table): 1 052 B/pt gathered, 44 B/pt
+// compulsory HBM at B=2^24.
+#include "grid_common.cuh"
+#include "../../include/ndjir_b200.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace ndjir {
+namespace lanczos {
+
+constexpr int W = 2;       // window size a
+constexpr int K = 2 * W;   // taps per axis
+
+__device__ __forceinline__ float sinc(float x) {  // common.cuh:54-59
+  if (x == 0.f) return 1.0f;
+  return sinf(x) / x;
+}
+__device__ __forceinline__ float lanczos_w(float x, int a) {  // common.cuh:62-69
+  auto z = M_PI * x;
+  auto u = sinc(z);
+  auto v = sinc(z / a);
+  return u * v;
+}
+__device__ __forceinline__ float grad_coefficient(float x, int a) {  // common.cuh:82-97
+  if (x == 0.f) return 0.0f;
+  auto z0 = M_PI * x;
+  auto z1 = M_PI * x / a;
+  auto sinc_z0 = sinc(z0);
+  auto sinc_z1 = sinc(z1);
+  auto t0 = (cosf(z0) - sinc_z0) * sinc_z1;
+  auto t1 = (cosf(z1) - sinc_z1) * sinc_z0;
+  return (t0 + t1) / x;
+}
+
+struct Strides { unsigned sx, sy, sz; };
+
+struct Taps {
+  unsigned ix[K], iy[K], iz[K];
+  float cx[K], cy[K], cz[K];
+  float gx[K], gy[K], gz[K];
+};
+
+template <bool DERIV>
+__device__ __forceinline__ void axis_taps(float q, float mn, float s, float g1, unsigned (&idx)[K], float (&c)[K],
+                                          float (&gc)[K]) {
+  float x = __fmul_rn(__fsub_rn(q, mn), s);
+  float x0 = floorf(x);
+#pragma unroll
+  for (int t = 0; t < K; ++t) {
+    float xi = fminf(fmaxf(x0 + (float)(t - W + 1), 0.f), g1);  // clamp(x0 + i, 0, G-1)
+    float dx = __fsub_rn(x, xi);
+    c[t] = lanczos_w(dx, W);
+    if (DERIV) gc[t] = grad_coefficient(dx, W);
+    idx[t] = (unsigned)xi;
+  }
+}
+
+template <bool DERIV>
+__device__ __forceinline__ Taps make_taps(const GridFrame& g, const float* q) {
+  Taps t;
+  axis_taps<DERIV>(__ldg(q), g.mnx, g.sx, g.gx1, t.ix, t.cx, t.gx);
+  axis_taps<DERIV>(__ldg(q + 1), g.mny, g.sy, g.gy1, t.iy, t.cy, t.gy);
+  axis_taps<DERIV>(__ldg(q + 2), g.mnz, g.sz, g.gz1, t.iz, t.cz, t.gz);
+  return t;
+}
+
+enum Mode { FWD = 0, GRAD_QUERY = 1, GGO = 2 };
+
+template <int MODE, int V, bool ACCUM>
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+gather_kernel(long long B, float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ gg,
+              const float* __restrict__ query, const float* __restrict__ feat, GridFrame g, Strides s, int D) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < B; p += stride) {
+    Taps t = make_taps<MODE != FWD>(g, query + p * 3);
+    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
+    if (MODE == GGO) { ggx = __ldg(gg + p * 3); ggy = __ldg(gg + p * 3 + 1); ggz = __ldg(gg + p * 3 + 2); }
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int d = 0; d < D; d += V) {
+      float f[V], gx[V], gy[V], gz[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) { f[j] = 0.f; gx[j] = 0.f; gy[j] = 0.f; gz[j] = 0.f; }
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+          const float* base = feat + t.ix[i] * s.sx + t.iy[jj] * s.sy + d;
+          Vec<V> v[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) v[k] = ldg_vec<V>(base + t.iz[k] * s.sz);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              if (MODE == FWD) {
+                f[j] += t.cx[i] * t.cy[jj] * t.cz[k] * v[k].v[j];            // :78-79
+              } else {
+                gx[j] += g.sx * t.gx[i] * t.cy[jj] * t.cz[k] * v[k].v[j];     // :168-170
+                gy[j] += g.sy * t.cx[i] * t.gy[jj] * t.cz[k] * v[k].v[j];
+                gz[j] += g.sz * t.cx[i] * t.cy[jj] * t.gz[k] * v[k].v[j];
+              }
+            }
+          }
+        }
+      }
+      if (MODE == FWD || MODE == GGO) {
+        Vec<V> o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = MODE == FWD ? f[j] : (ggx * gx[j] + ggy * gy[j] + ggz * gz[j]);
+        float* op = out + p * D + d;
+        if (ACCUM) {
+          Vec<V> prev = ld_vec<V>(op);
+#pragma unroll
+          for (int j = 0; j < V; ++j) o.v[j] += prev.v[j];
+        }
+        st_vec<V>(op, o);
+      } else {
+        Vec<V> go = ldg_vec<V>(a + p * D + d);
+#pragma unroll
+        for (int j = 0; j < V; ++j) { ax += go.v[j] * gx[j]; ay += go.v[j] * gy[j]; az += go.v[j] * gz[j]; }
+      }
+    }
+    if (MODE == GRAD_QUERY) {
+      float* op = out + p * 3;
+      if (ACCUM) { ax += op[0]; ay += op[1]; az += op[2]; }
+      op[0] = ax; op[1] = ay; op[2] = az;
+    }
+  }
+}
+
+template <bool SECOND, int V, bool AGG>
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go_, const float* __restrict__ gg,
+               const float* __restrict__ query, GridFrame g, Strides s, int D) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long rounds = (B + stride - 1) / stride;
+  for (long long r = 0; r < rounds; ++r) {
+    long long p = start + r * stride;
+    bool active = p < B;
+    long long pc = active ? p : (B - 1);
+    Taps t = make_taps<SECOND>(g, query + pc * 3);
+    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
+    if (SECOND) {
+      ggx = __ldg(gg + pc * 3) * g.sx; ggy = __ldg(gg + pc * 3 + 1) * g.sy; ggz = __ldg(gg + pc * 3 + 2) * g.sz;
+    }
+    for (int d = 0; d < D; d += V) {
+      Vec<V> o = ldg_vec<V>(go_ + pc * D + d);
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            float coef = SECOND ? (ggx * (t.gx[i] * t.cy[jj] * t.cz[k]) + ggy * (t.cx[i] * t.gy[jj] * t.cz[k]) +
+                                   ggz * (t.cx[i] * t.cy[jj] * t.gz[k]))
+                                : t.cx[i] * t.cy[jj] * t.cz[k];
+            Vec<V> val;
+#pragma unroll
+            for (int j = 0; j < V; ++j) val.v[j] = o.v[j] * coef;
+            unsigned idx = t.ix[i] * s.sx + t.iy[jj] * s.sy + t.iz[k] * s.sz + d;
+            if (AGG) warp_agg_red<V>(gf + idx, (unsigned long long)idx, val, active);
+            else if (active) red_vec<V>(gf + idx, val);
+          }
+        }
+      }
+    }
+  }
+}
+
+static bool bad_grid(const int* G, int D) {
+  if (!G || D <= 0 || G[0] <= 0 || G[1] <= 0 || G[2] <= 0) return true;
+  return (long long)G[0] * G[1] * G[2] * D >= (1ll << 32);
+}
+
+static Strides make_strides(const int* G, int D) {
+  Strides s;
+  s.sx = (unsigned)G[1] * (unsigned)G[2] * (unsigned)D;
+  s.sy = (unsigned)G[2] * (unsigned)D;
+  s.sz = (unsigned)D;
+  return s;
+}
+
+template <int MODE>
+static int launch_gather(long long B, float* out, const float* a, const float* gg, const float* query,
+                         const float* feat, const int* G, int D, const float* mn, const float* mx, bool accum,
+                         cudaStream_t st) {
+  if (B == 0) return NDJIR_OK;
+  if (B < 0 || bad_grid(G, D) || !out || !query || !feat || !mn || !mx) return NDJIR_ERR_ARG;
+  GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
+  Strides s = make_strides(G, D);
+  int V = pick_vec(D, feat, MODE == GRAD_QUERY ? (const void*)a : (const void*)out);
+  int grid = grid_for(B, NDJIR_BLOCK, 4);
+#define NDJIR_LAUNCH(VV)                                                                                   \
+  if (accum) gather_kernel<MODE, VV, true><<<grid, NDJIR_BLOCK, 0, st>>>(B, out, a, gg, query, feat, g, s, D); \
+  else gather_kernel<MODE, VV, false><<<grid, NDJIR_BLOCK, 0, st>>>(B, out, a, gg, query, feat, g, s, D);
+  if (V == 4) { NDJIR_LAUNCH(4) } else if (V == 2) { NDJIR_LAUNCH(2) } else { NDJIR_LAUNCH(1) }
+#undef NDJIR_LAUNCH
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+template <bool SECOND>
+static int launch_scatter(long long B, float* gf, const float* go, const float* gg, const float* query,
+                          const int* G, int D, const float* mn, const float* mx, cudaStream_t st) {
+  if (B == 0) return NDJIR_OK;
+  if (B < 0 || bad_grid(G, D) || !gf || !go || !query || !mn || !mx) return NDJIR_ERR_ARG;
+  GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
+  Strides s = make_strides(G, D);
+  int V = pick_vec(D, gf, go);
+  int grid = grid_for(B, NDJIR_BLOCK, 4);
+  bool agg = g_scatter_aggregate != 0;
+#define NDJIR_LAUNCH(VV)                                                                                  \
+  if (agg) scatter_kernel<SECOND, VV, true><<<grid, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, s, D); \
+  else scatter_kernel<SECOND, VV, false><<<grid, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, s, D);
+  if (V == 4) { NDJIR_LAUNCH(4) } else if (V == 2) { NDJIR_LAUNCH(2) } else { NDJIR_LAUNCH(1) }
+#undef NDJIR_LAUNCH
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+}  // namespace lanczos
+}  // namespace ndjir
+
+using namespace ndjir;
+using namespace ndjir::lanczos;
+
+extern "C" {
+
+int ndjir_lanczos_voxel_query_on_voxel(long long n_points, float* output, const float* query,
+                                       const float* feature, const int* grid_sizes, int D, const float* min3,
+                                       const float* max3, int accum, cudaStream_t stream) {
+  return launch_gather<FWD>(n_points, output, nullptr, nullptr, query, feature, grid_sizes, D, min3, max3,
+                            accum != 0, stream);
+}
+
+int ndjir_lanczos_voxel_grad_query(long long n_points, float* grad_query, const float* grad_output,
+                                   const float* query, const float* feature, const int* grid_sizes, int D,
+                                   const float* min3, const float* max3, int accum, cudaStream_t stream) {
+  if (n_points > 0 && !grad_output) return NDJIR_ERR_ARG;
+  return launch_gather<GRAD_QUERY>(n_points, grad_query, grad_output, nullptr, query, feature, grid_sizes, D,
+                                   min3, max3, accum != 0, stream);
+}
+
+int ndjir_lanczos_voxel_grad_feature(long long n_points, float* grad_feature, const float* grad_output,
+                                     const float* query, const int* grid_sizes, int D, const float* min3,
+                                     const float* max3, int accum, cudaStream_t stream) {
+  if (bad_grid(grid_sizes, D) || !grad_feature) return NDJIR_ERR_ARG;
+  if (!accum) fill_zero(grad_feature, (long long)grid_sizes[0] * grid_sizes[1] * grid_sizes[2] * D, stream);
+  return launch_scatter<false>(n_points, grad_feature, grad_output, nullptr, query, grid_sizes, D, min3, max3,
+                               stream);
+}
+
+int ndjir_lanczos_voxel_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                                                    const float* grad_grad_query, const float* query,
+                                                    const float* feature, const int* grid_sizes, int D,
+                                                    const float* min3, const float* max3, int accum,
+                                                    cudaStream_t stream) {
+  if (n_points > 0 && !grad_grad_query) return NDJIR_ERR_ARG;
+  return launch_gather<GGO>(n_points, grad_grad_output, nullptr, grad_grad_query, query, feature, grid_sizes, D,
+                            min3, max3, accum != 0, stream);
+}
+
+// Always accumulates (lanczos_voxel_feature_cuda.cu:585-607 has no zero-fill).
+int ndjir_lanczos_voxel_grad_query_grad_feature(long long n_points, float* grad_feature,
+                                                const float* grad_grad_query, const float* grad_output,
+                                                const float* query, const int* grid_sizes, int D,
+                                                const float* min3, const float* max3, cudaStream_t stream) {
+  if (n_points > 0 && !grad_grad_query) return NDJIR_ERR_ARG;
+  return launch_scatter<true>(n_points, grad_feature, grad_output, grad_grad_query, query, grid_sizes, D, min3,
+                              max3, stream);
+}
+
+}  // extern "C"
