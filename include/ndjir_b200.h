@@ -96,6 +96,10 @@ int ndjir_lanczos_voxel_grad_query_grad_feature(long long n_points, float* grad_
 long long ndjir_voxel_hash_num_params(int G0, float growth_factor, int T0, int L, int D);
 int ndjir_voxel_hash_level_table(int G0, float growth_factor, int T0, int L, int D, int* G_out, int* T_out,
                                  long long* offset_out); /* HOST outputs, L entries each */
+/* the table as the DEVICE evaluates it (device pow(float,int) is not exactly rounded: reference quirk q2);
+ * G_dev / T_dev are DEVICE int buffers of L entries */
+int ndjir_voxel_hash_level_table_device(int G0, float growth_factor, int T0, int L, int D, int* G_dev, int* T_dev,
+                                        cudaStream_t stream);
 /* hash_index :102 - the 8 hashed corner indices of one level as floats, (B, 8) */
 int ndjir_voxel_hash_hash_index(long long n_points, float* output, const float* query, int G, int T,
                                 const float* min3, const float* max3, cudaStream_t stream);
@@ -194,6 +198,131 @@ int ndjir_sample_importance_directions(long long size, float* light_dirs, const 
 int ndjir_squareplus_forward(long long size, float* output, const float* input, float b, cudaStream_t stream);
 int ndjir_squareplus_backward(long long size, float* dinput, const float* doutput, const float* input, float b,
                               int accum, cudaStream_t stream);
+
+/* ==== fused per-ray path ==================================================================================
+ * No native counterpart in the reference: there these stages are ~400 stock nnabla ops composed in
+ * python/sampler.py, network.py, renderer.py, specular_brdf.py and loss.py, differentiated by nnabla's autodiff.
+ * Here every stage (forward AND hand-derived backward) is one kernel; ndjir_b200/engine.py strings them into
+ * sample_points / pb_render / total_loss with the reference's signatures.  `ld*` are row strides in floats. */
+
+/* loss terms (python/loss.py:180-192); `losses` buffers hold NDJIR_N_LOSSES floats */
+enum { NDJIR_LOSS_TOTAL = 0, NDJIR_LOSS_RGB, NDJIR_LOSS_EIKONAL, NDJIR_LOSS_TV, NDJIR_LOSS_MASK,
+       NDJIR_LOSS_PRIOR_BASE_COLOR, NDJIR_LOSS_PRIOR_ROUGHNESS, NDJIR_LOSS_PRIOR_SPECULAR,
+       NDJIR_LOSS_REG_STD_ROUGHNESS, NDJIR_LOSS_REG_STD_SPECULAR, NDJIR_N_LOSSES };
+
+/* ---- MLP engine: C = epilogue(A(MxK) * B(KxN)); element strides; epilogues in csrc/gemm.cuh.
+ *      Replaces nnabla PF.affine + F.softplus(beta=100) and their backward products (python/network.py:84-93). */
+int ndjir_gemm(int M, int N, int K, const float* A, long long a_rs, long long a_cs, const float* B, long long b_rs,
+               long long b_cs, float* C, long long ldc, const float* bias, float alpha, float out_scale, float beta,
+               const float* H, long long ldh, float hscale, const float* U, long long ldu, float* C2,
+               long long ldc2, int split_k, int epilogue, cudaStream_t stream);
+
+/* ---- sample placement (python/sampler.py) ---- */
+/* :140-165  t = t_near + (t_far - t_near)/N0 * (i + xi) */
+int ndjir_stratified_dists(int n_rays, int N0, float* t, const float* t_near, const float* t_far, const float* xi,
+                           cudaStream_t stream);
+/* x[r,i,:] = camloc[r / R] + t[r,i] * raydir[r]   (:193, :276) */
+int ndjir_ray_points(int n_rays, int Nt, int R, float* x, const float* camloc, const float* raydir, const float* t,
+                     long long ldt, cudaStream_t stream);
+/* :196-240 one SDF-guided up-sampling round: Nt sorted distances + sdf -> Nt+M sorted distances */
+int ndjir_importance_round(int n_rays, int Nt, int M, const float* t_in, long long ld_in, const float* sdf,
+                           long long ld_sdf, const float* t_near, const float* t_far, float gain, float* t_out,
+                           long long ld_out, float* t_new_out, int* idx_out, cudaStream_t stream);
+/* :244-254, :282-291 background inverse-depth samples; t_bg (n_rays, Nb+1), x_bg (n_rays, Nb, 4) */
+int ndjir_background_samples(int n_rays, int Nb, int R, const float* camloc, const float* raydir,
+                             const float* t_far, const float* mask, const float* xi, float radius, float* t_bg,
+                             float* x_bg, cudaStream_t stream);
+/* :100 mask = n_hits > 1; mask_sum[0] += sum(mask) */
+int ndjir_hit_mask(int n_rays, const float* n_hits, float* mask, float* mask_sum, cudaStream_t stream);
+
+/* ---- data movement helpers ---- */
+int ndjir_copy2d(long long rows, int cols, float* dst, long long ld_dst, const float* src, long long ld_src, int rep,
+                 float alpha, int accum, cudaStream_t stream);          /* dst[r,c] (+)= alpha*src[r/rep,c] */
+int ndjir_colsum(long long rows, int cols, float* out, const float* src, long long ld_src, float alpha,
+                 cudaStream_t stream);                                   /* out[c] += alpha*sum_r src[r,c] */
+int ndjir_group_sum(long long n_groups, int group, int cols, float* out, long long ld_out, const float* src,
+                    long long ld_src, int accum, cudaStream_t stream);  /* out[g,c] (+)= sum_i src[g*group+i,c] */
+int ndjir_fill(long long n, float* p, float value, cudaStream_t stream);
+
+/* ---- positional encoding [x, cos(b), sin(b)], b[axis*bands+k] = x[axis]*2^k (python/network.py:96-117),
+ *      its input gradient (the nn.grad path of renderer.py:52) and the adjoint of that gradient ---- */
+int ndjir_positional_encoding(long long rows, int dim, int bands, const float* x, long long ld_x, int rep, float* out,
+                              long long ld_out, cudaStream_t stream);
+int ndjir_positional_encoding_grad_input(long long rows, int dim, int bands, const float* pe, long long ld_pe,
+                                         const float* g, long long ld_g, float* out, long long ld_out, int accum,
+                                         cudaStream_t stream);
+int ndjir_positional_encoding_grad_input_adjoint(long long rows, int dim, int bands, const float* pe, long long ld_pe,
+                                                 const float* nbar, long long ld_n, float* ghat, long long ld_g,
+                                                 cudaStream_t stream);
+
+/* ---- NeuS alpha and compositing (python/renderer.py:54-91) ---- */
+int ndjir_neus_alpha_forward(long long n_points, int N, float* alpha, const float* sdf, const float* normal,
+                             long long ld_n, const float* raydir, const float* t_fg, const float* gain_param,
+                             float cos_anneal_ratio, cudaStream_t stream);
+int ndjir_neus_alpha_backward(long long n_points, int N, const float* dalpha, const float* sdf, const float* normal,
+                              long long ld_n, const float* raydir, const float* t_fg, const float* gain_param,
+                              float cos_anneal_ratio, float* dsdf, float* dnormal, long long ld_dn,
+                              float* dgain_param, cudaStream_t stream);
+int ndjir_bg_alpha_forward(long long n, int Nb, float* alpha, const float* h0, long long ld_h, const float* t_bg,
+                           cudaStream_t stream);                         /* python/network.py:544-545 */
+int ndjir_bg_alpha_backward(long long n, int Nb, const float* dalpha, const float* h0, long long ld_h,
+                            const float* t_bg, float* dh0, long long ld_dh, cudaStream_t stream);
+int ndjir_composite_forward(int n_rays, int N, int Nb, const float* alpha_fg, const float* mask,
+                            const float* alpha_bg, float* weights, float* trans, cudaStream_t stream);
+int ndjir_composite_backward(int n_rays, int N, int Nb, const float* alpha_fg, const float* mask,
+                             const float* alpha_bg, const float* trans, const float* dweights, float* dalpha_fg,
+                             float* dalpha_bg, cudaStream_t stream);
+int ndjir_volume_render_forward(int n_rays, int N, int C, const float* w, long long ld_w, const float* V,
+                                long long ld_v, float* out, long long ld_out, cudaStream_t stream);
+int ndjir_volume_render_backward(int n_rays, int N, int C, const float* w, long long ld_w, const float* V,
+                                 long long ld_v, const float* dpix, long long ld_dpix, float* dV, long long ld_dv,
+                                 int accum_dv, float* dw, long long ld_dw, cudaStream_t stream);
+
+/* ---- per-sample material activations + priors (python/network.py:235-509, python/loss.py:70-176).
+ *      raw (P,16): bc 0:3 | ii 3 | ro 4:6 | sp 6:12 | pl 12 | bc_ptb 13:16;  att (P,12): ii | rough | spec(3) |
+ *      pl | bc*pl(3) | pad.  cfg10 (HOST): rough_lb, rough_prior, spec_prior, spec_scale, pl_gain, w_eik, w_bc,
+ *      w_ro, w_sp, bc_sym ---- */
+int ndjir_sample_attributes_forward(long long n_points, int N, const float* raw, float* att, const float* normal,
+                                    long long ld_n, const float* mask, const float* cfg10, float* losses,
+                                    cudaStream_t stream);
+int ndjir_sample_attributes_backward(long long n_points, int N, const float* raw, const float* datt,
+                                     const float* normal, long long ld_n, const float* mask, const float* cfg10,
+                                     const float* inv_denorm, float* draw, float* dnormal, long long ld_dn,
+                                     cudaStream_t stream);
+
+/* ---- per-ray shading + colour loss (python/renderer.py:88-180, python/specular_brdf.py:40-118).
+ *      cfg5 (HOST): eps_dot, specular weight, 1/(B*R over all ranks), entangle, l2 ---- */
+int ndjir_pixel_normal_forward(int n_rays, const float* npix, long long ld, float eps, float* nhat,
+                               cudaStream_t stream);
+int ndjir_pixel_normal_backward(int n_rays, const float* npix, long long ld, float eps, const float* dnhat,
+                                float* dnpix, long long ld_d, int accum, cudaStream_t stream);
+int ndjir_shade_forward(int n_rays, int M, const float* nhat, const float* attpix, const float* raydir,
+                        const float* dirs_u, const float* dirs_s, const float* el_raw, long long ld_el,
+                        const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
+                        const float* cfg5, float* color, float* losses, cudaStream_t stream);
+int ndjir_shade_backward(int n_rays, int M, const float* nhat, const float* attpix, const float* raydir,
+                         const float* dirs_u, const float* dirs_s, const float* el_raw, long long ld_el,
+                         const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
+                         const float* cfg5, float* d_el_raw, float* d_sv_raw, float* d_attpix, float* d_nhat,
+                         float* d_colbg, cudaStream_t stream);
+int ndjir_bg_color_forward(int n_rays, int Nb, const float* w_bg, long long ld_w, const float* raw, long long ld_raw,
+                           float* colbg, cudaStream_t stream);
+int ndjir_bg_color_backward(int n_rays, int Nb, const float* w_bg, long long ld_w, const float* raw, long long ld_raw,
+                            const float* dcolbg, float* dw_bg, long long ld_dw, float* draw, long long ld_draw,
+                            cudaStream_t stream);
+
+/* inverse squared camera distance fed to the photogrammetric-light network (python/network.py:396-400) */
+int ndjir_inv_sq_dist(long long n_points, long long points_per_view, const float* x, const float* camloc, float* out,
+                      long long ld_out, cudaStream_t stream);
+
+/* ---- loss plumbing (python/loss.py:59-192) ---- */
+int ndjir_ray_mask_fill(long long n_points, int N, int C, float* out, const float* mask, const float* dev_scalar,
+                        float scale, cudaStream_t stream);              /* out[p,c] = scale*mask[p/N]*(*dev_scalar) */
+int ndjir_masked_sum(long long n_points, int N, int C, const float* v, const float* mask, float* out,
+                     cudaStream_t stream);                               /* out[0] += sum v[p,c]*mask[p/N] */
+int ndjir_loss_inv_denorm(const float* mask_sum, int N, float* inv_denorm, cudaStream_t stream);
+int ndjir_finalize_losses(float* losses, const float* mask_sum, int N, float inv_rays, float w_eik, float w_tv,
+                          float w_bc, float w_ro, float w_sp, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,8 @@ class _Lib:
                     conv.append(ctypes.c_void_p(v))
                 elif isinstance(v, ctypes.Array):
                     conv.append(ctypes.cast(v, ctypes.c_void_p))
+                elif isinstance(v, ctypes.Structure):
+                    conv.append(ctypes.cast(ctypes.pointer(v), ctypes.c_void_p))
                 else:  # host sequence -> temporary C array
                     base = ty.replace("const ", "").rstrip("*").strip()
                     cty = {"float": ctypes.c_float, "int": ctypes.c_int, "long long": ctypes.c_longlong}[base]

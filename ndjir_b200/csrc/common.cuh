@@ -19,8 +19,9 @@
 
 namespace ndjir {
 
-// Grid sizing: a multiple of the SM count, enough CTAs per SM to cover memory latency, grid-stride inside.
-static inline int grid_for(long long work_items, int block = NDJIR_BLOCK, int ctas_per_sm = 8) {
+// Grid sizing: a multiple of the SM count when the work is large (many short waves of 256-thread CTAs, so the
+// tail of the last wave is negligible whatever the per-kernel occupancy is), grid-stride inside.
+static inline int grid_for(long long work_items, int block = NDJIR_BLOCK, int ctas_per_sm = 64) {
   long long need = (work_items + block - 1) / block;
   long long cap = (long long)NDJIR_NUM_SMS * ctas_per_sm;
   if (need < 1) need = 1;

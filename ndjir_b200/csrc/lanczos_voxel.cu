@@ -200,7 +200,7 @@ static int launch_gather(long long B, float* out, const float* a, const float* g
   GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
   Strides s = make_strides(G, D);
   int V = pick_vec(D, feat, MODE == GRAD_QUERY ? (const void*)a : (const void*)out);
-  int grid = grid_for(B, NDJIR_BLOCK, 4);
+  int grid = grid_for(B);
 #define NDJIR_LAUNCH(VV)                                                                                   \
   if (accum) gather_kernel<MODE, VV, true><<<grid, NDJIR_BLOCK, 0, st>>>(B, out, a, gg, query, feat, g, s, D); \
   else gather_kernel<MODE, VV, false><<<grid, NDJIR_BLOCK, 0, st>>>(B, out, a, gg, query, feat, g, s, D);
@@ -217,7 +217,7 @@ static int launch_scatter(long long B, float* gf, const float* go, const float* 
   GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
   Strides s = make_strides(G, D);
   int V = pick_vec(D, gf, go);
-  int grid = grid_for(B, NDJIR_BLOCK, 4);
+  int grid = grid_for(B);
   bool agg = g_scatter_aggregate != 0;
 #define NDJIR_LAUNCH(VV)                                                                                  \
   if (agg) scatter_kernel<SECOND, VV, true><<<grid, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, s, D); \

@@ -1,0 +1,262 @@
+// Ray-sample placement (sm_100a): stratified distances, SDF-guided hierarchical up-sampling, background
+// inverse-depth samples, ray points.
+//
+// The reference composes these from ~40 nnabla ops per up-sampling round under auto_forward
+// (python/sampler.py:140-165 stratified, :167-242 hierarchical, :244-254 + :282-291 background); here each is one
+// kernel.  The hierarchical round runs ONE WARP PER RAY: section alphas, a multiplicative warp scan for the
+// transmittance, an additive warp scan for the CDF, a per-quantile binary search (searchsorted, right=False) and
+// a bitonic sort of the merged distances in shared memory.  No gradient flows through any of this
+// (SamplePoints.backward_impl is empty, sampler.py:301).
+#include "common.cuh"
+#include "../../include/ndjir_b200.h"
+
+namespace ndjir {
+namespace sampler {
+
+constexpr int MAXS = 256;  // max samples per ray after a round (power of two for the bitonic network)
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+stratified_kernel(long long n, int N0, float* __restrict__ t, const float* __restrict__ t_near,
+                  const float* __restrict__ t_far, const float* __restrict__ xi) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
+    long long r = s / N0;
+    int i = (int)(s - r * N0);
+    float tn = __ldg(t_near + r), tf = __ldg(t_far + r);
+    float step = (tf - tn) / (float)N0;                      // sampler.py:159
+    t[s] = tn + step * ((float)i + __ldg(xi + s));           // sampler.py:160-163
+  }
+}
+
+// x[r, i, :] = camloc[r / R] + t[r, i] * raydir[r]
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+ray_points_kernel(long long n, int Nt, int R, float* __restrict__ x, const float* __restrict__ camloc,
+                  const float* __restrict__ raydir, const float* __restrict__ t, long long ldt) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
+    long long r = s / Nt;
+    int i = (int)(s - r * Nt);
+    const float* o = camloc + (r / R) * 3;
+    const float* d = raydir + r * 3;
+    float tv = __ldg(t + r * ldt + i);
+    x[s * 3 + 0] = __ldg(o + 0) + tv * __ldg(d + 0);
+    x[s * 3 + 1] = __ldg(o + 1) + tv * __ldg(d + 1);
+    x[s * 3 + 2] = __ldg(o + 2) + tv * __ldg(d + 2);
+  }
+}
+
+// bitonic sort of n_pow2 floats held in (warp-private) shared memory, ascending
+__device__ __forceinline__ void warp_bitonic_sort(float* v, int n_pow2, int lane) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n_pow2; i += 32) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          float a = v[i], b = v[ixj];
+          bool up = ((i & k) == 0);
+          if ((a > b) == up) { v[i] = b; v[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// One up-sampling round (sampler.py:196-240).  WARPS_PER_BLOCK warps, one ray each.
+constexpr int IWARPS = 4;
+__global__ void __launch_bounds__(IWARPS * 32)
+importance_round_kernel(int NR, int Nt, int M, const float* __restrict__ t_in, long long ld_in,
+                        const float* __restrict__ sdf, long long ld_sdf, const float* __restrict__ t_near,
+                        const float* __restrict__ t_far, float gain, float* __restrict__ t_out, long long ld_out,
+                        float* __restrict__ t_new_out, int* __restrict__ idx_out) {
+  __shared__ float s_t[IWARPS][MAXS];
+  __shared__ float s_w[IWARPS][MAXS];    // sdf, then alpha, then normalised weights
+  __shared__ float s_c[IWARPS][MAXS];    // cdf (inclusive)
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int r = blockIdx.x * IWARPS + warp;
+  if (r >= NR) return;
+  float* ts = s_t[warp];
+  float* ws = s_w[warp];
+  float* cs = s_c[warp];
+  for (int i = lane; i < Nt; i += 32) {
+    ts[i] = __ldg(t_in + (long long)r * ld_in + i);
+    cs[i] = __ldg(sdf + (long long)r * ld_sdf + i);   // sdf staged in cs
+  }
+  __syncwarp();
+  const int S = Nt - 1;   // sections
+  // section alpha (sampler.py:196-215)
+  for (int j = lane; j < S; j += 32) {
+    float s0v = cs[j], s1v = cs[j + 1];
+    float t0 = ts[j], t1 = ts[j + 1];
+    float mid = (s0v + s1v) * 0.5f;
+    float cos1 = (s1v - s0v) / (t1 - t0 + 1e-5f);
+    float cos0 = 1.f;
+    if (j > 0) cos0 = (s0v - cs[j - 1]) / (t0 - ts[j - 1] + 1e-5f);
+    float c = fminf(cos0, cos1);
+    c = fminf(fmaxf(c, -1e3f), 0.f);
+    float dist = t1 - t0;
+    float a0 = mid - c * dist * 0.5f;
+    float a1 = mid + c * dist * 0.5f;
+    float c0 = sigmoidf_(a0 * gain), c1 = sigmoidf_(a1 * gain);
+    float alpha = (c0 - c1 + 1e-5f) / (c0 + 1e-5f);
+    ws[j] = fminf(fmaxf(alpha, 0.f), 1.f);
+  }
+  __syncwarp();
+  // weights = alpha * exclusive cumprod(1 - alpha): chunked multiplicative warp scan (sampler.py:217-218)
+  float carry = 1.f;
+  float total = 0.f;
+  for (int base = 0; base < S; base += 32) {
+    int j = base + lane;
+    float a = (j < S) ? ws[j] : 0.f;
+    float om = 1.f - a;
+    float incl = om;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl *= up;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    float w = a * carry * excl;
+    if (j < S) ws[j] = w;
+    total += (j < S) ? w : 0.f;
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+  total = warp_sum(total);
+  __syncwarp();
+  // normalise + inclusive cumsum (sampler.py:221-222)
+  float run = 0.f;
+  for (int base = 0; base < S; base += 32) {
+    int j = base + lane;
+    float w = (j < S) ? ws[j] / total : 0.f;
+    float incl = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (j < S) { ws[j] = w; cs[j] = run + incl; }
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  float tn = __ldg(t_near + r), tf = __ldg(t_far + r);
+  // deterministic quantiles u_k = k / (M - 1 + 1/M) (sampler.py:179-189), searchsorted(right=False)
+  float newv[(MAXS / 2 + 31) / 32];
+  int nslot = 0;
+  for (int k = lane; k < M; k += 32) {
+    float u = (float)k / ((float)(M - 1) + 1.f / (float)M);
+    int lo = 0, hi = S;           // first i in [0,S) with cdf[i] >= u, else S
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cs[mid] < u) lo = mid + 1; else hi = mid;
+    }
+    int idx = lo;
+    int idx_w = idx < S - 1 ? idx : S - 1;           // q14: clamp the gathers on weights to Nt-2
+    float lower = idx == 0 ? 0.f : cs[idx - 1];
+    float ratio = (u - lower) / ws[idx_w];
+    float step = (idx < Nt - 1) ? (ts[idx + 1] - ts[idx]) : (tf - ts[Nt - 1]);
+    float tnew = ts[idx] + step * ratio;
+    tnew = fmaxf(fminf(tnew, tf), tn);
+    newv[nslot++] = tnew;
+    if (t_new_out) t_new_out[(long long)r * M + k] = tnew;
+    if (idx_out) idx_out[(long long)r * M + k] = idx;
+  }
+  __syncwarp();
+  nslot = 0;
+  for (int k = lane; k < M; k += 32) ts[Nt + k] = newv[nslot++];
+  int n_all = Nt + M;
+  int n_pow2 = 1;
+  while (n_pow2 < n_all) n_pow2 <<= 1;
+  for (int i = n_all + lane; i < n_pow2; i += 32) ts[i] = __int_as_float(0x7f800000);
+  __syncwarp();
+  warp_bitonic_sort(ts, n_pow2, lane);
+  for (int i = lane; i < n_all; i += 32) t_out[(long long)r * ld_out + i] = ts[i];
+}
+
+// Background samples (sampler.py:244-254, :282-291): t_bg = sort(t_base / xi), x_bg = (p/|p|, 1/|p|)
+constexpr int BWARPS = 4;
+__global__ void __launch_bounds__(BWARPS * 32)
+background_kernel(int NR, int Nb, int R, const float* __restrict__ camloc, const float* __restrict__ raydir,
+                  const float* __restrict__ t_far, const float* __restrict__ mask, const float* __restrict__ xi,
+                  float radius, float* __restrict__ t_bg, float* __restrict__ x_bg) {
+  __shared__ float s_t[BWARPS][MAXS];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int r = blockIdx.x * BWARPS + warp;
+  if (r >= NR) return;
+  float* ts = s_t[warp];
+  const float* o = camloc + (long long)(r / R) * 3;
+  const float* d = raydir + (long long)r * 3;
+  float ox = __ldg(o), oy = __ldg(o + 1), oz = __ldg(o + 2);
+  float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+  float m = __ldg(mask + r);
+  float camd = sqrtf(ox * ox + oy * oy + oz * oz);
+  float t_base = __ldg(t_far + r) * m + (camd - radius) * (1.f - m);
+  int n = Nb + 1;
+  int n_pow2 = 1;
+  while (n_pow2 < n) n_pow2 <<= 1;
+  for (int i = lane; i < n_pow2; i += 32)
+    ts[i] = i < n ? t_base / __ldg(xi + (long long)r * n + i) : __int_as_float(0x7f800000);
+  __syncwarp();
+  warp_bitonic_sort(ts, n_pow2, lane);
+  for (int i = lane; i < n; i += 32) t_bg[(long long)r * n + i] = ts[i];
+  for (int i = lane; i < Nb; i += 32) {
+    float tv = ts[i];
+    float px = ox + tv * dx, py = oy + tv * dy, pz = oz + tv * dz;
+    float dist = sqrtf(px * px + py * py + pz * pz) + 1e-6f;
+    float* xo = x_bg + ((long long)r * Nb + i) * 4;
+    xo[0] = px / dist; xo[1] = py / dist; xo[2] = pz / dist; xo[3] = 1.f / dist;
+  }
+}
+
+}  // namespace sampler
+}  // namespace ndjir
+
+using namespace ndjir;
+using namespace ndjir::sampler;
+
+extern "C" {
+
+int ndjir_stratified_dists(int n_rays, int N0, float* t, const float* t_near, const float* t_far, const float* xi,
+                           cudaStream_t stream) {
+  if (n_rays == 0) return NDJIR_OK;
+  if (n_rays < 0 || N0 <= 0 || !t || !t_near || !t_far || !xi) return NDJIR_ERR_ARG;
+  long long n = (long long)n_rays * N0;
+  stratified_kernel<<<grid_for(n), NDJIR_BLOCK, 0, stream>>>(n, N0, t, t_near, t_far, xi);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_ray_points(int n_rays, int Nt, int R, float* x, const float* camloc, const float* raydir, const float* t,
+                     long long ldt, cudaStream_t stream) {
+  if (n_rays == 0) return NDJIR_OK;
+  if (n_rays < 0 || Nt <= 0 || R <= 0 || !x || !camloc || !raydir || !t) return NDJIR_ERR_ARG;
+  long long n = (long long)n_rays * Nt;
+  ray_points_kernel<<<grid_for(n), NDJIR_BLOCK, 0, stream>>>(n, Nt, R, x, camloc, raydir, t, ldt);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_importance_round(int n_rays, int Nt, int M, const float* t_in, long long ld_in, const float* sdf,
+                           long long ld_sdf, const float* t_near, const float* t_far, float gain, float* t_out,
+                           long long ld_out, float* t_new_out, int* idx_out, cudaStream_t stream) {
+  if (n_rays == 0) return NDJIR_OK;
+  if (n_rays < 0 || Nt < 2 || M <= 0 || M > MAXS / 2 || Nt + M > MAXS || !t_in || !sdf || !t_near || !t_far || !t_out)
+    return NDJIR_ERR_ARG;
+  importance_round_kernel<<<(n_rays + IWARPS - 1) / IWARPS, IWARPS * 32, 0, stream>>>(
+      n_rays, Nt, M, t_in, ld_in, sdf, ld_sdf, t_near, t_far, gain, t_out, ld_out, t_new_out, idx_out);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_background_samples(int n_rays, int Nb, int R, const float* camloc, const float* raydir,
+                             const float* t_far, const float* mask, const float* xi, float radius, float* t_bg,
+                             float* x_bg, cudaStream_t stream) {
+  if (n_rays == 0) return NDJIR_OK;
+  if (n_rays < 0 || Nb <= 0 || Nb + 1 > MAXS || R <= 0 || !camloc || !raydir || !t_far || !mask || !xi || !t_bg ||
+      !x_bg)
+    return NDJIR_ERR_ARG;
+  background_kernel<<<(n_rays + BWARPS - 1) / BWARPS, BWARPS * 32, 0, stream>>>(n_rays, Nb, R, camloc, raydir, t_far,
+                                                                                mask, xi, radius, t_bg, x_bg);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+}  // extern "C"

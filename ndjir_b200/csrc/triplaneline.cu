@@ -199,8 +199,8 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
 #pragma unroll
             for (int j = 0; j < V; ++j) val.v[j] = go[i][j] * coef;
             long long off = (long long)us[k] * D;
-            // lines are tiny (3*G*D floats): collisions inside a warp are the norm, always aggregate
-            warp_agg_red<V>(gi + off, (unsigned long long)(i * plane_elems + off + d), val, active);
+            if (AGG) warp_agg_red<V>(gi + off, (unsigned long long)(i * plane_elems + off + d), val, active);
+            else if (active) red_vec<V>(gi + off, val);
           }
         }
       }

@@ -99,6 +99,14 @@ hash_index_kernel(long long B, float* __restrict__ out, const float* __restrict_
   }
 }
 
+// The level table as the DEVICE evaluates it (pow(float,int) on the device is not guaranteed to be exactly
+// rounded, so e.g. 16 * 1.5^4 may floor to 80 where the host's double pow gives 81 - a reference quirk, q2).
+__global__ void level_table_kernel(HashSpec h, int* __restrict__ G_out, int* __restrict__ T_out) {
+  __shared__ LevelTable tab;
+  build_table(tab, h);
+  if (threadIdx.x < h.L) { G_out[threadIdx.x] = tab.G[threadIdx.x]; T_out[threadIdx.x] = tab.T[threadIdx.x]; }
+}
+
 enum Mode { FWD = 0, GRAD_QUERY = 1, GGO = 2 };
 
 template <int MODE, int V, bool ACCUM>
@@ -253,6 +261,15 @@ int ndjir_voxel_hash_level_table(int G0, float growth_factor, int T0, int L, int
     o += force_align(T * D);
   }
   return NDJIR_OK;
+}
+
+int ndjir_voxel_hash_level_table_device(int G0, float growth_factor, int T0, int L, int D, int* G_dev, int* T_dev,
+                                        cudaStream_t st) {
+  HashSpec h;
+  const float mn[3] = {-1.f, -1.f, -1.f}, mx[3] = {1.f, 1.f, 1.f};
+  if (make_spec(h, G0, growth_factor, T0, L, D, mn, mx) || !G_dev || !T_dev) return NDJIR_ERR_ARG;
+  level_table_kernel<<<1, 64, 0, st>>>(h, G_dev, T_dev);
+  NDJIR_RETURN_LAST_ERROR();
 }
 
 int ndjir_voxel_hash_hash_index(long long n_points, float* output, const float* query, int G, int T,

@@ -495,9 +495,10 @@ def hash_force_align(size, mod=8):
     return size + size % mod
 
 
-def hash_level_table(G0, growth_factor, T0, L, D):
+def hash_level_table(G0, growth_factor, T0, L, D, Gs_override=None):
     """(G_l, T_l, offset_l) per level + total; common_voxel_hash.cuh:31-55 evaluated in fp32 like the
-    device code (pow(float,int) -> float, float product, floor)."""
+    device code (pow(float,int) -> float, float product, floor).  `Gs_override`: the level grid sizes as the
+    DEVICE evaluated them (its pow is not exactly rounded, q2); tests pass what the GPU reports."""
     Gs, Ts, offs = [], [], []
     off = 0
     gf = f32(growth_factor)
@@ -505,7 +506,7 @@ def hash_level_table(G0, growth_factor, T0, L, D):
         p = f32(1.0)
         for _ in range(l):      # exact for growth factors whose powers are fp32-exact (1.5, 2.0)
             p = f32(p * gf)
-        G = int(np.floor(f32(f32(G0) * p)))
+        G = int(np.floor(f32(f32(G0) * p))) if Gs_override is None else int(Gs_override[l])
         Gf = f32(G)
         T = min(int(min(f32(f32(Gf * Gf) * Gf), f32(T0))), int(T0))
         Gs.append(G); Ts.append(T); offs.append(off)
@@ -527,11 +528,11 @@ def hash_corner_indices(query, G, T, min_, max_):
     return np.stack([hash_index3(c[3], c[4], c[5], T) for c in _corners8(i0, i1, p0, p1)], axis=1)
 
 
-def voxel_hash_query(query, feature, G0, growth_factor, T0, L, D, min_, max_):
+def voxel_hash_query(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None):
     """kernel_voxel_hash_feature, voxel_hash_feature_cuda.cu:124-195.  Returns the reference's
     (D,L,B) layout (:190); transpose(2,0,1).reshape(B,D*L) gives the wrapper's output (c=d*L+l)."""
     feature = np.asarray(feature, dtype=f32).reshape(-1)
-    Gs, Ts, offs, _ = hash_level_table(G0, growth_factor, T0, L, D)
+    Gs, Ts, offs, _ = hash_level_table(G0, growth_factor, T0, L, D, Gs)
     B = np.asarray(query).reshape(-1, 3).shape[0]
     out = np.zeros((D, L, B), dtype=f32)
     for l in range(L):
@@ -545,10 +546,10 @@ def voxel_hash_query(query, feature, G0, growth_factor, T0, L, D, min_, max_):
     return out
 
 
-def _hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_):
+def _hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None):
     """(D,L,B,3) spatial gradient, voxel_hash_feature_cuda.cu:273-293."""
     feature = np.asarray(feature, dtype=f32).reshape(-1)
-    Gs, Ts, offs, _ = hash_level_table(G0, growth_factor, T0, L, D)
+    Gs, Ts, offs, _ = hash_level_table(G0, growth_factor, T0, L, D, Gs)
     B = np.asarray(query).reshape(-1, 3).shape[0]
     g = np.zeros((D, L, B, 3), dtype=np.float64)
     for l in range(L):
@@ -571,16 +572,16 @@ def _hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_):
     return g
 
 
-def voxel_hash_grad_query(grad_output_dlb, query, feature, G0, growth_factor, T0, L, D, min_, max_):
+def voxel_hash_grad_query(grad_output_dlb, query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None):
     """kernel_grad_query, voxel_hash_feature_cuda.cu:221-300; grad_output in (D,L,B) layout."""
-    g = _hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_)
+    g = _hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs)
     go = np.asarray(grad_output_dlb, dtype=np.float64).reshape(D, L, -1)
     return (go[..., None] * g).sum(axis=(0, 1))
 
 
-def voxel_hash_grad_feature(grad_output_dlb, query, G0, growth_factor, T0, L, D, min_, max_, out=None):
+def voxel_hash_grad_feature(grad_output_dlb, query, G0, growth_factor, T0, L, D, min_, max_, out=None, Gs=None):
     """kernel_grad_feature, voxel_hash_feature_cuda.cu:336-400."""
-    Gs, Ts, offs, total = hash_level_table(G0, growth_factor, T0, L, D)
+    Gs, Ts, offs, total = hash_level_table(G0, growth_factor, T0, L, D, Gs)
     go = np.asarray(grad_output_dlb, dtype=np.float64).reshape(D, L, -1)
     gf = np.zeros(total, dtype=np.float64) if out is None else out
     for l in range(L):
@@ -591,17 +592,17 @@ def voxel_hash_grad_feature(grad_output_dlb, query, G0, growth_factor, T0, L, D,
     return gf
 
 
-def voxel_hash_grad_query_grad_grad_output(grad_grad_query, query, feature, G0, growth_factor, T0, L, D, min_, max_):
+def voxel_hash_grad_query_grad_grad_output(grad_grad_query, query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None):
     """kernel_grad_query_grad_grad_output, voxel_hash_feature_cuda.cu:446-540 -> (D,L,B)."""
-    g = _hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_)
+    g = _hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs)
     gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
     return (g * gg[None, None, :, :]).sum(axis=-1)
 
 
 def voxel_hash_grad_query_grad_feature(grad_grad_query, grad_output_dlb, query, G0, growth_factor, T0, L, D,
-                                       min_, max_, out=None):
+                                       min_, max_, out=None, Gs=None):
     """kernel_grad_query_grad_feature, voxel_hash_feature_cuda.cu:673-750."""
-    Gs, Ts, offs, total = hash_level_table(G0, growth_factor, T0, L, D)
+    Gs, Ts, offs, total = hash_level_table(G0, growth_factor, T0, L, D, Gs)
     go = np.asarray(grad_output_dlb, dtype=np.float64).reshape(D, L, -1)
     gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
     gf = np.zeros(total, dtype=np.float64) if out is None else out

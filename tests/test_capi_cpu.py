@@ -1,0 +1,82 @@
+"""CPU: the C-ABI library builds/loads, exports every symbol include/ndjir_b200.h declares, and its host-only
+entry points agree with the oracle.  No compute calls (there is no GPU here)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from ndjir_b200 import _lib, compat
+from oracle import cpu_ref as R
+
+
+def test_library_exports_every_declared_symbol():
+    protos = _lib.parse_header()
+    assert len(protos) >= 44
+    cdll = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in protos if not hasattr(cdll, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+
+
+def test_loader_fails_loudly_without_library(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.NdjirError):
+        _lib._Lib()
+
+
+def test_compat_modules_mirror_reference_exports():
+    """Same module names and function names as the reference's PYBIND11_MODULE blocks."""
+    want = {
+        "voxel_feature_cuda": ["query_on_voxel", "grad_query", "grad_feature", "grad_query_grad_grad_output",
+                               "grad_query_grad_query", "grad_query_grad_feature", "grad_feature_grad_grad_output",
+                               "grad_feature_grad_query"],
+        "lanczos_voxel_feature_cuda": ["query_on_voxel", "grad_query", "grad_feature", "grad_query_grad_grad_output",
+                                       "grad_query_grad_feature"],
+        "voxel_hash_feature_cuda": ["hash_index", "voxel_hash_feature", "grad_query", "grad_feature",
+                                    "grad_query_grad_grad_output", "grad_query_grad_feature"],
+        "triplane_feature_cuda": ["query_on_triplane", "grad_query", "grad_feature", "grad_query_grad_grad_output",
+                                  "grad_query_grad_feature"],
+        "triline_feature_cuda": ["query_on_triline", "grad_query", "grad_feature", "grad_query_grad_grad_output",
+                                 "grad_query_grad_feature"],
+        "total_variation_loss_cuda": ["tv_loss_on_voxel", "tv_loss_on_voxel_backward"],
+        "total_variation_loss_on_triplane_cuda": ["tv_loss_on_triplane", "tv_loss_on_triplane_backward"],
+        "total_variation_loss_on_triline_cuda": ["tv_loss_on_triline", "tv_loss_on_triline_backward"],
+        "ray_aabb_intersection_cuda": ["ray_aabb_intersection"],
+        "ray_sphere_intersection_cuda": ["ray_sphere_intersection"],
+        "inverse_transform_cuda": ["sample_uniform_directions", "sample_importance_directions"],
+        "squareplus_cuda": ["forward", "backward"],
+    }
+    for mod, fns in want.items():
+        m = compat.load(mod)
+        for fn in fns:
+            assert callable(getattr(m, fn)), (mod, fn)
+
+
+@pytest.mark.parametrize("G0,gf,T0,L,D", [(16, 1.5, 2 ** 15, 16, 2), (2, 1.5, 2 ** 10, 4, 2), (4, 2.0, 2 ** 12, 6, 4),
+                                          (3, 1.5, 2 ** 10, 5, 1)])
+def test_hash_level_table_matches_oracle(G0, gf, T0, L, D):
+    G = (ctypes.c_int * L)(); T = (ctypes.c_int * L)(); O = (ctypes.c_longlong * L)()
+    _lib.call("ndjir_voxel_hash_level_table", G0, gf, T0, L, D, G, T, O)
+    Gs, Ts, offs, total = R.hash_level_table(G0, gf, T0, L, D)
+    assert list(G) == Gs and list(T) == Ts and list(O) == offs
+    assert _lib.call("ndjir_voxel_hash_num_params", G0, gf, T0, L, D) == total
+    # the Python-side formula of the reference wrapper (voxel_hash_feature.py:30-46) agrees for these growth factors
+    py_total = 0
+    for l in range(L):
+        g = int(G0 * gf ** l)
+        t = int(min(float(g) ** 3, T0))
+        py_total += t * D + (t * D) % 8
+    assert py_total == total
+
+
+def test_bench_hash_table_size_matches_survey():
+    assert _lib.call("ndjir_voxel_hash_num_params", 16, 1.5, 2 ** 15, 16, 2) == 953344
+
+
+def test_empty_batches_are_noops_without_gpu():
+    # n_points == 0 returns before any CUDA call, so this is safe on a CPU-only box
+    _lib.call("ndjir_voxel_query_on_voxel", 0, None, None, None, [2, 2, 2], 4, [-1.] * 3, [1.] * 3, 0, 0)
+    _lib.call("ndjir_triplane_query_on_triplane", 0, None, None, None, 8, 4, [-1.] * 3, [1.] * 3, 0, 0)
+    _lib.call("ndjir_ray_aabb_intersection", 0, None, None, None, None, None, 0, 1, [-1.] * 3, [1.] * 3, 0)
+    with pytest.raises(_lib.NdjirError):
+        _lib.call("ndjir_set_option", "no_such_option", 1)
