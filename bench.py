@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the NDJIR per-ray rendering hot path (BASELINE.json: train rays/s forward+backward at default.yaml;
+grid-query GB/s vs HBM peak).
+
+  python bench.py [--gpus N --steps K --warmup W]            our CUDA path (one process per GPU, torchrun for N>1)
+  python bench.py --impl reference [...]                     the reference path restated on the host CPU (oracle/)
+
+One "step" = one loss.forward() + loss.backward() of the reference (python/train.py:135-140) over one batch of
+B=4 views x R=512 rays of a synthetic DTU-shaped scene: sample placement (4 SDF-guided rounds), 512^3 x 4 voxel
+feature query, geometric / material / light MLPs, NeuS compositing, shading, all losses, and the full backward
+including the double-backward through the SDF normal, plus zeroing of every gradient buffer (the 2 GiB grid gradient
+included).  Multi-GPU: rays are sharded (weak scaling: every rank renders its own 2048 rays), parameters replicated,
+gradients all-reduced with NCCL inside the step.
+
+JSON line keys follow the driver's contract; `roofline` describes the dominant kernel (the MLP product kernel),
+`grid_query` the voxel-grid gather kernel against the measured HBM peak, `cpu_baseline` the oracle timed on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(conf):
+    r, tr = conf.renderer, conf.train
+    return dict(workload="default.yaml train step (fwd+bwd), synthetic DTU-shaped rays",
+                views=tr.batch_size, rays_per_view=tr.n_rays,
+                fg_samples=r.n_samples0 + r.n_upsamples * r.n_samples1, bg_samples=r.n_bg_samples,
+                light_dirs=2 * r.n_thetas * 2 * r.n_thetas,
+                grid=f"voxel {conf.geometric_network.voxel.grid_size}^3 x {conf.geometric_network.voxel.feature_size}",
+                l2="working set per step (~15 GB of activations + 4 GiB grid/grid-gradient) exceeds the 126 MB L2")
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (CPU restatement of the reference path; nnabla is not installable
+# here) on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_run(conf, steps, warmup, rays_per_step):
+    import torch
+    from ndjir_b200 import scene
+    from oracle import cpu_render as CR
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = scene.init_params(conf, seed=313)
+    v = conf.geometric_network.voxel
+    G, D = v.grid_size, v.feature_size
+    gen = torch.Generator().manual_seed(313)
+    grids = {"voxel": (torch.randn((G, G, G, D), generator=gen) * 1e-3).numpy()} if v.type == "voxel" else None
+    model = CR.Model(conf, P, dtype=torch.float32, grids=grids)
+    B, R = 1, rays_per_step
+    times = []
+    for s in range(warmup + steps):
+        camloc, raydir, color_gt = scene.make_batch(conf, step=s, B=B, R=R)
+        rnd = scene.make_randoms(conf, B, R, step=s)
+        t0 = time.perf_counter()
+        CR.train_step(model, camloc, raydir, color_gt, 0.0, rnd)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    return dict(value=B * R / (ms / 1e3), unit="rays/s", cores=cores, kind="port",
+                sample=f"{steps} steps of 1 view x {R} rays (default.yaml networks, 512^3x4 voxel grid, fwd+bwd incl. "
+                       f"dense grid gradient) with torch CPU fp32 on {cores} threads; oracle/cpu_render.py",
+                ms_per_step=ms)
+
+
+def run_reference(args, conf):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = args.ref_rays
+    cb = cpu_reference_run(conf, max(1, args.steps), min(args.warmup, 1), rays)
+    cfg = workload(conf)
+    cfg["sample"] = cb["sample"]
+    line = {"impl": "reference", "metric": "train_rays_per_sec_fwd_bwd", "value": cb["value"], "unit": "rays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg, "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def grid_query_roofline(eng, pk, torch):
+    """voxel-grid gather at the micro-benchmark shape (2^24 uniform points, the training grid): algorithmic
+    156 B/point (12 query + 16 output + 8 corners x 16 B) / CUDA-event time, vs the measured HBM copy peak."""
+    from ndjir_b200 import _lib
+    conf = eng.conf
+    v = conf.geometric_network.voxel
+    if v.type != "voxel":
+        return None
+    G, D = v.grid_size, v.feature_size
+    n = 1 << 24
+    gen = torch.Generator(device="cuda").manual_seed(412)
+    q = torch.rand((n, 3), device="cuda", generator=gen) * 2 - 1
+    out = torch.empty((n, D), device="cuda")
+    F = eng.params.grid["voxel"]
+    st = torch.cuda.current_stream().cuda_stream
+
+    def once():
+        _lib.call("ndjir_voxel_query_on_voxel", n, out.data_ptr(), q.data_ptr(), F.data_ptr(), [G, G, G], D, [-1.0] * 3,
+                  [1.0] * 3, 0, st)
+    for _ in range(3):
+        once()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    bytes_pt = 12 + 4 * D + 8 * 4 * D
+    ach = bytes_pt * n / (ms * 1e-3) / 1e9
+    return {"kernel": "voxel gather (query_on_voxel)", "points": n, "bytes_per_point": bytes_pt, "ms": ms,
+            "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+            "peak_source": pk["source"], "l2": "2 GiB table and 2^24 random points: far larger than L2"}
+
+
+def run_ours(args, conf):
+    import torch
+    import torch.distributed as dist
+    from ndjir_b200 import scene
+    from ndjir_b200.engine import Engine, LOSS_NAMES
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+    eng = Engine(conf, device=f"cuda:{local}", world_size=world, process_group=pg)
+    P = scene.init_params(conf, seed=313)
+    eng.params.load_reference(P)
+    eng.params.init_grid_on_device(scene.grid_shapes(conf), std=1e-3, seed=313)
+    tr = conf.train
+    B, R = tr.batch_size, tr.n_rays
+    nsteps = args.warmup + args.steps
+
+    # synthetic batches: every rank renders its own rays (weak scaling); host copies are pinned for the e2e arm
+    host = []
+    for s in range(nsteps):
+        camloc, raydir, color_gt = scene.make_batch(conf, step=s * world + rank)
+        rnd = scene.make_randoms(conf, B, R, step=s * world + rank)
+        item = {"camloc": camloc, "raydir": raydir, "color_gt": color_gt, **rnd}
+        host.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in item.items()})
+    h2d_bytes = sum(v.numel() * 4 for v in host[0].values())
+    resident = [{k: v.cuda(non_blocking=True) for k, v in item.items()} for item in host]
+    torch.cuda.synchronize()
+
+    def step_resident(item):
+        return eng.train_step(item["camloc"], item["raydir"], item["color_gt"], item, cos_anneal_ratio=0.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- value: inputs resident in HBM ----
+    for s in range(args.warmup):
+        step_resident(resident[s])
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.warmup, nsteps):
+        losses = step_resident(resident[s])
+    e1.record()
+    barrier()
+    ms_total = maxreduce(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    rays_per_step = B * R * world
+    value = rays_per_step / (ms_step * 1e-3)
+    loss_host = losses.detach().cpu().numpy()
+
+    # ---- e2e: host buffers in, loss out, copies inside the timed region ----
+    dev_bufs = {k: torch.empty_like(v, device="cuda") for k, v in host[0].items()}
+    loss_pinned = torch.empty(len(LOSS_NAMES), dtype=torch.float32).pin_memory()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for s in range(args.warmup, nsteps):
+        for k, v in host[s].items():
+            dev_bufs[k].copy_(v, non_blocking=True)
+        l_ = eng.train_step(dev_bufs["camloc"], dev_bufs["raydir"], dev_bufs["color_gt"], dev_bufs, cos_anneal_ratio=0.0)
+        loss_pinned.copy_(l_, non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the caller reads the loss every step (train.py:141-146)
+    e3.record()
+    barrier()
+    ms_e2e = maxreduce(e2.elapsed_time(e3)) / args.steps
+    e2e_value = rays_per_step / (ms_e2e * 1e-3)
+
+    # ---- instrumented step: launches and product-kernel time (CUDA events around every ndjir_gemm) ----
+    eng.profile = True
+    eng.prof_events, eng.n_launches = [], 0
+    step_resident(resident[-1])
+    torch.cuda.synchronize()
+    eng.profile = False
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in eng.prof_events)
+    gemm_flops = sum(f for _, _, f in eng.prof_events)
+    launches = eng.n_launches
+    pk = peaks()
+    roof = None
+    if gemm_ms > 0:
+        ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        roof = {"kernel": "ndjir::gemm::gemm_kernel (fused-epilogue MLP products, fp32 FFMA parity path)",
+                "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (bf16 sustained)",
+                "launches_per_step": len(eng.prof_events), "ms_per_step_in_kernel": gemm_ms,
+                "share_of_step": gemm_ms / ms_step,
+                "how": "CUDA events around every product launch of one instrumented step right after the timed region; "
+                       "achieved = algorithmic 2*M*N*K of all launches / summed duration"}
+    gq = grid_query_roofline(eng, pk, torch) if rank == 0 else None
+
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_run(conf, 2, 1, args.ref_rays)
+        cfg = workload(conf)
+        cfg["parallelism"] = f"ray-sharded x{world}, replicated parameters, NCCL gradient all-reduce" if world > 1 else "1 GPU"
+        line = {"metric": "train_rays_per_sec_fwd_bwd", "value": value, "unit": "rays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": len(LOSS_NAMES) * 4, "ms_per_step": ms_e2e},
+                "gpu_launches": launches * args.steps,
+                "roofline": roof, "grid_query": gq,
+                "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
+                "loss": {k: float(v) for k, v in zip(LOSS_NAMES, loss_host)}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="default")
+    ap.add_argument("--ref-rays", type=int, default=64, help="rays per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rays", type=int, default=0, help="override rays per view (debugging)")
+    ap.add_argument("--grid", type=int, default=0, help="override voxel grid size (debugging)")
+    args = ap.parse_args()
+    from ndjir_b200.config import make_conf
+    over = {}
+    if args.rays:
+        over["train"] = {"n_rays": args.rays}
+    if args.grid:
+        over["geometric_network"] = {"voxel": {"grid_size": args.grid}}
+    conf = make_conf(args.config, **over)
+    if args.impl == "reference":
+        run_reference(args, conf)
+    else:
+        run_ours(args, conf)
+
+
+if __name__ == "__main__":
+    main()

@@ -215,12 +215,14 @@ class Engine:
         self.one = torch.ones(4, dtype=torch.float32, device=self.device)
         self.rad = float(conf.renderer.bounding_sphere_radius)
         self.debug = {}
+        self.profile, self.prof_events, self.n_launches = False, [], 0
 
     # ------------------------------------------------------------------------------------------------
     def stream(self):
         return torch.cuda.current_stream().cuda_stream
 
     def call(self, name, *args):
+        self.n_launches += 1
         _lib.call(name, *args, self.stream())
 
     def buf(self, name, rows, cols, zero=False, dtype=torch.float32):
@@ -235,8 +237,14 @@ class Engine:
 
     def gemm(self, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, epi, bias=0, alpha=1.0, out_scale=1.0, H=0, ldh=0,
              hscale=1.0, U=0, ldu=0, C2=0, ldc2=0, split_k=1):
+        if self.profile:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         self.call("ndjir_gemm", M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha, out_scale, 100.0, H, ldh,
                   hscale, U, ldu, C2, ldc2, split_k, epi)
+        if self.profile:
+            e1.record()
+            self.prof_events.append((e0, e1, 2.0 * M * N * K))
 
     def wgrad(self, rows, K, N, A, lda, dZ, ldz, gW, ldw):
         """gW (K,N) += A(rows,K)^T dZ(rows,N): split-K over the rows with atomic accumulation."""

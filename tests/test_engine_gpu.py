@@ -54,8 +54,13 @@ class Report:
     def __init__(self, name):
         self.name, self.rows, self.bad = name, [], []
 
-    def check(self, what, a, b, tol):
+    def check(self, what, a, b, tol, b32=None):
+        """`b32` = the same quantity from the oracle run in float32: the fp32 evaluation noise of the reference's own
+        graph on this input.  Where that noise exceeds the base tolerance (ill-conditioned quantities such as a
+        normalised near-zero pixel normal) the bar is 4x the oracle's own fp32-vs-fp64 deviation."""
         e = relerr(a, b)
+        if b32 is not None:
+            tol = max(tol, 4.0 * relerr(b32, b))
         ok = bool(np.isfinite(e) and e <= tol)
         self.rows.append(dict(what=what, err=e, tol=tol, ok=ok))
         if not ok:
@@ -108,7 +113,7 @@ def test_sample_points_matches_oracle(kind):
         rep.check(f"round{u}.sdf", d_us["sdf"], d_or["sdf"], 2e-5)
         rep.check(f"round{u}.t_new", d_us["t_new"], d_or["t_new"], 1e-5)
         rep.check(f"round{u}.t_out", d_us["t_out"], d_or["t_out"], 1e-5)
-        same = (d_us["idx"].cpu().numpy() == d_or["idx"].numpy()).mean()
+        same = (d_us["idx"].cpu().numpy().reshape(-1) == d_or["idx"].numpy().reshape(-1)).mean()
         rep.rows.append(dict(what=f"round{u}.idx_equal_fraction", err=1 - float(same), tol=0.02, ok=bool(same > 0.98)))
         if same <= 0.98:
             rep.bad.append(f"round{u}.idx equal fraction {same}")
@@ -138,6 +143,11 @@ def test_train_step_matches_oracle(kind, cos_anneal):
     samples64 = [torch.as_tensor(s.cpu().numpy(), dtype=torch.float64) for s in samples32]
     ol, res, _ = CR.total_loss(model, camloc, raydir, color_gt, cos_anneal, rnd, return_all=True, samples=samples64,
                                fixed_dirs=fixed)
+    # the oracle again in float32: measures the conditioning of every compared quantity (see Report.check)
+    model32 = CR.Model(conf, P, dtype=torch.float32)
+    samples_f32 = [torch.as_tensor(s.cpu().numpy(), dtype=torch.float32) for s in samples32]
+    ol32, res32, _ = CR.total_loss(model32, camloc, raydir, color_gt, cos_anneal, rnd, return_all=True,
+                                   samples=samples_f32, fixed_dirs=fixed)
     # ---- forward intermediates ----
     rep.check("sdf", d["sdf"][:Pn], res["sdf_x_fg"], 2e-5)
     rep.check("feature", d["O"][:Pn, :Df], res["feature"], 2e-5)
@@ -147,7 +157,7 @@ def test_train_step_matches_oracle(kind, cos_anneal):
     rep.check("weights_fg", d["w"][:NR, :N], res["weights_fg"], 5e-5)
     rep.check("weights_bg", d["w"][:NR, N:], res["weights_bg"], 5e-5)
     rep.check("trans_fg", d["T"][:NR, :N], res["trans_fg"], 5e-5)
-    rep.check("normal_pixel", d["nhat"][:NR], res["normal_pixel"], 5e-5)
+    rep.check("normal_pixel", d["nhat"][:NR], res["normal_pixel"], 5e-5, res32["normal_pixel"])
     att = d["ATT"][:Pn]
     rep.check("implicit", att[:, 0], res["implicit"], 2e-5)
     rep.check("roughness", att[:, 1], res["roughness"], 2e-5)
@@ -155,7 +165,7 @@ def test_train_step_matches_oracle(kind, cos_anneal):
     rep.check("photogrammetric", att[:, 5], res["photogrammetric"], 2e-5)
     rep.check("base_color*pl", att[:, 6:9], res["base_color"] * res["photogrammetric"], 2e-5)
     rep.check("roughness_pixel", d["attpix"][:NR, 1], res["roughness_pixel"], 5e-5)
-    rep.check("color_pixel", d["color"][:NR], res["color_pixel"], 5e-5)
+    rep.check("color_pixel", d["color"][:NR], res["color_pixel"], 5e-5, res32["color_pixel"])
     for i, k in enumerate(["loss", "loss_rgb", "loss_eikonal", "loss_tv", None, "prior_base_color", "prior_roughness",
                            "prior_specular_reflectance", "reg_std_roughness", "reg_std_specular_reflectance"]):
         if k is not None:
@@ -171,13 +181,16 @@ def test_train_step_matches_oracle(kind, cos_anneal):
     for p in params.values():
         p.grad = None
     ol["loss"].backward()
+    params32 = model32.parameters()
+    ol32["loss"].backward()
     ours = eng.params.export_reference("grad")
     for k, p in params.items():
         want = p.grad.detach().numpy() if p.grad is not None else np.zeros(tuple(p.shape))
         if np.abs(want).max() == 0 and np.abs(ours[k]).max() == 0:
             rep.rows.append(dict(what=f"grad.{k}", err=0.0, tol=1e-4, ok=True))
             continue
-        rep.check(f"grad.{k}", ours[k], want, 1e-4)
+        w32 = params32[k].grad.detach().numpy() if params32[k].grad is not None else np.zeros(tuple(p.shape))
+        rep.check(f"grad.{k}", ours[k], want, 1e-4, w32)
     rep.finish()
 
 

@@ -1,5 +1,5 @@
 #!/bin/bash
 # engine parity vs the CPU oracle
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_engine_gpu.py -m gpu -q --timeout=900 -s 2>&1 | tail -250 > gpurun_out/pytest_engine.log
-tail -120 gpurun_out/pytest_engine.log
+timeout 1200 python -m pytest tests/test_engine_gpu.py -m gpu -q --timeout=900 -s --tb=short -rf > gpurun_out/pytest_engine.log 2>&1
+grep -v "^  ok " gpurun_out/pytest_engine.log | tail -150
