@@ -13,30 +13,6 @@ constexpr int BK = 16;
 constexpr int TM = 8;
 constexpr int APAD = 4;
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_store(const Args& a, int m, int n, float acc) {
-  long long ci = (long long)m * a.ldc + n;
-  if (EPI == EPI_BIAS) {
-    a.C[ci] = a.alpha * acc + (a.bias ? __ldg(a.bias + n) : 0.f);
-  } else if (EPI == EPI_SOFTPLUS) {
-    a.C[ci] = a.out_scale * softplus_beta(acc + (a.bias ? __ldg(a.bias + n) : 0.f), a.beta);
-  } else if (EPI == EPI_ACCUM) {
-    a.C[ci] += a.alpha * acc;
-  } else if (EPI == EPI_MUL_S) {
-    float s = sig_from_softplus(__ldg(a.H + (long long)m * a.ldh + n) * a.hscale, a.beta);
-    float v = a.alpha * acc * s;
-    if (a.U) v += __ldg(a.U + (long long)m * a.ldu + n);
-    a.C[ci] = v;
-  } else if (EPI == EPI_ADJ) {
-    float s = sig_from_softplus(__ldg(a.H + (long long)m * a.ldh + n) * a.hscale, a.beta);
-    float u = __ldg(a.U + (long long)m * a.ldu + n);
-    a.C[ci] = acc * u * a.beta * (1.f - s);
-    a.C2[(long long)m * a.ldc2 + n] = a.out_scale * acc * s;
-  } else if (EPI == EPI_ATOMIC) {
-    atomicAdd(a.C + ci, a.alpha * acc);
-  }
-}
-
 // A_KC: A is contiguous along k (row-major activations); otherwise contiguous along m (transposed use, X^T dY).
 // B_NC: B is contiguous along n (nnabla (in,out) weights used as-is); otherwise contiguous along k (W^T use).
 template <int BN, int TN, int EPI, bool A_KC, bool B_NC>
@@ -210,12 +186,15 @@ static void dispatch_tile(const Args& a, cudaStream_t st) {
   }
 }
 
+int g_mlp_tensor_cores = 1;   // 1: tcgen05 3xTF32 path where shapes allow (gemm_tc.cu), 0: fp32 FFMA everywhere
+
 int launch(const Args& a, int epi, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return NDJIR_OK;
   if (a.K < 0 || !a.A || !a.B || !a.C) return NDJIR_ERR_ARG;
   if (a.a_cs != 1 && a.a_rs != 1) return NDJIR_ERR_ARG;
   if (a.b_cs != 1 && a.b_rs != 1) return NDJIR_ERR_ARG;
   if (a.split_k > 1 && epi != EPI_ATOMIC) return NDJIR_ERR_ARG;
+  if (g_mlp_tensor_cores && tc_eligible(a, epi)) return launch_tc(a, epi, st);
   switch (epi) {
     case EPI_BIAS: dispatch_tile<EPI_BIAS>(a, st); break;
     case EPI_SOFTPLUS: dispatch_tile<EPI_SOFTPLUS>(a, st); break;

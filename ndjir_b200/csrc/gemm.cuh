@@ -61,7 +61,37 @@ __device__ __forceinline__ float softplus_beta(float x, float beta) {
 // sigmoid(beta * a) recovered from h = softplus(a, beta): 1 - exp(-beta h)
 __device__ __forceinline__ float sig_from_softplus(float h, float beta) { return -expm1f(-beta * h); }
 
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const Args& a, int m, int n, float acc) {
+  long long ci = (long long)m * a.ldc + n;
+  if (EPI == EPI_BIAS) {
+    a.C[ci] = a.alpha * acc + (a.bias ? __ldg(a.bias + n) : 0.f);
+  } else if (EPI == EPI_SOFTPLUS) {
+    a.C[ci] = a.out_scale * softplus_beta(acc + (a.bias ? __ldg(a.bias + n) : 0.f), a.beta);
+  } else if (EPI == EPI_ACCUM) {
+    a.C[ci] += a.alpha * acc;
+  } else if (EPI == EPI_MUL_S) {
+    float s = sig_from_softplus(__ldg(a.H + (long long)m * a.ldh + n) * a.hscale, a.beta);
+    float v = a.alpha * acc * s;
+    if (a.U) v += __ldg(a.U + (long long)m * a.ldu + n);
+    a.C[ci] = v;
+  } else if (EPI == EPI_ADJ) {
+    float s = sig_from_softplus(__ldg(a.H + (long long)m * a.ldh + n) * a.hscale, a.beta);
+    float u = __ldg(a.U + (long long)m * a.ldu + n);
+    a.C[ci] = acc * u * a.beta * (1.f - s);
+    a.C2[(long long)m * a.ldc2 + n] = a.out_scale * acc * s;
+  } else if (EPI == EPI_ATOMIC) {
+    atomicAdd(a.C + ci, a.alpha * acc);
+  }
+}
+
 int launch(const Args& a, int epi, cudaStream_t st);
+
+// tcgen05 path (gemm_tc.cu): 3xTF32 error-compensated products on the 5th-generation tensor cores
+extern int g_mlp_tensor_cores;
+extern int g_mlp_mask_hi;     // 1: the transform warps also clear the low 13 mantissa bits of the raw tiles
+bool tc_eligible(const Args& a, int epi);
+int launch_tc(const Args& a, int epi, cudaStream_t st);
 
 }  // namespace gemm
 }  // namespace ndjir

@@ -1,0 +1,391 @@
+// MLP products on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::tf32 with TMEM accumulators, operands
+// staged by TMA, 3xTF32 error compensation so the result keeps fp32 accuracy (parity bar 1e-5 forward):
+//
+//     x = hi + lo,  hi = x with the low 13 mantissa bits cleared (what a TF32 operand keeps),  lo = x - hi  (exact)
+//     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi            (the dropped lo*lo term is 2^-22 relative)
+//
+// One CTA computes one 128 x (<=256) output tile (optionally one K split of it):
+//   warp 0      TMA producer: raw fp32 tiles of A and B, 128-byte swizzle, 2-stage ring            (UTMALDG)
+//   warps 2-5   transform: lo = x - hi written to a second tile with the SAME swizzled addresses (pure element-wise
+//               pass over shared memory), fence.proxy.async, then signal the MMA warp
+//   warp 1      one elected thread issues 3 x 4 tcgen05.mma (128 x N x 8) per 32-wide K block        (UTCHMMA..)
+//   warps 2-5   epilogue: tcgen05.ld -> padded shared staging -> coalesced fused epilogue (bias / softplus /
+//               sigmoid factor / second-order term / atomics), shared with the FFMA path (gemm.cuh)
+// Operand layouts come straight from the MLP passes, no transposed copies:
+//   forward  C = A W      : A K-major,  B = W (in,out) MN-major
+//   dgrad    dA = dZ W^T  : A K-major,  B = W          K-major
+//   wgrad    gW = A^T dZ  : A MN-major, B MN-major, contraction over the sample rows, split over gridDim.z
+// Shapes that do not fit (N < 32, K < 16, unaligned views) stay on the FFMA kernel (gemm.cu).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "gemm.cuh"
+#include "../../include/ndjir_b200.h"
+
+namespace ndjir {
+namespace gemm {
+
+int g_mlp_mask_hi = 0;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 256;
+constexpr int TC_BK = 32;                       // fp32 elements = one 128-byte swizzle span
+constexpr int TC_STAGES = 2;
+constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+constexpr int B_TILE_BYTES = TC_BN * TC_BK * 4;  // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // raw + lo of both operands = 96 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024;      // + alignment slack
+constexpr int STG_LD = TC_BN + 4;               // padded row of the epilogue staging tile (floats)
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 256;
+static_assert(TC_BM * STG_LD * 4 <= TC_STAGES * STAGE_BYTES, "epilogue staging must fit in the operand ring");
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (tcgen05), version 1 (cute/arch/mma_sm100_desc.hpp:SmemDescriptor).
+// layout 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B: the only layout tcgen05 accepts for MN-major
+// 32-bit operands (32-byte chunks swizzled inside a 128-byte span over 4 rows; TMA mode SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+struct TcParams {
+  Args a;
+  int a_mn, b_mn;        // 1: operand is MN-major (contiguous along m / n), 0: K-major
+  int mask_hi;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 1];
+  __shared__ uint32_t tmem_base_sh;
+
+  const Args& a = p.a;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int n_valid = min(TC_BN, a.N - n0);
+  const int umma_n = (n_valid + 15) & ~15;
+  const int nkb_total = (a.K + TC_BK - 1) / TC_BK;
+  int kb0 = 0, kb1 = nkb_total;
+  if (a.split_k > 1) {
+    int per = (nkb_total + a.split_k - 1) / a.split_k;
+    kb0 = blockIdx.z * per;
+    kb1 = min(nkb_total, kb0 + per);
+    if (kb0 >= kb1) return;
+  }
+  const int nkb = kb1 - kb0;
+
+  auto bar_full = [&](int s) { return smem_u32(&bars[s]); };
+  auto bar_ready = [&](int s) { return smem_u32(&bars[TC_STAGES + s]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[2 * TC_STAGES + s]); };
+  const uint32_t bar_accum = smem_u32(&bars[3 * TC_STAGES]);
+  auto a_raw = [&](int s) { return smem_base + s * STAGE_BYTES; };
+  auto a_lo = [&](int s) { return smem_base + s * STAGE_BYTES + A_TILE_BYTES; };
+  auto b_raw = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_TILE_BYTES; };
+  auto b_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_TILE_BYTES + B_TILE_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_ready(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  const int b_chunks = (umma_n + 31) / 32;   // 32-wide n chunks actually loaded when B is MN-major
+  const uint32_t tx_bytes = A_TILE_BYTES + (p.b_mn ? b_chunks * TC_BK * 128 : B_TILE_BYTES);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        int s = i % TC_STAGES;
+        uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(bar_empty(s), ph ^ 1);
+        mbar_expect_tx(bar_full(s), tx_bytes);
+        int k0 = (kb0 + i) * TC_BK;
+        if (p.a_mn) {
+#pragma unroll
+          for (int c = 0; c < TC_BM / 32; ++c) tma_load_2d(a_raw(s) + c * TC_BK * 128, &mapA, m0 + c * 32, k0, bar_full(s));
+        } else {
+          tma_load_2d(a_raw(s), &mapA, k0, m0, bar_full(s));
+        }
+        if (p.b_mn) {
+          for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_raw(s) + c * TC_BK * 128, &mapB, n0 + c * 32, k0, bar_full(s));
+        } else {
+          tma_load_2d(b_raw(s), &mapB, k0, n0, bar_full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO), K step of 8 elements = +32 B.
+      // MN-major (SWIZZLE_128B_BASE32B): k rows of 128 B (32 mn elements), 4-row k groups 512 B apart (SBO), 32-wide
+      // mn chunks TC_BK*128 B apart (LBO), K step of 8 rows = +1024 B.
+      const uint32_t a_lbo = p.a_mn ? TC_BK * 128 : 16, a_sbo = p.a_mn ? 512 : 1024, a_step = p.a_mn ? 1024 : 32;
+      const uint32_t b_lbo = p.b_mn ? TC_BK * 128 : 16, b_sbo = p.b_mn ? 512 : 1024, b_step = p.b_mn ? 1024 : 32;
+      const uint32_t a_lay = p.a_mn ? 1 : 2, b_lay = p.b_mn ? 1 : 2;
+      for (int i = 0; i < nkb; ++i) {
+        int s = i % TC_STAGES;
+        uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(bar_ready(s), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          uint64_t da_hi = make_desc(a_raw(s) + ks * a_step, a_lbo, a_sbo, a_lay);
+          uint64_t da_lo = make_desc(a_lo(s) + ks * a_step, a_lbo, a_sbo, a_lay);
+          uint64_t db_hi = make_desc(b_raw(s) + ks * b_step, b_lbo, b_sbo, b_lay);
+          uint64_t db_lo = make_desc(b_lo(s) + ks * b_step, b_lbo, b_sbo, b_lay);
+          umma_tf32(tmem_base, da_lo, db_hi, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
+          umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+          umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+        }
+        umma_commit(bar_empty(s));   // frees the stage once these MMAs have read it
+      }
+      umma_commit(bar_accum);        // accumulator complete
+    }
+  } else {
+    // ===================== transform (lo tiles), then epilogue =====================
+    const int t = threadIdx.x - 64;   // 0..127
+    for (int i = 0; i < nkb; ++i) {
+      int s = i % TC_STAGES;
+      uint32_t ph = (i / TC_STAGES) & 1;
+      mbar_wait(bar_full(s), ph);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      // A: raw at 0, lo at A_TILE_BYTES;  B: raw at 2*A_TILE_BYTES, lo at 2*A_TILE_BYTES + B_TILE_BYTES
+#pragma unroll 4
+      for (int off = t * 16; off < A_TILE_BYTES; off += 128 * 16) {
+        float4 x = *reinterpret_cast<const float4*>(st + off);
+        float4 h;
+        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+        *reinterpret_cast<float4*>(st + A_TILE_BYTES + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        if (p.mask_hi) *reinterpret_cast<float4*>(st + off) = h;
+      }
+      const int b_bytes = p.b_mn ? b_chunks * TC_BK * 128 : B_TILE_BYTES;
+#pragma unroll 4
+      for (int off = t * 16; off < b_bytes; off += 128 * 16) {
+        float4 x = *reinterpret_cast<const float4*>(st + 2 * A_TILE_BYTES + off);
+        float4 h;
+        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+        *reinterpret_cast<float4*>(st + 2 * A_TILE_BYTES + B_TILE_BYTES + off) =
+            make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        if (p.mask_hi) *reinterpret_cast<float4*>(st + 2 * A_TILE_BYTES + off) = h;
+      }
+      fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bar_ready(s));
+    }
+    // ---- epilogue ----
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;                     // TMEM sub-partition of this warp: lanes 32q .. 32q+31
+    float* stg = reinterpret_cast<float*>(smem);
+    float* my_row = stg + (q * 32 + lane) * STG_LD;
+    for (int c = 0; c < umma_n; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(my_row + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    __syncwarp();
+    // coalesced pass over this warp's 32 rows: lanes across columns
+    for (int r = 0; r < 32; ++r) {
+      int m = m0 + q * 32 + r;
+      if (m >= a.M) break;
+      const float* row = stg + (q * 32 + r) * STG_LD;
+      for (int c = lane; c < n_valid; c += 32) epilogue_store<EPI>(a, m, n0 + c, row[c]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled get_encode() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+  }
+  return fn;
+}
+
+static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// inner = contiguous extent (elements), outer = number of rows, ld = row stride (elements)
+static bool make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_inner,
+                     int box_outer, bool mn_major) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool tc_eligible(const Args& a, int epi) {
+  if (a.N < 32 || a.K < 16 || a.M < 32) return false;
+  if (!al16p(a.A) || !al16p(a.B)) return false;
+  // operand row strides must be multiples of 16 bytes; one of the two element strides is 1 (checked by launch)
+  long long lda = a.a_cs == 1 ? a.a_rs : a.a_cs;
+  long long ldb = a.b_cs == 1 ? a.b_rs : a.b_cs;
+  if (a.a_cs == 1 && a.a_rs == 1) return false;   // degenerate views stay on the generic kernel
+  if (lda % 4 != 0 || ldb % 4 != 0 || lda <= 0 || ldb <= 0) return false;
+  if (a.a_cs == 1 && a.a_rs == 0) return false;
+  if (a.b_cs == 1 && a.b_rs == 0) return false;
+  (void)epi;
+  return get_encode() != nullptr;
+}
+
+template <int EPI>
+static int launch_tc_epi(const Args& a, cudaStream_t st) {
+  TcParams p;
+  p.a = a;
+  p.a_mn = (a.a_cs != 1);        // A(m,k) contiguous along m
+  p.b_mn = (a.b_cs == 1);        // B(k,n) contiguous along n
+  p.mask_hi = g_mlp_mask_hi;
+  if (a.b_cs == 1 && a.b_rs == 1) p.b_mn = 1;
+  CUtensorMap mapA, mapB;
+  bool ok;
+  if (p.a_mn) ok = make_map(&mapA, a.A, a.M, a.K, a.a_cs, 32, TC_BK, true);
+  else ok = make_map(&mapA, a.A, a.K, a.M, a.a_rs, TC_BK, TC_BM, false);
+  if (p.b_mn) ok = ok && make_map(&mapB, a.B, a.N, a.K, a.b_rs, 32, TC_BK, true);
+  else ok = ok && make_map(&mapB, a.B, a.K, a.N, a.b_cs, TC_BK, TC_BN, false);
+  if (!ok) return NDJIR_ERR_ARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.M + TC_BM - 1) / TC_BM, a.split_k > 1 ? a.split_k : 1);
+  gemm_tc_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, p);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int launch_tc(const Args& a, int epi, cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS: return launch_tc_epi<EPI_BIAS>(a, st);
+    case EPI_SOFTPLUS: return launch_tc_epi<EPI_SOFTPLUS>(a, st);
+    case EPI_ACCUM: return launch_tc_epi<EPI_ACCUM>(a, st);
+    case EPI_MUL_S: if (!a.H) return NDJIR_ERR_ARG; return launch_tc_epi<EPI_MUL_S>(a, st);
+    case EPI_ADJ: if (!a.H || !a.U || !a.C2) return NDJIR_ERR_ARG; return launch_tc_epi<EPI_ADJ>(a, st);
+    case EPI_ATOMIC: return launch_tc_epi<EPI_ATOMIC>(a, st);
+    default: return NDJIR_ERR_ARG;
+  }
+}
+
+}  // namespace gemm
+}  // namespace ndjir

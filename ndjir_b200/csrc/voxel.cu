@@ -9,6 +9,7 @@
 // Roofline: HBM-bound gather/scatter; algorithmic bytes per point at D=4: fwd 12+16+8*16 = 156 B,
 // grad_feature 12+16+2*8*16 = 284 B.
 #include "grid_common.cuh"
+#include "gemm.cuh"
 #include "../../include/ndjir_b200.h"
 
 namespace ndjir {
@@ -257,6 +258,14 @@ int ndjir_set_option(const char* key, int value) {
   int i = 0;
   while (k[i] && key[i] == k[i]) ++i;
   if (k[i] == 0 && key[i] == 0) { g_scatter_aggregate = value; return NDJIR_OK; }
+  const char* k2 = "mlp_tensor_cores";
+  i = 0;
+  while (k2[i] && key[i] == k2[i]) ++i;
+  if (k2[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_tensor_cores = value; return NDJIR_OK; }
+  const char* k3 = "mlp_mask_hi";
+  i = 0;
+  while (k3[i] && key[i] == k3[i]) ++i;
+  if (k3[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_mask_hi = value; return NDJIR_OK; }
   return NDJIR_ERR_ARG;
 }
 
