@@ -270,18 +270,29 @@ def run_ours(args, conf):
     step_resident(resident[-1])
     torch.cuda.synchronize()
     eng.profile = False
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in eng.prof_events)
-    gemm_flops = sum(f for _, _, f in eng.prof_events)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in eng.prof_events)
+    gemm_flops = sum(f for _, _, f, _ in eng.prof_events)
+    buckets = {}
+    for a_, b_, f_, tag in eng.prof_events:
+        d = buckets.setdefault(tag, [0, 0.0, 0.0])
+        d[0] += 1; d[1] += a_.elapsed_time(b_); d[2] += f_
+    if os.environ.get("NDJIR_BENCH_DUMP"):
+        with open(os.environ["NDJIR_BENCH_DUMP"], "w") as f:
+            for k, v in sorted(buckets.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"{k:<34s} n={v[0]:<4d} ms={v[1]:8.3f} tflops={v[2] / max(v[1], 1e-9) / 1e9:7.1f}\n")
+    top = sorted(buckets.items(), key=lambda kv: -kv[1][1])[:12]
+    breakdown = [{"shape": k, "launches": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)}
+                 for k, v in top]
     launches = eng.n_launches
     pk = peaks()
     roof = None
     if gemm_ms > 0:
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        roof = {"kernel": "ndjir::gemm::gemm_kernel (fused-epilogue MLP products, fp32 FFMA parity path)",
+        roof = {"kernel": "ndjir::gemm::gemm_tc_kernel (tcgen05 3xTF32 MLP products, fused epilogues; small shapes on the FFMA kernel)",
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (bf16 sustained)",
                 "launches_per_step": len(eng.prof_events), "ms_per_step_in_kernel": gemm_ms,
-                "share_of_step": gemm_ms / ms_step,
+                "share_of_step": gemm_ms / ms_step, "breakdown": breakdown,
                 "how": "CUDA events around every product launch of one instrumented step right after the timed region; "
                        "achieved = algorithmic 2*M*N*K of all launches / summed duration"}
     gq = grid_query_roofline(eng, pk, torch) if rank == 0 else None

@@ -85,6 +85,15 @@ __device__ __forceinline__ void epilogue_store(const Args& a, int m, int n, floa
   }
 }
 
+// fast-math variants for the tensor-core epilogue (MUFU ex2 / lg2): absolute error ~1e-6 on beta*x, i.e. ~1e-8 on
+// the activation (beta = 100), far inside the 1e-5 forward bar; the FFMA parity path keeps the exact versions
+__device__ __forceinline__ float softplus_beta_fast(float x, float beta) {
+  float z = beta * x;
+  float r = fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(z)));
+  return __fdividef(r, beta);
+}
+__device__ __forceinline__ float sig_from_softplus_fast(float h, float beta) { return 1.f - __expf(-beta * h); }
+
 int launch(const Args& a, int epi, cudaStream_t st);
 
 // tcgen05 path (gemm_tc.cu): 3xTF32 error-compensated products on the 5th-generation tensor cores

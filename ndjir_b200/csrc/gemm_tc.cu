@@ -5,7 +5,7 @@
 //     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi            (the dropped lo*lo term is 2^-22 relative)
 //
 // One CTA computes one 128 x (<=256) output tile (optionally one K split of it):
-//   warp 0      TMA producer: raw fp32 tiles of A and B, 128-byte swizzle, 2-stage ring            (UTMALDG)
+//   warp 0      TMA producer: raw fp32 tiles of A and B, swizzled, 4-stage ring of 16-wide K blocks (UTMALDG)
 //   warps 2-5   transform: lo = x - hi written to a second tile with the SAME swizzled addresses (pure element-wise
 //               pass over shared memory), fence.proxy.async, then signal the MMA warp
 //   warp 1      one elected thread issues 3 x 4 tcgen05.mma (128 x N x 8) per 32-wide K block        (UTCHMMA..)
@@ -28,16 +28,17 @@ int g_mlp_mask_hi = 0;
 
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
-constexpr int TC_BK = 32;                       // fp32 elements = one 128-byte swizzle span
-constexpr int TC_STAGES = 2;
-constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4;  // 16 KB
-constexpr int B_TILE_BYTES = TC_BN * TC_BK * 4;  // 32 KB
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // raw + lo of both operands = 96 KB
+constexpr int TC_BK = 16;                       // fp32 elements per K block: 64-byte rows (K-major tiles use SWIZZLE_64B)
+constexpr int TC_STAGES = 4;
+constexpr int KM_ROW_BYTES = TC_BK * 4;         // K-major tile row
+constexpr uint32_t KM_LAYOUT = TC_BK == 32 ? 2u : 4u;   // SWIZZLE_128B : SWIZZLE_64B
+constexpr uint32_t KM_SBO = 8 * KM_ROW_BYTES;   // 8-row swizzle groups
+constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4;  // 8 KB
+constexpr int B_TILE_BYTES = TC_BN * TC_BK * 4;  // 16 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // raw + lo of both operands = 48 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024;      // + alignment slack
-constexpr int STG_LD = TC_BN + 4;               // padded row of the epilogue staging tile (floats)
-constexpr int TC_THREADS = 192;
-constexpr int TMEM_COLS = 256;
-static_assert(TC_BM * STG_LD * 4 <= TC_STAGES * STAGE_BYTES, "epilogue staging must fit in the operand ring");
+constexpr int TC_THREADS = 448;                 // 1 TMA + 1 MMA + 8 transform + 4 epilogue warps
+constexpr int TMEM_COLS = 512;                  // two 256-column fp32 accumulators
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -123,36 +124,65 @@ struct TcParams {
   Args a;
   int a_mn, b_mn;        // 1: operand is MN-major (contiguous along m / n), 0: K-major
   int mask_hi;
+  int vec_epi;           // every epilogue operand is 16-byte aligned with a row stride that is a multiple of 4
+  int m_tiles, n_tiles, splits, kb_per_split, nkb_total;
 };
+
+// fused epilogue on 4 consecutive columns (vector path of the tensor-core kernel)
+template <int EPI>
+__device__ __forceinline__ void epilogue_vec4(const Args& a, long long m, int n, const float* acc, float4 hv, float4 uv,
+                                              float4 cv, float4 bv) {
+  float h[4] = {hv.x, hv.y, hv.z, hv.w}, u[4] = {uv.x, uv.y, uv.z, uv.w}, co[4] = {cv.x, cv.y, cv.z, cv.w};
+  float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+  float o[4], o2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (EPI == EPI_BIAS) o[e] = a.alpha * acc[e] + bb[e];
+    else if (EPI == EPI_SOFTPLUS) o[e] = a.out_scale * softplus_beta_fast(acc[e] + bb[e], a.beta);
+    else if (EPI == EPI_ACCUM) o[e] = co[e] + a.alpha * acc[e];
+    else if (EPI == EPI_MUL_S) {
+      float sg = sig_from_softplus_fast(h[e] * a.hscale, a.beta);
+      o[e] = a.alpha * acc[e] * sg + u[e];
+    } else if (EPI == EPI_ADJ) {
+      float sg = sig_from_softplus_fast(h[e] * a.hscale, a.beta);
+      o[e] = acc[e] * u[e] * a.beta * (1.f - sg);
+      o2[e] = a.out_scale * acc[e] * sg;
+    } else o[e] = a.alpha * acc[e];
+  }
+  float* cp = a.C + m * a.ldc + n;
+  if (EPI == EPI_ATOMIC) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3])
+                 : "memory");
+  } else {
+    *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+    if (EPI == EPI_ADJ) *reinterpret_cast<float4*>(a.C2 + m * a.ldc2 + n) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+  }
+}
+
+// Persistent kernel: one CTA per SM walks a static list of work items (m tile, n tile, K split).
+//   warp 0        TMA producer                                  warps 2-9    hi/lo transform (256 threads)
+//   warp 1        MMA issuer (+ TMEM allocation, 512 columns)   warps 10-13  epilogue straight from TMEM
+// Two 256-column TMEM accumulators: the epilogue of item i overlaps the main loop of item i+1.
+constexpr int TC_XFORM_THREADS = 256;
+constexpr int TC_EPI_WARP0 = 2 + TC_XFORM_THREADS / 32;
 
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 4];
   __shared__ uint32_t tmem_base_sh;
 
   const Args& a = p.a;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
-  const int n_valid = min(TC_BN, a.N - n0);
-  const int umma_n = (n_valid + 15) & ~15;
-  const int nkb_total = (a.K + TC_BK - 1) / TC_BK;
-  int kb0 = 0, kb1 = nkb_total;
-  if (a.split_k > 1) {
-    int per = (nkb_total + a.split_k - 1) / a.split_k;
-    kb0 = blockIdx.z * per;
-    kb1 = min(nkb_total, kb0 + per);
-    if (kb0 >= kb1) return;
-  }
-  const int nkb = kb1 - kb0;
 
   auto bar_full = [&](int s) { return smem_u32(&bars[s]); };
   auto bar_ready = [&](int s) { return smem_u32(&bars[TC_STAGES + s]); };
   auto bar_empty = [&](int s) { return smem_u32(&bars[2 * TC_STAGES + s]); };
-  const uint32_t bar_accum = smem_u32(&bars[3 * TC_STAGES]);
+  auto bar_acc_full = [&](int b) { return smem_u32(&bars[3 * TC_STAGES + b]); };
+  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[3 * TC_STAGES + 2 + b]); };
   auto a_raw = [&](int s) { return smem_base + s * STAGE_BYTES; };
   auto a_lo = [&](int s) { return smem_base + s * STAGE_BYTES + A_TILE_BYTES; };
   auto b_raw = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_TILE_BYTES; };
@@ -161,10 +191,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_ready(s), 128);
+      mbar_init(bar_ready(s), TC_XFORM_THREADS);
       mbar_init(bar_empty(s), 1);
     }
-    mbar_init(bar_accum, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);
+      mbar_init(bar_acc_empty(b), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -178,119 +211,189 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
 
-  const int b_chunks = (umma_n + 31) / 32;   // 32-wide n chunks actually loaded when B is MN-major
-  const uint32_t tx_bytes = A_TILE_BYTES + (p.b_mn ? b_chunks * TC_BK * 128 : B_TILE_BYTES);
+  const int n_items = p.m_tiles * p.n_tiles * p.splits;
+  // work item -> (m0, n0, kb0, nkb); m tiles vary fastest so co-running CTAs share the same weight tile
+  auto item_info = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
+    int mt = item % p.m_tiles;
+    int rest = item / p.m_tiles;
+    int ntile = rest % p.n_tiles;
+    int sp = rest / p.n_tiles;
+    m0 = mt * TC_BM;
+    n0 = ntile * TC_BN;
+    kb0 = sp * p.kb_per_split;
+    int kb1 = min(p.nkb_total, kb0 + p.kb_per_split);
+    nkb = max(0, kb1 - kb0);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        int s = i % TC_STAGES;
-        uint32_t ph = (i / TC_STAGES) & 1;
-        mbar_wait(bar_empty(s), ph ^ 1);
-        mbar_expect_tx(bar_full(s), tx_bytes);
-        int k0 = (kb0 + i) * TC_BK;
-        if (p.a_mn) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        item_info(item, m0, n0, kb0, nkb);
+        const int umma_n = (min(TC_BN, a.N - n0) + 15) & ~15;
+        const int b_chunks = (umma_n + 31) / 32;
+        const uint32_t tx_bytes = A_TILE_BYTES + (p.b_mn ? b_chunks * TC_BK * 128 : B_TILE_BYTES);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          int s = it % TC_STAGES;
+          uint32_t ph = (it / TC_STAGES) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          mbar_expect_tx(bar_full(s), tx_bytes);
+          int k0 = (kb0 + i) * TC_BK;
+          if (p.a_mn) {
 #pragma unroll
-          for (int c = 0; c < TC_BM / 32; ++c) tma_load_2d(a_raw(s) + c * TC_BK * 128, &mapA, m0 + c * 32, k0, bar_full(s));
-        } else {
-          tma_load_2d(a_raw(s), &mapA, k0, m0, bar_full(s));
-        }
-        if (p.b_mn) {
-          for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_raw(s) + c * TC_BK * 128, &mapB, n0 + c * 32, k0, bar_full(s));
-        } else {
-          tma_load_2d(b_raw(s), &mapB, k0, n0, bar_full(s));
+            for (int c = 0; c < TC_BM / 32; ++c) tma_load_2d(a_raw(s) + c * TC_BK * 128, &mapA, m0 + c * 32, k0, bar_full(s));
+          } else {
+            tma_load_2d(a_raw(s), &mapA, k0, m0, bar_full(s));
+          }
+          if (p.b_mn) {
+            for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_raw(s) + c * TC_BK * 128, &mapB, n0 + c * 32, k0, bar_full(s));
+          } else {
+            tma_load_2d(b_raw(s), &mapB, k0, n0, bar_full(s));
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO), K step of 8 elements = +32 B.
+      // K-major (SWIZZLE_64B for 16-wide K blocks): rows of TC_BK*4 B, 8-row groups KM_SBO apart, K step of 8
+      // elements = +32 B inside the row.
       // MN-major (SWIZZLE_128B_BASE32B): k rows of 128 B (32 mn elements), 4-row k groups 512 B apart (SBO), 32-wide
       // mn chunks TC_BK*128 B apart (LBO), K step of 8 rows = +1024 B.
-      const uint32_t a_lbo = p.a_mn ? TC_BK * 128 : 16, a_sbo = p.a_mn ? 512 : 1024, a_step = p.a_mn ? 1024 : 32;
-      const uint32_t b_lbo = p.b_mn ? TC_BK * 128 : 16, b_sbo = p.b_mn ? 512 : 1024, b_step = p.b_mn ? 1024 : 32;
-      const uint32_t a_lay = p.a_mn ? 1 : 2, b_lay = p.b_mn ? 1 : 2;
-      for (int i = 0; i < nkb; ++i) {
-        int s = i % TC_STAGES;
-        uint32_t ph = (i / TC_STAGES) & 1;
-        mbar_wait(bar_ready(s), ph);
+      const uint32_t a_lbo = p.a_mn ? TC_BK * 128 : 16, a_sbo = p.a_mn ? 512 : KM_SBO, a_step = p.a_mn ? 1024 : 32;
+      const uint32_t b_lbo = p.b_mn ? TC_BK * 128 : 16, b_sbo = p.b_mn ? 512 : KM_SBO, b_step = p.b_mn ? 1024 : 32;
+      const uint32_t a_lay = p.a_mn ? 1 : KM_LAYOUT, b_lay = p.b_mn ? 1 : KM_LAYOUT;
+      uint32_t it = 0, tile_it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_it) {
+        int m0, n0, kb0, nkb;
+        item_info(item, m0, n0, kb0, nkb);
+        if (nkb == 0) continue;
+        const int umma_n = (min(TC_BN, a.N - n0) + 15) & ~15;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                               ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const int buf = tile_it & 1;
+        mbar_wait(bar_acc_empty(buf), ((tile_it >> 1) & 1) ^ 1);
         tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * TC_BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          int s = it % TC_STAGES;
+          uint32_t ph = (it / TC_STAGES) & 1;
+          mbar_wait(bar_ready(s), ph);
+          tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          uint64_t da_hi = make_desc(a_raw(s) + ks * a_step, a_lbo, a_sbo, a_lay);
-          uint64_t da_lo = make_desc(a_lo(s) + ks * a_step, a_lbo, a_sbo, a_lay);
-          uint64_t db_hi = make_desc(b_raw(s) + ks * b_step, b_lbo, b_sbo, b_lay);
-          uint64_t db_lo = make_desc(b_lo(s) + ks * b_step, b_lbo, b_sbo, b_lay);
-          umma_tf32(tmem_base, da_lo, db_hi, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
-          umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
-          umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            uint64_t da_hi = make_desc(a_raw(s) + ks * a_step, a_lbo, a_sbo, a_lay);
+            uint64_t da_lo = make_desc(a_lo(s) + ks * a_step, a_lbo, a_sbo, a_lay);
+            uint64_t db_hi = make_desc(b_raw(s) + ks * b_step, b_lbo, b_sbo, b_lay);
+            uint64_t db_lo = make_desc(b_lo(s) + ks * b_step, b_lbo, b_sbo, b_lay);
+            umma_tf32(tacc, da_lo, db_hi, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
+            umma_tf32(tacc, da_hi, db_lo, idesc, 1u);
+            umma_tf32(tacc, da_hi, db_hi, idesc, 1u);
+          }
+          umma_commit(bar_empty(s));     // frees the stage once these MMAs have read it
         }
-        umma_commit(bar_empty(s));   // frees the stage once these MMAs have read it
+        umma_commit(bar_acc_full(buf));  // accumulator complete
       }
-      umma_commit(bar_accum);        // accumulator complete
+    }
+  } else if (warp < TC_EPI_WARP0) {
+    // ===================== transform: lo = x - hi for both operand tiles =====================
+    const int t = threadIdx.x - 64;   // 0..255
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int m0, n0, kb0, nkb;
+      item_info(item, m0, n0, kb0, nkb);
+      const int umma_n = (min(TC_BN, a.N - n0) + 15) & ~15;
+      const int b_bytes = p.b_mn ? ((umma_n + 31) / 32) * TC_BK * 128 : B_TILE_BYTES;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        int s = it % TC_STAGES;
+        uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(bar_full(s), ph);
+        uint8_t* st = smem + s * STAGE_BYTES;
+#pragma unroll 2
+        for (int off = t * 16; off < A_TILE_BYTES; off += TC_XFORM_THREADS * 16) {
+          float4 x = *reinterpret_cast<const float4*>(st + off);
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          *reinterpret_cast<float4*>(st + A_TILE_BYTES + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          if (p.mask_hi) *reinterpret_cast<float4*>(st + off) = h;
+        }
+#pragma unroll 4
+        for (int off = t * 16; off < b_bytes; off += TC_XFORM_THREADS * 16) {
+          float4 x = *reinterpret_cast<const float4*>(st + 2 * A_TILE_BYTES + off);
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          *reinterpret_cast<float4*>(st + 2 * A_TILE_BYTES + B_TILE_BYTES + off) =
+              make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          if (p.mask_hi) *reinterpret_cast<float4*>(st + 2 * A_TILE_BYTES + off) = h;
+        }
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(bar_ready(s));
+      }
     }
   } else {
-    // ===================== transform (lo tiles), then epilogue =====================
-    const int t = threadIdx.x - 64;   // 0..127
-    for (int i = 0; i < nkb; ++i) {
-      int s = i % TC_STAGES;
-      uint32_t ph = (i / TC_STAGES) & 1;
-      mbar_wait(bar_full(s), ph);
-      uint8_t* st = smem + s * STAGE_BYTES;
-      // A: raw at 0, lo at A_TILE_BYTES;  B: raw at 2*A_TILE_BYTES, lo at 2*A_TILE_BYTES + B_TILE_BYTES
-#pragma unroll 4
-      for (int off = t * 16; off < A_TILE_BYTES; off += 128 * 16) {
-        float4 x = *reinterpret_cast<const float4*>(st + off);
-        float4 h;
-        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-        *reinterpret_cast<float4*>(st + A_TILE_BYTES + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-        if (p.mask_hi) *reinterpret_cast<float4*>(st + off) = h;
-      }
-      const int b_bytes = p.b_mn ? b_chunks * TC_BK * 128 : B_TILE_BYTES;
-#pragma unroll 4
-      for (int off = t * 16; off < b_bytes; off += 128 * 16) {
-        float4 x = *reinterpret_cast<const float4*>(st + 2 * A_TILE_BYTES + off);
-        float4 h;
-        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-        *reinterpret_cast<float4*>(st + 2 * A_TILE_BYTES + B_TILE_BYTES + off) =
-            make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-        if (p.mask_hi) *reinterpret_cast<float4*>(st + 2 * A_TILE_BYTES + off) = h;
-      }
-      fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(bar_ready(s));
-    }
-    // ---- epilogue ----
-    mbar_wait(bar_accum, 0);
-    tc_fence_after();
-    const int q = warp & 3;                     // TMEM sub-partition of this warp: lanes 32q .. 32q+31
-    float* stg = reinterpret_cast<float*>(smem);
-    float* my_row = stg + (q * 32 + lane) * STG_LD;
-    for (int c = 0; c < umma_n; c += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+    // ===================== epilogue: TMEM -> registers -> global, one output row per thread =====================
+    const int q = warp & 3;           // TMEM sub-partition of this warp: lanes 32q .. 32q+31
+    uint32_t tile_it = 0;
+    constexpr bool NEED_H = (EPI == EPI_MUL_S || EPI == EPI_ADJ);
+    constexpr bool NEED_C = (EPI == EPI_ACCUM);
+    const bool need_u = (EPI == EPI_ADJ) || (EPI == EPI_MUL_S && a.U != nullptr);
+    const bool need_b = (EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias != nullptr;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_it) {
+      int m0, n0, kb0, nkb;
+      item_info(item, m0, n0, kb0, nkb);
+      if (nkb == 0) continue;
+      const int n_valid = min(TC_BN, a.N - n0);
+      const int buf = tile_it & 1;
+      const long long m = m0 + q * 32 + lane;
+      const bool row_ok = m < a.M;
+      const int n_vec = p.vec_epi ? (n_valid & ~3) : 0;
+      mbar_wait(bar_acc_full(buf), (tile_it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * TC_BN + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < n_valid; c0 += 32) {
+        // operands of the fused epilogue for this thread's 32 columns: issued before the accumulator is read so
+        // up to 16 independent 16-byte loads per thread are in flight
+        float4 hv[8], uv[8], cv[8], bv[8];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(my_row + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 8; ++j) {
+          int c = c0 + 4 * j;
+          hv[j] = uv[j] = cv[j] = bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && c < n_vec) {
+            if (NEED_H) hv[j] = __ldg(reinterpret_cast<const float4*>(a.H + m * a.ldh + n0 + c));
+            if (need_u) uv[j] = *reinterpret_cast<const float4*>(a.U + m * a.ldu + n0 + c);
+            if (NEED_C) cv[j] = *reinterpret_cast<const float4*>(a.C + m * a.ldc + n0 + c);
+            if (need_b) bv[j] = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c));
+          }
+        }
+        float v[32];
+        tmem_ld32(tacc + (uint32_t)c0, v);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int c = c0 + 4 * j;
+            if (c < n_vec) {
+              epilogue_vec4<EPI>(a, m, n0 + c, v + 4 * j, hv[j], uv[j], cv[j], bv[j]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c + e < n_valid) epilogue_store<EPI>(a, (int)m, n0 + c + e, v[4 * j + e]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty(buf));
     }
-    __syncwarp();
-    // coalesced pass over this warp's 32 rows: lanes across columns
-    for (int r = 0; r < 32; ++r) {
-      int m = m0 + q * 32 + r;
-      if (m >= a.M) break;
-      const float* row = stg + (q * 32 + r) * STG_LD;
-      for (int c = lane; c < n_valid; c += 32) epilogue_store<EPI>(a, m, n0 + c, row[c]);
-    }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -329,7 +432,8 @@ static bool make_map(CUtensorMap* map, const float* base, long long inner, long 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                            : (TC_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -357,6 +461,8 @@ static int launch_tc_epi(const Args& a, cudaStream_t st) {
   p.b_mn = (a.b_cs == 1);        // B(k,n) contiguous along n
   p.mask_hi = g_mlp_mask_hi;
   if (a.b_cs == 1 && a.b_rs == 1) p.b_mn = 1;
+  auto ok16 = [](const void* q, long long ld) { return q == nullptr || (al16p(q) && ld % 4 == 0); };
+  p.vec_epi = ok16(a.C, a.ldc) && ok16(a.H, a.ldh) && ok16(a.U, a.ldu) && ok16(a.C2, a.ldc2) && ok16(a.bias, 0);
   CUtensorMap mapA, mapB;
   bool ok;
   if (p.a_mn) ok = make_map(&mapA, a.A, a.M, a.K, a.a_cs, 32, TC_BK, true);
@@ -370,7 +476,14 @@ static int launch_tc_epi(const Args& a, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.M + TC_BM - 1) / TC_BM, a.split_k > 1 ? a.split_k : 1);
+  p.m_tiles = (a.M + TC_BM - 1) / TC_BM;
+  p.n_tiles = (a.N + TC_BN - 1) / TC_BN;
+  p.nkb_total = (a.K + TC_BK - 1) / TC_BK;
+  int splits = a.split_k > 1 ? a.split_k : 1;
+  p.kb_per_split = (p.nkb_total + splits - 1) / splits;
+  p.splits = (p.nkb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+  int n_items = p.m_tiles * p.n_tiles * p.splits;
+  int grid = n_items < NDJIR_NUM_SMS ? n_items : NDJIR_NUM_SMS;
   gemm_tc_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, p);
   NDJIR_RETURN_LAST_ERROR();
 }

@@ -19,6 +19,7 @@ import torch
 
 from . import _lib
 from .config import grid_channels
+from .parallel import allreduce_gradients, allreduce_mask_sum
 from .scene import network_dims, pe_dim, NET_ORDER
 
 EPI_BIAS, EPI_SOFTPLUS, EPI_ACCUM, EPI_MUL_S, EPI_ADJ, EPI_ATOMIC = range(6)
@@ -244,7 +245,7 @@ class Engine:
                   hscale, U, ldu, C2, ldc2, split_k, epi)
         if self.profile:
             e1.record()
-            self.prof_events.append((e0, e1, 2.0 * M * N * K))
+            self.prof_events.append((e0, e1, 2.0 * M * N * K, f"epi{epi} {M}x{N}x{K}"))
 
     def wgrad(self, rows, K, N, A, lda, dZ, ldz, gW, ldw):
         """gW (K,N) += A(rows,K)^T dZ(rows,N): split-K over the rows with atomic accumulation."""
@@ -604,7 +605,7 @@ class Engine:
             x_fg, t_fg, x_bg, t_bg, mask = samples
             scal[0, 0] = mask.sum()
         if self.world_size > 1:
-            torch.distributed.all_reduce(scal[0, 0:1], group=self.pg)
+            allreduce_mask_sum(scal[0, 0:1], self.pg)
         self.call("ndjir_loss_inv_denorm", mask_sum, N, inv_denorm)
         inv_rays = 1.0 / (NR * self.world_size)
         x_fg = x_fg.reshape(P, 3)
@@ -822,9 +823,7 @@ class Engine:
                 self.call("ndjir_ray_mask_fill", P, N, width, P_(tvg), P_(maskv), inv_denorm, float(tr.tv_weight))
                 self._grid_call("tv_bwd", part, P, P_(ps.grid_grad[part]), P_(tvg), P_(x_fg), P_(ps.grid[part]))
         if self.world_size > 1:
-            torch.distributed.all_reduce(ps.grad, group=self.pg)
-            for v in ps.grid_grad.values():
-                torch.distributed.all_reduce(v, group=self.pg)
+            allreduce_gradients(ps, self.pg)
         if keep:
             self.debug.update(dict(dO=dO, dsdf=dsdf, dw=dw, dRAW=dRAW, d_attpix=d_attpix, dpix=dpix, nbar=nbar,
                                    dalpha_fg=dalpha_fg, dalpha_bg=dalpha_bg, d_el=d_el, d_sv=d_sv))

@@ -1,9 +1,18 @@
 """GPU parity of the fused per-ray path (ndjir_b200.engine: sample_points, pb_render + total_loss forward and the
 hand-derived backward) against the CPU oracle oracle/cpu_render.py (torch autograd, float64) on identical seeded
-inputs.  Bars (BASELINE.json north_star): hit masks bit-exact; features / SDF / colour 1e-5 relative forward
-(max-norm, fp32 path vs float64 oracle: 2e-5 where a softplus(beta=100) chain amplifies rounding, stated per check);
-gradients 1e-4 relative (atomic-order tolerance).  Every check is evaluated and reported (gpurun_out/engine_parity.json)
-before the test asserts, so one GPU run shows the whole picture."""
+inputs, for both MLP product paths: the tcgen05 3xTF32 tensor-core path (default) and the fp32 FFMA path.
+
+Bars (BASELINE.json north_star), max-norm relative per tensor:
+  * hit masks bit-exact;
+  * SDF / features / rendered colour 1e-5 forward;
+  * quantities behind a gain*sdf sigmoid (alpha, weights, transmittance) and the nn.grad normal 5e-5;
+  * gradients 1e-4 on the FFMA path; on the tensor-core path 1e-4 in relative L2 norm and 2e-4 max-norm (the
+    tensor core accumulates ~100 partial products per output in fp32 with truncation, measured 2-8e-6 per product
+    in tests/test_gemm_gpu.py, which an 8-layer double-backward chain amplifies);
+  * where the oracle's own float32 evaluation deviates from its float64 evaluation by more than the bar
+    (ill-conditioned quantities: a normalised near-zero pixel normal, inverse-CDF steps through 1e-5 weights) the bar
+    is 4x that deviation (Report.check).
+Every check is evaluated and reported (gpurun_out/engine_parity_*.json) before the test asserts."""
 import json
 import os
 
@@ -46,6 +55,12 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / scale)
 
 
+def rel_l2(a, b):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a.reshape(b.shape) - b) / max(np.linalg.norm(b), 1e-30))
+
+
 def dev(x):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).cuda()
 
@@ -54,7 +69,7 @@ class Report:
     def __init__(self, name):
         self.name, self.rows, self.bad = name, [], []
 
-    def check(self, what, a, b, tol, b32=None):
+    def check(self, what, a, b, tol, b32=None, l2_tol=None):
         """`b32` = the same quantity from the oracle run in float32: the fp32 evaluation noise of the reference's own
         graph on this input.  Where that noise exceeds the base tolerance (ill-conditioned quantities such as a
         normalised near-zero pixel normal) the bar is 4x the oracle's own fp32-vs-fp64 deviation."""
@@ -62,9 +77,17 @@ class Report:
         if b32 is not None:
             tol = max(tol, 4.0 * relerr(b32, b))
         ok = bool(np.isfinite(e) and e <= tol)
-        self.rows.append(dict(what=what, err=e, tol=tol, ok=ok))
+        row = dict(what=what, err=e, tol=tol, ok=ok)
+        if l2_tol is not None:
+            e2 = rel_l2(a, b)
+            if b32 is not None:
+                l2_tol = max(l2_tol, 4.0 * rel_l2(b32, b))
+            row.update(l2_err=e2, l2_tol=l2_tol)
+            ok = ok and bool(np.isfinite(e2) and e2 <= l2_tol)
+            row["ok"] = ok
+        self.rows.append(row)
         if not ok:
-            self.bad.append(f"{what}: {e:.3e} > {tol:.1e}")
+            self.bad.append(f"{what}: {e:.3e} > {tol:.1e}" + (f" (l2 {row.get('l2_err', 0):.3e})" if l2_tol else ""))
 
     def finish(self):
         out = os.path.join(ROOT, "gpurun_out")
@@ -129,11 +152,20 @@ def test_sample_points_matches_oracle(kind):
     rep.finish()
 
 
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "ffma"])
+def mlp_path(request):
+    from ndjir_b200 import _lib
+    _lib.call("ndjir_set_option", "mlp_tensor_cores", request.param)
+    yield request.param
+    _lib.call("ndjir_set_option", "mlp_tensor_cores", 1)
+
+
 @pytest.mark.parametrize("kind,cos_anneal", [("default", 0.0), ("default", 0.7), ("triplaneline", 0.3),
                                               ("no_voxel", 1.0)])
-def test_train_step_matches_oracle(kind, cos_anneal):
+def test_train_step_matches_oracle(kind, cos_anneal, mlp_path):
     conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind)
-    rep = Report(f"train_{kind}_{cos_anneal}")
+    rep = Report(f"train_{kind}_{cos_anneal}_{'tc' if mlp_path else 'ffma'}")
+    g_tol = 2e-4 if mlp_path else 1e-4
     # identical sample placement on both sides (placement itself is covered by the test above)
     samples = CR.sample_points(model, camloc, raydir, rnd["stratified"], rnd["background"])
     samples32 = [dev(s.numpy()) for s in samples]
@@ -154,8 +186,8 @@ def test_train_step_matches_oracle(kind, cos_anneal):
     ol32, res32, _ = CR.total_loss(model32, camloc, raydir, color_gt, cos_anneal, rnd, return_all=True,
                                    samples=samples_f32, fixed_dirs=fixed)
     # ---- forward intermediates ----
-    rep.check("sdf", d["sdf"][:Pn], res["sdf_x_fg"], 2e-5)
-    rep.check("feature", d["O"][:Pn, :Df], res["feature"], 2e-5)
+    rep.check("sdf", d["sdf"][:Pn], res["sdf_x_fg"], 1e-5)
+    rep.check("feature", d["O"][:Pn, :Df], res["feature"], 1e-5)
     rep.check("normal (nn.grad)", d["nrm"][:Pn], res["grad_x_fg"], 5e-5)
     rep.check("alpha_fg", d["alpha_fg"][:Pn], res["alpha_fg"], 5e-5)
     rep.check("alpha_bg", d["alpha_bg"][:NR * Nb], res["alpha_bg"], 2e-5)
@@ -170,7 +202,7 @@ def test_train_step_matches_oracle(kind, cos_anneal):
     rep.check("photogrammetric", att[:, 5], res["photogrammetric"], 2e-5)
     rep.check("base_color*pl", att[:, 6:9], res["base_color"] * res["photogrammetric"], 2e-5)
     rep.check("roughness_pixel", d["attpix"][:NR, 1], res["roughness_pixel"], 5e-5)
-    rep.check("color_pixel", d["color"][:NR], res["color_pixel"], 5e-5, res32["color_pixel"])
+    rep.check("color_pixel", d["color"][:NR], res["color_pixel"], 1e-5, res32["color_pixel"])
     for i, k in enumerate(["loss", "loss_rgb", "loss_eikonal", "loss_tv", None, "prior_base_color", "prior_roughness",
                            "prior_specular_reflectance", "reg_std_roughness", "reg_std_specular_reflectance"]):
         if k is not None:
@@ -192,10 +224,10 @@ def test_train_step_matches_oracle(kind, cos_anneal):
     for k, p in params.items():
         want = p.grad.detach().numpy() if p.grad is not None else np.zeros(tuple(p.shape))
         if np.abs(want).max() == 0 and np.abs(ours[k]).max() == 0:
-            rep.rows.append(dict(what=f"grad.{k}", err=0.0, tol=1e-4, ok=True))
+            rep.rows.append(dict(what=f"grad.{k}", err=0.0, tol=g_tol, ok=True))
             continue
         w32 = params32[k].grad.detach().numpy() if params32[k].grad is not None else np.zeros(tuple(p.shape))
-        rep.check(f"grad.{k}", ours[k], want, 1e-4, w32)
+        rep.check(f"grad.{k}", ours[k], want, g_tol, w32, l2_tol=1e-4)
     rep.finish()
 
 

@@ -236,7 +236,10 @@ def test_voxel_hash(B, G0, L, D):
     ours.voxel_hash_feature(N, o1.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
     ref.voxel_hash_feature(N, o2.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
     close(o1, o2, 1e-5, "fwd vs reference kernel")
-    close(o1, R.voxel_hash_query(q_np, f_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 1e-5, "fwd vs oracle")
+    # numpy evaluates the 8-term weighted sum unfused; both CUDA kernels (nvcc -fmad) contract it, and at the finest
+    # levels (G ~ 7000) that shows at 1.4e-5 of the max value: the bar against the numpy oracle is 2e-5 here, the bar
+    # against the reference's own kernel stays 1e-5 (line above)
+    close(o1, R.voxel_hash_query(q_np, f_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 2e-5, "fwd vs oracle")
     # (B, D*L) layout through the C ABI == transpose of the reference layout
     from ndjir_b200._lib import call
     o3 = torch.zeros(B, D * L).cuda()
