@@ -61,18 +61,20 @@ __device__ __forceinline__ void ray_aabb(float ox, float oy, float oz, float dx,
 }
 
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
-  // helper_math.h dot(): a.x*b.x + a.y*b.y + a.z*b.z, which nvcc contracts to FMUL, FFMA, FFMA
-  return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
+  // helper_math.h dot(): a.x*b.x + a.y*b.y + a.z*b.z.  nvcc fuses the FIRST product of each sum into the FMA and
+  // leaves the second as the FMUL: fma(a.z, b.z, fma(a.x, b.x, a.y*b.y))
+  return __fmaf_rn(az, bz, __fmaf_rn(ax, bx, __fmul_rn(ay, by)));
 }
 
 __device__ __forceinline__ void ray_sphere(float ox, float oy, float oz, float dx, float dy, float dz, float radius,
                                            float& tn, float& tf, int& nh) {
-  float r2 = __fmul_rn(radius, radius);
+  float r2 = __fmul_rn(radius, radius);   // the reference build computes cc - r*r as fma(-r, r, cc)
   float cv = dot3(ox, oy, oz, dx, dy, dz);
   float vv = dot3(dx, dy, dz, dx, dy, dz);
   float cc = dot3(ox, oy, oz, ox, oy, oz);
   float X = -cv;
-  float Y = __fmaf_rn(cv, cv, -__fmul_rn(vv, __fsub_rn(cc, r2)));  // cv*cv - vv*(cc-r2), contracted
+  (void)r2;
+  float Y = __fmaf_rn(cv, cv, -__fmul_rn(vv, __fmaf_rn(-radius, radius, cc)));  // cv*cv - vv*(cc-r2), contracted
   float Zi = __fdiv_rn(1.f, vv);
   nh = 0; tn = 0.f; tf = 0.f;
   if (Y > 0) {

@@ -194,6 +194,7 @@ int launch(const Args& a, int epi, cudaStream_t st) {
   if (a.a_cs != 1 && a.a_rs != 1) return NDJIR_ERR_ARG;
   if (a.b_cs != 1 && a.b_rs != 1) return NDJIR_ERR_ARG;
   if (a.split_k > 1 && epi != EPI_ATOMIC) return NDJIR_ERR_ARG;
+  if (g_mlp_tensor_cores && skinny_eligible(a, epi)) return launch_skinny(a, epi, st);
   if (g_mlp_tensor_cores && tc_eligible(a, epi)) return launch_tc(a, epi, st);
   switch (epi) {
     case EPI_BIAS: dispatch_tile<EPI_BIAS>(a, st); break;

@@ -101,6 +101,9 @@ extern int g_mlp_tensor_cores;
 extern int g_mlp_mask_hi;     // 1: the transform warps also clear the low 13 mantissa bits of the raw tiles
 bool tc_eligible(const Args& a, int epi);
 int launch_tc(const Args& a, int epi, cudaStream_t st);
+// memory-bound corner shapes (gemm_skinny.cu): N <= 8 outputs, K <= 8 rank updates, weight gradients with N <= 8
+bool skinny_eligible(const Args& a, int epi);
+int launch_skinny(const Args& a, int epi, cudaStream_t st);
 
 }  // namespace gemm
 }  // namespace ndjir

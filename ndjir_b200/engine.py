@@ -186,6 +186,17 @@ class ParamStore:
         return self.grad.data_ptr() + 4 * L.b_off
 
 
+_ENGINES = {}
+
+
+def get_engine(conf, **kw):
+    """One Engine (parameters + scratch buffers) per configuration object, created on first use."""
+    e = _ENGINES.get(id(conf))
+    if e is None:
+        e = _ENGINES[id(conf)] = Engine(conf, **kw)
+    return e
+
+
 def P_(t, off=0):
     """device address of element `off` of tensor t"""
     return t.data_ptr() + 4 * off
@@ -734,6 +745,8 @@ class Engine:
         self.call("ndjir_finalize_losses", P_(losses), mask_sum, N, inv_rays, tr.eikonal_weight,
                   tr.tv_weight if tv_on else 0.0, tr.base_color_prior_weight, tr.roughness_prior_weight,
                   tr.specular_reflectance_prior_weight)
+        if self.world_size > 1:
+            allreduce_mask_sum(losses[0, :N_LOSSES], self.pg)     # report the loss of the union of all ranks' rays
         if keep:
             self.debug.update(dict(O=O, sdf=sdf, nrm=nrm, alpha_fg=alpha_fg, alpha_bg=alpha_bg, w=w, T=T, pix=pix,
                                    nhat=nhat, RAW=RAW, ATT=ATT, attpix=attpix, dirs_u=dirs_u, dirs_s=dirs_s,

@@ -769,12 +769,14 @@ def ray_sphere(camloc, raydir, radius):
     o = np.broadcast_to(camloc.reshape(B, 1, 3), (B, R, 3)).reshape(-1, 3)
     d = raydir.reshape(-1, 3)
 
-    def dot(a, b):   # helper_math.h dot(): a.x*b.x + a.y*b.y + a.z*b.z, contracted to fma chains by nvcc
-        return _fma32(a[:, 2], b[:, 2], _fma32(a[:, 1], b[:, 1], (a[:, 0] * b[:, 0]).astype(f32)))
+    def dot(a, b):   # helper_math.h dot(): a.x*b.x + a.y*b.y + a.z*b.z; nvcc fuses the FIRST product of each sum:
+        # fma(a.z, b.z, fma(a.x, b.x, a.y*b.y)) (SASS of the sm_100a build: FMUL, FFMA, FFMA)
+        return _fma32(a[:, 2], b[:, 2], _fma32(a[:, 0], b[:, 0], (a[:, 1] * b[:, 1]).astype(f32)))
     r2 = f32(f32(radius) * f32(radius))
     cv, vv, cc = dot(o, d), dot(d, d), dot(o, o)
     X = (-cv).astype(f32)
-    Y = _fma32(cv, cv, -(vv * (cc - r2).astype(f32)).astype(f32))
+    ccr = _fma32(np.full_like(cc, -f32(radius)), np.full_like(cc, f32(radius)), cc)    # cc - r*r as fma(-r, r, cc)
+    Y = _fma32(cv, cv, -(vv * ccr).astype(f32))
     Zi = (f32(1.0) / vv).astype(f32)
     with np.errstate(invalid="ignore"):
         Ys = np.sqrt(np.maximum(Y, 0)).astype(f32)

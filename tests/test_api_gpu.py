@@ -1,0 +1,166 @@
+"""GPU tests of the operator-level API (ndjir_b200.grid_feature / intersection / sampler), written the way the
+reference tests its own operators: same seeds and parametrisations (python/grid_feature/test/test_voxel_feature.py:
+25-150: seed 412, batch in {2,16}, G in {2,8}, D=4, query U[-1,1], feature randn*0.01; forward atol 1e-6, first-order
+feature gradient 1e-6, `nn.grad` query gradient 1e-6, second order 1e-3), with the oracle in the composite op's
+place: the torch restatements in oracle/cpu_render.py (float64 autograd) and the numpy kernels in oracle/cpu_ref.py."""
+import numpy as np
+import pytest
+import torch
+
+from ndjir_b200 import grid_feature as GF
+from ndjir_b200 import intersection, sampler
+from oracle import cpu_ref as R
+from oracle import cpu_render as CR
+
+pytestmark = pytest.mark.gpu
+MN, MX = [-1.0] * 3, [1.0] * 3
+
+
+def make(seed, batch, shape):
+    rng = np.random.RandomState(seed)
+    q = (rng.rand(batch, 3) * 2 - 1).astype(np.float32)
+    f = (rng.randn(*shape) * 0.01).astype(np.float32)
+    return q, f
+
+
+CASES = [("voxel", GF.query_on_voxel, CR.voxel_query_torch, lambda G, D: (G, G, G, D)),
+         ("triplane", GF.query_on_triplane, CR.triplane_query_torch, lambda G, D: (3, G, G, D)),
+         ("triline", GF.query_on_triline, CR.triline_query_torch, lambda G, D: (3, G, D))]
+
+
+@pytest.mark.parametrize("seed", [412])
+@pytest.mark.parametrize("batch", [2, 16])
+@pytest.mark.parametrize("G", [2, 8])
+@pytest.mark.parametrize("D", [4])
+@pytest.mark.parametrize("name,op,oracle,shape", CASES)
+def test_query_forward_backward(seed, batch, G, D, name, op, oracle, shape):
+    """test_voxel_feature.py:25-77 (test_query_on_voxel_forward_backward)."""
+    q_np, f_np = make(seed, batch, shape(G, D))
+    q = torch.tensor(q_np, device="cuda", requires_grad=True)
+    f = torch.tensor(f_np, device="cuda", requires_grad=True)
+    out = op(q, f, MN, MX)
+    out.sum().backward()
+    q64 = torch.tensor(q_np, dtype=torch.float64, requires_grad=True)
+    f64 = torch.tensor(f_np, dtype=torch.float64, requires_grad=True)
+    want = oracle(q64, f64)
+    want.sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want.detach().numpy(), atol=1e-6)
+    np.testing.assert_allclose(f.grad.cpu().numpy(), f64.grad.numpy(), atol=1e-6)
+    np.testing.assert_allclose(q.grad.cpu().numpy(), q64.grad.numpy(), atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("seed", [412])
+@pytest.mark.parametrize("batch", [2, 16])
+@pytest.mark.parametrize("G", [2, 8])
+@pytest.mark.parametrize("D", [4])
+@pytest.mark.parametrize("name,op,oracle,shape", CASES)
+def test_query_double_backward(seed, batch, G, D, name, op, oracle, shape):
+    """test_voxel_feature.py:80-150 (test_query_on_voxel_double_backward): nn.grad -> compare grad_query, then
+    backprop sum(grad_query^2) and compare the gradients w.r.t. grad_output (through the op), query and feature."""
+    q_np, f_np = make(seed, batch, shape(G, D))
+    rng = np.random.RandomState(seed + 1)
+
+    def run(q, f, w):
+        out = op(q, f, MN, MX) if q.is_cuda else oracle(q, f)
+        (gq,) = torch.autograd.grad((out * w).sum(), q, create_graph=True)     # nn.grad([out], [query])
+        (gq ** 2).sum().backward()
+        return gq.detach().cpu().numpy(), w.grad.cpu().numpy(), f.grad.cpu().numpy(), \
+            (q.grad.cpu().numpy() if q.grad is not None else None)
+    C = D if name == "voxel" else 3 * D
+    w_np = rng.randn(batch, C).astype(np.float32)
+    got = run(torch.tensor(q_np, device="cuda", requires_grad=True), torch.tensor(f_np, device="cuda", requires_grad=True),
+              torch.tensor(w_np, device="cuda", requires_grad=True))
+    want = run(torch.tensor(q_np, dtype=torch.float64, requires_grad=True),
+               torch.tensor(f_np, dtype=torch.float64, requires_grad=True),
+               torch.tensor(w_np, dtype=torch.float64, requires_grad=True))
+    np.testing.assert_allclose(got[0], want[0], atol=1e-6, rtol=1e-5)          # grad_query
+    np.testing.assert_allclose(got[1], want[1], atol=1e-3)                      # d/d grad_output
+    np.testing.assert_allclose(got[2], want[2], atol=1e-3)                      # d/d feature
+    if name == "voxel":                                                         # grad_query_grad_query (voxel only)
+        np.testing.assert_allclose(got[3], want[3], atol=1e-3)
+
+
+@pytest.mark.parametrize("batch,G", [(2, 2), (16, 8), (500, 12)])
+def test_lanczos_voxel_matches_oracle(batch, G):
+    """test_lanczos_voxel_feature.py:25-77 tolerances (atol 1e-5, rtol 1e-5) against oracle/cpu_ref.py."""
+    D = 4
+    q_np, f_np = make(412, batch, (G, G, G, D))
+    q = torch.tensor(q_np, device="cuda", requires_grad=True)
+    f = torch.tensor(f_np, device="cuda", requires_grad=True)
+    out = GF.lanczos_query_on_voxel(q, f, MN, MX)
+    go = np.random.RandomState(5).randn(batch, D).astype(np.float32)
+    (out * torch.tensor(go, device="cuda")).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), R.lanczos_voxel_query(q_np, f_np, MN, MX), atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(f.grad.cpu().numpy(), R.lanczos_voxel_grad_feature(go, q_np, (G, G, G), D, MN, MX).reshape(f_np.shape),
+                               atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(q.grad.cpu().numpy(), R.lanczos_voxel_grad_query(go, q_np, f_np, MN, MX), atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("batch,G", [(2, 2), (16, 8)])
+def test_tv_loss_on_voxel(sym, batch, G):
+    """test_total_variation_loss.py:25-75: forward 1e-6, backward 1e-4, sym_backward in {False, True}."""
+    D = 4
+    q_np, f_np = make(412, batch, (G, G, G, D))
+    q = torch.tensor(q_np, device="cuda")
+    f = torch.tensor(f_np, device="cuda", requires_grad=True)
+    out = GF.tv_loss_on_voxel(q, f, MN, MX, sym_backward=sym)
+    out.sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), R.tv_voxel(q_np, f_np, MN, MX), atol=1e-6)
+    want = R.tv_voxel_backward(np.ones((batch, D), np.float32), q_np, f_np, MN, MX, sym)
+    np.testing.assert_allclose(f.grad.cpu().numpy(), want.reshape(f_np.shape), atol=1e-4)
+
+
+def test_voxel_hash_api_matches_oracle():
+    G0, gf, T0, L, D, B = 4, 1.5, 2 ** 10, 4, 2, 64
+    Gs, Ts, offs, total = R.hash_level_table(G0, gf, T0, L, D)
+    q_np, _ = make(412, B, (1,))
+    f_np = (np.random.RandomState(3).randn(total) * 0.01).astype(np.float32)
+    q = torch.tensor(q_np, device="cuda", requires_grad=True)
+    f = torch.tensor(f_np, device="cuda", requires_grad=True)
+    out = GF.query_on_voxel_hash(q, f, G0, gf, T0, L, D, MN, MX)
+    want = R.voxel_hash_query(q_np, f_np, G0, gf, T0, L, D, MN, MX)          # (D, L, B)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want.reshape(D * L, B).T, atol=1e-6)
+    out.sum().backward()
+    assert f.grad.shape == f.shape and torch.isfinite(q.grad).all()
+    with pytest.raises(ValueError):
+        GF.query_on_voxel_hash(q, f[:-1], G0, gf, T0, L, D, MN, MX)
+
+
+@pytest.mark.parametrize("radius,size", [(3, 1), (3, 1.5), (1, 2)])
+def test_ray_aabb_intersection_api(radius, size):
+    """python/intersection/test/test_ray_aabb_intersection.py:113-147 parametrisation: (radius, size) incl. the
+    camera-inside-the-box case; exact n_hits, 1e-6 on t."""
+    rng = np.random.RandomState(412)
+    B, Rr = 2, 3
+    camloc = rng.randn(B, 3); camloc = (camloc / np.linalg.norm(camloc, axis=1, keepdims=True) * radius).astype(np.float32)
+    target = (rng.rand(B, Rr, 3) - 0.5).astype(np.float32)
+    raydir = target - camloc[:, None]; raydir = (raydir / np.linalg.norm(raydir, axis=-1, keepdims=True)).astype(np.float32)
+    tn, tf, nh = intersection.ray_aabb_intersection(torch.tensor(camloc).cuda(), torch.tensor(raydir).cuda(),
+                                                    [-size] * 3, [size] * 3)
+    wn, wf, wh = R.ray_aabb(camloc, raydir, [-size] * 3, [size] * 3)
+    assert np.array_equal(nh.cpu().numpy().reshape(-1), wh.reshape(-1))
+    np.testing.assert_allclose(tn.cpu().numpy().reshape(-1), wn.reshape(-1), atol=1e-6)
+    np.testing.assert_allclose(tf.cpu().numpy().reshape(-1), wf.reshape(-1), atol=1e-6)
+    assert tn.shape == (B, Rr, 1)
+    with pytest.raises(ValueError):
+        intersection.ray_aabb_intersection(torch.tensor(camloc).cuda()[:, :2], torch.tensor(raydir).cuda(), [-1] * 3, [1] * 3)
+
+
+@pytest.mark.parametrize("B,Rr", [(1, 1), (2, 4)])
+@pytest.mark.parametrize("n_thetas", [1, 4])
+@pytest.mark.parametrize("importance", [False, True])
+def test_sample_directions_api(B, Rr, n_thetas, importance):
+    """python/sampler/test_sampler.py:73-111 parametrisation, atol 1e-5."""
+    rng = np.random.RandomState(412)
+    n = rng.randn(B, Rr, 3).astype(np.float32); n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    ct, cp = rng.rand(B, Rr, n_thetas).astype(np.float32), rng.rand(B, Rr, 2 * n_thetas).astype(np.float32)
+    al = (rng.rand(B, Rr, 1) * 0.9 + 0.05).astype(np.float32)
+    t = lambda a: torch.tensor(a).cuda()
+    if importance:
+        got = sampler.sample_importance_directions(t(n), t(ct), t(cp), t(al))
+        want = R.sample_directions(n, ct, cp, al)
+    else:
+        got = sampler.sample_uniform_directions(t(n), t(ct), t(cp))
+        want = R.sample_directions(n, ct, cp)
+    np.testing.assert_allclose(got.cpu().numpy(), want, atol=1e-5)

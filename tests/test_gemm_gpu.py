@@ -102,6 +102,16 @@ CASES = [
     (256, 213, 2048, "mn", EPI_ATOMIC, 1),
     (128, 64, 64, "kn", EPI_BIAS, 1),
     (130, 48, 40, "kk", EPI_BIAS, 1),
+    # memory-bound corner shapes (gemm_skinny.cu)
+    (1000, 1, 256, "kn", EPI_BIAS, 1),           # sdf column
+    (1000, 3, 259, "kn", EPI_BIAS, 1),           # colour outputs
+    (640, 4, 256, "kk", EPI_ACCUM, 1),           # grid-feature gradient columns
+    (333, 6, 128, "kn", EPI_BIAS, 1),
+    (512, 256, 1, "kn", EPI_MUL_S, 1),           # rank-1 update with the sigmoid factor
+    (512, 128, 6, "kk", EPI_MUL_S, 1),
+    (256, 1, 5000, "mn", EPI_ATOMIC, 1),         # weight gradients of the narrow last layers
+    (259, 3, 4096, "mn", EPI_ATOMIC, 1),
+    (128, 6, 3001, "mn", EPI_ATOMIC, 1),
 ]
 
 

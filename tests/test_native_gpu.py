@@ -459,7 +459,9 @@ def test_squareplus():
         ours.forward(x.numel(), y1.data_ptr(), x.data_ptr(), b)
         ref.forward(x.numel(), y2.data_ptr(), x.data_ptr(), b)
         assert torch.equal(y1, y2)
-        np.testing.assert_allclose(y1.cpu().numpy(), R.squareplus_forward(x_np, b), rtol=1e-6)
+        # bit-identical to the reference kernel (above); numpy's sqrt differs from sqrtf's last ulp, which the
+        # x + sqrt(x^2+b) cancellation for x < 0 turns into ~5e-6 relative on small outputs: absolute bar 5e-7
+        np.testing.assert_allclose(y1.cpu().numpy(), R.squareplus_forward(x_np, b), rtol=1e-6, atol=5e-7)
         for accum in (False, True):
             d1, d2 = torch.ones_like(x), torch.ones_like(x)
             ours.backward(x.numel(), d1.data_ptr(), dy.data_ptr(), x.data_ptr(), b, accum)
