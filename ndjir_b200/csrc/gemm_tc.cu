@@ -25,6 +25,7 @@ namespace ndjir {
 namespace gemm {
 
 int g_mlp_mask_hi = 0;
+int g_mlp_dbg = 0;   // experiment switches (profiling only): 1 = skip the lo transform, 2 = issue only the hi*hi product
 
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
@@ -37,7 +38,7 @@ constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4;  // 8 KB
 constexpr int B_TILE_BYTES = TC_BN * TC_BK * 4;  // 16 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // raw + lo of both operands = 48 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024;      // + alignment slack
-constexpr int TC_THREADS = 448;                 // 1 TMA + 1 MMA + 8 transform + 4 epilogue warps
+constexpr int TC_THREADS = 576;                 // 1 TMA + 1 MMA + 8 transform + 8 epilogue warps (<= 112 registers)
 constexpr int TMEM_COLS = 512;                  // two 256-column fp32 accumulators
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -77,6 +78,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// L2 prefetch of one TMA box / of a contiguous byte range: no shared memory is reserved, so HBM requests for the NEXT
+// work item are in flight while the current one occupies the whole operand ring
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -107,6 +122,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor (tcgen05), version 1 (cute/arch/mma_sm100_desc.hpp:SmemDescriptor).
 // layout 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B: the only layout tcgen05 accepts for MN-major
 // 32-bit operands (32-byte chunks swizzled inside a 128-byte span over 4 rows; TMA mode SWIZZLE_128B_ATOM_32B).
@@ -124,6 +151,8 @@ struct TcParams {
   Args a;
   int a_mn, b_mn;        // 1: operand is MN-major (contiguous along m / n), 0: K-major
   int mask_hi;
+  int dbg;
+  int a_3d, b_3d;        // MN-major operand loaded with ONE 3-D TMA request per K block (extent % 32 == 0)
   int vec_epi;           // every epilogue operand is 16-byte aligned with a row stride that is a multiple of 4
   int m_tiles, n_tiles, splits, kb_per_split, nkb_total;
 };
@@ -161,10 +190,12 @@ __device__ __forceinline__ void epilogue_vec4(const Args& a, long long m, int n,
 
 // Persistent kernel: one CTA per SM walks a static list of work items (m tile, n tile, K split).
 //   warp 0        TMA producer                                  warps 2-9    hi/lo transform (256 threads)
-//   warp 1        MMA issuer (+ TMEM allocation, 512 columns)   warps 10-13  epilogue straight from TMEM
+//   warp 1        MMA issuer (+ TMEM allocation, 512 columns)   warps 10-17  epilogue straight from TMEM (2 warps per
+//                                                                            sub-partition, alternate 16-column chunks)
 // Two 256-column TMEM accumulators: the epilogue of item i overlaps the main loop of item i+1.
 constexpr int TC_XFORM_THREADS = 256;
 constexpr int TC_EPI_WARP0 = 2 + TC_XFORM_THREADS / 32;
+constexpr int TC_EPI_THREADS = 256;            // two warps per TMEM sub-partition, each takes half of the columns
 
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -196,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), 128);
+      mbar_init(bar_acc_empty(b), TC_EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -234,20 +265,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         item_info(item, m0, n0, kb0, nkb);
         const int umma_n = (min(TC_BN, a.N - n0) + 15) & ~15;
         const int b_chunks = (umma_n + 31) / 32;
-        const uint32_t tx_bytes = A_TILE_BYTES + (p.b_mn ? b_chunks * TC_BK * 128 : B_TILE_BYTES);
+        const uint32_t tx_bytes = A_TILE_BYTES + ((p.b_mn && !p.b_3d) ? b_chunks * TC_BK * 128 : B_TILE_BYTES);
         for (int i = 0; i < nkb; ++i, ++it) {
           int s = it % TC_STAGES;
           uint32_t ph = (it / TC_STAGES) & 1;
           mbar_wait(bar_empty(s), ph ^ 1);
           mbar_expect_tx(bar_full(s), tx_bytes);
           int k0 = (kb0 + i) * TC_BK;
-          if (p.a_mn) {
+          if (p.a_3d) {
+            tma_load_3d(a_raw(s), &mapA, 0, k0, m0 / 32, bar_full(s));
+          } else if (p.a_mn) {
 #pragma unroll
             for (int c = 0; c < TC_BM / 32; ++c) tma_load_2d(a_raw(s) + c * TC_BK * 128, &mapA, m0 + c * 32, k0, bar_full(s));
           } else {
             tma_load_2d(a_raw(s), &mapA, k0, m0, bar_full(s));
           }
-          if (p.b_mn) {
+          if (p.b_3d) {
+            tma_load_3d(b_raw(s), &mapB, 0, k0, n0 / 32, bar_full(s));
+          } else if (p.b_mn) {
             for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_raw(s) + c * TC_BK * 128, &mapB, n0 + c * 32, k0, bar_full(s));
           } else {
             tma_load_2d(b_raw(s), &mapB, k0, n0, bar_full(s));
@@ -288,9 +323,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             uint64_t da_lo = make_desc(a_lo(s) + ks * a_step, a_lbo, a_sbo, a_lay);
             uint64_t db_hi = make_desc(b_raw(s) + ks * b_step, b_lbo, b_sbo, b_lay);
             uint64_t db_lo = make_desc(b_lo(s) + ks * b_step, b_lbo, b_sbo, b_lay);
-            umma_tf32(tacc, da_lo, db_hi, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
-            umma_tf32(tacc, da_hi, db_lo, idesc, 1u);
-            umma_tf32(tacc, da_hi, db_hi, idesc, 1u);
+            if (p.dbg & 2) {
+              umma_tf32(tacc, da_hi, db_hi, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            } else {
+              umma_tf32(tacc, da_lo, db_hi, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
+              umma_tf32(tacc, da_hi, db_lo, idesc, 1u);
+              umma_tf32(tacc, da_hi, db_hi, idesc, 1u);
+            }
           }
           umma_commit(bar_empty(s));     // frees the stage once these MMAs have read it
         }
@@ -299,18 +338,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp < TC_EPI_WARP0) {
     // ===================== transform: lo = x - hi for both operand tiles =====================
-    const int t = threadIdx.x - 64;   // 0..255
+    const int t = threadIdx.x - 64;   // 0..TC_XFORM_THREADS-1
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int m0, n0, kb0, nkb;
       item_info(item, m0, n0, kb0, nkb);
       const int umma_n = (min(TC_BN, a.N - n0) + 15) & ~15;
-      const int b_bytes = p.b_mn ? ((umma_n + 31) / 32) * TC_BK * 128 : B_TILE_BYTES;
+      const int b_bytes = (p.b_mn && !p.b_3d) ? ((umma_n + 31) / 32) * TC_BK * 128 : B_TILE_BYTES;
       for (int i = 0; i < nkb; ++i, ++it) {
         int s = it % TC_STAGES;
         uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(bar_full(s), ph);
         uint8_t* st = smem + s * STAGE_BYTES;
+        if (p.dbg & 1) { fence_proxy_async(); mbar_arrive(bar_ready(s)); continue; }
 #pragma unroll 2
         for (int off = t * 16; off < A_TILE_BYTES; off += TC_XFORM_THREADS * 16) {
           float4 x = *reinterpret_cast<const float4*>(st + off);
@@ -341,6 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {
     // ===================== epilogue: TMEM -> registers -> global, one output row per thread =====================
     const int q = warp & 3;           // TMEM sub-partition of this warp: lanes 32q .. 32q+31
+    const int chalf = (warp - TC_EPI_WARP0) >> 2;   // 0: even 16-column chunks, 1: odd chunks
     uint32_t tile_it = 0;
     constexpr bool NEED_H = (EPI == EPI_MUL_S || EPI == EPI_ADJ);
     constexpr bool NEED_C = (EPI == EPI_ACCUM);
@@ -358,12 +399,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(bar_acc_full(buf), (tile_it >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * TC_BN + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < n_valid; c0 += 32) {
-        // operands of the fused epilogue for this thread's 32 columns: issued before the accumulator is read so
-        // up to 16 independent 16-byte loads per thread are in flight
-        float4 hv[8], uv[8], cv[8], bv[8];
+      for (int c0 = chalf * 16; c0 < n_valid; c0 += 32) {
+        // operands of the fused epilogue for this thread's 16 columns: issued before the accumulator is read so
+        // up to 8 independent 16-byte loads per thread (x 256 epilogue threads) are in flight
+        float4 hv[4], uv[4], cv[4], bv[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           int c = c0 + 4 * j;
           hv[j] = uv[j] = cv[j] = bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row_ok && c < n_vec) {
@@ -373,11 +414,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (need_b) bv[j] = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c));
           }
         }
-        float v[32];
-        tmem_ld32(tacc + (uint32_t)c0, v);
+        float v[16];
+        tmem_ld16(tacc + (uint32_t)c0, v);
+        if (p.dbg & 4) { if (v[0] == 1.2345e-30f && row_ok) a.C[m * a.ldc + n0 + c0] = v[1]; continue; }
         if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             int c = c0 + 4 * j;
             if (c < n_vec) {
               epilogue_vec4<EPI>(a, m, n0 + c, v + 4 * j, hv[j], uv[j], cv[j], bv[j]);
@@ -439,6 +481,21 @@ static bool make_map(CUtensorMap* map, const float* base, long long inner, long 
   return r == CUDA_SUCCESS;
 }
 
+// MN-major operand as a 3-D tensor (32 contiguous elements, K rows, 32-wide chunks): one request fills the whole
+// [chunk][k][32] tile.  Only used when the MN extent is a multiple of 32 (no partial chunk).
+static bool make_map3(CUtensorMap* map, const float* base, long long mn, long long rows, long long ld, int box_chunks) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(mn / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)TC_BK, (cuuint32_t)box_chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 bool tc_eligible(const Args& a, int epi) {
   if (a.N < 32 || a.K < 16 || a.M < 32) return false;
   if (!al16p(a.A) || !al16p(a.B)) return false;
@@ -460,14 +517,20 @@ static int launch_tc_epi(const Args& a, cudaStream_t st) {
   p.a_mn = (a.a_cs != 1);        // A(m,k) contiguous along m
   p.b_mn = (a.b_cs == 1);        // B(k,n) contiguous along n
   p.mask_hi = g_mlp_mask_hi;
+  p.dbg = g_mlp_dbg;
+
   if (a.b_cs == 1 && a.b_rs == 1) p.b_mn = 1;
   auto ok16 = [](const void* q, long long ld) { return q == nullptr || (al16p(q) && ld % 4 == 0); };
   p.vec_epi = ok16(a.C, a.ldc) && ok16(a.H, a.ldh) && ok16(a.U, a.ldu) && ok16(a.C2, a.ldc2) && ok16(a.bias, 0);
   CUtensorMap mapA, mapB;
   bool ok;
-  if (p.a_mn) ok = make_map(&mapA, a.A, a.M, a.K, a.a_cs, 32, TC_BK, true);
+  p.a_3d = p.a_mn && a.M % 32 == 0;
+  p.b_3d = p.b_mn && a.N % 32 == 0;
+  if (p.a_3d) ok = make_map3(&mapA, a.A, a.M, a.K, a.a_cs, TC_BM / 32);
+  else if (p.a_mn) ok = make_map(&mapA, a.A, a.M, a.K, a.a_cs, 32, TC_BK, true);
   else ok = make_map(&mapA, a.A, a.K, a.M, a.a_rs, TC_BK, TC_BM, false);
-  if (p.b_mn) ok = ok && make_map(&mapB, a.B, a.N, a.K, a.b_rs, 32, TC_BK, true);
+  if (p.b_3d) ok = ok && make_map3(&mapB, a.B, a.N, a.K, a.b_rs, TC_BN / 32);
+  else if (p.b_mn) ok = ok && make_map(&mapB, a.B, a.N, a.K, a.b_rs, 32, TC_BK, true);
   else ok = ok && make_map(&mapB, a.B, a.K, a.N, a.b_cs, TC_BK, TC_BN, false);
   if (!ok) return NDJIR_ERR_ARG;
   static bool attr_set = false;

@@ -309,6 +309,10 @@ int ndjir_set_option(const char* key, int value) {
   i = 0;
   while (k2[i] && key[i] == k2[i]) ++i;
   if (k2[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_tensor_cores = value; return NDJIR_OK; }
+  const char* k4 = "mlp_dbg";
+  i = 0;
+  while (k4[i] && key[i] == k4[i]) ++i;
+  if (k4[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_dbg = value; return NDJIR_OK; }
   const char* k3 = "mlp_mask_hi";
   i = 0;
   while (k3[i] && key[i] == k3[i]) ++i;

@@ -20,8 +20,11 @@ shapes = {
   "wgrad 256x256": lambda: call(256, 256, P, A, 1, 256, C, 256, 1, gW, 256, EPI_ATOMIC, split=74),
 }
 out = []
-for tc in (1, 0):
+import sys as _s
+modes = [(1, 0), (1, 3), (1, 4), (1, 7)] if "--dbg" in _s.argv else [(1, 0), (0, 0)]
+for tc, dbg in modes:
     _lib.call("ndjir_set_option", "mlp_tensor_cores", tc)
+    _lib.call("ndjir_set_option", "mlp_dbg", dbg)
     for name, fn in shapes.items():
         for _ in range(3): fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,6 +32,7 @@ for tc in (1, 0):
         for _ in range(10): fn()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        r = dict(name=name, tc=tc, ms=ms, tflops=2.0 * P * 256 * 256 / ms / 1e9)
+        r = dict(name=name, tc=tc, dbg=dbg, ms=ms, tflops=2.0 * P * 256 * 256 / ms / 1e9)
         out.append(r); print(json.dumps(r), flush=True)
 _lib.call("ndjir_set_option", "mlp_tensor_cores", 1)
+_lib.call("ndjir_set_option", "mlp_dbg", 0)
