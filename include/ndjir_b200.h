@@ -243,6 +243,8 @@ int ndjir_colsum(long long rows, int cols, float* out, const float* src, long lo
 int ndjir_group_sum(long long n_groups, int group, int cols, float* out, long long ld_out, const float* src,
                     long long ld_src, int accum, cudaStream_t stream);  /* out[g,c] (+)= sum_i src[g*group+i,c] */
 int ndjir_fill(long long n, float* p, float value, cudaStream_t stream);
+int ndjir_transpose(int rows, int cols, float* dst, long long ld_dst, const float* src, long long ld_src,
+                    cudaStream_t stream);                                /* dst[c,r] = src[r,c] */
 
 /* ---- positional encoding [x, cos(b), sin(b)], b[axis*bands+k] = x[axis]*2^k (python/network.py:96-117),
  *      its input gradient (the nn.grad path of renderer.py:52) and the adjoint of that gradient ---- */

@@ -69,6 +69,24 @@ group_sum_kernel(int group, int cols, float* __restrict__ out, long long ld_out,
   }
 }
 
+// dst[c, r] = src[r, c]  (32 x 32 tiles through shared memory; used for the transposed weight copies of the dgrad
+// products: W^T stored row-major is an MN-major operand the TMA fetches in 128-byte rows)
+__global__ void __launch_bounds__(256) transpose_kernel(int rows, int cols, float* __restrict__ dst, long long ld_dst,
+                                                        const float* __restrict__ src, long long ld_src) {
+  __shared__ float tile[32][33];
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? __ldg(src + (long long)r * ld_src + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) dst[(long long)c * ld_dst + r] = tile[tx][i];
+  }
+}
+
 __global__ void __launch_bounds__(NDJIR_BLOCK) fill_kernel(long long n, float* __restrict__ p, float v) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) p[s] = v;
@@ -860,6 +878,15 @@ int ndjir_group_sum(long long n_groups, int group, int cols, float* out, long lo
   if (n_groups < 0 || group <= 0 || cols < 0 || !out || !src) return NDJIR_ERR_ARG;
   int threads = cols >= 256 ? 256 : ((cols + 31) / 32) * 32;
   group_sum_kernel<<<(unsigned)n_groups, threads, 0, stream>>>(group, cols, out, ld_out, src, ld_src, accum);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_transpose(int rows, int cols, float* dst, long long ld_dst, const float* src, long long ld_src,
+                    cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return NDJIR_OK;
+  if (rows < 0 || cols < 0 || !dst || !src) return NDJIR_ERR_ARG;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_kernel<<<grid, 256, 0, stream>>>(rows, cols, dst, ld_dst, src, ld_src);
   NDJIR_RETURN_LAST_ERROR();
 }
 

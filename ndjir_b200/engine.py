@@ -42,7 +42,8 @@ class Layer:
         self.ldw = r4(N)
         self.rowmap = np.arange(K) if rowmap is None else np.asarray(rowmap)
         self.col0 = col0            # first reference output column held by this layer (split last layers)
-        self.w_off = self.b_off = -1
+        self.w_off = self.b_off = self.t_off = -1
+        self.ldt = r4(K)            # row stride of the transposed copy W^T (N, ldt)
 
 
 class ParamStore:
@@ -103,6 +104,12 @@ class ParamStore:
                 L.b_off = n; n += r4(L.N)
         self.gain_off = n; n += 4
         self.n_mlp = n
+        nt = 0
+        for name in NET_ORDER:
+            for L in self.nets[name]:
+                L.t_off = nt; nt += r4(L.N) * L.ldt
+        # transposed weight copies for the input-gradient products (refreshed once per step, engine.refresh_transposes)
+        self.data_t = torch.zeros(max(nt, 4), dtype=torch.float32, device=device)
         self.data = torch.zeros(n, dtype=torch.float32, device=device)
         self.grad = torch.zeros(n, dtype=torch.float32, device=device)
         self.grid = {}        # name -> tensor
@@ -178,6 +185,13 @@ class ParamStore:
 
     def b(self, L):
         return self.data.data_ptr() + 4 * L.b_off
+
+    def Bt(self, L, row0=0):
+        """Operand B(k, n) = W[row0 + n, k] of the input-gradient products as (pointer, b_rs, b_cs): the transposed copy
+        (contiguous along n: TMA-friendly 128-byte rows) when the view is 16-byte aligned, else W itself."""
+        if row0 % 4 == 0:
+            return self.data_t.data_ptr() + 4 * (L.t_off + row0), L.ldt, 1
+        return self.W(L, row0), 1, L.ldw
 
     def gW(self, L, row=0):
         return self.grad.data_ptr() + 4 * (L.w_off + row * L.ldw)
@@ -266,6 +280,13 @@ class Engine:
 
     def copy2d(self, rows, cols, dst, ld_dst, src, ld_src, rep=1, alpha=1.0, accum=0):
         self.call("ndjir_copy2d", rows, cols, dst, ld_dst, src, ld_src, rep, alpha, accum)
+
+    def refresh_transposes(self):
+        """W^T copies used by every input-gradient product; call after the parameters change (once per step)."""
+        ps = self.params
+        for name in NET_ORDER:
+            for L in ps.nets[name]:
+                self.call("ndjir_transpose", L.K, L.N, ps.data_t.data_ptr() + 4 * L.t_off, L.ldt, ps.W(L), L.ldw)
 
     # ------------------------------------------------------------------------------------------------
     # grid feature dispatch (python/network.py:120-151 query_on_grid)
@@ -356,22 +377,22 @@ class Engine:
         c = self.cskip
         # top: gA_{L-1}[p,:] = w_sdf ; GZ[nl-1] = gA * s
         top = A[nl]
-        self.gemm(rows, Ls.K, 1, P_(self.one), 0, 1, ps.W(Ls), 1, Ls.ldw, P_(GZ[nl - 1]), GZ[nl - 1].shape[1],
+        self.gemm(rows, Ls.K, 1, P_(self.one), 0, 1, *ps.Bt(Ls), P_(GZ[nl - 1]), GZ[nl - 1].shape[1],
                   EPI_MUL_S, H=P_(top), ldh=top.shape[1])
         skip_wrote = False
         for l in range(nl - 1, 0, -1):
             L = net[l]
             is_skip = (l == self.skip)
             n_prev = net[l - 1].N
-            self.gemm(rows, n_prev, L.N, P_(GZ[l]), GZ[l].shape[1], 1, ps.W(L), 1, L.ldw, P_(GZ[l - 1]),
+            self.gemm(rows, n_prev, L.N, P_(GZ[l]), GZ[l].shape[1], 1, *ps.Bt(L), P_(GZ[l - 1]),
                       GZ[l - 1].shape[1], EPI_MUL_S, alpha=(c if is_skip else 1.0), H=P_(A[l]), ldh=A[l].shape[1],
                       hscale=(1.0 / c if is_skip else 1.0))
             if is_skip:
-                self.gemm(rows, self.din, L.N, P_(GZ[l]), GZ[l].shape[1], 1, ps.W(L, n_prev), 1, L.ldw, P_(Gin),
+                self.gemm(rows, self.din, L.N, P_(GZ[l]), GZ[l].shape[1], 1, *ps.Bt(L, n_prev), P_(Gin),
                           self.ld0, EPI_BIAS, alpha=c)
                 skip_wrote = True
         L0 = net[0]
-        self.gemm(rows, self.din, L0.N, P_(GZ[0]), GZ[0].shape[1], 1, ps.W(L0), 1, L0.ldw, P_(Gin), self.ld0,
+        self.gemm(rows, self.din, L0.N, P_(GZ[0]), GZ[0].shape[1], 1, *ps.Bt(L0), P_(Gin), self.ld0,
                   EPI_ACCUM if skip_wrote else EPI_BIAS)
         g = self.conf.geometric_network
         self.call("ndjir_positional_encoding_grad_input", rows, 3, g.pe_bands, P_(A[0]), self.ld0, P_(Gin), self.ld0,
@@ -436,12 +457,12 @@ class Engine:
         self.call("ndjir_colsum", rows, Lf.N, ps.gb(Lf), P_(dO), self.LDO, 1.0)
         cur = pp[0]
         ldc = cur.shape[1]
-        self.gemm(rows, Lf.K, Lf.N, P_(dO), self.LDO, 1, ps.W(Lf), 1, Lf.ldw, P_(cur), ldc, EPI_MUL_S, H=P_(last),
+        self.gemm(rows, Lf.K, Lf.N, P_(dO), self.LDO, 1, *ps.Bt(Lf), P_(cur), ldc, EPI_MUL_S, H=P_(last),
                   ldh=last.shape[1], U=(P_(Z2[nl - 1]) if Z2 else 0), ldu=(Z2[nl - 1].shape[1] if Z2 else 0))
         if dsdf is not None:
             self.wgrad(rows, Ls.K, 1, P_(last), last.shape[1], P_(dsdf), 1, ps.gW(Ls), Ls.ldw)
             self.call("ndjir_colsum", rows, 1, ps.gb(Ls), P_(dsdf), 1, 1.0)
-            self.gemm(rows, Ls.K, 1, P_(dsdf), 1, 1, ps.W(Ls), 1, Ls.ldw, P_(cur), ldc, EPI_MUL_S, H=P_(last),
+            self.gemm(rows, Ls.K, 1, P_(dsdf), 1, 1, *ps.Bt(Ls), P_(cur), ldc, EPI_MUL_S, H=P_(last),
                       ldh=last.shape[1], U=P_(cur), ldu=ldc)
         dgrid = self.buf("geo_dgrid", rows, max(self.Dg, 1)) if self.Dg else None
         skip_wrote = False
@@ -454,17 +475,17 @@ class Engine:
                 is_skip = (l == self.skip)
                 n_prev = net[l - 1].N
                 nxt = pp[1] if cur is pp[0] else pp[0]
-                self.gemm(rows, n_prev, L.N, P_(cur), ldc, 1, ps.W(L), 1, L.ldw, P_(nxt), nxt.shape[1], EPI_MUL_S,
+                self.gemm(rows, n_prev, L.N, P_(cur), ldc, 1, *ps.Bt(L), P_(nxt), nxt.shape[1], EPI_MUL_S,
                           alpha=(c if is_skip else 1.0), H=P_(Al), ldh=Al.shape[1],
                           hscale=(1.0 / c if is_skip else 1.0), U=(P_(Z2[l - 1]) if Z2 else 0),
                           ldu=(Z2[l - 1].shape[1] if Z2 else 0))
                 if is_skip and self.Dg:
-                    self.gemm(rows, self.Dg, L.N, P_(cur), ldc, 1, ps.W(L, n_prev + self.npe), 1, L.ldw, P_(dgrid),
+                    self.gemm(rows, self.Dg, L.N, P_(cur), ldc, 1, *ps.Bt(L, n_prev + self.npe), P_(dgrid),
                               self.Dg, EPI_BIAS, alpha=c)
                     skip_wrote = True
                 cur, ldc = nxt, nxt.shape[1]
             elif self.Dg:
-                self.gemm(rows, self.Dg, L.N, P_(cur), ldc, 1, ps.W(L, self.npe), 1, L.ldw, P_(dgrid), self.Dg,
+                self.gemm(rows, self.Dg, L.N, P_(cur), ldc, 1, *ps.Bt(L, self.npe), P_(dgrid), self.Dg,
                           EPI_ACCUM if skip_wrote else EPI_BIAS)
         for part, width, off in self._grid_parts():
             tmp = self.buf(f"gg_{part}", rows, width)
@@ -506,10 +527,10 @@ class Engine:
             self.wgrad(rows, L.K, L.N, lastA, lda, dptr, ldd, ps.gW(L), L.ldw)
             self.call("ndjir_colsum", rows, L.N, ps.gb(L), dptr, ldd, 1.0)
             if nh:
-                self.gemm(rows, L.K, L.N, dptr, ldd, 1, ps.W(L), 1, L.ldw, P_(cur), wmax, EPI_MUL_S, H=lastA, ldh=lda,
+                self.gemm(rows, L.K, L.N, dptr, ldd, 1, *ps.Bt(L), P_(cur), wmax, EPI_MUL_S, H=lastA, ldh=lda,
                           U=(0 if first else P_(cur)), ldu=(0 if first else wmax))
             elif dX:
-                self.gemm(rows, dx_cols or L.K, L.N, dptr, ldd, 1, ps.W(L), 1, L.ldw, dX, lddx,
+                self.gemm(rows, dx_cols or L.K, L.N, dptr, ldd, 1, *ps.Bt(L), dX, lddx,
                           EPI_ACCUM if (accum_dx or not first) else EPI_BIAS)
             first = False
         for l in range(nh - 1, -1, -1):
@@ -519,11 +540,11 @@ class Engine:
             self.call("ndjir_colsum", rows, L.N, ps.gb(L), P_(cur), wmax, 1.0)
             if l > 0:
                 nxt = pp[1] if cur is pp[0] else pp[0]
-                self.gemm(rows, L.K, L.N, P_(cur), wmax, 1, ps.W(L), 1, L.ldw, P_(nxt), wmax, EPI_MUL_S, H=Aptr,
+                self.gemm(rows, L.K, L.N, P_(cur), wmax, 1, *ps.Bt(L), P_(nxt), wmax, EPI_MUL_S, H=Aptr,
                           ldh=lda)
                 cur = nxt
             elif dX:
-                self.gemm(rows, dx_cols or L.K, L.N, P_(cur), wmax, 1, ps.W(L), 1, L.ldw, dX, lddx,
+                self.gemm(rows, dx_cols or L.K, L.N, P_(cur), wmax, 1, *ps.Bt(L), dX, lddx,
                           EPI_ACCUM if accum_dx else EPI_BIAS)
 
     # ------------------------------------------------------------------------------------------------
@@ -606,6 +627,7 @@ class Engine:
         S = N + Nb
         if zero_grad:
             ps.zero_grad()
+        self.refresh_transposes()       # the normal pass (forward half) already needs W^T
         losses = self.buf("losses", 1, 16, zero=True)
         scal = self.buf("scalars", 1, 8, zero=True)      # [mask_sum, inv_denorm]
         mask_sum, inv_denorm = P_(scal, 0), P_(scal, 1)
