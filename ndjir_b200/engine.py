@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .config import grid_channels
-from .parallel import allreduce_gradients, allreduce_mask_sum
+from .parallel import allgather_rows, allreduce_gradients, allreduce_mask_sum
 from .scene import network_dims, pe_dim, NET_ORDER
 
 EPI_BIAS, EPI_SOFTPLUS, EPI_ACCUM, EPI_MUL_S, EPI_ADJ, EPI_ATOMIC = range(6)
@@ -217,13 +217,18 @@ def P_(t, off=0):
 
 
 class Engine:
-    def __init__(self, conf, device="cuda", world_size=1, process_group=None):
+    def __init__(self, conf, device="cuda", world_size=1, process_group=None, grid_exchange="auto"):
         if not torch.cuda.is_available():
             raise _lib.NdjirError("ndjir_b200 needs a CUDA device (there is no CPU fallback)")
         _lib.lib()   # raises if the CUDA library is missing
         self.conf, self.device = conf, torch.device(device)
         self.params = ParamStore(conf, self.device)
         self.world_size, self.pg = world_size, process_group
+        # multi-GPU exchange of the grid gradient: "dense" all-reduce of the table gradient, or "sparse" all-gather of
+        # the per-sample scatter inputs followed by a replicated scatter (parallel.allgather_rows); auto = sparse for
+        # tables above 256 MB (the 2 GiB voxel grid), dense for small ones
+        self.grid_exchange = grid_exchange
+        self._gather_cache = {}
         g = conf.geometric_network
         self.Df = g.feature_size
         self.Dg = grid_channels(conf)
@@ -280,6 +285,36 @@ class Engine:
 
     def copy2d(self, rows, cols, dst, ld_dst, src, ld_src, rep=1, alpha=1.0, accum=0):
         self.call("ndjir_copy2d", rows, cols, dst, ld_dst, src, ld_src, rep, alpha, accum)
+
+    def _sparse_grid(self):
+        if self.world_size <= 1:
+            return False
+        if self.grid_exchange == "auto":
+            big = max([v.numel() * 4 for v in self.params.grid.values()] + [0])
+            return big > (256 << 20)
+        return self.grid_exchange == "sparse"
+
+    def _gathered(self, t, rows, name, cache=False):
+        """(world*rows, c) concatenation over ranks of t[:rows].  Query points are cached per step (the same x feeds
+        several scatters); gradient rows are not (their scratch buffers are reused)."""
+        key = (t.data_ptr(), rows, t.shape[1])
+        if cache and key in self._gather_cache:
+            return self._gather_cache[key]
+        out = self.buf(f"gather_{name}", rows * self.world_size, t.shape[1])[:rows * self.world_size]
+        g = allgather_rows(out, t[:rows].contiguous(), self.pg)
+        if cache:
+            self._gather_cache[key] = g
+        return g
+
+    def _grid_scatter(self, kind, part, rows, x, arrays, with_feature=False):
+        """Scatter into the grid gradient (grad_feature / gqgf / tv_bwd).  arrays: dense (rows, c) per-sample tensors in
+        the C-ABI order between grad_feature and query."""
+        if self._sparse_grid():
+            arrays = [self._gathered(a, rows, f"{kind}_{i}") for i, a in enumerate(arrays)]
+            x = self._gathered(x, rows, f"x_{len(self._gather_cache)}_{x.data_ptr() % 9973}", cache=True)
+            rows = rows * self.world_size
+        tail = [P_(self.params.grid[part])] if with_feature else []
+        self._grid_call(kind, part, rows, P_(self.params.grid_grad[part]), *[P_(a) for a in arrays], P_(x), *tail)
 
     def refresh_transposes(self):
         """W^T copies used by every input-gradient product; call after the parameters change (once per step)."""
@@ -419,7 +454,7 @@ class Engine:
             tmp2 = self.buf(f"ggo_{part}", rows, width)
             self._grid_call("ggo", part, rows, P_(tmp2), P_(nbar), P_(x), P_(self.params.grid[part]))
             self.copy2d(rows, width, P_(Ghat[0], self.npe + off), self.ld0, P_(tmp2), width)
-            self._grid_call("gqgf", part, rows, P_(self.params.grid_grad[part]), P_(nbar), P_(tmp), P_(x))
+            self._grid_scatter("gqgf", part, rows, x, [nbar, tmp])
         Z2 = []
         for l in range(nl):
             L = net[l]
@@ -490,7 +525,7 @@ class Engine:
         for part, width, off in self._grid_parts():
             tmp = self.buf(f"gg_{part}", rows, width)
             self.copy2d(rows, width, P_(tmp), width, P_(dgrid, off), self.Dg)
-            self._grid_call("grad_feature", part, rows, P_(self.params.grid_grad[part]), P_(tmp), P_(x))
+            self._grid_scatter("grad_feature", part, rows, x, [tmp])
 
     # ------------------------------------------------------------------------------------------------
     # generic softplus MLP (heads): forward keeps layer inputs, backward accumulates weight gradients
@@ -628,6 +663,7 @@ class Engine:
         if zero_grad:
             ps.zero_grad()
         self.refresh_transposes()       # the normal pass (forward half) already needs W^T
+        self._gather_cache = {}
         losses = self.buf("losses", 1, 16, zero=True)
         scal = self.buf("scalars", 1, 8, zero=True)      # [mask_sum, inv_denorm]
         mask_sum, inv_denorm = P_(scal, 0), P_(scal, 1)
@@ -856,9 +892,9 @@ class Engine:
             for part, width, off in self._grid_parts():
                 tvg = self.buf(f"tvg_{part}", P, width)
                 self.call("ndjir_ray_mask_fill", P, N, width, P_(tvg), P_(maskv), inv_denorm, float(tr.tv_weight))
-                self._grid_call("tv_bwd", part, P, P_(ps.grid_grad[part]), P_(tvg), P_(x_fg), P_(ps.grid[part]))
+                self._grid_scatter("tv_bwd", part, P, x_fg, [tvg], with_feature=True)
         if self.world_size > 1:
-            allreduce_gradients(ps, self.pg)
+            allreduce_gradients(ps, self.pg, include_grid=not self._sparse_grid())
         if keep:
             self.debug.update(dict(dO=dO, dsdf=dsdf, dw=dw, dRAW=dRAW, d_attpix=d_attpix, dpix=dpix, nbar=nbar,
                                    dalpha_fg=dalpha_fg, dalpha_bg=dalpha_bg, d_el=d_el, d_sv=d_sv))

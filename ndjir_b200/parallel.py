@@ -31,10 +31,21 @@ def allreduce_mask_sum(mask_sum, group=None):
     return mask_sum
 
 
-def allreduce_gradients(params, group=None):
-    """Sums params.grad (flat MLP gradients) and every grid gradient over the group, in place."""
+def allreduce_gradients(params, group=None, include_grid=True):
+    """Sums params.grad (flat MLP gradients) and, unless the grid gradient was exchanged sparsely
+    (allgather_rows + replicated scatter), every grid gradient over the group, in place."""
     if not (dist.is_initialized() and dist.get_world_size(group) > 1):
         return
     dist.all_reduce(params.grad, op=dist.ReduceOp.SUM, group=group)
-    for v in params.grid_grad.values():
-        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    if include_grid:
+        for v in params.grid_grad.values():
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+
+
+def allgather_rows(out, local, group=None):
+    """out (world*rows, c) <- concatenation over ranks of local (rows, c).  Used for the SPARSE exchange of the grid
+    gradient: instead of all-reducing the dense table gradient (2 GiB for the 512^3 x 4 voxel grid), every rank
+    gathers the per-sample scatter inputs of all ranks (query point + gradient rows, ~100 B per sample, ~26 MB per
+    rank and step) and runs the scatter kernels over the union, so each replica ends with the full gradient."""
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 from ndjir_b200 import scene
 from ndjir_b200.config import make_conf
 from ndjir_b200.engine import ParamStore
-from ndjir_b200.parallel import allreduce_gradients, allreduce_mask_sum, shard_rays
+from ndjir_b200.parallel import allgather_rows, allreduce_gradients, allreduce_mask_sum, shard_rays
 
 
 def small():
@@ -67,6 +67,15 @@ def _worker(rank, world, port, q):
     ms = torch.tensor([3.0 + rank])
     allreduce_mask_sum(ms)
     allreduce_gradients(ps)
+    # sparse exchange: every rank ends with the rows of all ranks, in rank order
+    rows = torch.full((5, 3), float(rank))
+    allr = allgather_rows(torch.empty(5 * world, 3), rows)
+    assert torch.equal(allr, torch.cat([torch.full((5, 3), float(r)) for r in range(world)]))
+    flat_only = ps.grad.clone()
+    grid_before = ps.grid_grad["voxel"].clone()
+    allreduce_gradients(ps, include_grid=False)          # sparse mode: the grid gradient is not all-reduced
+    assert torch.equal(ps.grid_grad["voxel"], grid_before) and torch.allclose(ps.grad, flat_only * world)
+    ps.grad.copy_(flat_only)
     q.put((rank, local[0].numpy(), local[1].numpy(), ps.grad.numpy().copy(), ps.grid_grad["voxel"].numpy().copy(),
            float(ms)))
     dist.destroy_process_group()
