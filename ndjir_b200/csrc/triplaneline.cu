@@ -208,6 +208,85 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
   }
 }
 
+// Forward with one thread per (point, channel chunk of V): D/V times as many independent gathers in flight as the
+// one-thread-per-point mapping, and the 3*V outputs of a chunk are still contiguous (three vector stores).
+// (A thread per (point, plane) was tried and lost to its stride-3 scalar stores: 4.18 ms vs 2.90 ms at 2^24 points.)
+template <bool PLANE, int V, bool ACCUM>
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+gather_fwd_chunk_kernel(long long B, float* __restrict__ out, const float* __restrict__ query,
+                        const float* __restrict__ feat, GridFrame g, int G, int D) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  const long long plane_elems = PLANE ? (long long)G * G * D : (long long)G * D;
+  const int nchunk = D / V;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < B * nchunk; w += stride) {
+    long long p = w / nchunk;
+    int d = (int)(w - p * nchunk) * V;
+    const float* q = query + p * 3;
+    Cell c = make_cell(g, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+    float o[3][V];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      Axis2 x = plane_axes(i, c, g, 0.f, 0.f, 0.f);
+      const float* fi = feat + i * plane_elems + d;
+      if (PLANE) {
+        Vec<V> f00 = ldg_vec<V>(fi + ((long long)x.u0 * G + x.v0) * D);
+        Vec<V> f01 = ldg_vec<V>(fi + ((long long)x.u0 * G + x.v1) * D);
+        Vec<V> f10 = ldg_vec<V>(fi + ((long long)x.u1 * G + x.v0) * D);
+        Vec<V> f11 = ldg_vec<V>(fi + ((long long)x.u1 * G + x.v1) * D);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          o[i][j] = x.a0 * x.b0 * f00.v[j] + x.a0 * x.b1 * f01.v[j] + x.a1 * x.b0 * f10.v[j] + x.a1 * x.b1 * f11.v[j];
+      } else {
+        Vec<V> f0 = ldg_vec<V>(fi + (long long)x.u0 * D);
+        Vec<V> f1 = ldg_vec<V>(fi + (long long)x.u1 * D);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[i][j] = x.a0 * f0.v[j] + x.a1 * f1.v[j];
+      }
+    }
+    store_chunk<V>(out + p * 3 * D, d, o, ACCUM);
+  }
+}
+
+// Scatter with one thread per (point, plane|line, corner): 12 (6) threads per point, one vector reduction per
+// channel chunk each.
+template <bool PLANE, bool SECOND, int V>
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+scatter_split_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go_, const float* __restrict__ gg,
+                     const float* __restrict__ query, GridFrame g, int G, int D) {
+  constexpr int NC = PLANE ? 4 : 2;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  const long long plane_elems = PLANE ? (long long)G * G * D : (long long)G * D;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < B * 3 * NC; w += stride) {
+    long long p = w / (3 * NC);
+    int rem = (int)(w - p * 3 * NC);
+    int i = rem / NC, k = rem - i * NC;
+    const float* q = query + p * 3;
+    Cell c = make_cell(g, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
+    if (SECOND) { ggx = __ldg(gg + p * 3); ggy = __ldg(gg + p * 3 + 1); ggz = __ldg(gg + p * 3 + 2); }
+    Axis2 x = plane_axes(i, c, g, ggx, ggy, ggz);
+    float coef;
+    long long off;
+    if (PLANE) {
+      int cu = k >> 1, cv = k & 1;
+      float au = cu ? x.a1 : x.a0, bv = cv ? x.b1 : x.b0;
+      coef = SECOND ? (x.ggu * x.su * ((cu ? 1.f : -1.f) * bv) + x.ggv * x.sv * ((cv ? 1.f : -1.f) * au)) : au * bv;
+      off = ((long long)(cu ? x.u1 : x.u0) * G + (cv ? x.v1 : x.v0)) * D;
+    } else {
+      coef = SECOND ? (x.ggu * x.su * (k ? 1.f : -1.f)) : (k ? x.a1 : x.a0);
+      off = (long long)(k ? x.u1 : x.u0) * D;
+    }
+    const float* grow = go_ + p * 3 * D + i;
+    float* gi = gf + i * plane_elems + off;
+    for (int d = 0; d < D; d += V) {
+      Vec<V> val;
+#pragma unroll
+      for (int j = 0; j < V; ++j) val.v[j] = __ldg(grow + (d + j) * 3) * coef;
+      red_vec<V>(gi + d, val);
+    }
+  }
+}
+
 static bool bad(int G, int D) {
   return G <= 0 || D <= 0 || (long long)G * G * D * 3 >= (1ll << 40);
 }
@@ -221,6 +300,15 @@ static int launch_gather(long long B, float* out, const float* a, const float* b
   GridFrame g = make_frame(G, G, G, mn, mx);
   int V = pick_vec(D, feat, MODE == GRAD_QUERY ? (const void*)a : (const void*)out);
   int grid = grid_for(B);
+  if (MODE == FWD && D / V > 1) {
+    int gridc = grid_for(B * (D / V));
+#define NDJIR_LAUNCH_S(VV)                                                                                           \
+  if (accum) gather_fwd_chunk_kernel<PLANE, VV, true><<<gridc, NDJIR_BLOCK, 0, st>>>(B, out, query, feat, g, G, D);   \
+  else gather_fwd_chunk_kernel<PLANE, VV, false><<<gridc, NDJIR_BLOCK, 0, st>>>(B, out, query, feat, g, G, D);
+    if (V == 4) { NDJIR_LAUNCH_S(4) } else if (V == 2) { NDJIR_LAUNCH_S(2) } else { NDJIR_LAUNCH_S(1) }
+#undef NDJIR_LAUNCH_S
+    NDJIR_RETURN_LAST_ERROR();
+  }
 #define NDJIR_LAUNCH(VV)                                                                                          \
   if (accum) gather_kernel<PLANE, MODE, VV, true><<<grid, NDJIR_BLOCK, 0, st>>>(B, out, a, b, query, feat, g, G, D); \
   else gather_kernel<PLANE, MODE, VV, false><<<grid, NDJIR_BLOCK, 0, st>>>(B, out, a, b, query, feat, g, G, D);
@@ -238,6 +326,16 @@ static int launch_scatter(long long B, float* gf, const float* go, const float* 
   int V = pick_vec(D, gf, go);
   int grid = grid_for(B);
   bool agg = g_scatter_aggregate != 0;
+  if (!agg) {
+    // triline: the table is tiny (49 152 cells at G=2048) and the reductions are contention-bound (1.6 ms at 2^24
+    // points; tried and rejected: scalar reductions 6.0 ms, a shared-memory private copy of the table 3.1 ms)
+    int V2 = pick_vec(D, gf);
+    int gridc = grid_for(B * 3 * (PLANE ? 4 : 2));
+    if (V2 == 4) scatter_split_kernel<PLANE, SECOND, 4><<<gridc, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, G, D);
+    else if (V2 == 2) scatter_split_kernel<PLANE, SECOND, 2><<<gridc, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, G, D);
+    else scatter_split_kernel<PLANE, SECOND, 1><<<gridc, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, G, D);
+    NDJIR_RETURN_LAST_ERROR();
+  }
 #define NDJIR_LAUNCH(VV)                                                                                       \
   if (agg) scatter_kernel<PLANE, SECOND, VV, true><<<grid, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, G, D); \
   else scatter_kernel<PLANE, SECOND, VV, false><<<grid, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, G, D);
