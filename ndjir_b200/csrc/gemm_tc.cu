@@ -92,6 +92,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+// explicit shared-space accesses for the transform pass: a pointer rebuilt from an aligned integer loses its address
+// space and nvcc emits generic LD.E/ST.E (seen in the ncu source page: the transform stalled on them)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -349,30 +359,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int s = it % TC_STAGES;
         uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(bar_full(s), ph);
-        uint8_t* st = smem + s * STAGE_BYTES;
+        const uint32_t st = smem_base + s * STAGE_BYTES;
         if (p.dbg & 1) { fence_proxy_async(); mbar_arrive(bar_ready(s)); continue; }
-#pragma unroll 2
+        // A: raw at 0, lo at A_TILE_BYTES;  B: raw at 2*A_TILE_BYTES, lo at 2*A_TILE_BYTES + B_TILE_BYTES
+#pragma unroll
         for (int off = t * 16; off < A_TILE_BYTES; off += TC_XFORM_THREADS * 16) {
-          float4 x = *reinterpret_cast<const float4*>(st + off);
+          float4 x = lds128(st + off);
           float4 h;
           h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-          *reinterpret_cast<float4*>(st + A_TILE_BYTES + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-          if (p.mask_hi) *reinterpret_cast<float4*>(st + off) = h;
+          sts128(st + A_TILE_BYTES + off, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
+          if (p.mask_hi) sts128(st + off, h);
         }
 #pragma unroll 4
         for (int off = t * 16; off < b_bytes; off += TC_XFORM_THREADS * 16) {
-          float4 x = *reinterpret_cast<const float4*>(st + 2 * A_TILE_BYTES + off);
+          float4 x = lds128(st + 2 * A_TILE_BYTES + off);
           float4 h;
           h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-          *reinterpret_cast<float4*>(st + 2 * A_TILE_BYTES + B_TILE_BYTES + off) =
-              make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-          if (p.mask_hi) *reinterpret_cast<float4*>(st + 2 * A_TILE_BYTES + off) = h;
+          sts128(st + 2 * A_TILE_BYTES + B_TILE_BYTES + off, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
+          if (p.mask_hi) sts128(st + 2 * A_TILE_BYTES + off, h);
         }
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(bar_ready(s));

@@ -21,7 +21,7 @@ shapes = {
 }
 out = []
 import sys as _s
-modes = [(1, 0), (1, 3), (1, 4), (1, 7)] if "--dbg" in _s.argv else [(1, 0), (0, 0)]
+modes = [(1, 0), (1, 8), (1, 7), (1, 15)] if "--dbg" in _s.argv else [(1, 0), (0, 0)]
 for tc, dbg in modes:
     _lib.call("ndjir_set_option", "mlp_tensor_cores", tc)
     _lib.call("ndjir_set_option", "mlp_dbg", dbg)
