@@ -30,7 +30,8 @@ int g_mlp_dbg = 0;   // experiment switches (profiling only): 1 = skip the lo tr
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
 constexpr int TC_BK = 16;                       // fp32 elements per K block: 64-byte rows (K-major tiles use SWIZZLE_64B)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 4;                    // (tried: 6 raw + 2 lo stages in the same 192 KB: no gain, the ring is
+                                                //  not latency bound; L2 prefetch of the next item: no gain either)
 constexpr int KM_ROW_BYTES = TC_BK * 4;         // K-major tile row
 constexpr uint32_t KM_LAYOUT = TC_BK == 32 ? 2u : 4u;   // SWIZZLE_128B : SWIZZLE_64B
 constexpr uint32_t KM_SBO = 8 * KM_ROW_BYTES;   // 8-row swizzle groups
