@@ -98,6 +98,7 @@ int launch(const Args& a, int epi, cudaStream_t st);
 
 // tcgen05 path (gemm_tc.cu): 3xTF32 error-compensated products on the 5th-generation tensor cores
 extern int g_mlp_tensor_cores;
+extern int g_mlp_cta_pair;
 extern int g_mlp_dbg;
 extern int g_mlp_mask_hi;     // 1: the transform warps also clear the low 13 mantissa bits of the raw tiles
 bool tc_eligible(const Args& a, int epi);

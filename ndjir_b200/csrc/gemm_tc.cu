@@ -25,11 +25,13 @@ namespace ndjir {
 namespace gemm {
 
 int g_mlp_mask_hi = 0;
+int g_mlp_cta_pair = 0;   // 1: activation-row products run on CTA pairs (tcgen05 cta_group::2)
 int g_mlp_dbg = 0;   // experiment switches (profiling only): 1 = skip the lo transform, 2 = issue only the hi*hi product
 
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
-constexpr int TC_BK = 16;                       // fp32 elements per K block: 64-byte rows (K-major tiles use SWIZZLE_64B)
+constexpr int TC_BK = 16;                       // fp32 elements per K block: 64-byte rows (K-major tiles use SWIZZLE_64B);
+                                                // 32-wide blocks with 2 stages measured the same
 constexpr int TC_STAGES = 4;                    // (tried: 6 raw + 2 lo stages in the same 192 KB: no gain, the ring is
                                                 //  not latency bound; L2 prefetch of the next item: no gain either)
 constexpr int KM_ROW_BYTES = TC_BK * 4;         // K-major tile row
@@ -311,6 +313,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t a_lbo = p.a_mn ? TC_BK * 128 : 16, a_sbo = p.a_mn ? 512 : KM_SBO, a_step = p.a_mn ? 1024 : 32;
       const uint32_t b_lbo = p.b_mn ? TC_BK * 128 : 16, b_sbo = p.b_mn ? 512 : KM_SBO, b_step = p.b_mn ? 1024 : 32;
       const uint32_t a_lay = p.a_mn ? 1 : KM_LAYOUT, b_lay = p.b_mn ? 1 : KM_LAYOUT;
+      const uint64_t da_hi0 = make_desc(a_raw(0), a_lbo, a_sbo, a_lay), da_lo0 = make_desc(a_lo(0), a_lbo, a_sbo, a_lay);
+      const uint64_t db_hi0 = make_desc(b_raw(0), b_lbo, b_sbo, b_lay), db_lo0 = make_desc(b_lo(0), b_lbo, b_sbo, b_lay);
       uint32_t it = 0, tile_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_it) {
         int m0, n0, kb0, nkb;
@@ -330,10 +334,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            uint64_t da_hi = make_desc(a_raw(s) + ks * a_step, a_lbo, a_sbo, a_lay);
-            uint64_t da_lo = make_desc(a_lo(s) + ks * a_step, a_lbo, a_sbo, a_lay);
-            uint64_t db_hi = make_desc(b_raw(s) + ks * b_step, b_lbo, b_sbo, b_lay);
-            uint64_t db_lo = make_desc(b_lo(s) + ks * b_step, b_lbo, b_sbo, b_lay);
+            // descriptors differ from the stage-0 ones only in the 14-bit start-address field (units of 16 bytes):
+            // one 64-bit add per operand instead of rebuilding them (the single issuing thread is on the critical path)
+            const uint64_t oa = (uint64_t)((s * STAGE_BYTES + ks * a_step) >> 4);
+            const uint64_t ob = (uint64_t)((s * STAGE_BYTES + ks * b_step) >> 4);
+            uint64_t da_hi = da_hi0 + oa, da_lo = da_lo0 + oa, db_hi = db_hi0 + ob, db_lo = db_lo0 + ob;
             if (p.dbg & 2) {
               umma_tf32(tacc, da_hi, db_hi, idesc, (i > 0 || ks > 0) ? 1u : 0u);
             } else {
@@ -456,6 +461,296 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// CTA-PAIR variant (tcgen05 cta_group::2) for the activation-row products (A K-major, M large).
+// Two CTAs of a cluster - the two SMs of a TPC - compute one 256 x (<=256) tile: each stages ITS 128 rows of A and
+// ITS HALF of the B columns, the leader's elected thread issues 256 x N x 8 MMAs that read both SMs' shared memory,
+// and every CTA finds the accumulator rows of its own 128 rows in its own TMEM.  Per SM and K block this halves the B
+// traffic through shared memory (TMA fill, hi/lo transform, MMA operand reads: 144 KB -> 96 KB), which is what bounds
+// the single-CTA kernel (l1tex data pipe at ~90 %).
+// Synchronisation: the peer's transform threads arrive on the LEADER's `ready` barrier (mapa + remote arrive), the
+// leader's tcgen05.commit multicasts to the `empty` / `acc_full` barriers of both CTAs, and both CTAs' epilogue
+// threads release the accumulator on the leader's `acc_empty` barrier.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+constexpr int P2_BNH = 128;                                  // B columns staged per CTA
+constexpr int P2_B_TILE_BYTES = P2_BNH * TC_BK * 4;          // 8 KB
+constexpr int P2_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * P2_B_TILE_BYTES;   // 32 KB
+constexpr int P2_STAGES = 3;
+constexpr int P2_SMEM_BYTES = P2_STAGES * P2_STAGE_BYTES + 1024;
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * P2_STAGES + 4];
+  __shared__ uint32_t tmem_base_sh;
+
+  const Args& a = p.a;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  auto bar_full = [&](int s) { return smem_u32(&bars[s]); };
+  auto bar_ready = [&](int s) { return smem_u32(&bars[P2_STAGES + s]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[2 * P2_STAGES + s]); };
+  auto bar_acc_full = [&](int b) { return smem_u32(&bars[3 * P2_STAGES + b]); };
+  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[3 * P2_STAGES + 2 + b]); };
+  auto a_raw = [&](int s) { return smem_base + s * P2_STAGE_BYTES; };
+  auto a_lo = [&](int s) { return smem_base + s * P2_STAGE_BYTES + A_TILE_BYTES; };
+  auto b_raw = [&](int s) { return smem_base + s * P2_STAGE_BYTES + 2 * A_TILE_BYTES; };
+  auto b_lo = [&](int s) { return smem_base + s * P2_STAGE_BYTES + 2 * A_TILE_BYTES + P2_B_TILE_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P2_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_ready(s), 2 * TC_XFORM_THREADS);     // only the leader's copy is used
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);
+      mbar_init(bar_acc_empty(b), 2 * TC_EPI_THREADS);   // only the leader's copy is used
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  // work items: (pair of m tiles, n tile); clusters walk them round-robin
+  const int pair_tiles = (p.m_tiles + 1) / 2;
+  const int n_items = pair_tiles * p.n_tiles;
+  const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  auto item_info = [&](int item, int& m0, int& n0, int& umma_n) {
+    int pt = item % pair_tiles;
+    int ntile = item / pair_tiles;
+    m0 = pt * 2 * TC_BM;
+    n0 = ntile * TC_BN;
+    umma_n = (min(TC_BN, a.N - n0) + 63) & ~63;   // both halves are multiples of 32 columns
+  };
+  const int nkb = p.nkb_total;
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA: its A rows, its half of B) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        int m0, n0, umma_n;
+        item_info(item, m0, n0, umma_n);
+        const int half = umma_n / 2, chunks = half / 32;
+        const int mr = m0 + rank * TC_BM, nr = n0 + rank * half;
+        const uint32_t tx_bytes = A_TILE_BYTES + ((p.b_mn && !p.b_3d) ? chunks * TC_BK * 128 : P2_B_TILE_BYTES);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          int s = it % P2_STAGES;
+          uint32_t ph = (it / P2_STAGES) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          mbar_expect_tx(bar_full(s), tx_bytes);
+          int k0 = i * TC_BK;
+          tma_load_2d(a_raw(s), &mapA, k0, mr, bar_full(s));
+          if (p.b_3d) {
+            tma_load_3d(b_raw(s), &mapB, 0, k0, nr / 32, bar_full(s));
+          } else if (p.b_mn) {
+            for (int c = 0; c < chunks; ++c) tma_load_2d(b_raw(s) + c * TC_BK * 128, &mapB, nr + c * 32, k0, bar_full(s));
+          } else {
+            tma_load_2d(b_raw(s), &mapB, k0, nr, bar_full(s));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the leader CTA only =====================
+    if (leader && lane == 0) {
+      const uint32_t a_lbo = 16, a_sbo = KM_SBO, a_step = 32, a_lay = KM_LAYOUT;
+      const uint32_t b_lbo = p.b_mn ? TC_BK * 128 : 16, b_sbo = p.b_mn ? 512 : KM_SBO, b_step = p.b_mn ? 1024 : 32;
+      const uint32_t b_lay = p.b_mn ? 1 : KM_LAYOUT;
+      const uint64_t da_hi0 = make_desc(a_raw(0), a_lbo, a_sbo, a_lay), da_lo0 = make_desc(a_lo(0), a_lbo, a_sbo, a_lay);
+      const uint64_t db_hi0 = make_desc(b_raw(0), b_lbo, b_sbo, b_lay), db_lo0 = make_desc(b_lo(0), b_lbo, b_sbo, b_lay);
+      uint32_t it = 0, tile_it = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters, ++tile_it) {
+        int m0, n0, umma_n;
+        item_info(item, m0, n0, umma_n);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.b_mn << 16) |
+                               ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+        const int buf = tile_it & 1;
+        mbar_wait_cluster(bar_acc_empty(buf), ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * TC_BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          int s = it % P2_STAGES;
+          uint32_t ph = (it / P2_STAGES) & 1;
+          mbar_wait_cluster(bar_ready(s), ph);       // 512 arrivals: the transform threads of both CTAs
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t oa = (uint64_t)((s * P2_STAGE_BYTES + ks * a_step) >> 4);
+            const uint64_t ob = (uint64_t)((s * P2_STAGE_BYTES + ks * b_step) >> 4);
+            uint64_t da_hi = da_hi0 + oa, da_lo = da_lo0 + oa, db_hi = db_hi0 + ob, db_lo = db_lo0 + ob;
+            umma_tf32_pair(tacc, da_lo, db_hi, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32_pair(tacc, da_hi, db_lo, idesc, 1u);
+            umma_tf32_pair(tacc, da_hi, db_hi, idesc, 1u);
+          }
+          umma_commit_pair(bar_empty(s));       // frees the stage in both CTAs
+        }
+        umma_commit_pair(bar_acc_full(buf));    // accumulator complete, both CTAs
+      }
+    }
+  } else if (warp < TC_EPI_WARP0) {
+    // ===================== transform: lo = x - hi for this CTA's tiles; arrive on the LEADER's barrier ==========
+    const int t = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int item = cluster_id; item < n_items; item += n_clusters) {
+      int m0, n0, umma_n;
+      item_info(item, m0, n0, umma_n);
+      const int half = umma_n / 2;
+      const int b_bytes = (p.b_mn && !p.b_3d) ? (half / 32) * TC_BK * 128 : P2_B_TILE_BYTES;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        int s = it % P2_STAGES;
+        uint32_t ph = (it / P2_STAGES) & 1;
+        mbar_wait(bar_full(s), ph);
+        const uint32_t st = smem_base + s * P2_STAGE_BYTES;
+#pragma unroll
+        for (int off = t * 16; off < A_TILE_BYTES; off += TC_XFORM_THREADS * 16) {
+          float4 x = lds128(st + off);
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          sts128(st + A_TILE_BYTES + off, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
+        }
+#pragma unroll
+        for (int off = t * 16; off < b_bytes; off += TC_XFORM_THREADS * 16) {
+          float4 x = lds128(st + 2 * A_TILE_BYTES + off);
+          float4 h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          sts128(st + 2 * A_TILE_BYTES + P2_B_TILE_BYTES + off, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
+        }
+        fence_proxy_async();
+        if (leader) mbar_arrive(bar_ready(s));
+        else mbar_arrive_cluster(mapa_cluster(bar_ready(s), 0));
+      }
+    }
+  } else {
+    // ===================== epilogue: this CTA's 128 accumulator rows, all columns =====================
+    const int q = warp & 3;
+    const int chalf = (warp - TC_EPI_WARP0) >> 2;
+    uint32_t tile_it = 0;
+    constexpr bool NEED_H = (EPI == EPI_MUL_S || EPI == EPI_ADJ);
+    constexpr bool NEED_C = (EPI == EPI_ACCUM);
+    const bool need_u = (EPI == EPI_ADJ) || (EPI == EPI_MUL_S && a.U != nullptr);
+    const bool need_b = (EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias != nullptr;
+    for (int item = cluster_id; item < n_items; item += n_clusters, ++tile_it) {
+      int m0, n0, umma_n;
+      item_info(item, m0, n0, umma_n);
+      const int n_valid = min(TC_BN, a.N - n0);
+      const int buf = tile_it & 1;
+      const long long m = m0 + rank * TC_BM + q * 32 + lane;
+      const bool row_ok = m < a.M;
+      const int n_vec = p.vec_epi ? (n_valid & ~3) : 0;
+      mbar_wait(bar_acc_full(buf), (tile_it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * TC_BN + ((uint32_t)(q * 32) << 16);
+      for (int c0 = chalf * 16; c0 < n_valid; c0 += 32) {
+        float4 hv[4], uv[4], cv[4], bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int c = c0 + 4 * j;
+          hv[j] = uv[j] = cv[j] = bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && c < n_vec) {
+            if (NEED_H) hv[j] = __ldg(reinterpret_cast<const float4*>(a.H + m * a.ldh + n0 + c));
+            if (need_u) uv[j] = *reinterpret_cast<const float4*>(a.U + m * a.ldu + n0 + c);
+            if (NEED_C) cv[j] = *reinterpret_cast<const float4*>(a.C + m * a.ldc + n0 + c);
+            if (need_b) bv[j] = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c));
+          }
+        }
+        float v[16];
+        tmem_ld16(tacc + (uint32_t)c0, v);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            int c = c0 + 4 * j;
+            if (c < n_vec) {
+              epilogue_vec4<EPI>(a, m, n0 + c, v + 4 * j, hv[j], uv[j], cv[j], bv[j]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c + e < n_valid) epilogue_store<EPI>(a, (int)m, n0 + c + e, v[4 * j + e]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      if (leader) mbar_arrive(bar_acc_empty(buf));
+      else mbar_arrive_cluster(mapa_cluster(bar_acc_empty(buf), 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // no CTA leaves (or frees TMEM) while its peer may still touch its barriers / smem
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled get_encode() {
@@ -522,7 +817,56 @@ bool tc_eligible(const Args& a, int epi) {
 }
 
 template <int EPI>
+static int launch_tc2_epi(const Args& a, cudaStream_t st) {
+  TcParams p;
+  p.a = a;
+  p.a_mn = 0;
+  p.b_mn = (a.b_cs == 1);
+  p.mask_hi = 0; p.dbg = 0; p.a_3d = 0;
+  auto ok16 = [](const void* q, long long ld) { return q == nullptr || (al16p(q) && ld % 4 == 0); };
+  p.vec_epi = ok16(a.C, a.ldc) && ok16(a.H, a.ldh) && ok16(a.U, a.ldu) && ok16(a.C2, a.ldc2) && ok16(a.bias, 0);
+  p.b_3d = p.b_mn && a.N % 64 == 0;
+  CUtensorMap mapA, mapB;
+  bool ok = make_map(&mapA, a.A, a.K, a.M, a.a_rs, TC_BK, TC_BM, false);
+  if (p.b_3d) ok = ok && make_map3(&mapB, a.B, a.N, a.K, a.b_rs, P2_BNH / 32);
+  else if (p.b_mn) ok = ok && make_map(&mapB, a.B, a.N, a.K, a.b_rs, 32, TC_BK, true);
+  else ok = ok && make_map(&mapB, a.B, a.K, a.N, a.b_cs, TC_BK, P2_BNH, false);
+  if (!ok) return NDJIR_ERR_ARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  p.m_tiles = (a.M + TC_BM - 1) / TC_BM;
+  p.n_tiles = (a.N + TC_BN - 1) / TC_BN;
+  p.nkb_total = (a.K + TC_BK - 1) / TC_BK;
+  p.splits = 1; p.kb_per_split = p.nkb_total;
+  int n_items = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  int clusters = n_items < NDJIR_NUM_SMS / 2 ? n_items : NDJIR_NUM_SMS / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = P2_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, mapA, mapB, p);
+  if (e != cudaSuccess) return (int)e;
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+static bool tc2_eligible(const Args& a, int epi) {
+  // activation-row products only: A row-major (K-major), many rows, no split-K
+  return g_mlp_cta_pair && a.a_cs == 1 && a.M >= 4096 && a.split_k <= 1 && epi != EPI_ATOMIC && a.N >= 64;
+}
+
+template <int EPI>
 static int launch_tc_epi(const Args& a, cudaStream_t st) {
+  if (tc2_eligible(a, EPI)) return launch_tc2_epi<EPI>(a, st);
   TcParams p;
   p.a = a;
   p.a_mn = (a.a_cs != 1);        // A(m,k) contiguous along m

@@ -347,6 +347,10 @@ int ndjir_set_option(const char* key, int value) {
   i = 0;
   while (k2[i] && key[i] == k2[i]) ++i;
   if (k2[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_tensor_cores = value; return NDJIR_OK; }
+  const char* k5 = "mlp_cta_pair";
+  i = 0;
+  while (k5[i] && key[i] == k5[i]) ++i;
+  if (k5[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_cta_pair = value; return NDJIR_OK; }
   const char* k4 = "mlp_dbg";
   i = 0;
   while (k4[i] && key[i] == k4[i]) ++i;

@@ -123,6 +123,27 @@ def test_gemm_matches_float64(M, N, K, layout, epi, split_k, tc):
     assert err <= 1e-5, err
 
 
+PAIR_CASES = [
+    (8192, 256, 256, "kn", EPI_SOFTPLUS),      # forward hidden layer on CTA pairs (tcgen05 cta_group::2)
+    (4100, 213, 43, "kn", EPI_SOFTPLUS),       # ragged rows, odd K, N rounded up to 256
+    (4096, 128, 128, "kn", EPI_BIAS),          # N = 128: 64 columns per CTA
+    (6000, 262, 128, "kn", EPI_ACCUM),         # two n tiles
+    (5000, 256, 256, "kk", EPI_MUL_S),         # K-major B fallback
+    (4608, 256, 301, "kn", EPI_ADJ),
+]
+
+
+@pytest.mark.parametrize("M,N,K,layout,epi", PAIR_CASES)
+def test_cta_pair_kernel_matches_float64(M, N, K, layout, epi):
+    _lib.call("ndjir_set_option", "mlp_cta_pair", 1)
+    try:
+        err = run(M, N, K, layout, epi, 1)
+    finally:
+        _lib.call("ndjir_set_option", "mlp_cta_pair", 0)
+    print(f"  pair gemm M={M} N={N} K={K} {layout} epi={epi}: rel err {err:.2e}")
+    assert err <= 1e-5, err
+
+
 def test_tf32_operand_truncation_is_harmless():
     """3xTF32 relies on hi + lo == x with hi = what the tensor core keeps of a raw fp32 operand.  Clearing the low
     mantissa bits explicitly (mlp_mask_hi=1) and leaving them (0) must agree to fp32 accuracy."""

@@ -21,9 +21,10 @@ shapes = {
 }
 out = []
 import sys as _s
-modes = [(1, 0), (1, 8), (1, 7), (1, 15)] if "--dbg" in _s.argv else [(1, 0), (0, 0)]
+modes = [(1, d) for d in range(8)] if "--dbg" in _s.argv else ([(1, 0), (2, 0)] if "--pair" in _s.argv else [(1, 0), (0, 0)])
 for tc, dbg in modes:
-    _lib.call("ndjir_set_option", "mlp_tensor_cores", tc)
+    _lib.call("ndjir_set_option", "mlp_tensor_cores", 1 if tc else 0)
+    _lib.call("ndjir_set_option", "mlp_cta_pair", 1 if tc == 2 else 0)
     _lib.call("ndjir_set_option", "mlp_dbg", dbg)
     for name, fn in shapes.items():
         for _ in range(3): fn()
@@ -36,3 +37,4 @@ for tc, dbg in modes:
         out.append(r); print(json.dumps(r), flush=True)
 _lib.call("ndjir_set_option", "mlp_tensor_cores", 1)
 _lib.call("ndjir_set_option", "mlp_dbg", 0)
+_lib.call("ndjir_set_option", "mlp_cta_pair", 0)
