@@ -519,7 +519,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on
 constexpr int P2_BNH = 128;                                  // B columns staged per CTA
 constexpr int P2_B_TILE_BYTES = P2_BNH * TC_BK * 4;          // 8 KB
 constexpr int P2_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * P2_B_TILE_BYTES;   // 32 KB
-constexpr int P2_STAGES = 3;
+constexpr int P2_STAGES = 6;
 constexpr int P2_SMEM_BYTES = P2_STAGES * P2_STAGE_BYTES + 1024;
 
 template <int EPI>
