@@ -70,6 +70,26 @@ int ndjir_voxel_grad_feature_grad_query(long long n_points, float* grad_query, c
                                         const float* grad_output, const float* query, const int* grid_sizes,
                                         int D, const float* min3, const float* max3, cudaStream_t stream);
 
+/* Brick-ordered variants for LARGE batches on tables far larger than L2 (no reference counterpart; same results
+ * as query_on_voxel :101 / grad_feature :289 / grad_query_grad_feature :616 up to fp32 summation order).  Points
+ * are counting-sorted by the ~16 MB table brick of their lower corner so that every brick is pulled into L2 once.
+ * `workspace`: DEVICE scratch of ndjir_voxel_binned_workspace_bytes(n_points) bytes, 16-byte aligned, caller-owned.
+ * The reference-signature entry points above take this path by themselves (scratch from the stream-ordered CUDA
+ * pool, cudaMallocAsync) when n_points >= 2^21 and the table is >= 96 MB; option "voxel_binned" (-1 auto, 0 off,
+ * 1 whenever possible) and "voxel_bin_mb" (brick size) control it. */
+long long ndjir_voxel_binned_workspace_bytes(long long n_points);
+int ndjir_voxel_query_on_voxel_binned(long long n_points, float* output, const float* query, const float* feature,
+                                      const int* grid_sizes, int D, const float* min3, const float* max3, int accum,
+                                      void* workspace, long long workspace_bytes, cudaStream_t stream);
+int ndjir_voxel_grad_feature_binned(long long n_points, float* grad_feature, const float* grad_output,
+                                    const float* query, const int* grid_sizes, int D, const float* min3,
+                                    const float* max3, int accum, void* workspace, long long workspace_bytes,
+                                    cudaStream_t stream);
+int ndjir_voxel_grad_query_grad_feature_binned(long long n_points, float* grad_feature, const float* grad_grad_query,
+                                               const float* grad_output, const float* query, const int* grid_sizes,
+                                               int D, const float* min3, const float* max3, void* workspace,
+                                               long long workspace_bytes, cudaStream_t stream);
+
 /* ---- lanczos_voxel_feature_cuda (csrc/grid_feature/lanczos_voxel_feature_cuda.cu:822-834) ----------- */
 int ndjir_lanczos_voxel_query_on_voxel(long long n_points, float* output, const float* query,
                                        const float* feature, const int* grid_sizes, int D, const float* min3,

@@ -10,6 +10,7 @@
 // grad_feature 12+16+2*8*16 = 284 B.
 #include "grid_common.cuh"
 #include "gemm.cuh"
+#include "voxel_binned.cuh"
 #include "../../include/ndjir_b200.h"
 
 namespace ndjir {
@@ -290,6 +291,14 @@ static int launch_gather(long long B, float* out, const float* a, const float* b
   const void* vec_a = (MODE == GRAD_QUERY || MODE == GQ_GQ) ? a : nullptr;
   int V = pick_vec(D, feat, vec_out, vec_a);
   int grid = grid_for(B);
+  if (MODE == FWD && voxel_binned::worthwhile(B, G, D)) {
+    long long wsb = voxel_binned::workspace_bytes(B);
+    if (void* ws = voxel_binned::scratch_alloc(wsb, st)) {
+      int rc = voxel_binned::query(B, out, query, feat, G, D, mn, mx, accum, ws, wsb, st);
+      voxel_binned::scratch_free(ws, st);
+      return rc;
+    }
+  }
   if (MODE == FWD && V == 4) {
     int grid4 = grid_for(B * 4);
     if (accum) gather4_kernel<true><<<grid4, NDJIR_BLOCK, 0, st>>>(B, out, query, feat, g, s, D);
@@ -311,6 +320,14 @@ static int launch_scatter(long long B, float* gf, const float* go, const float* 
   if (B < 0 || bad_grid(G, D) || !gf || !go || !query) return NDJIR_ERR_ARG;
   GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
   Strides s = make_strides(G, D);
+  if (voxel_binned::worthwhile(B, G, D)) {
+    long long wsb = voxel_binned::workspace_bytes(B);
+    if (void* ws = voxel_binned::scratch_alloc(wsb, st)) {
+      int rc = voxel_binned::scatter(SECOND, B, gf, go, gg, query, G, D, mn, mx, ws, wsb, st);
+      voxel_binned::scratch_free(ws, st);
+      return rc;
+    }
+  }
   int V = pick_vec(D, gf, go);
   int grid = grid_for(B);
   bool agg = g_scatter_aggregate != 0;
@@ -359,6 +376,14 @@ int ndjir_set_option(const char* key, int value) {
   i = 0;
   while (k3[i] && key[i] == k3[i]) ++i;
   if (k3[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_mask_hi = value; return NDJIR_OK; }
+  const char* k6 = "voxel_binned";
+  i = 0;
+  while (k6[i] && key[i] == k6[i]) ++i;
+  if (k6[i] == 0 && key[i] == 0) { ndjir::g_voxel_binned = value; return NDJIR_OK; }
+  const char* k7 = "voxel_bin_mb";
+  i = 0;
+  while (k7[i] && key[i] == k7[i]) ++i;
+  if (k7[i] == 0 && key[i] == 0) { ndjir::g_voxel_bin_mb = value; return NDJIR_OK; }
   return NDJIR_ERR_ARG;
 }
 

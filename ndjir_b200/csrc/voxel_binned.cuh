@@ -1,0 +1,23 @@
+// Brick-ordered voxel gather / scatter (voxel_binned.cu): interface used by the dispatch in voxel.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ndjir {
+
+extern int g_voxel_binned;  // -1 auto (large batch on a table far larger than L2), 0 never, 1 whenever possible
+extern int g_voxel_bin_mb;  // target brick size in MiB
+
+namespace voxel_binned {
+
+long long workspace_bytes(long long n_points);
+bool shape_ok(long long B, const int* G, int D);
+bool worthwhile(long long B, const int* G, int D);
+int query(long long B, float* out, const float* query, const float* feat, const int* G, int D, const float* mn,
+          const float* mx, bool accum, void* ws, long long ws_bytes, cudaStream_t st);
+int scatter(bool second, long long B, float* gf, const float* go, const float* gg, const float* query, const int* G,
+            int D, const float* mn, const float* mx, void* ws, long long ws_bytes, cudaStream_t st);
+void* scratch_alloc(long long bytes, cudaStream_t st);
+void scratch_free(void* p, cudaStream_t st);
+
+}  // namespace voxel_binned
+}  // namespace ndjir
