@@ -248,6 +248,15 @@ int ndjir_ray_points(int n_rays, int Nt, int R, float* x, const float* camloc, c
 int ndjir_importance_round(int n_rays, int Nt, int M, const float* t_in, long long ld_in, const float* sdf,
                            long long ld_sdf, const float* t_near, const float* t_far, float gain, float* t_out,
                            long long ld_out, float* t_new_out, int* idx_out, cudaStream_t stream);
+/* Incremental form of the same round: (t, sdf) hold Nt sorted pairs per ray (in place, row strides ld_t / ld_sdf);
+ * the Mp pending samples of the previous round (dense t_pend (n_rays, Mp) with their freshly evaluated sdf_pend) are
+ * merged in first, then M new distances are placed from the merged Nt+Mp pairs and written densely to t_new_out
+ * (n_rays, M) for the caller to evaluate.  M == 0 merges only.  Identical results to re-evaluating the SDF at every
+ * current sample each round (sampler.py:190-192) at 112 instead of 352 network evaluations per ray. */
+int ndjir_importance_round_incremental(int n_rays, int Nt, int Mp, int M, float* t, long long ld_t, float* sdf,
+                                       long long ld_sdf, const float* t_pend, const float* sdf_pend,
+                                       const float* t_near, const float* t_far, float gain, float* t_new_out,
+                                       int* idx_out, cudaStream_t stream);
 /* :244-254, :282-291 background inverse-depth samples; t_bg (n_rays, Nb+1), x_bg (n_rays, Nb, 4) */
 int ndjir_background_samples(int n_rays, int Nb, int R, const float* camloc, const float* raydir,
                              const float* t_far, const float* mask, const float* xi, float radius, float* t_bg,

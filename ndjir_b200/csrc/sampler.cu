@@ -64,13 +64,43 @@ __device__ __forceinline__ void warp_bitonic_sort(float* v, int n_pow2, int lane
   }
 }
 
+// same network, (key, value) pairs
+__device__ __forceinline__ void warp_bitonic_sort_kv(float* v, float* w, int n_pow2, int lane) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n_pow2; i += 32) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          float a = v[i], b = v[ixj];
+          bool up = ((i & k) == 0);
+          if ((a > b) == up) {
+            v[i] = b; v[ixj] = a;
+            float wa = w[i]; w[i] = w[ixj]; w[ixj] = wa;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // One up-sampling round (sampler.py:196-240).  WARPS_PER_BLOCK warps, one ray each.
 constexpr int IWARPS = 4;
+//
+// INCREMENTAL mode (Mp >= 0): the reference re-evaluates the SDF network at ALL current samples in every round
+// (sampler.py:190-192: 64 + 80 + 96 + 112 = 352 evaluations per ray).  The SDF at a distance already on the ray does
+// not change between rounds and an MLP row does not depend on the other rows of its batch, so the values are carried
+// along instead: the kernel first MERGES the Mp pending samples of the previous round (t_pend with their freshly
+// evaluated sdf_pend) into the Nt sorted (t, sdf) pairs with a key-value sort, writes the merged pairs, and then
+// places the M new samples from them (dense t_new_out, to be evaluated by the caller: 64 + 3 x 16 = 112 evaluations
+// per ray).  M == 0: merge only (the final t_fg).  Results are identical to the full re-evaluation.
 __global__ void __launch_bounds__(IWARPS * 32)
-importance_round_kernel(int NR, int Nt, int M, const float* __restrict__ t_in, long long ld_in,
-                        const float* __restrict__ sdf, long long ld_sdf, const float* __restrict__ t_near,
-                        const float* __restrict__ t_far, float gain, float* __restrict__ t_out, long long ld_out,
-                        float* __restrict__ t_new_out, int* __restrict__ idx_out) {
+importance_round_kernel(int NR, int Nt, int M, const float* t_in, long long ld_in,
+                        const float* sdf, long long ld_sdf, const float* __restrict__ t_near,
+                        const float* __restrict__ t_far, float gain, float* t_out, long long ld_out,
+                        float* __restrict__ t_new_out, int* __restrict__ idx_out, int Mp,
+                        const float* __restrict__ t_pend, const float* __restrict__ sdf_pend, float* sdf_out,
+                        long long ld_sdf_out) {
   __shared__ float s_t[IWARPS][MAXS];
   __shared__ float s_w[IWARPS][MAXS];    // sdf, then alpha, then normalised weights
   __shared__ float s_c[IWARPS][MAXS];    // cdf (inclusive)
@@ -81,8 +111,26 @@ importance_round_kernel(int NR, int Nt, int M, const float* __restrict__ t_in, l
   float* ws = s_w[warp];
   float* cs = s_c[warp];
   for (int i = lane; i < Nt; i += 32) {
-    ts[i] = __ldg(t_in + (long long)r * ld_in + i);
-    cs[i] = __ldg(sdf + (long long)r * ld_sdf + i);   // sdf staged in cs
+    ts[i] = t_in[(long long)r * ld_in + i];
+    cs[i] = sdf[(long long)r * ld_sdf + i];   // sdf staged in cs
+  }
+  const bool incremental = Mp >= 0;
+  if (incremental) {
+    for (int k = lane; k < Mp; k += 32) {
+      ts[Nt + k] = __ldg(t_pend + (long long)r * Mp + k);
+      cs[Nt + k] = __ldg(sdf_pend + (long long)r * Mp + k);
+    }
+    Nt += Mp;
+    int n_pow2 = 1;
+    while (n_pow2 < Nt) n_pow2 <<= 1;
+    for (int i = Nt + lane; i < n_pow2; i += 32) { ts[i] = __int_as_float(0x7f800000); cs[i] = 0.f; }
+    __syncwarp();
+    warp_bitonic_sort_kv(ts, cs, n_pow2, lane);
+    for (int i = lane; i < Nt; i += 32) {
+      t_out[(long long)r * ld_out + i] = ts[i];
+      sdf_out[(long long)r * ld_sdf_out + i] = cs[i];
+    }
+    if (M == 0) return;
   }
   __syncwarp();
   const int S = Nt - 1;   // sections
@@ -163,6 +211,7 @@ importance_round_kernel(int NR, int Nt, int M, const float* __restrict__ t_in, l
     if (t_new_out) t_new_out[(long long)r * M + k] = tnew;
     if (idx_out) idx_out[(long long)r * M + k] = idx;
   }
+  if (incremental) return;
   __syncwarp();
   nslot = 0;
   for (int k = lane; k < M; k += 32) ts[Nt + k] = newv[nslot++];
@@ -243,7 +292,22 @@ int ndjir_importance_round(int n_rays, int Nt, int M, const float* t_in, long lo
   if (n_rays < 0 || Nt < 2 || M <= 0 || M > MAXS / 2 || Nt + M > MAXS || !t_in || !sdf || !t_near || !t_far || !t_out)
     return NDJIR_ERR_ARG;
   importance_round_kernel<<<(n_rays + IWARPS - 1) / IWARPS, IWARPS * 32, 0, stream>>>(
-      n_rays, Nt, M, t_in, ld_in, sdf, ld_sdf, t_near, t_far, gain, t_out, ld_out, t_new_out, idx_out);
+      n_rays, Nt, M, t_in, ld_in, sdf, ld_sdf, t_near, t_far, gain, t_out, ld_out, t_new_out, idx_out, -1, nullptr,
+      nullptr, nullptr, 0);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_importance_round_incremental(int n_rays, int Nt, int Mp, int M, float* t, long long ld_t, float* sdf,
+                                       long long ld_sdf, const float* t_pend, const float* sdf_pend,
+                                       const float* t_near, const float* t_far, float gain, float* t_new_out,
+                                       int* idx_out, cudaStream_t stream) {
+  if (n_rays == 0) return NDJIR_OK;
+  if (n_rays < 0 || Nt < 0 || Mp < 0 || M < 0 || Nt + Mp < 2 || M > MAXS / 2 || Nt + Mp > MAXS || !t || !sdf ||
+      (Mp > 0 && (!t_pend || !sdf_pend)) || (M > 0 && (!t_near || !t_far || !t_new_out)))
+    return NDJIR_ERR_ARG;
+  importance_round_kernel<<<(n_rays + IWARPS - 1) / IWARPS, IWARPS * 32, 0, stream>>>(
+      n_rays, Nt, M, t, ld_t, sdf, ld_sdf, t_near, t_far, gain, t, ld_t, t_new_out, idx_out, Mp, t_pend, sdf_pend,
+      sdf, ld_sdf);
   NDJIR_RETURN_LAST_ERROR();
 }
 

@@ -25,14 +25,15 @@ namespace ndjir {
 
 int g_voxel_binned = -1;    // -1 auto, 0 never, 1 always (when the shape allows it)
 int g_voxel_bin_mb = 16;    // target brick size
+int g_voxel_prefetch = 0;   // gather sweep: 0 no software prefetch, 1 records, 2 records + table lines (measured: no gain)
+int g_voxel_pair256 = 0;    // 256-bit loads for z-neighbour pairs that share a sector
 
 namespace voxel_binned {
 
-constexpr int kMaxBins = 1024;
+constexpr int kMaxBins = 512;
 constexpr int kPlaceBlock = 256;
-constexpr int kPlacePerThread = 16;
-constexpr int kChunk = kPlaceBlock * kPlacePerThread;
-constexpr long long kHeaderBytes = 8192;  // kMaxBins cursors (4 KB) + padding; records start 16-byte aligned
+constexpr int kPfRec = 3072, kPfTab = 1024;  // prefetch distances of the gather sweep, in CTAs (888 are resident)
+constexpr long long kHeaderBytes = 8192;  // kMaxBins cursors + padding; records start 16-byte aligned
 
 struct Bins {
   unsigned px, py;   // planes / rows per brick
@@ -102,44 +103,97 @@ bin_scan_kernel(unsigned* __restrict__ counts, int n) {
   if (t < n) counts[t] = s[t] - v;
 }
 
+// Exclusive scan of n <= kMaxBins shared-memory counters by one CTA of kPlaceBlock threads (4 counters per thread).
+__device__ __forceinline__ void block_exclusive_scan(const unsigned* __restrict__ in, unsigned* __restrict__ out,
+                                                     int n, unsigned* warp_tot) {
+  constexpr int per = kMaxBins / kPlaceBlock;
+  int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  unsigned v[per], sum = 0;
+#pragma unroll
+  for (int k = 0; k < per; ++k) { int i = t * per + k; v[k] = i < n ? in[i] : 0u; sum += v[k]; }
+  unsigned inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  unsigned before = 0;
+  for (int k = 0; k < w; ++k) before += warp_tot[k];
+  unsigned run = before + inc - sum;
+#pragma unroll
+  for (int k = 0; k < per; ++k) { int i = t * per + k; if (i < n) out[i] = run; run += v[k]; }
+  __syncthreads();
+}
+
+// Records are staged in shared memory in brick order within the CTA's chunk, then written out so that consecutive
+// threads write consecutive 16/32-byte records of one run (full sectors) instead of 32 scattered partial sectors per
+// store instruction.  WIDE: 32-byte records {qx,qy,qz,index | payload(4)} carrying the point's grad_output row
+// (D = 4), so that the scatter sweep needs no random 16-byte read per point (a 128-byte DRAM fetch each).
+template <bool WIDE>
 __global__ void __launch_bounds__(kPlaceBlock)
-bin_place_kernel(long long B, const float* __restrict__ query, GridFrame g, Bins b, unsigned* __restrict__ cursors,
-                 float4* __restrict__ rec) {
-  __shared__ unsigned hist[kMaxBins];
-  __shared__ unsigned base[kMaxBins];
+bin_place_kernel(long long B, const float* __restrict__ query, const float* __restrict__ payload, GridFrame g, Bins b,
+                 unsigned* __restrict__ cursors, float4* __restrict__ rec) {
+  constexpr int kPlacePerThread = WIDE ? 4 : 8;   // 32 KB of staged records per chunk either way
+  constexpr int kChunk = kPlaceBlock * kPlacePerThread;
+  __shared__ unsigned hist[kMaxBins];    // counts, then running local cursors
+  __shared__ unsigned loff[kMaxBins];    // chunk-local exclusive offsets
+  __shared__ unsigned base[kMaxBins];    // global position of the chunk's run minus loff
+  __shared__ unsigned warp_tot[kPlaceBlock / 32];
+  __shared__ unsigned short sbin[kChunk];
+  __shared__ float4 stage[kChunk * (WIDE ? 2 : 1)];
   long long n_chunks = (B + kChunk - 1) / kChunk;
   for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
     for (int i = threadIdx.x; i < (int)b.n; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     long long p0 = ch * kChunk + threadIdx.x;
+    float qx[kPlacePerThread], qy[kPlacePerThread], qz[kPlacePerThread];
     unsigned short bins[kPlacePerThread];
 #pragma unroll
     for (int k = 0; k < kPlacePerThread; ++k) {
       long long p = p0 + (long long)k * kPlaceBlock;
       unsigned bi = 0;
+      qx[k] = qy[k] = qz[k] = 0.f;
       if (p < B) {
         const float* q = query + p * 3;
-        bi = bin_of(g, b, __ldg(q), __ldg(q + 1));
+        qx[k] = __ldg(q); qy[k] = __ldg(q + 1); qz[k] = __ldg(q + 2);
+        bi = bin_of(g, b, qx[k], qy[k]);
         atomicAdd(&hist[bi], 1u);
       }
       bins[k] = (unsigned short)bi;
     }
     __syncthreads();
+    block_exclusive_scan(hist, loff, (int)b.n, warp_tot);
     for (int i = threadIdx.x; i < (int)b.n; i += blockDim.x) {
       unsigned c = hist[i];
-      base[i] = c ? atomicAdd(&cursors[i], c) : 0u;
-      hist[i] = 0;
+      base[i] = (c ? atomicAdd(&cursors[i], c) : 0u) - loff[i];
+      hist[i] = loff[i];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPlacePerThread; ++k) {
       long long p = p0 + (long long)k * kPlaceBlock;
       if (p < B) {
-        const float* q = query + p * 3;
         unsigned bi = bins[k];
-        unsigned pos = base[bi] + atomicAdd(&hist[bi], 1u);
-        rec[pos] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __uint_as_float((unsigned)p));
+        unsigned slot = atomicAdd(&hist[bi], 1u);
+        sbin[slot] = (unsigned short)bi;
+        float4 r = make_float4(qx[k], qy[k], qz[k], __uint_as_float((unsigned)p));
+        if (WIDE) {
+          stage[2 * slot] = r;
+          stage[2 * slot + 1] = __ldg(reinterpret_cast<const float4*>(payload) + p);
+        } else {
+          stage[slot] = r;
+        }
       }
+    }
+    __syncthreads();
+    long long left = B - ch * kChunk;
+    int cnt = (int)(left < kChunk ? left : kChunk);
+    if (WIDE) {
+      for (int j = threadIdx.x; j < 2 * cnt; j += blockDim.x) {
+        int slot = j >> 1;
+        rec[2 * (long long)(base[sbin[slot]] + slot) + (j & 1)] = stage[j];
+      }
+    } else {
+      for (int j = threadIdx.x; j < cnt; j += blockDim.x) rec[base[sbin[j]] + j] = stage[j];
     }
     __syncthreads();
   }
@@ -150,37 +204,83 @@ struct Strides { unsigned sx, sy, sz; };
 // Forward gather over the records, FOUR LANES PER POINT (lane (cx,cy) fetches the two z-neighbour cells of its
 // column), like voxel::gather4_kernel; expression shape per channel as voxel_feature_cuda.cu:87-94 up to the
 // association of the 8-term sum (pairs per column, then a 4-lane butterfly).
-template <int V, bool ACCUM>
-__global__ void __launch_bounds__(256, 8)
+// One 32-byte request for a column whose two z-neighbour cells share a sector (D = 4, z0 even): the sweep is bound
+// by L2 request throughput, not DRAM (ncu: 11.5 sector reads per point, 10 TB/s through the L2 slices).
+__device__ __forceinline__ void ldg_pair256(const float* p, Vec<4>& a, Vec<4>& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.v[0]), "=f"(a.v[1]), "=f"(a.v[2]), "=f"(a.v[3]), "=f"(b.v[0]), "=f"(b.v[1]), "=f"(b.v[2]),
+                 "=f"(b.v[3])
+               : "l"(p));
+}
+
+template <int V, bool ACCUM, bool PAIR256>
+__global__ void __launch_bounds__(256, 6)
 gather_kernel(long long B, float* __restrict__ out, const float4* __restrict__ rec, const float* __restrict__ feat,
-              GridFrame g, Strides s, int D) {
+              GridFrame g, Strides s, int D, int pf) {
   const int sub = threadIdx.x & 3;
   const int cx = sub >> 1, cy = sub & 1;
-  // NO grid-stride loop: CTA k owns records [64k, 64k+64).  The hardware hands out CTAs in blockIdx order as slots
-  // free up, so the set of records in flight is a sliding window of (resident CTAs x 64) ~ 76k records = 9 MB of
+  // NO grid-stride loop: CTA k owns records [128k, 128k+128), two per lane group (both issued before either is
+  // used: the sweep is latency-bound, not DRAM-bound).  The hardware hands out CTAs in blockIdx order as slots free
+  // up, so the set of records in flight is a sliding window of (resident CTAs x 128) ~ 114k records = 14 MB of
   // table; a persistent grid-stride sweep lets fast CTAs run many rounds ahead and the window (and with it the
-  // L2 footprint) grows without bound (measured: 8.0 GB of DRAM reads instead of ~2.5 GB).
-  {
-    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4;
-    bool active = i < B;
-    float4 rc = __ldg(rec + (active ? i : B - 1));
-    unsigned p = __float_as_uint(rc.w);
-    Cell c = make_cell(g, rc.x, rc.y, rc.z);
-    unsigned base = (cx ? c.x1 : c.x0) * s.sx + (cy ? c.y1 : c.y0) * s.sy;
-    float wxy = (cx ? c.p1 : c.p0) * (cy ? c.q1 : c.q0);
-    float w0 = wxy * c.r0, w1 = wxy * c.r1;
-    for (int d = 0; d < D; d += V) {
-      Vec<V> f0 = ldg_vec<V>(feat + base + c.z0 * s.sz + d);
-      Vec<V> f1 = ldg_vec<V>(feat + base + c.z1 * s.sz + d);
+  // L2 footprint) grows without bound (measured: 8.0 GB of DRAM reads instead of 2.9 GB).
+  long long i0 = (long long)blockIdx.x * 128 + (threadIdx.x >> 2);
+  // Software prefetch into L2 for CTAs that start later (each CTA is one dependent chain record -> cells -> store
+  // and lives only a few microseconds, so without it every link of the chain is a DRAM-latency miss):
+  //   pf >= 1: the record block of CTA k + kPfRec;  pf >= 2: the table lines of CTA k + kPfTab's points (their
+  //   records were prefetched by CTA k + kPfTab - kPfRec).
+  if (pf >= 1 && threadIdx.x < 16) {
+    long long j = ((long long)blockIdx.x + kPfRec) * 128 + threadIdx.x * 8;
+    if (j < B) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + j));
+  }
+  bool active[2];
+  float4 rc[2], rn[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    long long i = i0 + 64 * u;
+    active[u] = i < B;
+    rc[u] = __ldg(rec + (active[u] ? i : B - 1));
+    long long in = i + (long long)kPfTab * 128;
+    if (pf >= 2) rn[u] = __ldg(rec + (in < B ? in : B - 1));
+  }
+  if (pf >= 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      Cell c = make_cell(g, rn[u].x, rn[u].y, rn[u].z);
+      const float* a0 = feat + ((cx ? c.x1 : c.x0) * s.sx + (cy ? c.y1 : c.y0) * s.sy + c.z0 * s.sz);
+      const float* a1 = a0 + (c.z1 - c.z0) * s.sz + (D - 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a0));
+      if ((reinterpret_cast<uintptr_t>(a0) ^ reinterpret_cast<uintptr_t>(a1)) >> 7)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a1));
+    }
+  }
+  for (int d = 0; d < D; d += V) {
+    Vec<V> f0[2], f1[2];
+    float w0[2], w1[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      Cell c = make_cell(g, rc[u].x, rc[u].y, rc[u].z);
+      unsigned base = (cx ? c.x1 : c.x0) * s.sx + (cy ? c.y1 : c.y0) * s.sy;
+      float wxy = (cx ? c.p1 : c.p0) * (cy ? c.q1 : c.q0);
+      w0[u] = wxy * c.r0; w1[u] = wxy * c.r1;
+      if (PAIR256 && V == 4 && (c.z0 & 1u) == 0u && c.z1 == c.z0 + 1u) {
+        ldg_pair256(feat + base + c.z0 * s.sz, *reinterpret_cast<Vec<4>*>(&f0[u]), *reinterpret_cast<Vec<4>*>(&f1[u]));
+      } else {
+        f0[u] = ldg_vec<V>(feat + base + c.z0 * s.sz + d);
+        f1[u] = ldg_vec<V>(feat + base + c.z1 * s.sz + d);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
       Vec<V> o;
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        o.v[j] = w0 * f0.v[j] + w1 * f1.v[j];
+        o.v[j] = w0[u] * f0[u].v[j] + w1[u] * f1[u].v[j];
         o.v[j] += __shfl_xor_sync(0xffffffffu, o.v[j], 1);
         o.v[j] += __shfl_xor_sync(0xffffffffu, o.v[j], 2);
       }
-      if (active && sub == 0) {
-        float* op = out + (long long)p * D + d;
+      if (active[u] && sub == 0) {
+        float* op = out + (long long)__float_as_uint(rc[u].w) * D + d;
         if (ACCUM) {
           Vec<V> pv = ld_vec<V>(op);
 #pragma unroll
@@ -193,7 +293,8 @@ gather_kernel(long long B, float* __restrict__ out, const float4* __restrict__ r
 }
 
 // Scatter over the records, EIGHT LANES PER POINT (one corner each), like voxel::scatter8_kernel.
-template <bool SECOND, int V>
+// WIDE (first order, D = 4): the record carries the grad_output row, nothing is read at `point index`.
+template <bool SECOND, int V, bool WIDE>
 __global__ void __launch_bounds__(256, 8)
 scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go, const float* __restrict__ gg,
                const float4* __restrict__ rec, GridFrame g, Strides s, int D) {
@@ -201,7 +302,8 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
   const int cx = (k >> 2) & 1, cy = (k >> 1) & 1, cz = k & 1;
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 8;  // one pass per CTA (see gather_kernel)
   if (i < B) {
-    float4 rc = __ldg(rec + i);
+    float4 rc = __ldg(rec + (WIDE ? 2 * i : i));
+    float4 pay = WIDE ? __ldg(rec + 2 * i + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     long long p = (long long)__float_as_uint(rc.w);
     Cell c = make_cell(g, rc.x, rc.y, rc.z);
     float pw = cx ? c.p1 : c.p0, qw = cy ? c.q1 : c.q0, rw = cz ? c.r1 : c.r0;
@@ -214,6 +316,12 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
              ggz * ((cz ? 1.f : -1.f) * pw * qw);
     }
     float* dst = gf + ((cx ? c.x1 : c.x0) * s.sx + (cy ? c.y1 : c.y0) * s.sy + (cz ? c.z1 : c.z0) * s.sz);
+    if (WIDE) {
+      Vec<4> o;
+      o.v[0] = pay.x * coef; o.v[1] = pay.y * coef; o.v[2] = pay.z * coef; o.v[3] = pay.w * coef;
+      red_vec<4>(dst, o);
+      return;
+    }
     for (int d = 0; d < D; d += V) {
       Vec<V> o = ldg_vec<V>(go + p * D + d);
 #pragma unroll
@@ -225,7 +333,7 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
 
 long long workspace_bytes(long long n_points) {
   if (n_points < 0) return -1;
-  return kHeaderBytes + 16 * n_points;
+  return kHeaderBytes + 32 * n_points;
 }
 
 bool shape_ok(long long B, const int* G, int D) {
@@ -241,8 +349,8 @@ bool worthwhile(long long B, const int* G, int D) {
 }
 
 // Builds the brick-ordered records in `ws`; returns the record pointer through *rec_out.
-static int build_records(long long B, const float* query, const GridFrame& g, const int* G, int D, void* ws,
-                         long long ws_bytes, cudaStream_t st, const float4** rec_out) {
+static int build_records(long long B, const float* query, const float* payload, const GridFrame& g, const int* G,
+                         int D, void* ws, long long ws_bytes, cudaStream_t st, const float4** rec_out) {
   if (!ws || ws_bytes < workspace_bytes(B) || (reinterpret_cast<uintptr_t>(ws) & 15)) return NDJIR_ERR_ARG;
   Bins b = make_bins(G, D, g_voxel_bin_mb);
   unsigned* cursors = reinterpret_cast<unsigned*>(ws);
@@ -252,9 +360,12 @@ static int build_records(long long B, const float* query, const GridFrame& g, co
   int grid = grid_for(B, 256, 8);
   bin_count_kernel<<<grid, 256, 0, st>>>(B, query, g, b, cursors);
   bin_scan_kernel<<<1, kMaxBins, 0, st>>>(cursors, (int)b.n);
-  long long n_chunks = (B + kChunk - 1) / kChunk;
-  long long cap = (long long)NDJIR_NUM_SMS * 8;
-  bin_place_kernel<<<(int)(n_chunks < cap ? n_chunks : cap), kPlaceBlock, 0, st>>>(B, query, g, b, cursors, rec);
+  long long chunk = kPlaceBlock * (payload ? 4 : 8);
+  long long n_chunks = (B + chunk - 1) / chunk;
+  long long cap = (long long)NDJIR_NUM_SMS * 16;
+  int pgrid = (int)(n_chunks < cap ? n_chunks : cap);
+  if (payload) bin_place_kernel<true><<<pgrid, kPlaceBlock, 0, st>>>(B, query, payload, g, b, cursors, rec);
+  else bin_place_kernel<false><<<pgrid, kPlaceBlock, 0, st>>>(B, query, nullptr, g, b, cursors, rec);
   *rec_out = rec;
   return NDJIR_OK;
 }
@@ -279,15 +390,19 @@ int query(long long B, float* out, const float* query_, const float* feat, const
   if (!shape_ok(B, G, D) || !out || !query_ || !feat) return NDJIR_ERR_ARG;
   GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
   const float4* rec = nullptr;
-  int rc = build_records(B, query_, g, G, D, ws, ws_bytes, st, &rec);
+  int rc = build_records(B, query_, nullptr, g, G, D, ws, ws_bytes, st, &rec);
   if (rc != NDJIR_OK) return rc;
   Strides s = make_strides(G, D);
   int V = pick_vec(D, feat, out);
-  unsigned grid = (unsigned)sweep_grid(B, 4);
+  unsigned grid = (unsigned)((B + 127) / 128);
 #define NDJIR_LAUNCH(VV)                                                                        \
-  if (accum) gather_kernel<VV, true><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D);         \
-  else gather_kernel<VV, false><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D);
-  if (V == 4) { NDJIR_LAUNCH(4) } else if (V == 2) { NDJIR_LAUNCH(2) } else { NDJIR_LAUNCH(1) }
+  if (accum) gather_kernel<VV, true, false><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D, g_voxel_prefetch);  \
+  else gather_kernel<VV, false, false><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D, g_voxel_prefetch);
+  bool pair256 = V == 4 && D == 4 && (G[2] & 1) == 0 && (reinterpret_cast<uintptr_t>(feat) & 31) == 0 && g_voxel_pair256;
+  if (pair256) {
+    if (accum) gather_kernel<4, true, true><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D, g_voxel_prefetch);
+    else gather_kernel<4, false, true><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D, g_voxel_prefetch);
+  } else if (V == 4) { NDJIR_LAUNCH(4) } else if (V == 2) { NDJIR_LAUNCH(2) } else { NDJIR_LAUNCH(1) }
 #undef NDJIR_LAUNCH
   NDJIR_RETURN_LAST_ERROR();
 }
@@ -298,14 +413,19 @@ int scatter(bool second, long long B, float* gf, const float* go, const float* g
   if (!shape_ok(B, G, D) || !gf || !go || !query_ || (second && !gg)) return NDJIR_ERR_ARG;
   GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
   const float4* rec = nullptr;
-  int rc = build_records(B, query_, g, G, D, ws, ws_bytes, st, &rec);
+  int V = pick_vec(D, gf, go);
+  bool wide = !second && D == 4 && V == 4;
+  int rc = build_records(B, query_, wide ? go : nullptr, g, G, D, ws, ws_bytes, st, &rec);
   if (rc != NDJIR_OK) return rc;
   Strides s = make_strides(G, D);
-  int V = pick_vec(D, gf, go);
   unsigned grid = (unsigned)sweep_grid(B, 8);
+  if (wide) {
+    scatter_kernel<false, 4, true><<<grid, 256, 0, st>>>(B, gf, go, gg, rec, g, s, D);
+    NDJIR_RETURN_LAST_ERROR();
+  }
 #define NDJIR_LAUNCH(VV)                                                                          \
-  if (second) scatter_kernel<true, VV><<<grid, 256, 0, st>>>(B, gf, go, gg, rec, g, s, D);        \
-  else scatter_kernel<false, VV><<<grid, 256, 0, st>>>(B, gf, go, gg, rec, g, s, D);
+  if (second) scatter_kernel<true, VV, false><<<grid, 256, 0, st>>>(B, gf, go, gg, rec, g, s, D); \
+  else scatter_kernel<false, VV, false><<<grid, 256, 0, st>>>(B, gf, go, gg, rec, g, s, D);
   if (V == 4) { NDJIR_LAUNCH(4) } else if (V == 2) { NDJIR_LAUNCH(2) } else { NDJIR_LAUNCH(1) }
 #undef NDJIR_LAUNCH
   NDJIR_RETURN_LAST_ERROR();

@@ -504,7 +504,7 @@ def test_voxel_binned_matches_direct_and_reference(B, G, D, spread, mb):
     q, f, go, gg = dev(q_np), dev(f_np), dev(go_np), dev(gg_np)
     N = B * D
     wsb = call("ndjir_voxel_binned_workspace_bytes", B)
-    assert wsb == 8192 + 16 * B
+    assert wsb == 8192 + 32 * B
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     call("ndjir_set_option", "voxel_bin_mb", mb)
     try:
@@ -529,6 +529,13 @@ def test_voxel_binned_matches_direct_and_reference(B, G, D, spread, mb):
         call("ndjir_voxel_grad_query_grad_feature_binned", B, b1, gg, go, q, list(G), D, MN, MX, ws, wsb, 0)
         ref.grad_query_grad_feature(N, b2.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, False)
         close(b1, b2, 1e-4, "binned gq_gf")
+        # experiment switches of the gather sweep (L2 software prefetch, 256-bit z-pair loads) do not change results
+        for key, val in (("voxel_prefetch", 1), ("voxel_prefetch", 2), ("voxel_pair256", 1)):
+            call("ndjir_set_option", key, val)
+            o4 = torch.empty((B, D)).cuda()
+            call("ndjir_voxel_query_on_voxel_binned", B, o4, q, f, list(G), D, MN, MX, 0, ws, wsb, 0)
+            call("ndjir_set_option", key, 0)
+            close(o4, o2, 1e-5, f"binned fwd with {key}={val}")
         # the reference-signature entry points take the binned path by themselves when forced
         call("ndjir_set_option", "voxel_binned", 1)
         o3 = torch.empty((B, D)).cuda()

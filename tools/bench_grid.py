@@ -82,15 +82,16 @@ def main():
         results.append(r)
         print(json.dumps(r), flush=True)
 
-    def run_family(tag, modname, fwd_name, feat, spec, D, C, bytes_fwd, bytes_bwd, hash_args=None, agg_modes=(0,)):
+    def run_family(tag, modname, fwd_name, feat, spec, D, C, bytes_fwd, bytes_bwd, hash_args=None, agg_modes=(0,),
+                   ours_label="ndjir_b200", with_ref=True):
         if only and tag not in only:
             return
-        ours, ref = compat.load(modname), (None if args.no_ref else ref_or_none(modname))
+        ours, ref = compat.load(modname), (None if (args.no_ref or not with_ref) else ref_or_none(modname))
         out = torch.empty(B * C, device="cuda")
         go = torch.ones(B * C, device="cuda")
         gf = torch.zeros_like(feat)
         N = B * C if hash_args is None else B * hash_args[3]
-        for impl, mod in (("ndjir_b200", ours), ("reference_sm100a", ref)):
+        for impl, mod in ((ours_label, ours), ("reference_sm100a", ref)):
             if mod is None:
                 continue
             if hash_args is None:
@@ -101,8 +102,8 @@ def main():
                 bwd = lambda: mod.grad_feature(N, gf.data_ptr(), go.data_ptr(), q.data_ptr(), *hash_args, MN, MX, False, True)
             m, mi = T.time(fwd, args.iters)
             record(tag, "fwd", m, mi, bytes_fwd, impl)
-            for agg in (agg_modes if impl == "ndjir_b200" else (0,)):
-                if impl == "ndjir_b200":
+            for agg in (agg_modes if impl == ours_label else (0,)):
+                if impl == ours_label:
                     call("ndjir_set_option", "scatter_aggregate", agg)
                 m, mi = T.time(bwd, args.iters)
                 record(tag, "grad_feature", m, mi, bytes_bwd, impl, dict(scatter_aggregate=agg))
@@ -113,7 +114,13 @@ def main():
     if not only or "voxel" in only:
         G, D = 512, 4
         feat = (torch.randn(G, G, G, D, device="cuda") * 0.01)
-        run_family("voxel", "voxel_feature_cuda", "query_on_voxel", feat, (G, G, G), D, D, 156, 284, agg_modes=(0, 1))
+        # default dispatch: brick-ordered sweep (voxel_binned.cu) for >= 2^21 points on a table >= 96 MB
+        run_family("voxel", "voxel_feature_cuda", "query_on_voxel", feat, (G, G, G), D, D, 156, 284,
+                   ours_label="ndjir_b200 (brick-ordered, default)", with_ref=False)
+        call("ndjir_set_option", "voxel_binned", 0)
+        run_family("voxel", "voxel_feature_cuda", "query_on_voxel", feat, (G, G, G), D, D, 156, 284, agg_modes=(0, 1),
+                   ours_label="ndjir_b200 (direct)")
+        call("ndjir_set_option", "voxel_binned", -1)
         del feat
     # triplane / triline at triplaneline.yaml: G=2048, D=8
     if not only or "triplane" in only:

@@ -12,7 +12,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--log2-points", type=int, default=24)
 ap.add_argument("--mbs", default="4,8,16,32,64")
 ap.add_argument("--G", type=int, default=512)
+ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32/64/128), 0 = leave")
 args = ap.parse_args()
+if args.l2_fetch:
+    import ctypes
+    torch.cuda.init(); torch.zeros(1, device="cuda")
+    rt = ctypes.CDLL("libcudart.so.12")
+    v = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(v), 5); print("L2 fetch granularity before:", v.value)
+    print("set ->", rt.cudaDeviceSetLimit(5, ctypes.c_size_t(args.l2_fetch)))
+    rt.cudaDeviceGetLimit(ctypes.byref(v), 5); print("L2 fetch granularity after:", v.value)
 B, G, D = 1 << args.log2_points, args.G, 4
 MN, MX = [-1.0] * 3, [1.0] * 3
 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -64,6 +73,11 @@ for mb in [int(x) for x in args.mbs.split(",")]:
          t(lambda: call("ndjir_voxel_grad_feature_binned", B, gf, go, q, [G] * 3, D, MN, MX, 1, ws, wsb, 0)), 284)
     print(f"    max-norm rel. diff vs direct: fwd {err:.2e}, grad_feature {err2:.2e}", flush=True)
 call("ndjir_set_option", "voxel_bin_mb", 16)
+for pf in (0, 1, 2):
+    call("ndjir_set_option", "voxel_prefetch", pf)
+    show(f"gather binned, 16 MiB, prefetch mode {pf}",
+         t(lambda: call("ndjir_voxel_query_on_voxel_binned", B, out, q, feat, [G] * 3, D, MN, MX, 0, ws, wsb, 0)), 156)
+    print("    diff", (out - ref_out).abs().max().item())
 call("ndjir_set_option", "voxel_binned", -1)
 show("gather auto (cudaMallocAsync scratch)", t(lambda: call("ndjir_voxel_query_on_voxel", B, out, q, feat, [G] * 3, D, MN, MX, 0, 0)), 156)
 show("scatter auto accum=0", t(lambda: call("ndjir_voxel_grad_feature", B, gf, go, q, [G] * 3, D, MN, MX, 0, 0)), 284)
