@@ -264,6 +264,22 @@ int ndjir_background_samples(int n_rays, int Nb, int R, const float* camloc, con
 /* :100 mask = n_hits > 1; mask_sum[0] += sum(mask) */
 int ndjir_hit_mask(int n_rays, const float* n_hits, float* mask, float* mask_sum, cudaStream_t stream);
 
+/* ---- optimizer (python/solver.py:29-69 over nnabla S.Adam; python/train.py:135-148) --------------------
+ * One fused pass per parameter buffer: g' = g + weight_decay*w; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2;
+ * w -= alpha_t m / (sqrt(v) + eps); g = 0 when zero_grad.  alpha_t = alpha*sqrt(1-b2^t)/(1-b1^t) with t read from
+ * the DEVICE counter t_dev (ndjir_adam_tick advances it on steps that are not skipped, like nnabla's update()
+ * count); t_dev == NULL: `alpha` is used as alpha_t.
+ * skip_flags: DEVICE int[2] or NULL; the update is skipped (gradient still zeroed) when BOTH are non-zero - the
+ * reference's `and` between its two solvers (solver.py:67-69). */
+int ndjir_adam_tick(int* t_dev, const int* skip_flags, cudaStream_t stream);
+int ndjir_adam_step(long long n, float* w, float* g, float* m, float* v, float alpha, float beta1, float beta2,
+                    float eps, float weight_decay, const int* t_dev, const int* skip_flags, int zero_grad,
+                    cudaStream_t stream);
+/* flag[0] |= any(!isfinite(g)); the scan is skipped when only_if != NULL and *only_if == 0 (device) */
+int ndjir_nonfinite_flag(long long n, const float* g, int* flag, const int* only_if, cudaStream_t stream);
+/* g += rate * w: S.Adam.weight_decay as its own pass (solver.py:48-50) */
+int ndjir_weight_decay(long long n, float* g, const float* w, float rate, cudaStream_t stream);
+
 /* ---- data movement helpers ---- */
 int ndjir_copy2d(long long rows, int cols, float* dst, long long ld_dst, const float* src, long long ld_src, int rep,
                  float alpha, int accum, cudaStream_t stream);          /* dst[r,c] (+)= alpha*src[r/rep,c] */

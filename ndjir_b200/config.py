@@ -43,7 +43,9 @@ DEFAULT = {
                  "n_thetas": 8,
                  "diffuse_cdf_the_seed": 412, "diffuse_cdf_phi_seed": 124, "specular_cdf_the_seed": 810,
                  "specular_cdf_phi_seed": 108, "stratified_sample_seed": 913, "background_sample_seed": 510},
-    "train": {"batch_size": 4, "n_rays": 512, "sigmoid_gain": 0.3, "sigmoid_gain_lv_start": 1,
+    "train": {"batch_size": 4, "n_rays": 512, "epoch": 1500, "base_learning_rate_weight": 5e-4,
+              "base_learning_rate_feat": 5e-4, "learning_rate_end_ratio": 0.01, "warmup_term_ratio": 0.015,
+              "cos_anneal_term_ratio": 0.15, "weight_decay": 1e-3, "clip_grad_norm": 0, "sigmoid_gain": 0.3, "sigmoid_gain_lv_start": 1,
               "sigmoid_gain_lv_end": 1, "rgb_loss": "l1", "eikonal_weight": 0.1, "tv_weight": 0.1,
               "tv_sym_backward": True, "mask_weight": 0.0, "base_color_prior_weight": 0.1,
               "base_color_prior_sym_backward": True, "base_color_perturb_seed": 913,
