@@ -280,6 +280,18 @@ int ndjir_nonfinite_flag(long long n, const float* g, int* flag, const int* only
 /* g += rate * w: S.Adam.weight_decay as its own pass (solver.py:48-50) */
 int ndjir_weight_decay(long long n, float* g, const float* w, float rate, cudaStream_t stream);
 
+/* Pre-split weight operand of the tensor-core products: lo[i] = x[i] - (x[i] with the low 13 mantissa bits cleared).
+ * ndjir_gemm_presplit is ndjir_gemm with the lo part of B supplied by the caller (same strides as B; NULL = split in
+ * the kernel): B then arrives as two TMA tiles (raw + lo) and the in-kernel hi/lo transform only handles A.  The
+ * result is bit-identical.  The CALLER keeps the copy current (ndjir_split_lo after every parameter change).
+ * Option "mlp_presplit" (default 1) switches the use of B_lo off. */
+int ndjir_split_lo(long long n, float* lo, const float* x, cudaStream_t stream);
+int ndjir_gemm_presplit(int M, int N, int K, const float* A, long long a_rs, long long a_cs, const float* B,
+                        const float* B_lo, long long b_rs, long long b_cs, float* C, long long ldc, const float* bias,
+                        float alpha, float out_scale, float beta, const float* H, long long ldh, float hscale,
+                        const float* U, long long ldu, float* C2, long long ldc2, int split_k, int epilogue,
+                        cudaStream_t stream);
+
 /* ---- data movement helpers ---- */
 int ndjir_copy2d(long long rows, int cols, float* dst, long long ld_dst, const float* src, long long ld_src, int rep,
                  float alpha, int accum, cudaStream_t stream);          /* dst[r,c] (+)= alpha*src[r/rep,c] */

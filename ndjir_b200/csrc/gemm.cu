@@ -223,3 +223,16 @@ extern "C" int ndjir_gemm(int M, int N, int K, const float* A, long long a_rs, l
   a.U = U; a.ldu = ldu; a.C2 = C2; a.ldc2 = ldc2; a.split_k = split_k;
   return ndjir::gemm::launch(a, epilogue, stream);
 }
+
+// Same product with the pre-split lo part of the weight operand supplied by the caller (B_lo may be NULL).
+extern "C" int ndjir_gemm_presplit(int M, int N, int K, const float* A, long long a_rs, long long a_cs, const float* B,
+                                   const float* B_lo, long long b_rs, long long b_cs, float* C, long long ldc,
+                                   const float* bias, float alpha, float out_scale, float beta, const float* H,
+                                   long long ldh, float hscale, const float* U, long long ldu, float* C2,
+                                   long long ldc2, int split_k, int epilogue, cudaStream_t stream) {
+  ndjir::gemm::Args a = ndjir::gemm::make_args(M, N, K);
+  a.A = A; a.a_rs = a_rs; a.a_cs = a_cs; a.B = B; a.B_lo = B_lo; a.b_rs = b_rs; a.b_cs = b_cs; a.C = C; a.ldc = ldc;
+  a.bias = bias; a.alpha = alpha; a.out_scale = out_scale; a.beta = beta; a.H = H; a.ldh = ldh; a.hscale = hscale;
+  a.U = U; a.ldu = ldu; a.C2 = C2; a.ldc2 = ldc2; a.split_k = split_k;
+  return ndjir::gemm::launch(a, epilogue, stream);
+}

@@ -28,6 +28,7 @@ struct Args {
   int M, N, K;
   const float* A; long long a_rs, a_cs;  // A(m,k) = A[m*a_rs + k*a_cs]
   const float* B; long long b_rs, b_cs;  // B(k,n) = B[k*b_rs + n*b_cs]
+  const float* B_lo;                     // optional pre-split lo part of B (same strides): x - tf32(x), or nullptr
   float* C; long long ldc;               // C(m,n) = C[m*ldc + n]
   const float* bias;                     // [N] or nullptr
   float alpha;                           // scale on the accumulator
@@ -43,7 +44,7 @@ static inline Args make_args(int M, int N, int K) {
   Args a;
   a.M = M; a.N = N; a.K = K;
   a.A = nullptr; a.a_rs = 0; a.a_cs = 1;
-  a.B = nullptr; a.b_rs = 0; a.b_cs = 1;
+  a.B = nullptr; a.b_rs = 0; a.b_cs = 1; a.B_lo = nullptr;
   a.C = nullptr; a.ldc = 0; a.bias = nullptr;
   a.alpha = 1.f; a.out_scale = 1.f; a.beta = 100.f;
   a.H = nullptr; a.ldh = 0; a.hscale = 1.f;
@@ -100,6 +101,7 @@ int launch(const Args& a, int epi, cudaStream_t st);
 extern int g_mlp_tensor_cores;
 extern int g_mlp_cta_pair;
 extern int g_mlp_dbg;
+extern int g_mlp_presplit;    // 1: a B operand that comes with its lo part is fetched as raw + lo TMA tiles
 extern int g_mlp_mask_hi;     // 1: the transform warps also clear the low 13 mantissa bits of the raw tiles
 bool tc_eligible(const Args& a, int epi);
 int launch_tc(const Args& a, int epi, cudaStream_t st);

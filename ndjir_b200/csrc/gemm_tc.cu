@@ -166,6 +166,7 @@ struct TcParams {
   int mask_hi;
   int dbg;
   int a_3d, b_3d;        // MN-major operand loaded with ONE 3-D TMA request per K block (extent % 32 == 0)
+  int b_lo_tma;          // the lo part of B comes pre-split from global memory (registered weights): no B transform
   int vec_epi;           // every epilogue operand is 16-byte aligned with a row stride that is a multiple of 4
   int m_tiles, n_tiles, splits, kb_per_split, nkb_total;
 };
@@ -212,7 +213,8 @@ constexpr int TC_EPI_THREADS = 256;            // two warps per TMEM sub-partiti
 
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapBlo, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 4];
   __shared__ uint32_t tmem_base_sh;
@@ -278,7 +280,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         item_info(item, m0, n0, kb0, nkb);
         const int umma_n = (min(TC_BN, a.N - n0) + 15) & ~15;
         const int b_chunks = (umma_n + 31) / 32;
-        const uint32_t tx_bytes = A_TILE_BYTES + ((p.b_mn && !p.b_3d) ? b_chunks * TC_BK * 128 : B_TILE_BYTES);
+        const uint32_t b_tx = (p.b_mn && !p.b_3d) ? b_chunks * TC_BK * 128 : B_TILE_BYTES;
+        const uint32_t tx_bytes = A_TILE_BYTES + (p.b_lo_tma ? 2 * b_tx : b_tx);
         for (int i = 0; i < nkb; ++i, ++it) {
           int s = it % TC_STAGES;
           uint32_t ph = (it / TC_STAGES) & 1;
@@ -299,6 +302,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_raw(s) + c * TC_BK * 128, &mapB, n0 + c * 32, k0, bar_full(s));
           } else {
             tma_load_2d(b_raw(s), &mapB, k0, n0, bar_full(s));
+          }
+          if (p.b_lo_tma) {   // same box, same swizzle, from the pre-split copy of the weights
+            if (p.b_3d) {
+              tma_load_3d(b_lo(s), &mapBlo, 0, k0, n0 / 32, bar_full(s));
+            } else if (p.b_mn) {
+              for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_lo(s) + c * TC_BK * 128, &mapBlo, n0 + c * 32, k0, bar_full(s));
+            } else {
+              tma_load_2d(b_lo(s), &mapBlo, k0, n0, bar_full(s));
+            }
           }
         }
       }
@@ -379,6 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           sts128(st + A_TILE_BYTES + off, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
           if (p.mask_hi) sts128(st + off, h);
         }
+        if (!p.b_lo_tma)
 #pragma unroll 4
         for (int off = t * 16; off < b_bytes; off += TC_XFORM_THREADS * 16) {
           float4 x = lds128(st + 2 * A_TILE_BYTES + off);
@@ -802,6 +815,11 @@ static bool make_map3(CUtensorMap* map, const float* base, long long mn, long lo
   return r == CUDA_SUCCESS;
 }
 
+// Pre-split weights: when the caller supplies the lo part of B (Args::B_lo = x - tf32(x), same strides - the engine
+// keeps such copies of its weight buffers and refreshes them when the parameters change, ndjir_split_lo), the B
+// operand is fetched as two TMA tiles (raw + lo) and the in-kernel hi/lo transform only handles A.
+int g_mlp_presplit = 1;
+
 bool tc_eligible(const Args& a, int epi) {
   if (a.N < 32 || a.K < 16 || a.M < 32) return false;
   if (!al16p(a.A) || !al16p(a.B)) return false;
@@ -822,7 +840,7 @@ static int launch_tc2_epi(const Args& a, cudaStream_t st) {
   p.a = a;
   p.a_mn = 0;
   p.b_mn = (a.b_cs == 1);
-  p.mask_hi = 0; p.dbg = 0; p.a_3d = 0;
+  p.mask_hi = 0; p.dbg = 0; p.a_3d = 0; p.b_lo_tma = 0;
   auto ok16 = [](const void* q, long long ld) { return q == nullptr || (al16p(q) && ld % 4 == 0); };
   p.vec_epi = ok16(a.C, a.ldc) && ok16(a.H, a.ldh) && ok16(a.U, a.ldu) && ok16(a.C2, a.ldc2) && ok16(a.bias, 0);
   p.b_3d = p.b_mn && a.N % 64 == 0;
@@ -887,6 +905,14 @@ static int launch_tc_epi(const Args& a, cudaStream_t st) {
   if (p.b_3d) ok = ok && make_map3(&mapB, a.B, a.N, a.K, a.b_rs, TC_BN / 32);
   else if (p.b_mn) ok = ok && make_map(&mapB, a.B, a.N, a.K, a.b_rs, 32, TC_BK, true);
   else ok = ok && make_map(&mapB, a.B, a.K, a.N, a.b_cs, TC_BK, TC_BN, false);
+  CUtensorMap mapBlo = mapB;
+  const float* blo = g_mlp_presplit ? a.B_lo : nullptr;
+  p.b_lo_tma = (blo != nullptr && al16p(blo)) ? 1 : 0;
+  if (p.b_lo_tma) {
+    if (p.b_3d) ok = ok && make_map3(&mapBlo, blo, a.N, a.K, a.b_rs, TC_BN / 32);
+    else if (p.b_mn) ok = ok && make_map(&mapBlo, blo, a.N, a.K, a.b_rs, 32, TC_BK, true);
+    else ok = ok && make_map(&mapBlo, blo, a.K, a.N, a.b_cs, TC_BK, TC_BN, false);
+  }
   if (!ok) return NDJIR_ERR_ARG;
   static bool attr_set = false;
   if (!attr_set) {
@@ -902,7 +928,7 @@ static int launch_tc_epi(const Args& a, cudaStream_t st) {
   p.splits = (p.nkb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   int n_items = p.m_tiles * p.n_tiles * p.splits;
   int grid = n_items < NDJIR_NUM_SMS ? n_items : NDJIR_NUM_SMS;
-  gemm_tc_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, p);
+  gemm_tc_kernel<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapBlo, p);
   NDJIR_RETURN_LAST_ERROR();
 }
 
@@ -920,3 +946,27 @@ int launch_tc(const Args& a, int epi, cudaStream_t st) {
 
 }  // namespace gemm
 }  // namespace ndjir
+
+namespace {
+// lo = x - trunc_tf32(x): what the in-kernel transform computes (the tensor core itself truncates the raw operand)
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+split_lo_kernel(long long n, float* __restrict__ lo, const float* __restrict__ x) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = x[i];
+    lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int ndjir_split_lo(long long n, float* lo, const float* x, cudaStream_t stream) {
+  if (n == 0) return NDJIR_OK;
+  if (n < 0 || !lo || !x) return NDJIR_ERR_ARG;
+  split_lo_kernel<<<ndjir::grid_for(n), NDJIR_BLOCK, 0, stream>>>(n, lo, x);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+}  // extern "C"
+

@@ -111,6 +111,10 @@ class ParamStore:
         # transposed weight copies for the input-gradient products (refreshed once per step, engine.refresh_transposes)
         self.data_t = torch.zeros(max(nt, 4), dtype=torch.float32, device=device)
         self.data = torch.zeros(n, dtype=torch.float32, device=device)
+        # lo parts (x - tf32(x)) of both weight buffers for the tensor-core products (registered with the library in
+        # Engine.__init__, refreshed together with the transposes)
+        self.data_lo = torch.zeros_like(self.data)
+        self.data_t_lo = torch.zeros_like(self.data_t)
         self.grad = torch.zeros(n, dtype=torch.float32, device=device)
         self.grid = {}        # name -> tensor
         self.grid_grad = {}
@@ -179,6 +183,16 @@ class ParamStore:
         self.grad.zero_()
         for v in self.grid_grad.values():
             v.zero_()
+
+    def lo_of(self, ptr):
+        """Address of the pre-split lo part (x - tf32(x)) of a weight operand inside `data` / `data_t`, else 0."""
+        if not isinstance(ptr, int):
+            return 0
+        for buf, lo in ((self.data, self.data_lo), (self.data_t, self.data_t_lo)):
+            off = ptr - buf.data_ptr()
+            if 0 <= off < 4 * buf.numel():
+                return lo.data_ptr() + off
+        return 0
 
     def W(self, L, row=0):
         return self.data.data_ptr() + 4 * (L.w_off + row * L.ldw)
@@ -271,8 +285,8 @@ class Engine:
         if self.profile:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.call("ndjir_gemm", M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, bias, alpha, out_scale, 100.0, H, ldh,
-                  hscale, U, ldu, C2, ldc2, split_k, epi)
+        self.call("ndjir_gemm_presplit", M, N, K, A, a_rs, a_cs, B, self.params.lo_of(B), b_rs, b_cs, C, ldc, bias,
+                  alpha, out_scale, 100.0, H, ldh, hscale, U, ldu, C2, ldc2, split_k, epi)
         if self.profile:
             e1.record()
             self.prof_events.append((e0, e1, 2.0 * M * N * K, f"epi{epi} {M}x{N}x{K}"))
@@ -322,6 +336,9 @@ class Engine:
         for name in NET_ORDER:
             for L in ps.nets[name]:
                 self.call("ndjir_transpose", L.K, L.N, ps.data_t.data_ptr() + 4 * L.t_off, L.ldt, ps.W(L), L.ldw)
+        # pre-split lo parts of W and W^T: the weight operand of every tensor-core product arrives as two TMA tiles
+        self.call("ndjir_split_lo", ps.data.numel(), ps.data_lo, ps.data)
+        self.call("ndjir_split_lo", ps.data_t.numel(), ps.data_t_lo, ps.data_t)
 
     # ------------------------------------------------------------------------------------------------
     # grid feature dispatch (python/network.py:120-151 query_on_grid)
@@ -591,6 +608,8 @@ class Engine:
         r = self.conf.renderer
         B, R, _ = raydir.shape
         NR = B * R
+        if not getattr(self, "_weights_synced", False):
+            self.refresh_transposes()   # standalone call: the registered lo copies of the weights must be current
         N0, M, U, Nb = r.n_samples0, r.n_samples1, r.n_upsamples, r.n_bg_samples
         N = N0 + U * M
         tn, tf, nh = (self.buf(k, NR, 1) for k in ("t_near", "t_far", "n_hits"))
@@ -670,6 +689,7 @@ class Engine:
         if zero_grad:
             ps.zero_grad()
         self.refresh_transposes()       # the normal pass (forward half) already needs W^T
+        self._weights_synced = True
         self._gather_cache = {}
         losses = self.buf("losses", 1, 16, zero=True)
         scal = self.buf("scalars", 1, 8, zero=True)      # [mask_sum, inv_denorm]
@@ -818,6 +838,7 @@ class Engine:
                                    elraw=elraw, svraw=svraw, color=color, colbg=colbg, bgraw=bgraw, x_fg=x_fg,
                                    t_fg=t_fg, x_bg=x_bg, t_bg=t_bg, mask=mask, dims=(B, R, N, Nb, M)))
         if not backward:
+            self._weights_synced = False
             return losses[0, :N_LOSSES]
 
         # ======================================= backward =======================================
@@ -905,4 +926,5 @@ class Engine:
         if keep:
             self.debug.update(dict(dO=dO, dsdf=dsdf, dw=dw, dRAW=dRAW, d_attpix=d_attpix, dpix=dpix, nbar=nbar,
                                    dalpha_fg=dalpha_fg, dalpha_bg=dalpha_bg, d_el=d_el, d_sv=d_sv))
+        self._weights_synced = False
         return losses[0, :N_LOSSES]

@@ -73,6 +73,7 @@ def sdf_volume(conf, grid_size, batch_size=1 << 20, rank=0, world_size=1):
     out = torch.empty((len(xs), G, G), dtype=torch.float32, device="cuda")
     yz = torch.stack(torch.meshgrid(lin, lin, indexing="ij"), dim=-1).reshape(-1, 2)
     per = max(1, batch_size // (G * G))
+    eng.refresh_transposes()      # W^T and the pre-split lo copies of the weights must match the current parameters
     for s0 in range(0, len(xs), per):
         sl = xs[s0:s0 + per]
         pts = torch.cat([torch.cat([lin[i].expand(G * G, 1), yz], dim=1) for i in sl], dim=0).contiguous()

@@ -25,7 +25,7 @@ def softplus(x, beta=100.0):
     return (np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))) / beta
 
 
-def run(M, N, K, layout, epi, tc, split_k=1, seed=0, mask_hi=0):
+def run(M, N, K, layout, epi, tc, split_k=1, seed=0, mask_hi=0, presplit=0, ret_out=False):
     rng = np.random.RandomState(seed)
     A = rng.randn(M, K).astype(np.float32)
     B = (rng.randn(K, N) / np.sqrt(K)).astype(np.float32)
@@ -73,9 +73,17 @@ def run(M, N, K, layout, epi, tc, split_k=1, seed=0, mask_hi=0):
     dbias = dev(bias)
     _lib.call("ndjir_set_option", "mlp_tensor_cores", int(tc))
     _lib.call("ndjir_set_option", "mlp_mask_hi", int(mask_hi))
+    dB_lo = None
+    if presplit:      # the weight operand comes with its pre-split lo copy (two TMA tiles, no B transform)
+        dB_lo = torch.empty_like(dB)
+        _lib.call("ndjir_split_lo", dB.numel(), dB_lo, dB, 0)
     try:
-        _lib.call("ndjir_gemm", M, N, K, dA, a_rs, a_cs, dB, b_rs, b_cs, dC, ldc, dbias, alpha, out_scale, 100.0, dH, ldc,
-                  hscale, dU, ldc, dC2, ldc, split_k, epi, 0)
+        if presplit:
+            _lib.call("ndjir_gemm_presplit", M, N, K, dA, a_rs, a_cs, dB, dB_lo, b_rs, b_cs, dC, ldc, dbias, alpha,
+                      out_scale, 100.0, dH, ldc, hscale, dU, ldc, dC2, ldc, split_k, epi, 0)
+        else:
+            _lib.call("ndjir_gemm", M, N, K, dA, a_rs, a_cs, dB, b_rs, b_cs, dC, ldc, dbias, alpha, out_scale, 100.0,
+                      dH, ldc, hscale, dU, ldc, dC2, ldc, split_k, epi, 0)
         torch.cuda.synchronize()
     finally:
         _lib.call("ndjir_set_option", "mlp_tensor_cores", 1)
@@ -86,6 +94,8 @@ def run(M, N, K, layout, epi, tc, split_k=1, seed=0, mask_hi=0):
     assert np.array_equal(got[:, N:], C0[:, N:].astype(np.float64)), "wrote outside the tile"
     if want2 is not None:
         err = max(err, np.abs(dC2.cpu().numpy()[:, :N] - want2).max() / np.abs(want2).max())
+    if ret_out:
+        return err, dC.cpu().numpy()
     return err
 
 
@@ -151,3 +161,16 @@ def test_tf32_operand_truncation_is_harmless():
     e1 = run(512, 256, 256, "kn", EPI_BIAS, 1, mask_hi=1)
     print(f"  raw hi operand: {e0:.2e}; masked hi operand: {e1:.2e}")
     assert e0 <= 1e-5 and e1 <= 1e-5
+
+
+PRESPLIT_CASES = [c for c in CASES if c[4] != EPI_ATOMIC and c[1] >= 32 and c[2] >= 16]
+
+
+@pytest.mark.parametrize("M,N,K,layout,epi,split_k", PRESPLIT_CASES)
+def test_presplit_weights_are_bit_identical(M, N, K, layout, epi, split_k):
+    """A registered B operand (weights) arrives as raw + lo TMA tiles (ndjir_split_lo / ndjir_gemm_presplit) instead
+    of being split by the transform warps: same tiles in shared memory, so the product is bit-identical."""
+    e0, c0 = run(M, N, K, layout, epi, 1, split_k, presplit=0, ret_out=True)
+    e1, c1 = run(M, N, K, layout, epi, 1, split_k, presplit=1, ret_out=True)
+    assert e1 <= 1e-5, e1
+    assert np.array_equal(c0, c1, equal_nan=True), f"pre-split result differs (errors {e0:.2e} / {e1:.2e})"

@@ -21,6 +21,24 @@ shapes = {
 }
 out = []
 import sys as _s
+if "--presplit" in _s.argv:
+    W_lo = torch.empty_like(W)
+    _lib.call("ndjir_split_lo", W.numel(), W_lo, W, 0)
+    def call(M, N, K, A_, ars, acs, B_, brs, bcs, C_, ldc, epi, split=1, Hh=None, Uu=None, C2_=None):  # noqa: F811
+        _lib.call("ndjir_gemm_presplit", M, N, K, A_, ars, acs, B_, W_lo if B_ is W else None, brs, bcs, C_, ldc, b, 1.0,
+                  1.0, 100.0, Hh, 256, 1.0, Uu, 256, C2_, 256, split, epi, 0)
+    for pre in (0, 1, 0, 1):
+        _lib.call("ndjir_set_option", "mlp_presplit", pre)
+        for name, fn in shapes.items():
+            for _ in range(3): fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(20): fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(json.dumps(dict(name=name, presplit=pre, ms=ms, tflops=2.0 * P * 256 * 256 / ms / 1e9)), flush=True)
+    _lib.call("ndjir_set_option", "mlp_presplit", 1)
+    _s.exit(0)
 modes = [(1, d) for d in range(8)] if "--dbg" in _s.argv else ([(1, 0), (2, 0)] if "--pair" in _s.argv else [(1, 0), (0, 0)])
 for tc, dbg in modes:
     _lib.call("ndjir_set_option", "mlp_tensor_cores", 1 if tc else 0)
