@@ -275,8 +275,17 @@ def run_ours(args, conf):
     resident = [{k: v.cuda(non_blocking=True) for k, v in item.items()} for item in host]
     torch.cuda.synchronize()
 
-    def step_resident(item):
+    use_graph = world == 1 and not args.no_graph      # CUDA-graph replay of the step (Engine.train_step_graphed)
+    rnd_keys = [k for k in host[0] if k not in ("camloc", "raydir", "color_gt")]
+
+    def run_step(item):
+        if use_graph:
+            return eng.train_step_graphed(item["camloc"], item["raydir"], item["color_gt"], {k: item[k] for k in rnd_keys},
+                                          cos_anneal_ratio=0.0)
         return eng.train_step(item["camloc"], item["raydir"], item["color_gt"], item, cos_anneal_ratio=0.0)
+
+    def step_resident(item):
+        return run_step(item)
 
     def barrier():
         if world > 1:
@@ -317,9 +326,12 @@ def run_ours(args, conf):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for s in range(args.warmup, nsteps):
-        for k, v in host[s].items():
-            dev_bufs[k].copy_(v, non_blocking=True)
-        l_ = eng.train_step(dev_bufs["camloc"], dev_bufs["raydir"], dev_bufs["color_gt"], dev_bufs, cos_anneal_ratio=0.0)
+        if use_graph:       # the graphed step copies the pinned host tensors straight into its static device inputs
+            l_ = run_step(host[s])
+        else:
+            for k, v in host[s].items():
+                dev_bufs[k].copy_(v, non_blocking=True)
+            l_ = run_step(dev_bufs)
         loss_pinned.copy_(l_, non_blocking=True)
         torch.cuda.current_stream().synchronize()     # the caller reads the loss every step (train.py:141-146)
     e3.record()
@@ -330,7 +342,8 @@ def run_ours(args, conf):
     # ---- instrumented step: launches and product-kernel time (CUDA events around every ndjir_gemm) ----
     eng.profile = True
     eng.prof_events, eng.n_launches = [], 0
-    step_resident(resident[-1])
+    it = resident[-1]
+    eng.train_step(it["camloc"], it["raydir"], it["color_gt"], it, cos_anneal_ratio=0.0)     # eager: events per launch
     torch.cuda.synchronize()
     eng.profile = False
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in eng.prof_events)
@@ -370,6 +383,8 @@ def run_ours(args, conf):
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(conf, 1, 1, args.ref_rays)
         cfg = workload(conf)
+        cfg["launch"] = ("one CUDA-graph replay per step (Engine.train_step_graphed)" if use_graph
+                         else "eager: every kernel enqueued from the host")
         cfg["parallelism"] = f"ray-sharded x{world}, replicated parameters, NCCL gradient all-reduce" if world > 1 else "1 GPU"
         line = {"metric": "train_rays_per_sec_fwd_bwd", "value": value, "unit": "rays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -402,6 +417,8 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=256, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays", type=int, default=0, help="override rays per view (debugging)")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying "
+                    "the captured CUDA graph of the step")
     ap.add_argument("--grid", type=int, default=0, help="override voxel grid size (debugging)")
     args = ap.parse_args()
     from ndjir_b200.config import make_conf

@@ -256,6 +256,7 @@ class Engine:
         assert conf.background_modeling
         self.cskip = 1.0 / math.sqrt(2.0) if g.use_inv_square else 1.0
         self._bufs = {}
+        self._graphs = {}
         self._reserve = 0
         self.one = torch.ones(4, dtype=torch.float32, device=self.device)
         self.rad = float(conf.renderer.bounding_sphere_radius)
@@ -667,6 +668,48 @@ class Engine:
                   self.rad, P_(t_bg), P_(x_bg))
         self.debug["sampler"] = dbg
         return x_fg, t_fg, x_bg, t_bg, mask[:NR].reshape(B, R, 1, 1)
+
+    # ------------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole step
+    # ------------------------------------------------------------------------------------------------
+    def train_step_graphed(self, camloc, raydir, color_gt, rnd, cos_anneal_ratio=0.0):
+        """train_step(zero_grad=True) captured ONCE in a CUDA graph and replayed: the step is ~2200 kernel launches
+        (31 ms of host time to enqueue for 45 ms of device time, and the gaps between dependent small kernels cost
+        ~1 ms per step - tools/exp/graph_step.py).  Inputs (device or pinned-host tensors) are copied into static
+        device buffers, the returned loss tensor is the graph's static output.  The host scalars baked into the kernel
+        arguments (cos_anneal_ratio, the light-visibility gain) and the input shapes key the cache: a change captures
+        a new graph.  Single-process only (the NCCL exchanges of the ray-sharded mode stay on the eager path)."""
+        if self.world_size > 1:
+            return self.train_step(camloc, raydir, color_gt, rnd, cos_anneal_ratio=cos_anneal_ratio)
+        inputs = {"camloc": camloc, "raydir": raydir, "color_gt": color_gt, **rnd}
+        key = (float(cos_anneal_ratio), float(self.params.pl_gain),
+               tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items())))
+        st = self._graphs.get(key)
+        if st is None:
+            static = {k: torch.empty(v.shape, dtype=torch.float32, device=self.device) for k, v in inputs.items()}
+            for k, v in inputs.items():
+                static[k].copy_(v, non_blocking=True)
+
+            def run():
+                rest = {k: v for k, v in static.items() if k not in ("camloc", "raydir", "color_gt")}
+                return self.train_step(static["camloc"], static["raydir"], static["color_gt"], rest,
+                                       cos_anneal_ratio=cos_anneal_ratio)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):       # eager warm-up: sizes every scratch buffer, sets kernel attributes
+                run()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = run()
+            st = self._graphs[key] = (graph, static, out)
+            if len(self._graphs) > 4:           # graphs pin their scratch memory: keep only the most recent ones
+                self._graphs.pop(next(iter(self._graphs)))
+        graph, static, out = st
+        for k, v in inputs.items():
+            static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return out
 
     # ------------------------------------------------------------------------------------------------
     # total_loss forward + backward (python/loss.py:27-192 over python/renderer.py:32-209)

@@ -245,3 +245,25 @@ def test_full_step_with_own_sampling_is_close():
     ol = CR.total_loss(model, camloc, raydir, color_gt, 0.0, rnd, fixed_dirs=fixed)
     want, got = float(ol["loss"].detach()), float(losses[0])
     assert abs(got - want) <= 1e-3 * abs(want), (got, want)
+
+
+def test_graphed_step_equals_eager_step():
+    """Engine.train_step_graphed (one CUDA-graph replay per step) against the eager step on two different batches: same
+    losses and gradients up to the atomic summation order of the scatter / split-K kernels."""
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup("default")
+    outs = []
+    for seed in (0, 1, 0):
+        c2, r2, g2 = scene.make_batch(conf, step=seed, B=conf.train.batch_size, R=conf.train.n_rays)
+        rn = {k: dev(v) for k, v in scene.make_randoms(conf, conf.train.batch_size, conf.train.n_rays, step=seed).items()}
+        le = eng.train_step(dev(c2), dev(r2), dev(g2), rn, cos_anneal_ratio=0.3).clone()
+        ge = eng.params.grad.clone()
+        gge = {k: v.clone() for k, v in eng.params.grid_grad.items()}
+        lg = eng.train_step_graphed(dev(c2), dev(r2), dev(g2), rn, cos_anneal_ratio=0.3).clone()
+        torch.cuda.synchronize()
+        assert relerr(lg, le) < 1e-5, (seed, lg, le)
+        assert relerr(eng.params.grad, ge) < 1e-4
+        for k in gge:
+            assert relerr(eng.params.grid_grad[k], gge[k]) < 1e-4
+        outs.append(lg)
+    assert len(eng._graphs) == 1, "one capture, three replays"
+    assert relerr(outs[2], outs[0]) < 1e-5 and relerr(outs[1], outs[0]) > 1e-6
