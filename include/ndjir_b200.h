@@ -90,6 +90,29 @@ int ndjir_voxel_grad_query_grad_feature_binned(long long n_points, float* grad_f
                                                int D, const float* min3, const float* max3, void* workspace,
                                                long long workspace_bytes, cudaStream_t stream);
 
+/* ---- cosine_voxel_feature_cuda (csrc/grid_feature/cosine_voxel_feature_cuda.cu:855-866; 5 exports: the
+ *      second-order grad_query_grad_query / grad_feature_* are commented out in the reference).  Same cells and
+ *      corner order as voxel_feature_cuda; weights 0.5 cos(pi frac) + 0.5 (:65-66), derivative factor
+ *      0.5 pi sin(pi frac) per axis (:163). -------------------------------------------------------------------- */
+int ndjir_cosine_voxel_query_on_voxel(long long n_points, float* output, const float* query, const float* feature,
+                                      const int* grid_sizes, int D, const float* min3, const float* max3, int accum,
+                                      cudaStream_t stream);
+int ndjir_cosine_voxel_grad_query(long long n_points, float* grad_query, const float* grad_output, const float* query,
+                                  const float* feature, const int* grid_sizes, int D, const float* min3,
+                                  const float* max3, int accum, cudaStream_t stream);
+int ndjir_cosine_voxel_grad_feature(long long n_points, float* grad_feature, const float* grad_output,
+                                    const float* query, const int* grid_sizes, int D, const float* min3,
+                                    const float* max3, int accum, cudaStream_t stream);
+int ndjir_cosine_voxel_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                                                   const float* grad_grad_query, const float* query,
+                                                   const float* feature, const int* grid_sizes, int D,
+                                                   const float* min3, const float* max3, int accum,
+                                                   cudaStream_t stream);
+/* always accumulates (:626-650 never reads accum) */
+int ndjir_cosine_voxel_grad_query_grad_feature(long long n_points, float* grad_feature, const float* grad_grad_query,
+                                               const float* grad_output, const float* query, const int* grid_sizes,
+                                               int D, const float* min3, const float* max3, cudaStream_t stream);
+
 /* ---- lanczos_voxel_feature_cuda (csrc/grid_feature/lanczos_voxel_feature_cuda.cu:822-834) ----------- */
 int ndjir_lanczos_voxel_query_on_voxel(long long n_points, float* output, const float* query,
                                        const float* feature, const int* grid_sizes, int D, const float* min3,
@@ -172,6 +195,34 @@ int ndjir_triline_grad_query_grad_grad_output(long long n_points, float* grad_gr
                    const float* grad_grad_query, const float* query, const float* feature, int G, int D,
                    const float* min3, const float* max3, int accum, cudaStream_t stream);
 int ndjir_triline_grad_query_grad_feature(long long n_points, float* grad_feature, const float* grad_grad_query,
+                   const float* grad_output, const float* query, int G, int D, const float* min3,
+                   const float* max3, cudaStream_t stream);
+/* cosine_triplane_feature_cuda / cosine_triline_feature_cuda (csrc/grid_feature/cosine_triplane_feature_cuda.cu,
+ * cosine_triline_feature_cuda.cu; 5 exports each): same layouts and semantics with the cosine weights. */
+int ndjir_cosine_triplane_query_on_triplane(long long n_points, float* output, const float* query, const float* feature, int G, int D,
+                   const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_cosine_triplane_grad_query(long long n_points, float* grad_query, const float* grad_output, const float* query,
+                   const float* feature, int G, int D, const float* min3, const float* max3, int accum,
+                   cudaStream_t stream);
+int ndjir_cosine_triplane_grad_feature(long long n_points, float* grad_feature, const float* grad_output, const float* query,
+                   int G, int D, const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_cosine_triplane_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                   const float* grad_grad_query, const float* query, const float* feature, int G, int D,
+                   const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_cosine_triplane_grad_query_grad_feature(long long n_points, float* grad_feature, const float* grad_grad_query,
+                   const float* grad_output, const float* query, int G, int D, const float* min3,
+                   const float* max3, cudaStream_t stream);
+int ndjir_cosine_triline_query_on_triline(long long n_points, float* output, const float* query, const float* feature, int G, int D,
+                   const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_cosine_triline_grad_query(long long n_points, float* grad_query, const float* grad_output, const float* query,
+                   const float* feature, int G, int D, const float* min3, const float* max3, int accum,
+                   cudaStream_t stream);
+int ndjir_cosine_triline_grad_feature(long long n_points, float* grad_feature, const float* grad_output, const float* query,
+                   int G, int D, const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_cosine_triline_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                   const float* grad_grad_query, const float* query, const float* feature, int G, int D,
+                   const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_cosine_triline_grad_query_grad_feature(long long n_points, float* grad_feature, const float* grad_grad_query,
                    const float* grad_output, const float* query, int G, int D, const float* min3,
                    const float* max3, cudaStream_t stream);
 

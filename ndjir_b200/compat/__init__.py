@@ -17,6 +17,9 @@ MODULES = [
     "voxel_hash_feature_cuda",
     "triplane_feature_cuda",
     "triline_feature_cuda",
+    "cosine_voxel_feature_cuda",
+    "cosine_triplane_feature_cuda",
+    "cosine_triline_feature_cuda",
     "total_variation_loss_cuda",
     "total_variation_loss_on_triplane_cuda",
     "total_variation_loss_on_triline_cuda",

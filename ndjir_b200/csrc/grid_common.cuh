@@ -8,10 +8,13 @@
 
 namespace ndjir {
 
+enum Interp { INTERP_LINEAR = 0, INTERP_COSINE = 1 };
+
 struct GridFrame {
   float mnx, mny, mnz;   // min
   float sx, sy, sz;      // (G-1)/(max-min)
   float gx1, gy1, gz1;   // G-1
+  int interp;            // INTERP_LINEAR (voxel / triplane / triline) or INTERP_COSINE (the cosine_* families)
 };
 
 static inline GridFrame make_frame(int Gx, int Gy, int Gz, const float* mn, const float* mx) {
@@ -21,12 +24,17 @@ static inline GridFrame make_frame(int Gx, int Gy, int Gz, const float* mn, cons
   volatile float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
   volatile float sx = f.gx1 / dx, sy = f.gy1 / dy, sz = f.gz1 / dz;
   f.sx = sx; f.sy = sy; f.sz = sz;
+  f.interp = INTERP_LINEAR;
   return f;
 }
 
 struct Cell {
   unsigned x0, y0, z0, x1, y1, z1;
   float p0, q0, r0, p1, q1, r1;
+  // d(weight of the upper corner)/d(query) per axis: the frame scale for the linear families; for the cosine families
+  // scale * 0.5 pi sin(pi frac) (cosine_voxel_feature_cuda.cu:163, :188-196: every derivative is the linear one with
+  // cosine weights and this extra per-axis factor)
+  float sx, sy, sz;
 };
 
 __device__ __forceinline__ void cell_axis(float q, float mn, float s, float g1, unsigned& i0, unsigned& i1,
@@ -42,11 +50,34 @@ __device__ __forceinline__ void cell_axis(float q, float mn, float s, float g1, 
   i1 = (unsigned)f1;
 }
 
+// cosine_voxel_feature_cuda.cu:52-67: same cell, weights 0.5 cos(pi (x - x0)) + 0.5 (fp32 pi, cosf / sinf)
+__device__ __forceinline__ void cell_axis_cosine(float q, float mn, float s, float g1, unsigned& i0, unsigned& i1,
+                                                 float& w0, float& w1, float& ds) {
+  float x = __fmul_rn(__fsub_rn(q, mn), s);
+  float f0 = floorf(x);
+  f0 = fmaxf(f0, 0.f);
+  f0 = fminf(f0, g1);
+  float f1 = fminf(__fadd_rn(f0, 1.f), g1);
+  float ang = __fmul_rn(3.14159274f, __fsub_rn(x, f0));
+  w0 = 0.5f * cosf(ang) + 0.5f;
+  w1 = __fsub_rn(1.f, w0);
+  ds = s * (1.57079637f * sinf(ang));
+  i0 = (unsigned)f0;
+  i1 = (unsigned)f1;
+}
+
 __device__ __forceinline__ Cell make_cell(const GridFrame& g, float qx, float qy, float qz) {
   Cell c;
+  if (g.interp == INTERP_COSINE) {
+    cell_axis_cosine(qx, g.mnx, g.sx, g.gx1, c.x0, c.x1, c.p0, c.p1, c.sx);
+    cell_axis_cosine(qy, g.mny, g.sy, g.gy1, c.y0, c.y1, c.q0, c.q1, c.sy);
+    cell_axis_cosine(qz, g.mnz, g.sz, g.gz1, c.z0, c.z1, c.r0, c.r1, c.sz);
+    return c;
+  }
   cell_axis(qx, g.mnx, g.sx, g.gx1, c.x0, c.x1, c.p0, c.p1);
   cell_axis(qy, g.mny, g.sy, g.gy1, c.y0, c.y1, c.q0, c.q1);
   cell_axis(qz, g.mnz, g.sz, g.gz1, c.z0, c.z1, c.r0, c.r1);
+  c.sx = g.sx; c.sy = g.sy; c.sz = g.sz;
   return c;
 }
 

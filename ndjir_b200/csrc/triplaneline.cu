@@ -29,13 +29,13 @@ __device__ __forceinline__ Axis2 plane_axes(int i, const Cell& c, const GridFram
   Axis2 r;
   if (i == 0) {
     r.u0 = c.x0; r.u1 = c.x1; r.v0 = c.y0; r.v1 = c.y1; r.a0 = c.p0; r.a1 = c.p1; r.b0 = c.q0; r.b1 = c.q1;
-    r.su = g.sx; r.sv = g.sy; r.ggu = ggx; r.ggv = ggy; r.au = 0; r.av = 1;
+    r.su = c.sx; r.sv = c.sy; r.ggu = ggx; r.ggv = ggy; r.au = 0; r.av = 1;
   } else if (i == 1) {
     r.u0 = c.y0; r.u1 = c.y1; r.v0 = c.z0; r.v1 = c.z1; r.a0 = c.q0; r.a1 = c.q1; r.b0 = c.r0; r.b1 = c.r1;
-    r.su = g.sy; r.sv = g.sz; r.ggu = ggy; r.ggv = ggz; r.au = 1; r.av = 2;
+    r.su = c.sy; r.sv = c.sz; r.ggu = ggy; r.ggv = ggz; r.au = 1; r.av = 2;
   } else {
     r.u0 = c.z0; r.u1 = c.z1; r.v0 = c.x0; r.v1 = c.x1; r.a0 = c.r0; r.a1 = c.r1; r.b0 = c.p0; r.b1 = c.p1;
-    r.su = g.sz; r.sv = g.sx; r.ggu = ggz; r.ggv = ggx; r.au = 2; r.av = 0;
+    r.su = c.sz; r.sv = c.sx; r.ggu = ggz; r.ggv = ggx; r.au = 2; r.av = 0;
   }
   return r;
 }
@@ -294,10 +294,11 @@ static bool bad(int G, int D) {
 template <bool PLANE, int MODE>
 static int launch_gather(long long B, float* out, const float* a, const float* b, const float* query,
                          const float* feat, int G, int D, const float* mn, const float* mx, bool accum,
-                         cudaStream_t st) {
+                         cudaStream_t st, int interp = INTERP_LINEAR) {
   if (B == 0) return NDJIR_OK;
   if (B < 0 || bad(G, D) || !out || !query || !feat || !mn || !mx) return NDJIR_ERR_ARG;
   GridFrame g = make_frame(G, G, G, mn, mx);
+  g.interp = interp;
   int V = pick_vec(D, feat, MODE == GRAD_QUERY ? (const void*)a : (const void*)out);
   int grid = grid_for(B);
   if (MODE == FWD && D / V > 1) {
@@ -319,10 +320,11 @@ static int launch_gather(long long B, float* out, const float* a, const float* b
 
 template <bool PLANE, bool SECOND>
 static int launch_scatter(long long B, float* gf, const float* go, const float* gg, const float* query, int G,
-                          int D, const float* mn, const float* mx, cudaStream_t st) {
+                          int D, const float* mn, const float* mx, cudaStream_t st, int interp = INTERP_LINEAR) {
   if (B == 0) return NDJIR_OK;
   if (B < 0 || bad(G, D) || !gf || !go || !query || !mn || !mx) return NDJIR_ERR_ARG;
   GridFrame g = make_frame(G, G, G, mn, mx);
+  g.interp = interp;
   int V = pick_vec(D, gf, go);
   int grid = grid_for(B);
   bool agg = g_scatter_aggregate != 0;
@@ -350,25 +352,26 @@ static int launch_scatter(long long B, float* gf, const float* go, const float* 
 using namespace ndjir;
 using namespace ndjir::tpl;
 
-#define NDJIR_DEFINE_FAMILY(NAME, FWDNAME, PLANE, TABLE_ELEMS)                                                    \
+#define NDJIR_DEFINE_FAMILY(NAME, FWDNAME, PLANE, TABLE_ELEMS, INTERP)                                            \
   int ndjir_##NAME##_##FWDNAME(long long n, float* output, const float* query, const float* feature, int G,      \
                                int D, const float* min3, const float* max3, int accum, cudaStream_t st) {        \
     return launch_gather<PLANE, FWD>(n, output, nullptr, nullptr, query, feature, G, D, min3, max3, accum != 0,  \
-                                     st);                                                                        \
+                                     st, INTERP);                                                                \
   }                                                                                                              \
   int ndjir_##NAME##_grad_query(long long n, float* grad_query, const float* grad_output, const float* query,    \
                                 const float* feature, int G, int D, const float* min3, const float* max3,        \
                                 int accum, cudaStream_t st) {                                                    \
     if (n > 0 && !grad_output) return NDJIR_ERR_ARG;                                                             \
     return launch_gather<PLANE, GRAD_QUERY>(n, grad_query, grad_output, nullptr, query, feature, G, D, min3,     \
-                                            max3, accum != 0, st);                                               \
+                                            max3, accum != 0, st, INTERP);                                       \
   }                                                                                                              \
   int ndjir_##NAME##_grad_feature(long long n, float* grad_feature, const float* grad_output,                    \
                                   const float* query, int G, int D, const float* min3, const float* max3,        \
                                   int accum, cudaStream_t st) {                                                  \
     if (bad(G, D) || !grad_feature) return NDJIR_ERR_ARG;                                                        \
     if (!accum) fill_zero(grad_feature, (long long)(TABLE_ELEMS), st);                                           \
-    return launch_scatter<PLANE, false>(n, grad_feature, grad_output, nullptr, query, G, D, min3, max3, st);     \
+    return launch_scatter<PLANE, false>(n, grad_feature, grad_output, nullptr, query, G, D, min3, max3, st,      \
+                                        INTERP);                                                                 \
   }                                                                                                              \
   int ndjir_##NAME##_grad_query_grad_grad_output(long long n, float* grad_grad_output,                           \
                                                  const float* grad_grad_query, const float* query,               \
@@ -376,19 +379,24 @@ using namespace ndjir::tpl;
                                                  const float* max3, int accum, cudaStream_t st) {                \
     if (n > 0 && !grad_grad_query) return NDJIR_ERR_ARG;                                                         \
     return launch_gather<PLANE, GGO>(n, grad_grad_output, nullptr, grad_grad_query, query, feature, G, D, min3,  \
-                                     max3, accum != 0, st);                                                      \
+                                     max3, accum != 0, st, INTERP);                                              \
   }                                                                                                              \
   int ndjir_##NAME##_grad_query_grad_feature(long long n, float* grad_feature, const float* grad_grad_query,     \
                                              const float* grad_output, const float* query, int G, int D,         \
                                              const float* min3, const float* max3, cudaStream_t st) {            \
     if (n > 0 && !grad_grad_query) return NDJIR_ERR_ARG;                                                         \
     return launch_scatter<PLANE, true>(n, grad_feature, grad_output, grad_grad_query, query, G, D, min3, max3,   \
-                                       st);                                                                      \
+                                       st, INTERP);                                                              \
   }
 
 extern "C" {
 // triline grad_feature zero-fills 3*G*D floats: the reference zeroes 3*G*G*D there, out of bounds
-// (triline_feature_cuda.cu:247) - deliberately not reproduced.
-NDJIR_DEFINE_FAMILY(triplane, query_on_triplane, true, 3ll * G * G * D)
-NDJIR_DEFINE_FAMILY(triline, query_on_triline, false, 3ll * G * D)
+// (triline_feature_cuda.cu:247, cosine_triline_feature_cuda.cu:248-250) - deliberately not
+// reproduced.
+NDJIR_DEFINE_FAMILY(triplane, query_on_triplane, true, 3ll * G * G * D, INTERP_LINEAR)
+NDJIR_DEFINE_FAMILY(triline, query_on_triline, false, 3ll * G * D, INTERP_LINEAR)
+// cosine_triplane_feature_cuda.cu / cosine_triline_feature_cuda.cu (5 exports each): the same kernels with the
+// cosine cell (weights 0.5 cos(pi frac) + 0.5, derivative factor 0.5 pi sin(pi frac), grid_common.cuh)
+NDJIR_DEFINE_FAMILY(cosine_triplane, query_on_triplane, true, 3ll * G * G * D, INTERP_COSINE)
+NDJIR_DEFINE_FAMILY(cosine_triline, query_on_triline, false, 3ll * G * D, INTERP_COSINE)
 }

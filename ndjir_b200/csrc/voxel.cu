@@ -99,9 +99,9 @@ gather_kernel(long long B, float* __restrict__ out, const float* __restrict__ a,
           float f000 = k.f000.v[j], f001 = k.f001.v[j], f010 = k.f010.v[j], f011 = k.f011.v[j];
           float f100 = k.f100.v[j], f101 = k.f101.v[j], f110 = k.f110.v[j], f111 = k.f111.v[j];
           if (MODE == GRAD_QUERY || MODE == GGO) {
-            float gx = dterm(g.sx, c.q0, c.q1, c.r0, c.r1, f100 - f000, f101 - f001, f110 - f010, f111 - f011);
-            float gy = dterm(g.sy, c.p0, c.p1, c.r0, c.r1, f010 - f000, f011 - f001, f110 - f100, f111 - f101);
-            float gz = dterm(g.sz, c.p0, c.p1, c.q0, c.q1, f001 - f000, f011 - f010, f101 - f100, f111 - f110);
+            float gx = dterm(c.sx, c.q0, c.q1, c.r0, c.r1, f100 - f000, f101 - f001, f110 - f010, f111 - f011);
+            float gy = dterm(c.sy, c.p0, c.p1, c.r0, c.r1, f010 - f000, f011 - f001, f110 - f100, f111 - f101);
+            float gz = dterm(c.sz, c.p0, c.p1, c.q0, c.q1, f001 - f000, f011 - f010, f101 - f100, f111 - f110);
             if (MODE == GRAD_QUERY) {
               ax += av.v[j] * gx; ay += av.v[j] * gy; az += av.v[j] * gz;
             } else {
@@ -214,7 +214,7 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
     }
     float ggx = 0.f, ggy = 0.f, ggz = 0.f;
     if (SECOND) {
-      ggx = __ldg(gg + pc * 3) * g.sx; ggy = __ldg(gg + pc * 3 + 1) * g.sy; ggz = __ldg(gg + pc * 3 + 2) * g.sz;
+      ggx = __ldg(gg + pc * 3) * c.sx; ggy = __ldg(gg + pc * 3 + 1) * c.sy; ggz = __ldg(gg + pc * 3 + 2) * c.sz;
     }
     for (int d = 0; d < D; d += V) {
       Vec<V> o = ldg_vec<V>(go + pc * D + d);
@@ -253,7 +253,7 @@ scatter8_kernel(long long B, float* __restrict__ gf, const float* __restrict__ g
     if (!SECOND) {
       coef = pw * qw * rw;
     } else {
-      float ggx = __ldg(gg + p * 3) * g.sx, ggy = __ldg(gg + p * 3 + 1) * g.sy, ggz = __ldg(gg + p * 3 + 2) * g.sz;
+      float ggx = __ldg(gg + p * 3) * c.sx, ggy = __ldg(gg + p * 3 + 1) * c.sy, ggz = __ldg(gg + p * 3 + 2) * c.sz;
       coef = ggx * ((cx ? 1.f : -1.f) * qw * rw) + ggy * ((cy ? 1.f : -1.f) * pw * rw) + ggz * ((cz ? 1.f : -1.f) * pw * qw);
     }
     float* dst = gf + fidx(s, cx ? c.x1 : c.x0, cy ? c.y1 : c.y0, cz ? c.z1 : c.z0);
@@ -282,16 +282,17 @@ static bool bad_grid(const int* G, int D) {
 template <int MODE>
 static int launch_gather(long long B, float* out, const float* a, const float* b, const float* query,
                          const float* feat, const int* G, int D, const float* mn, const float* mx, bool accum,
-                         cudaStream_t st) {
+                         cudaStream_t st, int interp = INTERP_LINEAR) {
   if (B == 0) return NDJIR_OK;
-  if (B < 0 || bad_grid(G, D) || !out || !query || !feat) return NDJIR_ERR_ARG;
+  if (B < 0 || bad_grid(G, D) || !out || !query || !feat || !mn || !mx) return NDJIR_ERR_ARG;
   GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
+  g.interp = interp;
   Strides s = make_strides(G, D);
   const void* vec_out = (MODE == FWD || MODE == GGO) ? out : nullptr;
   const void* vec_a = (MODE == GRAD_QUERY || MODE == GQ_GQ) ? a : nullptr;
   int V = pick_vec(D, feat, vec_out, vec_a);
   int grid = grid_for(B);
-  if (MODE == FWD && voxel_binned::worthwhile(B, G, D)) {
+  if (MODE == FWD && interp == INTERP_LINEAR && voxel_binned::worthwhile(B, G, D)) {
     long long wsb = voxel_binned::workspace_bytes(B);
     if (void* ws = voxel_binned::scratch_alloc(wsb, st)) {
       int rc = voxel_binned::query(B, out, query, feat, G, D, mn, mx, accum, ws, wsb, st);
@@ -315,12 +316,14 @@ static int launch_gather(long long B, float* out, const float* a, const float* b
 
 template <bool SECOND>
 static int launch_scatter(long long B, float* gf, const float* go, const float* gg, const float* query,
-                          const int* G, int D, const float* mn, const float* mx, cudaStream_t st) {
+                          const int* G, int D, const float* mn, const float* mx, cudaStream_t st,
+                          int interp = INTERP_LINEAR) {
   if (B == 0) return NDJIR_OK;
-  if (B < 0 || bad_grid(G, D) || !gf || !go || !query) return NDJIR_ERR_ARG;
+  if (B < 0 || bad_grid(G, D) || !gf || !go || !query || !mn || !mx) return NDJIR_ERR_ARG;
   GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
+  g.interp = interp;
   Strides s = make_strides(G, D);
-  if (voxel_binned::worthwhile(B, G, D)) {
+  if (interp == INTERP_LINEAR && voxel_binned::worthwhile(B, G, D)) {
     long long wsb = voxel_binned::workspace_bytes(B);
     if (void* ws = voxel_binned::scratch_alloc(wsb, st)) {
       int rc = voxel_binned::scatter(SECOND, B, gf, go, gg, query, G, D, mn, mx, ws, wsb, st);
@@ -468,6 +471,51 @@ int ndjir_voxel_grad_feature_grad_query(long long n_points, float* grad_query, c
   if (n_points > 0 && !grad_output) return NDJIR_ERR_ARG;
   return launch_gather<GRAD_QUERY>(n_points, grad_query, grad_output, nullptr, query, grad_grad_feature,
                                    grid_sizes, D, min3, max3, true, stream);
+}
+
+// ---- cosine_voxel_feature_cuda (csrc/grid_feature/cosine_voxel_feature_cuda.cu:855-866): same cells and corner
+// order, weights 0.5 cos(pi frac) + 0.5 and derivative factor 0.5 pi sin(pi frac) per axis ------------------------------
+int ndjir_cosine_voxel_query_on_voxel(long long n_points, float* output, const float* query, const float* feature,
+                                      const int* grid_sizes, int D, const float* min3, const float* max3, int accum,
+                                      cudaStream_t stream) {
+  return launch_gather<FWD>(n_points, output, nullptr, nullptr, query, feature, grid_sizes, D, min3, max3,
+                            accum != 0, stream, INTERP_COSINE);
+}
+
+int ndjir_cosine_voxel_grad_query(long long n_points, float* grad_query, const float* grad_output, const float* query,
+                                  const float* feature, const int* grid_sizes, int D, const float* min3,
+                                  const float* max3, int accum, cudaStream_t stream) {
+  if (n_points > 0 && !grad_output) return NDJIR_ERR_ARG;
+  return launch_gather<GRAD_QUERY>(n_points, grad_query, grad_output, nullptr, query, feature, grid_sizes, D,
+                                   min3, max3, accum != 0, stream, INTERP_COSINE);
+}
+
+int ndjir_cosine_voxel_grad_feature(long long n_points, float* grad_feature, const float* grad_output,
+                                    const float* query, const int* grid_sizes, int D, const float* min3,
+                                    const float* max3, int accum, cudaStream_t stream) {
+  if (bad_grid(grid_sizes, D) || !grad_feature) return NDJIR_ERR_ARG;
+  if (!accum) fill_zero(grad_feature, (long long)grid_sizes[0] * grid_sizes[1] * grid_sizes[2] * D, stream);
+  return launch_scatter<false>(n_points, grad_feature, grad_output, nullptr, query, grid_sizes, D, min3, max3,
+                               stream, INTERP_COSINE);
+}
+
+int ndjir_cosine_voxel_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                                                   const float* grad_grad_query, const float* query,
+                                                   const float* feature, const int* grid_sizes, int D,
+                                                   const float* min3, const float* max3, int accum,
+                                                   cudaStream_t stream) {
+  if (n_points > 0 && !grad_grad_query) return NDJIR_ERR_ARG;
+  return launch_gather<GGO>(n_points, grad_grad_output, nullptr, grad_grad_query, query, feature, grid_sizes, D,
+                            min3, max3, accum != 0, stream, INTERP_COSINE);
+}
+
+// Always accumulates (cosine_voxel_feature_cuda.cu:626-650 never reads `accum`).
+int ndjir_cosine_voxel_grad_query_grad_feature(long long n_points, float* grad_feature, const float* grad_grad_query,
+                                               const float* grad_output, const float* query, const int* grid_sizes,
+                                               int D, const float* min3, const float* max3, cudaStream_t stream) {
+  if (n_points > 0 && !grad_grad_query) return NDJIR_ERR_ARG;
+  return launch_scatter<true>(n_points, grad_feature, grad_output, grad_grad_query, query, grid_sizes, D, min3,
+                              max3, stream, INTERP_COSINE);
 }
 
 }  // extern "C"

@@ -311,7 +311,7 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
     if (!SECOND) {
       coef = pw * qw * rw;
     } else {
-      float ggx = __ldg(gg + p * 3) * g.sx, ggy = __ldg(gg + p * 3 + 1) * g.sy, ggz = __ldg(gg + p * 3 + 2) * g.sz;
+      float ggx = __ldg(gg + p * 3) * c.sx, ggy = __ldg(gg + p * 3 + 1) * c.sy, ggz = __ldg(gg + p * 3 + 2) * c.sz;
       coef = ggx * ((cx ? 1.f : -1.f) * qw * rw) + ggy * ((cy ? 1.f : -1.f) * pw * rw) +
              ggz * ((cz ? 1.f : -1.f) * pw * qw);
     }

@@ -27,6 +27,9 @@ SCOPED = [
     "grid_feature/voxel_hash_feature_cuda.cu",
     "grid_feature/triplane_feature_cuda.cu",
     "grid_feature/triline_feature_cuda.cu",
+    "grid_feature/cosine_voxel_feature_cuda.cu",
+    "grid_feature/cosine_triplane_feature_cuda.cu",
+    "grid_feature/cosine_triline_feature_cuda.cu",
     "grid_feature/total_variation_loss_cuda.cu",
     "grid_feature/total_variation_loss_on_triplane_cuda.cu",
     "grid_feature/total_variation_loss_on_triline_cuda.cu",
@@ -36,9 +39,6 @@ SCOPED = [
     "activation/squareplus_cuda.cu",
 ]
 EXTRA = [
-    "grid_feature/cosine_voxel_feature_cuda.cu",
-    "grid_feature/cosine_triplane_feature_cuda.cu",
-    "grid_feature/cosine_triline_feature_cuda.cu",
     "grid_feature/lanczos_triplane_feature_cuda.cu",
     "grid_feature/lanczos_triline_feature_cuda.cu",
     "grid_feature/lanczos_voxel_hash_feature_cuda.cu",

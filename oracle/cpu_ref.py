@@ -33,6 +33,38 @@ def _f3(v):
 # shared cell arithmetic: csrc/grid_feature/voxel_feature_cuda.cu:52-70 (identical text in every
 # linear family: triplane_feature_cuda.cu:56-67, triline_feature_cuda.cu:52-63, voxel_hash :146-162)
 # --------------------------------------------------------------------------------------
+_INTERP = ["linear"]
+
+
+class interp:
+    """`with interp("cosine"):` switches cell() to the weights of the cosine_* families
+    (csrc/grid_feature/cosine_voxel_feature_cuda.cu:52-67, :163; cosine_triplane_feature_cuda.cu:65, :145;
+    cosine_triline_feature_cuda.cu:61, :138): pqr0 = 0.5 cos(pi (xyz - xyz0)) + 0.5 and a per-point derivative scale
+    scales * 0.5 pi sin(pi (xyz - xyz0)).  Everything else (cells, corner order, scatter signs) is shared."""
+
+    def __init__(self, kind):
+        assert kind in ("linear", "cosine")
+        self.kind = kind
+
+    def __enter__(self):
+        _INTERP.append(self.kind)
+
+    def __exit__(self, *exc):
+        _INTERP.pop()
+
+
+def _s(s, axis):
+    """derivative scale on `axis` broadcastable against (B, D): a float (linear) or a (B,1) column (cosine)"""
+    s = np.asarray(s, dtype=np.float64)
+    return float(s[axis]) if s.ndim == 1 else s[:, axis][:, None]
+
+
+def _s1(s, axis):
+    """the same, broadcastable against (B,)"""
+    s = np.asarray(s, dtype=np.float64)
+    return float(s[axis]) if s.ndim == 1 else s[:, axis]
+
+
 def cell(query, grid_sizes, min_, max_):
     """Returns (xyz0 uint32, xyz1 uint32, pqr0, pqr1, scales, xyz) for queries (B,3)."""
     q = np.asarray(query, dtype=f32).reshape(-1, 3)
@@ -46,6 +78,12 @@ def cell(query, grid_sizes, min_, max_):
     xyz0 = np.maximum(xyz0, f32(0.0))
     xyz0 = np.minimum(xyz0, g1)
     xyz1 = np.minimum(xyz0 + f32(1.0), g1)
+    if _INTERP[-1] == "cosine":
+        ang = (f32(np.pi) * (xyz - xyz0).astype(f32)).astype(f32)
+        pqr0 = (f32(0.5) * np.cos(ang).astype(f32) + f32(0.5)).astype(f32)
+        pqr1 = (f32(1.0) - pqr0).astype(f32)
+        dscale = (scales[None, :] * (f32(0.5 * np.pi) * np.sin(ang).astype(f32))).astype(f32)   # (B,3)
+        return xyz0.astype(np.uint32), xyz1.astype(np.uint32), pqr0, pqr1, dscale, xyz
     pqr0 = (xyz1 - xyz).astype(f32)
     pqr1 = (f32(1.0) - pqr0).astype(f32)
     return xyz0.astype(np.uint32), xyz1.astype(np.uint32), pqr0, pqr1, scales, xyz
@@ -116,11 +154,11 @@ def _voxel_dfdq(query, feature, min_, max_):
     a = lambda v: v[:, None]
     px0, py0, pz0 = a(P0[:, 0]), a(P0[:, 1]), a(P0[:, 2])
     px1, py1, pz1 = a(P1[:, 0]), a(P1[:, 1]), a(P1[:, 2])
-    gx = s[0] * (py0 * pz0 * (f[1, 0, 0] - f[0, 0, 0]) + py0 * pz1 * (f[1, 0, 1] - f[0, 0, 1])
+    gx = _s(s, 0) * (py0 * pz0 * (f[1, 0, 0] - f[0, 0, 0]) + py0 * pz1 * (f[1, 0, 1] - f[0, 0, 1])
                  + py1 * pz0 * (f[1, 1, 0] - f[0, 1, 0]) + py1 * pz1 * (f[1, 1, 1] - f[0, 1, 1]))
-    gy = s[1] * (px0 * pz0 * (f[0, 1, 0] - f[0, 0, 0]) + px0 * pz1 * (f[0, 1, 1] - f[0, 0, 1])
+    gy = _s(s, 1) * (px0 * pz0 * (f[0, 1, 0] - f[0, 0, 0]) + px0 * pz1 * (f[0, 1, 1] - f[0, 0, 1])
                  + px1 * pz0 * (f[1, 1, 0] - f[1, 0, 0]) + px1 * pz1 * (f[1, 1, 1] - f[1, 0, 1]))
-    gz = s[2] * (px0 * py0 * (f[0, 0, 1] - f[0, 0, 0]) + px0 * py1 * (f[0, 1, 1] - f[0, 1, 0])
+    gz = _s(s, 2) * (px0 * py0 * (f[0, 0, 1] - f[0, 0, 0]) + px0 * py1 * (f[0, 1, 1] - f[0, 1, 0])
                  + px1 * py0 * (f[1, 0, 1] - f[1, 0, 0]) + px1 * py1 * (f[1, 1, 1] - f[1, 1, 0]))
     return np.stack([gx, gy, gz], axis=-1)
 
@@ -181,7 +219,7 @@ def voxel_grad_query_grad_feature(grad_grad_query, grad_output, query, grid_size
     go = np.asarray(grad_output, dtype=np.float64).reshape(i0.shape[0], D)
     gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
     gf = np.zeros(G + (D,), dtype=np.float64) if out is None else out
-    sx, sy, sz = (float(v) for v in s)
+    sx, sy, sz = _s1(s, 0), _s1(s, 1), _s1(s, 2)
     for (cx, cy, cz, ix, iy, iz, wx, wy, wz) in _corners8(i0, i1, p0.astype(np.float64), p1.astype(np.float64)):
         sgx, sgy, sgz = (1.0 if cx else -1.0), (1.0 if cy else -1.0), (1.0 if cz else -1.0)
         coef = gg[:, 0] * sx * (sgx * wy * wz) + gg[:, 1] * sy * (sgy * wx * wz) + gg[:, 2] * sz * (sgz * wx * wy)
@@ -238,8 +276,8 @@ def _triplane_dfdq(query, feature, min_, max_):
                           p0[:, av].astype(np.float64)[:, None], p1[:, av].astype(np.float64)[:, None])
         F = feature[i].astype(np.float64)
         f00, f01, f10, f11 = F[u0, v0], F[u0, v1], F[u1, v0], F[u1, v1]
-        g[:, :, i, au] = float(s[au]) * (b0 * (f10 - f00) + b1 * (f11 - f01))
-        g[:, :, i, av] = float(s[av]) * (a0 * (f01 - f00) + a1 * (f11 - f10))
+        g[:, :, i, au] = _s(s, au) * (b0 * (f10 - f00) + b1 * (f11 - f01))
+        g[:, :, i, av] = _s(s, av) * (a0 * (f01 - f00) + a1 * (f11 - f10))
     return g
 
 
@@ -278,7 +316,7 @@ def triplane_grad_query_grad_feature(grad_grad_query, grad_output, query, G, D, 
     gf = np.zeros((3, G, G, D), dtype=np.float64) if out is None else out
     P0, P1 = p0.astype(np.float64), p1.astype(np.float64)
     for i, (au, av) in enumerate(_PLANE_AXES):
-        ggu, ggv, su, sv = gg[:, au], gg[:, av], float(s[au]), float(s[av])
+        ggu, ggv, su, sv = gg[:, au], gg[:, av], _s1(s, au), _s1(s, av)
         for cu, (u, a) in enumerate(((i0[:, au], P0[:, au]), (i1[:, au], P1[:, au]))):
             for cv, (v, b) in enumerate(((i0[:, av], P0[:, av]), (i1[:, av], P1[:, av]))):
                 coef = ggu * su * ((1.0 if cu else -1.0) * b) + ggv * sv * ((1.0 if cv else -1.0) * a)
@@ -307,7 +345,7 @@ def _triline_dfdq(query, feature, min_, max_):
     g = np.zeros((i0.shape[0], D, 3), dtype=np.float64)   # line i only moves along axis i
     for i in range(3):
         F = feature[i].astype(np.float64)
-        g[:, :, i] = float(s[i]) * (F[i1[:, i]] - F[i0[:, i]])
+        g[:, :, i] = _s(s, i) * (F[i1[:, i]] - F[i0[:, i]])
     return g
 
 
@@ -343,7 +381,7 @@ def triline_grad_query_grad_feature(grad_grad_query, grad_output, query, G, D, m
     gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
     gf = np.zeros((3, G, D), dtype=np.float64) if out is None else out
     for i in range(3):
-        v = go[:, :, i] * (gg[:, i] * float(s[i]))[:, None]
+        v = go[:, :, i] * (gg[:, i] * _s1(s, i))[:, None]
         np.add.at(gf[i], i0[:, i], -v)
         np.add.at(gf[i], i1[:, i], v)
     return gf
@@ -351,6 +389,36 @@ def triline_grad_query_grad_feature(grad_grad_query, grad_output, query, G, D, m
 
 # --------------------------------------------------------------------------------------
 # Lanczos voxel: csrc/grid_feature/lanczos_voxel_feature_cuda.cu, common.cuh:54-97
+# --------------------------------------------------------------------------------------
+# cosine_voxel / cosine_triplane / cosine_triline: csrc/grid_feature/cosine_{voxel,triplane,triline}_feature_cuda.cu
+# (5 exports each).  Same kernels as the linear families with the cosine cell (see `interp`).
+# --------------------------------------------------------------------------------------
+def _cosine(fn):
+    def wrapped(*args, **kw):
+        with interp("cosine"):
+            return fn(*args, **kw)
+    wrapped.__name__ = "cosine_" + fn.__name__
+    wrapped.__doc__ = "cosine-weight variant of " + fn.__name__ + ": " + (fn.__doc__ or "")
+    return wrapped
+
+
+cosine_voxel_query = _cosine(voxel_query)
+cosine_voxel_grad_query = _cosine(voxel_grad_query)
+cosine_voxel_grad_feature = _cosine(voxel_grad_feature)
+cosine_voxel_grad_query_grad_grad_output = _cosine(voxel_grad_query_grad_grad_output)
+cosine_voxel_grad_query_grad_feature = _cosine(voxel_grad_query_grad_feature)
+cosine_triplane_query = _cosine(triplane_query)
+cosine_triplane_grad_query = _cosine(triplane_grad_query)
+cosine_triplane_grad_feature = _cosine(triplane_grad_feature)
+cosine_triplane_grad_query_grad_grad_output = _cosine(triplane_grad_query_grad_grad_output)
+cosine_triplane_grad_query_grad_feature = _cosine(triplane_grad_query_grad_feature)
+cosine_triline_query = _cosine(triline_query)
+cosine_triline_grad_query = _cosine(triline_grad_query)
+cosine_triline_grad_feature = _cosine(triline_grad_feature)
+cosine_triline_grad_query_grad_grad_output = _cosine(triline_grad_query_grad_grad_output)
+cosine_triline_grad_query_grad_feature = _cosine(triline_grad_query_grad_feature)
+
+
 # --------------------------------------------------------------------------------------
 def _sinc32(x):
     """common.cuh:54-59 (argument already narrowed to float)."""
@@ -562,11 +630,11 @@ def _hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None)
         a = lambda v: v[:, None]
         px0, py0, pz0 = a(P0[:, 0]), a(P0[:, 1]), a(P0[:, 2])
         px1, py1, pz1 = a(P1[:, 0]), a(P1[:, 1]), a(P1[:, 2])
-        gx = s[0] * (py0 * pz0 * (f[1, 0, 0] - f[0, 0, 0]) + py0 * pz1 * (f[1, 0, 1] - f[0, 0, 1])
+        gx = _s(s, 0) * (py0 * pz0 * (f[1, 0, 0] - f[0, 0, 0]) + py0 * pz1 * (f[1, 0, 1] - f[0, 0, 1])
                      + py1 * pz0 * (f[1, 1, 0] - f[0, 1, 0]) + py1 * pz1 * (f[1, 1, 1] - f[0, 1, 1]))
-        gy = s[1] * (px0 * pz0 * (f[0, 1, 0] - f[0, 0, 0]) + px0 * pz1 * (f[0, 1, 1] - f[0, 0, 1])
+        gy = _s(s, 1) * (px0 * pz0 * (f[0, 1, 0] - f[0, 0, 0]) + px0 * pz1 * (f[0, 1, 1] - f[0, 0, 1])
                      + px1 * pz0 * (f[1, 1, 0] - f[1, 0, 0]) + px1 * pz1 * (f[1, 1, 1] - f[1, 0, 1]))
-        gz = s[2] * (px0 * py0 * (f[0, 0, 1] - f[0, 0, 0]) + px0 * py1 * (f[0, 1, 1] - f[0, 1, 0])
+        gz = _s(s, 2) * (px0 * py0 * (f[0, 0, 1] - f[0, 0, 0]) + px0 * py1 * (f[0, 1, 1] - f[0, 1, 0])
                      + px1 * py0 * (f[1, 0, 1] - f[1, 0, 0]) + px1 * py1 * (f[1, 1, 1] - f[1, 1, 0]))
         g[:, l, :, 0], g[:, l, :, 1], g[:, l, :, 2] = gx.T, gy.T, gz.T
     return g

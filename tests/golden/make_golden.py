@@ -5,7 +5,7 @@ Nothing is copied: functions are pulled out of the reference files with `ast` at
     (python/intersection/test/test_ray_aabb_intersection.py:24-110, test_ray_sphere_intersection.py:25-76,
     python/sampler/test_sampler.py:23-70), driven with the reference tests' seeds and parametrisations.
   * grid families: the reference's pure-op "composite" statements
-    (python/grid_feature/{voxel,triplane,triline,lanczos_voxel}_feature_composite.py,
+    (python/grid_feature/{voxel,triplane,triline,lanczos_voxel,cosine_voxel,cosine_triplane,cosine_triline}_feature_composite.py,
     total_variation_loss{,_on_triplane,_on_triline}_composite.py) executed through a small torch(float64)-backed
     stand-in for `nnabla.functions` (only the dozen ops those files use); first- and second-order gradients
     come from torch autograd of that same reference code, mirroring what the reference tests do with nnabla
@@ -225,6 +225,25 @@ def golden_grids():
                     out[f"{tag}_grad_feature"] = gf.detach().numpy().astype(np.float64)
             k += 1
     out["n_cases"] = np.int64(k)
+    # cosine families (python/grid_feature/cosine_{voxel,triplane,triline}_feature_composite.py), same parametrisation;
+    # a generator of their own so that the entries above keep their values
+    (cvoxel,) = load_composite("cosine_voxel_feature_composite.py", ["query_on_voxel"])
+    (ctriplane,) = load_composite("cosine_triplane_feature_composite.py", ["query_on_triplane"])
+    (ctriline,) = load_composite("cosine_triline_feature_composite.py", ["query_on_triline"])
+    k = 0
+    for B in (2, 16):
+        for G in (2, 8):
+            D = 4
+            rng = np.random.RandomState(412)
+            query = (rng.rand(B, 3).astype(np.float32) * 1.98 - 0.99).astype(np.float32)
+            for name, fn, shape in (("cosine_voxel", cvoxel, (G, G, G, D)), ("cosine_triplane", ctriplane, (3, G, G, D)),
+                                    ("cosine_triline", ctriline, (3, G, D))):
+                feat = (rng.randn(*shape) * 0.01).astype(np.float32)
+                res = run_query_family(fn, query, feat, mn, mx, rng)
+                out[f"{name}{k}_query"], out[f"{name}{k}_feature"] = query, feat
+                for kk, vv in res.items():
+                    out[f"{name}{k}_{kk}"] = vv
+            k += 1
     np.savez_compressed(os.path.join(OUT, "grids.npz"), **out)
     return out
 

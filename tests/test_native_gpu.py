@@ -46,7 +46,7 @@ VOXEL_CASES = [(2, (2, 2, 2), 4, 1.0), (16, (8, 8, 8), 4, 1.0), (16, (2, 2, 2), 
 
 
 @pytest.mark.parametrize("B,G,D,spread", VOXEL_CASES)
-@pytest.mark.parametrize("family", ["voxel_feature_cuda", "lanczos_voxel_feature_cuda"])
+@pytest.mark.parametrize("family", ["voxel_feature_cuda", "lanczos_voxel_feature_cuda", "cosine_voxel_feature_cuda"])
 def test_voxel_families(B, G, D, spread, family):
     if family.startswith("lanczos") and B > 5000:
         B = 5000
@@ -60,6 +60,9 @@ def test_voxel_families(B, G, D, spread, family):
     lz = family.startswith("lanczos")
     O = {"voxel_feature_cuda": ("voxel_query", "voxel_grad_query", "voxel_grad_feature",
                                 "voxel_grad_query_grad_grad_output", "voxel_grad_query_grad_feature"),
+         "cosine_voxel_feature_cuda": ("cosine_voxel_query", "cosine_voxel_grad_query", "cosine_voxel_grad_feature",
+                                       "cosine_voxel_grad_query_grad_grad_output",
+                                       "cosine_voxel_grad_query_grad_feature"),
          "lanczos_voxel_feature_cuda": ("lanczos_voxel_query", "lanczos_voxel_grad_query", "lanczos_voxel_grad_feature",
                                         "lanczos_voxel_grad_query_grad_grad_output",
                                         "lanczos_voxel_grad_query_grad_feature")}[family]
@@ -111,7 +114,7 @@ def test_voxel_families(B, G, D, spread, family):
     if small:
         close(b1, getattr(R, O[4])(gg_np, go_np, q_np, G, D, MN, MX), 1e-4, "gq_gf vs oracle")
 
-    if not lz:
+    if family == "voxel_feature_cuda":   # the other two families export five functions only
         c1, c2 = torch.zeros(B, 3).cuda(), torch.zeros(B, 3).cuda()
         ours.grad_query_grad_query(N, c1.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), f.data_ptr(), G, D,
                                    MN, MX, False, False)
@@ -159,9 +162,10 @@ TPL_CASES = [(2, 2, 4, 1.0), (16, 8, 4, 1.0), (4097, 9, 3, 1.3), (1000, 33, 2, 1
 
 
 @pytest.mark.parametrize("B,G,D,spread", TPL_CASES)
-@pytest.mark.parametrize("family", ["triplane", "triline"])
+@pytest.mark.parametrize("family", ["triplane", "triline", "cosine_triplane", "cosine_triline"])
 def test_triplane_triline(B, G, D, spread, family):
     ours, ref = compat.load(f"{family}_feature_cuda"), ref_mod(f"{family}_feature_cuda")
+    oname, family = family, family.replace("cosine_", "")      # oracle prefix / layout kind
     q_np, rng = queries(B, spread=spread)
     shape = (3, G, G, D) if family == "triplane" else (3, G, D)
     f_np = (rng.randn(*shape) * 0.01).astype(np.float32)
@@ -174,13 +178,13 @@ def test_triplane_triline(B, G, D, spread, family):
     fwd1(N, o1.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False)
     fwd2(N, o2.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False)
     close(o1, o2, 1e-5, "fwd vs reference kernel")
-    close(o1, getattr(R, f"{family}_query")(q_np, f_np, MN, MX), 1e-5, "fwd vs oracle")
+    close(o1, getattr(R, f"{oname}_query")(q_np, f_np, MN, MX), 1e-5, "fwd vs oracle")
     for accum in (False, True):
         g1, g2 = torch.full((B, 3), 0.5).cuda(), torch.full((B, 3), 0.5).cuda()
         ours.grad_query(N, g1.data_ptr(), go.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False, accum)
         ref.grad_query(N, g2.data_ptr(), go.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False, accum)
         close(g1, g2, 1e-4, f"grad_query accum={accum}")
-    close(g1 - 0.5, getattr(R, f"{family}_grad_query")(go_np, q_np, f_np, MN, MX), 1e-4, "grad_query vs oracle")
+    close(g1 - 0.5, getattr(R, f"{oname}_grad_query")(go_np, q_np, f_np, MN, MX), 1e-4, "grad_query vs oracle")
     # grad_feature: accum=True only against the reference for triline when accum=False would trip its OOB zero-fill (q8)
     for accum in ((True,) if family == "triline" else (False, True)):
         gf1, gf2 = torch.full(shape, 0.25).cuda(), torch.full(shape, 0.25).cuda()
@@ -189,17 +193,17 @@ def test_triplane_triline(B, G, D, spread, family):
         close(gf1, gf2, 1e-4, f"grad_feature accum={accum}")
     gf0 = torch.full(shape, 0.25).cuda()
     ours.grad_feature(N, gf0.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, False)
-    close(gf0, getattr(R, f"{family}_grad_feature")(go_np, q_np, G, D, MN, MX), 1e-4, "grad_feature vs oracle")
+    close(gf0, getattr(R, f"{oname}_grad_feature")(go_np, q_np, G, D, MN, MX), 1e-4, "grad_feature vs oracle")
     a1, a2 = torch.zeros(B, D * 3).cuda(), torch.zeros(B, D * 3).cuda()
     ours.grad_query_grad_grad_output(N, a1.data_ptr(), gg.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False, False)
     ref.grad_query_grad_grad_output(N, a2.data_ptr(), gg.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False, False)
     close(a1, a2, 1e-4, "gq_ggo")
-    close(a1, getattr(R, f"{family}_grad_query_grad_grad_output")(gg_np, q_np, f_np, MN, MX), 1e-4, "gq_ggo vs oracle")
+    close(a1, getattr(R, f"{oname}_grad_query_grad_grad_output")(gg_np, q_np, f_np, MN, MX), 1e-4, "gq_ggo vs oracle")
     b1, b2 = torch.zeros(shape).cuda(), torch.zeros(shape).cuda()
     ours.grad_query_grad_feature(N, b1.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, False)
     ref.grad_query_grad_feature(N, b2.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, False)
     close(b1, b2, 1e-4, "gq_gf")
-    close(b1, getattr(R, f"{family}_grad_query_grad_feature")(gg_np, go_np, q_np, G, D, MN, MX), 1e-4, "gq_gf vs oracle")
+    close(b1, getattr(R, f"{oname}_grad_query_grad_feature")(gg_np, go_np, q_np, G, D, MN, MX), 1e-4, "gq_gf vs oracle")
 
 
 HASH_CASES = [(2, 2, 1, 2), (8, 4, 4, 2), (8, 2, 4, 2), (5000, 16, 16, 2), (3001, 4, 6, 4), (1234, 3, 5, 1)]

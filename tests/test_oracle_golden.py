@@ -61,6 +61,24 @@ FAMILIES = {
         gf=lambda go, q, f: R.triline_grad_feature(go, q, f.shape[1], f.shape[2], MN, MX),
         ggo=lambda gg, q, f: R.triline_grad_query_grad_grad_output(gg, q, f, MN, MX),
         gqgf=lambda gg, go, q, f: R.triline_grad_query_grad_feature(gg, go, q, f.shape[1], f.shape[2], MN, MX)),
+    "cosine_voxel": dict(
+        fwd=lambda q, f: R.cosine_voxel_query(q, f, MN, MX),
+        gq=lambda go, q, f: R.cosine_voxel_grad_query(go, q, f, MN, MX),
+        gf=lambda go, q, f: R.cosine_voxel_grad_feature(go, q, f.shape[:3], f.shape[3], MN, MX),
+        ggo=lambda gg, q, f: R.cosine_voxel_grad_query_grad_grad_output(gg, q, f, MN, MX),
+        gqgf=lambda gg, go, q, f: R.cosine_voxel_grad_query_grad_feature(gg, go, q, f.shape[:3], f.shape[3], MN, MX)),
+    "cosine_triplane": dict(
+        fwd=lambda q, f: R.cosine_triplane_query(q, f, MN, MX),
+        gq=lambda go, q, f: R.cosine_triplane_grad_query(go, q, f, MN, MX),
+        gf=lambda go, q, f: R.cosine_triplane_grad_feature(go, q, f.shape[1], f.shape[3], MN, MX),
+        ggo=lambda gg, q, f: R.cosine_triplane_grad_query_grad_grad_output(gg, q, f, MN, MX),
+        gqgf=lambda gg, go, q, f: R.cosine_triplane_grad_query_grad_feature(gg, go, q, f.shape[1], f.shape[3], MN, MX)),
+    "cosine_triline": dict(
+        fwd=lambda q, f: R.cosine_triline_query(q, f, MN, MX),
+        gq=lambda go, q, f: R.cosine_triline_grad_query(go, q, f, MN, MX),
+        gf=lambda go, q, f: R.cosine_triline_grad_feature(go, q, f.shape[1], f.shape[2], MN, MX),
+        ggo=lambda gg, q, f: R.cosine_triline_grad_query_grad_grad_output(gg, q, f, MN, MX),
+        gqgf=lambda gg, go, q, f: R.cosine_triline_grad_query_grad_feature(gg, go, q, f.shape[1], f.shape[2], MN, MX)),
     "lanczos_voxel": dict(
         fwd=lambda q, f: R.lanczos_voxel_query(q, f, MN, MX),
         gq=lambda go, q, f: R.lanczos_voxel_grad_query(go, q, f, MN, MX),
