@@ -225,6 +225,34 @@ int ndjir_cosine_triline_grad_query_grad_grad_output(long long n_points, float* 
 int ndjir_cosine_triline_grad_query_grad_feature(long long n_points, float* grad_feature, const float* grad_grad_query,
                    const float* grad_output, const float* query, int G, int D, const float* min3,
                    const float* max3, cudaStream_t stream);
+/* lanczos_triplane_feature_cuda / lanczos_triline_feature_cuda (csrc/grid_feature/lanczos_triplane_feature_cuda.cu:795-808,
+ * lanczos_triline_feature_cuda.cu:735-748; 5 exports each): Lanczos-2 windows, 4x4 / 4 clamped taps per plane / line. */
+int ndjir_lanczos_triplane_query_on_triplane(long long n_points, float* output, const float* query, const float* feature, int G, int D,
+                   const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_lanczos_triplane_grad_query(long long n_points, float* grad_query, const float* grad_output, const float* query,
+                   const float* feature, int G, int D, const float* min3, const float* max3, int accum,
+                   cudaStream_t stream);
+int ndjir_lanczos_triplane_grad_feature(long long n_points, float* grad_feature, const float* grad_output, const float* query,
+                   int G, int D, const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_lanczos_triplane_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                   const float* grad_grad_query, const float* query, const float* feature, int G, int D,
+                   const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_lanczos_triplane_grad_query_grad_feature(long long n_points, float* grad_feature, const float* grad_grad_query,
+                   const float* grad_output, const float* query, int G, int D, const float* min3,
+                   const float* max3, cudaStream_t stream);
+int ndjir_lanczos_triline_query_on_triline(long long n_points, float* output, const float* query, const float* feature, int G, int D,
+                   const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_lanczos_triline_grad_query(long long n_points, float* grad_query, const float* grad_output, const float* query,
+                   const float* feature, int G, int D, const float* min3, const float* max3, int accum,
+                   cudaStream_t stream);
+int ndjir_lanczos_triline_grad_feature(long long n_points, float* grad_feature, const float* grad_output, const float* query,
+                   int G, int D, const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_lanczos_triline_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                   const float* grad_grad_query, const float* query, const float* feature, int G, int D,
+                   const float* min3, const float* max3, int accum, cudaStream_t stream);
+int ndjir_lanczos_triline_grad_query_grad_feature(long long n_points, float* grad_feature, const float* grad_grad_query,
+                   const float* grad_output, const float* query, int G, int D, const float* min3,
+                   const float* max3, cudaStream_t stream);
 
 /* ---- total_variation_loss*_cuda (csrc/grid_feature/total_variation_loss_cuda.cu:203-209,
  *      ..._on_triplane_cuda.cu:188-194, ..._on_triline_cuda.cu:180-186); backward always accumulates -------- */

@@ -20,6 +20,8 @@ MODULES = [
     "cosine_voxel_feature_cuda",
     "cosine_triplane_feature_cuda",
     "cosine_triline_feature_cuda",
+    "lanczos_triplane_feature_cuda",
+    "lanczos_triline_feature_cuda",
     "total_variation_loss_cuda",
     "total_variation_loss_on_triplane_cuda",
     "total_variation_loss_on_triline_cuda",

@@ -11,6 +11,7 @@
 // Roofline: HBM gather; triplane G=2048,D=8 fwd = 12+96+3*4*32 = 492 B/pt; triline = 12+96 = 108 B/pt
 // (its 192 KiB table is L2-resident).
 #include "grid_common.cuh"
+#include "chunk_io.cuh"
 #include "../../include/ndjir_b200.h"
 
 namespace ndjir {
@@ -38,45 +39,6 @@ __device__ __forceinline__ Axis2 plane_axes(int i, const Cell& c, const GridFram
     r.su = c.sz; r.sv = c.sx; r.ggu = ggz; r.ggv = ggx; r.au = 2; r.av = 0;
   }
   return r;
-}
-
-// Write / read the 3*V contiguous values [d*3 .. (d+V)*3) of a (B, D*3) row as three Vec<V>.
-template <int V>
-__device__ __forceinline__ void store_chunk(float* row, int d, const float (&o)[3][V], bool accum) {
-  float flat[3 * V];
-#pragma unroll
-  for (int j = 0; j < V; ++j)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) flat[j * 3 + i] = o[i][j];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    Vec<V> t;
-    float* dst = row + d * 3 + k * V;
-    if (accum) {
-      Vec<V> prev = ld_vec<V>(dst);
-#pragma unroll
-      for (int j = 0; j < V; ++j) t.v[j] = prev.v[j] + flat[k * V + j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < V; ++j) t.v[j] = flat[k * V + j];
-    }
-    st_vec<V>(dst, t);
-  }
-}
-
-template <int V>
-__device__ __forceinline__ void load_chunk(const float* row, int d, float (&o)[3][V]) {
-  float flat[3 * V];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    Vec<V> t = ldg_vec<V>(row + d * 3 + k * V);
-#pragma unroll
-    for (int j = 0; j < V; ++j) flat[k * V + j] = t.v[j];
-  }
-#pragma unroll
-  for (int j = 0; j < V; ++j)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) o[i][j] = flat[j * 3 + i];
 }
 
 // PLANE=true: triplane, PLANE=false: triline.

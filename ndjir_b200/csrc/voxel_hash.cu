@@ -72,6 +72,7 @@ __device__ __forceinline__ GridFrame level_frame(const HashSpec& h, int G) {
   float g1 = (float)G - 1.f;
   g.gx1 = g.gy1 = g.gz1 = g1;
   g.sx = __fdiv_rn(g1, h.dx); g.sy = __fdiv_rn(g1, h.dy); g.sz = __fdiv_rn(g1, h.dz);
+  g.interp = INTERP_LINEAR;
   return g;
 }
 

@@ -30,6 +30,8 @@ SCOPED = [
     "grid_feature/cosine_voxel_feature_cuda.cu",
     "grid_feature/cosine_triplane_feature_cuda.cu",
     "grid_feature/cosine_triline_feature_cuda.cu",
+    "grid_feature/lanczos_triplane_feature_cuda.cu",
+    "grid_feature/lanczos_triline_feature_cuda.cu",
     "grid_feature/total_variation_loss_cuda.cu",
     "grid_feature/total_variation_loss_on_triplane_cuda.cu",
     "grid_feature/total_variation_loss_on_triline_cuda.cu",
@@ -39,8 +41,6 @@ SCOPED = [
     "activation/squareplus_cuda.cu",
 ]
 EXTRA = [
-    "grid_feature/lanczos_triplane_feature_cuda.cu",
-    "grid_feature/lanczos_triline_feature_cuda.cu",
     "grid_feature/lanczos_voxel_hash_feature_cuda.cu",
     "grid_feature/total_variation_loss_on_voxel_hash_cuda.cu",
 ]

@@ -556,6 +556,152 @@ def lanczos_voxel_grad_query_grad_feature(grad_grad_query, grad_output, query, g
 
 
 # --------------------------------------------------------------------------------------
+# lanczos triplane / triline: csrc/grid_feature/lanczos_triplane_feature_cuda.cu, lanczos_triline_feature_cuda.cu
+# (4x4 / 4 taps per plane / line with the same clamped tap coordinates and window functions as the voxel family;
+# output (B, D*3), c = d*3 + plane)
+# --------------------------------------------------------------------------------------
+def lanczos_triplane_query(query, feature, min_, max_, w=2):
+    """kernel_query_on_triplane, lanczos_triplane_feature_cuda.cu:38-83."""
+    feature = np.asarray(feature, dtype=f32)
+    G, D = feature.shape[1], feature.shape[3]
+    taps, c, _, _ = _lanczos_taps(query, (G, G, G), min_, max_, w)
+    B, K = taps.shape[0], 2 * w
+    out = np.zeros((B, D, 3), dtype=f32)
+    for l, (au, av) in enumerate(_PLANE_AXES):
+        f = np.zeros((B, D), dtype=f32)
+        for i in range(K):
+            for j in range(K):
+                cij = (c[:, au, i] * c[:, av, j]).astype(f32)
+                f = (f + cij[:, None] * feature[l][taps[:, au, i], taps[:, av, j]]).astype(f32)
+        out[:, :, l] = f
+    return out.reshape(B, D * 3)
+
+
+def _lanczos_triplane_dfdq(query, feature, min_, max_, w=2):
+    """(B, D, 3 planes, 3 axes), lanczos_triplane_feature_cuda.cu:149-162."""
+    feature = np.asarray(feature, dtype=f32)
+    G, D = feature.shape[1], feature.shape[3]
+    taps, c, gc, s = _lanczos_taps(query, (G, G, G), min_, max_, w)
+    B, K = taps.shape[0], 2 * w
+    C, GC = c.astype(np.float64), gc.astype(np.float64)
+    g = np.zeros((B, D, 3, 3), dtype=np.float64)
+    for l, (au, av) in enumerate(_PLANE_AXES):
+        for i in range(K):
+            for j in range(K):
+                f = feature[l][taps[:, au, i], taps[:, av, j]].astype(np.float64)
+                g[:, :, l, au] += (float(s[au]) * GC[:, au, i] * C[:, av, j])[:, None] * f
+                g[:, :, l, av] += (float(s[av]) * C[:, au, i] * GC[:, av, j])[:, None] * f
+    return g
+
+
+def lanczos_triplane_grad_query(grad_output, query, feature, min_, max_, w=2):
+    """kernel_grad_query, lanczos_triplane_feature_cuda.cu:117-175."""
+    g = _lanczos_triplane_dfdq(query, feature, min_, max_, w)
+    go = np.asarray(grad_output, dtype=np.float64).reshape(g.shape[0], g.shape[1], 3)
+    return (go[..., None] * g).sum(axis=(1, 2))
+
+
+def lanczos_triplane_grad_feature(grad_output, query, G, D, min_, max_, w=2, out=None):
+    """kernel_grad_feature, lanczos_triplane_feature_cuda.cu:208-262."""
+    taps, c, _, _ = _lanczos_taps(query, (G, G, G), min_, max_, w)
+    go = np.asarray(grad_output, dtype=np.float64).reshape(taps.shape[0], D, 3)
+    gf = np.zeros((3, G, G, D), dtype=np.float64) if out is None else out
+    C, K = c.astype(np.float64), 2 * w
+    for l, (au, av) in enumerate(_PLANE_AXES):
+        for i in range(K):
+            for j in range(K):
+                np.add.at(gf[l], (taps[:, au, i], taps[:, av, j]), go[:, :, l] * (C[:, au, i] * C[:, av, j])[:, None])
+    return gf
+
+
+def lanczos_triplane_grad_query_grad_grad_output(grad_grad_query, query, feature, min_, max_, w=2):
+    """kernel_grad_query_grad_grad_output, lanczos_triplane_feature_cuda.cu:304-365 -> (B, D*3)."""
+    g = _lanczos_triplane_dfdq(query, feature, min_, max_, w)
+    gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
+    return (g * gg[:, None, None, :]).sum(axis=-1).reshape(g.shape[0], -1)
+
+
+def lanczos_triplane_grad_query_grad_feature(grad_grad_query, grad_output, query, G, D, min_, max_, w=2, out=None):
+    """kernel_grad_query_grad_feature, lanczos_triplane_feature_cuda.cu:503-560."""
+    taps, c, gc, s = _lanczos_taps(query, (G, G, G), min_, max_, w)
+    go = np.asarray(grad_output, dtype=np.float64).reshape(taps.shape[0], D, 3)
+    gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
+    gf = np.zeros((3, G, G, D), dtype=np.float64) if out is None else out
+    C, GC, K = c.astype(np.float64), gc.astype(np.float64), 2 * w
+    for l, (au, av) in enumerate(_PLANE_AXES):
+        for i in range(K):
+            for j in range(K):
+                coef = (gg[:, au] * float(s[au]) * GC[:, au, i] * C[:, av, j]
+                        + gg[:, av] * float(s[av]) * C[:, au, i] * GC[:, av, j])
+                np.add.at(gf[l], (taps[:, au, i], taps[:, av, j]), go[:, :, l] * coef[:, None])
+    return gf
+
+
+def lanczos_triline_query(query, feature, min_, max_, w=2):
+    """kernel_query_on_triline, lanczos_triline_feature_cuda.cu:37-77."""
+    feature = np.asarray(feature, dtype=f32)
+    G, D = feature.shape[1], feature.shape[2]
+    taps, c, _, _ = _lanczos_taps(query, (G, G, G), min_, max_, w)
+    B, K = taps.shape[0], 2 * w
+    out = np.zeros((B, D, 3), dtype=f32)
+    for l in range(3):
+        f = np.zeros((B, D), dtype=f32)
+        for i in range(K):
+            f = (f + c[:, l, i][:, None] * feature[l][taps[:, l, i]]).astype(f32)
+        out[:, :, l] = f
+    return out.reshape(B, D * 3)
+
+
+def _lanczos_triline_dfdq(query, feature, min_, max_, w=2):
+    feature = np.asarray(feature, dtype=f32)
+    G, D = feature.shape[1], feature.shape[2]
+    taps, c, gc, s = _lanczos_taps(query, (G, G, G), min_, max_, w)
+    g = np.zeros((taps.shape[0], D, 3), dtype=np.float64)      # line l only moves along axis l
+    for l in range(3):
+        for i in range(2 * w):
+            g[:, :, l] += (float(s[l]) * gc[:, l, i].astype(np.float64))[:, None] * feature[l][taps[:, l, i]]
+    return g
+
+
+def lanczos_triline_grad_query(grad_output, query, feature, min_, max_, w=2):
+    """kernel_grad_query, lanczos_triline_feature_cuda.cu:107-150."""
+    g = _lanczos_triline_dfdq(query, feature, min_, max_, w)
+    go = np.asarray(grad_output, dtype=np.float64).reshape(g.shape)
+    return (go * g).sum(axis=1)
+
+
+def lanczos_triline_grad_feature(grad_output, query, G, D, min_, max_, w=2, out=None):
+    """kernel_grad_feature, lanczos_triline_feature_cuda.cu:182-228."""
+    taps, c, _, _ = _lanczos_taps(query, (G, G, G), min_, max_, w)
+    go = np.asarray(grad_output, dtype=np.float64).reshape(taps.shape[0], D, 3)
+    gf = np.zeros((3, G, D), dtype=np.float64) if out is None else out
+    for l in range(3):
+        for i in range(2 * w):
+            np.add.at(gf[l], taps[:, l, i], go[:, :, l] * c[:, l, i].astype(np.float64)[:, None])
+    return gf
+
+
+def lanczos_triline_grad_query_grad_grad_output(grad_grad_query, query, feature, min_, max_, w=2):
+    """kernel_grad_query_grad_grad_output, lanczos_triline_feature_cuda.cu:267-317."""
+    g = _lanczos_triline_dfdq(query, feature, min_, max_, w)
+    gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
+    return (g * gg[:, None, :]).reshape(g.shape[0], -1)
+
+
+def lanczos_triline_grad_query_grad_feature(grad_grad_query, grad_output, query, G, D, min_, max_, w=2, out=None):
+    """kernel_grad_query_grad_feature, lanczos_triline_feature_cuda.cu:455-505."""
+    taps, c, gc, s = _lanczos_taps(query, (G, G, G), min_, max_, w)
+    go = np.asarray(grad_output, dtype=np.float64).reshape(taps.shape[0], D, 3)
+    gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
+    gf = np.zeros((3, G, D), dtype=np.float64) if out is None else out
+    for l in range(3):
+        for i in range(2 * w):
+            coef = gg[:, l] * float(s[l]) * gc[:, l, i].astype(np.float64)
+            np.add.at(gf[l], taps[:, l, i], go[:, :, l] * coef[:, None])
+    return gf
+
+
+# --------------------------------------------------------------------------------------
 # voxel hash: csrc/grid_feature/voxel_hash_feature_cuda.cu, common_voxel_hash.cuh:24-55
 # --------------------------------------------------------------------------------------
 def hash_force_align(size, mod=8):

@@ -230,6 +230,8 @@ def golden_grids():
     (cvoxel,) = load_composite("cosine_voxel_feature_composite.py", ["query_on_voxel"])
     (ctriplane,) = load_composite("cosine_triplane_feature_composite.py", ["query_on_triplane"])
     (ctriline,) = load_composite("cosine_triline_feature_composite.py", ["query_on_triline"])
+    (ltriplane,) = load_composite("lanczos_triplane_feature_composite.py", ["query_on_triplane"])
+    (ltriline,) = load_composite("lanczos_triline_feature_composite.py", ["query_on_triline"])
     k = 0
     for B in (2, 16):
         for G in (2, 8):
@@ -237,7 +239,8 @@ def golden_grids():
             rng = np.random.RandomState(412)
             query = (rng.rand(B, 3).astype(np.float32) * 1.98 - 0.99).astype(np.float32)
             for name, fn, shape in (("cosine_voxel", cvoxel, (G, G, G, D)), ("cosine_triplane", ctriplane, (3, G, G, D)),
-                                    ("cosine_triline", ctriline, (3, G, D))):
+                                    ("cosine_triline", ctriline, (3, G, D)), ("lanczos_triplane", ltriplane, (3, G, G, D)),
+                                    ("lanczos_triline", ltriline, (3, G, D))):
                 feat = (rng.randn(*shape) * 0.01).astype(np.float32)
                 res = run_query_family(fn, query, feat, mn, mx, rng)
                 out[f"{name}{k}_query"], out[f"{name}{k}_feature"] = query, feat

@@ -162,10 +162,14 @@ TPL_CASES = [(2, 2, 4, 1.0), (16, 8, 4, 1.0), (4097, 9, 3, 1.3), (1000, 33, 2, 1
 
 
 @pytest.mark.parametrize("B,G,D,spread", TPL_CASES)
-@pytest.mark.parametrize("family", ["triplane", "triline", "cosine_triplane", "cosine_triline"])
+@pytest.mark.parametrize("family", ["triplane", "triline", "cosine_triplane", "cosine_triline", "lanczos_triplane",
+                                    "lanczos_triline"])
 def test_triplane_triline(B, G, D, spread, family):
+    if family.startswith("lanczos") and B > 5000:
+        B = 5000          # the numpy oracle walks 3 x 16 taps
     ours, ref = compat.load(f"{family}_feature_cuda"), ref_mod(f"{family}_feature_cuda")
-    oname, family = family, family.replace("cosine_", "")      # oracle prefix / layout kind
+    oname, family = family, family.replace("cosine_", "").replace("lanczos_", "")      # oracle prefix / layout kind
+    ftol = 2e-5 if oname.startswith("lanczos") else 1e-5
     q_np, rng = queries(B, spread=spread)
     shape = (3, G, G, D) if family == "triplane" else (3, G, D)
     f_np = (rng.randn(*shape) * 0.01).astype(np.float32)
@@ -177,8 +181,8 @@ def test_triplane_triline(B, G, D, spread, family):
     o1, o2 = torch.full((B, D * 3), 7.0).cuda(), torch.full((B, D * 3), 7.0).cuda()
     fwd1(N, o1.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False)
     fwd2(N, o2.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False)
-    close(o1, o2, 1e-5, "fwd vs reference kernel")
-    close(o1, getattr(R, f"{oname}_query")(q_np, f_np, MN, MX), 1e-5, "fwd vs oracle")
+    close(o1, o2, ftol, "fwd vs reference kernel")
+    close(o1, getattr(R, f"{oname}_query")(q_np, f_np, MN, MX), ftol, "fwd vs oracle")
     for accum in (False, True):
         g1, g2 = torch.full((B, 3), 0.5).cuda(), torch.full((B, 3), 0.5).cuda()
         ours.grad_query(N, g1.data_ptr(), go.data_ptr(), q.data_ptr(), f.data_ptr(), G, D, MN, MX, False, accum)
@@ -186,7 +190,7 @@ def test_triplane_triline(B, G, D, spread, family):
         close(g1, g2, 1e-4, f"grad_query accum={accum}")
     close(g1 - 0.5, getattr(R, f"{oname}_grad_query")(go_np, q_np, f_np, MN, MX), 1e-4, "grad_query vs oracle")
     # grad_feature: accum=True only against the reference for triline when accum=False would trip its OOB zero-fill (q8)
-    for accum in ((True,) if family == "triline" else (False, True)):
+    for accum in ((True,) if (family == "triline" and not oname.startswith("lanczos")) else (False, True)):
         gf1, gf2 = torch.full(shape, 0.25).cuda(), torch.full(shape, 0.25).cuda()
         ours.grad_feature(N, gf1.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, accum)
         ref.grad_feature(N, gf2.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, accum)

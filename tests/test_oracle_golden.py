@@ -79,6 +79,18 @@ FAMILIES = {
         gf=lambda go, q, f: R.cosine_triline_grad_feature(go, q, f.shape[1], f.shape[2], MN, MX),
         ggo=lambda gg, q, f: R.cosine_triline_grad_query_grad_grad_output(gg, q, f, MN, MX),
         gqgf=lambda gg, go, q, f: R.cosine_triline_grad_query_grad_feature(gg, go, q, f.shape[1], f.shape[2], MN, MX)),
+    "lanczos_triplane": dict(
+        fwd=lambda q, f: R.lanczos_triplane_query(q, f, MN, MX),
+        gq=lambda go, q, f: R.lanczos_triplane_grad_query(go, q, f, MN, MX),
+        gf=lambda go, q, f: R.lanczos_triplane_grad_feature(go, q, f.shape[1], f.shape[3], MN, MX),
+        ggo=lambda gg, q, f: R.lanczos_triplane_grad_query_grad_grad_output(gg, q, f, MN, MX),
+        gqgf=lambda gg, go, q, f: R.lanczos_triplane_grad_query_grad_feature(gg, go, q, f.shape[1], f.shape[3], MN, MX)),
+    "lanczos_triline": dict(
+        fwd=lambda q, f: R.lanczos_triline_query(q, f, MN, MX),
+        gq=lambda go, q, f: R.lanczos_triline_grad_query(go, q, f, MN, MX),
+        gf=lambda go, q, f: R.lanczos_triline_grad_feature(go, q, f.shape[1], f.shape[2], MN, MX),
+        ggo=lambda gg, q, f: R.lanczos_triline_grad_query_grad_grad_output(gg, q, f, MN, MX),
+        gqgf=lambda gg, go, q, f: R.lanczos_triline_grad_query_grad_feature(gg, go, q, f.shape[1], f.shape[2], MN, MX)),
     "lanczos_voxel": dict(
         fwd=lambda q, f: R.lanczos_voxel_query(q, f, MN, MX),
         gq=lambda go, q, f: R.lanczos_voxel_grad_query(go, q, f, MN, MX),
@@ -92,7 +104,7 @@ FAMILIES = {
 def test_grid_family_golden(golden, family):
     g = golden["grids"]
     fam = FAMILIES[family]
-    lz = family == "lanczos_voxel"
+    lz = family.startswith("lanczos")
     a1 = dict(atol=1e-5, rtol=1e-5) if lz else dict(atol=1e-6)
     a2 = dict(atol=5e-3, rtol=1e-1) if lz else dict(atol=1e-3)
     for k in range(int(g["n_cases"])):
