@@ -169,6 +169,34 @@ int ndjir_voxel_hash_grad_query_grad_feature(long long n_points, float* grad_fea
                                              int D, const float* min3, const float* max3, int layout,
                                              cudaStream_t stream);
 
+/* ---- lanczos_voxel_hash_feature_cuda (csrc/grid_feature/lanczos_voxel_hash_feature_cuda.cu:959-976): the same level
+ * table, offsets and layouts with Lanczos-2 windows over 4x4x4 clamped, hashed taps per level.  hash_index (:54-66)
+ * hashes ONE integer cell (stored as 3 floats) per row into `output` (n_points floats). */
+int ndjir_lanczos_voxel_hash_hash_index(long long n_points, float* output, const float* query, int T,
+                                        cudaStream_t stream);
+int ndjir_lanczos_voxel_hash_voxel_hash_feature(long long n_points, float* output, const float* query,
+                                        const float* feature, int G0, float growth_factor, int T0, int L, int D,
+                                        const float* min3, const float* max3, int layout, int accum,
+                                        cudaStream_t stream);
+int ndjir_lanczos_voxel_hash_grad_query(long long n_points, float* grad_query, const float* grad_output,
+                                const float* query, const float* feature, int G0, float growth_factor, int T0,
+                                int L, int D, const float* min3, const float* max3, int layout, int accum,
+                                cudaStream_t stream);
+int ndjir_lanczos_voxel_hash_grad_feature(long long n_points, float* grad_feature, const float* grad_output,
+                                  const float* query, int G0, float growth_factor, int T0, int L, int D,
+                                  const float* min3, const float* max3, int layout, int accum,
+                                  cudaStream_t stream);
+int ndjir_lanczos_voxel_hash_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                                                 const float* grad_grad_query, const float* query,
+                                                 const float* feature, int G0, float growth_factor, int T0,
+                                                 int L, int D, const float* min3, const float* max3, int layout,
+                                                 int accum, cudaStream_t stream);
+int ndjir_lanczos_voxel_hash_grad_query_grad_feature(long long n_points, float* grad_feature,
+                                             const float* grad_grad_query, const float* grad_output,
+                                             const float* query, int G0, float growth_factor, int T0, int L,
+                                             int D, const float* min3, const float* max3, int layout,
+                                             cudaStream_t stream);
+
 /* ---- triplane_feature_cuda / triline_feature_cuda (csrc/grid_feature/triplane_feature_cuda.cu:793-805,
  *      triline_feature_cuda.cu:756-768).  feature (3,G,G,D) / (3,G,D); values (B, D*3), c = d*3 + plane. */
 int ndjir_triplane_query_on_triplane(long long n_points, float* output, const float* query, const float* feature, int G, int D,
@@ -274,6 +302,15 @@ int ndjir_tv_loss_on_triline(long long n_points, float* output, const float* que
 int ndjir_tv_loss_on_triline_backward(long long n_points, float* grad_feature, const float* grad_output,
                                       const float* query, const float* feature, int G, int D, const float* min3,
                                       const float* max3, int sym_backward, cudaStream_t stream);
+/* total_variation_loss_on_voxel_hash_cuda (csrc/grid_feature/total_variation_loss_on_voxel_hash_cuda.cu:229-234): values in
+ * the hash family's layouts (0 = (D,L,B), 1 = (B, D*L)); the backward reaches the three upper neighbours only. */
+int ndjir_tv_loss_on_voxel_hash(long long n_points, float* output, const float* query, const float* feature, int G0,
+                                float growth_factor, int T0, int L, int D, const float* min3, const float* max3,
+                                int layout, cudaStream_t stream);
+int ndjir_tv_loss_on_voxel_hash_backward(long long n_points, float* grad_feature, const float* grad_output,
+                                         const float* query, const float* feature, int G0, float growth_factor,
+                                         int T0, int L, int D, const float* min3, const float* max3, int layout,
+                                         cudaStream_t stream);
 
 /* ---- ray_aabb_intersection_cuda / ray_sphere_intersection_cuda (csrc/intersection/*.cu:145-169, :81-104);
  *      camloc (B,3), raydir (B,R,3) -> t_near, t_far, n_hits (B,R,1); n_rays = B*R -------------------------- */

@@ -22,9 +22,11 @@ MODULES = [
     "cosine_triline_feature_cuda",
     "lanczos_triplane_feature_cuda",
     "lanczos_triline_feature_cuda",
+    "lanczos_voxel_hash_feature_cuda",
     "total_variation_loss_cuda",
     "total_variation_loss_on_triplane_cuda",
     "total_variation_loss_on_triline_cuda",
+    "total_variation_loss_on_voxel_hash_cuda",
     "ray_aabb_intersection_cuda",
     "ray_sphere_intersection_cuda",
     "inverse_transform_cuda",

@@ -13,6 +13,7 @@
 // Roofline: bench table (3.8 MB) is L2-resident -> L2-gather-bound; algorithmic HBM bytes 12 + 4*D*L per
 // point (+ table once), L2 gather bytes 8*4*D*L per point.
 #include "grid_common.cuh"
+#include "lanczos_common.cuh"
 #include "../../include/ndjir_b200.h"
 
 namespace ndjir {
@@ -211,6 +212,174 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
   }
 }
 
+// ---- Lanczos-2 variant (csrc/grid_feature/lanczos_voxel_hash_feature_cuda.cu, 6 exports :959-976): per level the
+// 4x4x4 clamped taps of lanczos_voxel, each hashed into the level's table; same level table, offsets and output
+// layouts as the trilinear family.  The window weights are evaluated once per (level, point), the 64 hashed indices
+// once per tap (the reference recomputes both per channel). ---------------------------------------------------------
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+lz_hash_index_kernel(long long B, float* __restrict__ out, const float* __restrict__ query, unsigned T) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+    const float* q = query + b * 3;   // integer cell coordinates stored as floats (:54-66)
+    out[b] = (float)hash3((unsigned)__ldg(q), (unsigned)__ldg(q + 1), (unsigned)__ldg(q + 2), T);
+  }
+}
+
+template <int MODE, int V, bool ACCUM>
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+lz_gather_kernel(long long B, float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ gg,
+                 const float* __restrict__ query, const float* __restrict__ feat, HashSpec h, int layout) {
+  using namespace ndjir::lanczos;
+  __shared__ LevelTable tab;
+  build_table(tab, h);
+  const long long N = B * h.L;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += stride) {
+    int l = (int)(n / B);
+    long long b = n - (long long)l * B;
+    GridFrame g = level_frame(h, tab.G[l]);
+    unsigned T = (unsigned)tab.T[l];
+    const float* fl = feat + tab.off[l];
+    Taps t = make_taps<MODE != FWD>(g, query + b * 3);
+    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
+    if (MODE == GGO) { ggx = __ldg(gg + b * 3); ggy = __ldg(gg + b * 3 + 1); ggz = __ldg(gg + b * 3 + 2); }
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int d = 0; d < h.D; d += V) {
+      float f[V], gx[V], gy[V], gz[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) { f[j] = 0.f; gx[j] = 0.f; gy[j] = 0.f; gz[j] = 0.f; }
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+          Vec<V> v[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) v[k] = ldg_vec<V>(fl + hash3(t.ix[i], t.iy[jj], t.iz[k], T) * h.D + d);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              if (MODE == FWD) {
+                f[j] += t.cx[i] * t.cy[jj] * t.cz[k] * v[k].v[j];                 // :184-186
+              } else {
+                gx[j] += g.sx * t.gx[i] * t.cy[jj] * t.cz[k] * v[k].v[j];          // :283-285
+                gy[j] += g.sy * t.cx[i] * t.gy[jj] * t.cz[k] * v[k].v[j];
+                gz[j] += g.sz * t.cx[i] * t.cy[jj] * t.gz[k] * v[k].v[j];
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        long long oi = out_index(layout, d + j, l, b, h.L, B, h.D);
+        if (MODE == FWD) {
+          out[oi] = ACCUM ? out[oi] + f[j] : f[j];
+        } else if (MODE == GRAD_QUERY) {
+          float go = __ldg(a + oi);
+          ax += go * gx[j]; ay += go * gy[j]; az += go * gz[j];
+        } else {
+          float v = ggx * gx[j] + ggy * gy[j] + ggz * gz[j];
+          out[oi] = ACCUM ? out[oi] + v : v;
+        }
+      }
+    }
+    if (MODE == GRAD_QUERY) {
+      atomicAdd(out + b * 3, ax); atomicAdd(out + b * 3 + 1, ay); atomicAdd(out + b * 3 + 2, az);
+    }
+  }
+}
+
+template <bool SECOND, int V>
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+lz_scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go_, const float* __restrict__ gg,
+                  const float* __restrict__ query, HashSpec h, int layout) {
+  using namespace ndjir::lanczos;
+  __shared__ LevelTable tab;
+  build_table(tab, h);
+  const long long N = B * h.L;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += stride) {
+    int l = (int)(n / B);
+    long long b = n - (long long)l * B;
+    GridFrame g = level_frame(h, tab.G[l]);
+    unsigned T = (unsigned)tab.T[l];
+    float* gl = gf + tab.off[l];
+    Taps t = make_taps<SECOND>(g, query + b * 3);
+    float ggx = 0.f, ggy = 0.f, ggz = 0.f;
+    if (SECOND) {
+      ggx = __ldg(gg + b * 3) * g.sx; ggy = __ldg(gg + b * 3 + 1) * g.sy; ggz = __ldg(gg + b * 3 + 2) * g.sz;
+    }
+    for (int d = 0; d < h.D; d += V) {
+      Vec<V> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] = __ldg(go_ + out_index(layout, d + j, l, b, h.L, B, h.D));
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            float coef = SECOND ? (ggx * (t.gx[i] * t.cy[jj] * t.cz[k]) + ggy * (t.cx[i] * t.gy[jj] * t.cz[k]) +
+                                   ggz * (t.cx[i] * t.cy[jj] * t.gz[k]))                       // :690-697
+                                : t.cx[i] * t.cy[jj] * t.cz[k];                                  // :362-369
+            Vec<V> val;
+#pragma unroll
+            for (int j = 0; j < V; ++j) val.v[j] = o.v[j] * coef;
+            red_vec<V>(gl + hash3(t.ix[i], t.iy[jj], t.iz[k], T) * h.D + d, val);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- total variation on the hashed levels (csrc/grid_feature/total_variation_loss_on_voxel_hash_cuda.cu:50-106 forward,
+// :132-196 backward): sqrt of the squared forward differences at the lower corner; the backward sends
+// ograd * delta * rsqrt(sum + 1e-12) (double intermediate, like the reference's literal) to the three upper
+// neighbours only - the lower corner itself gets no gradient in this family (no sym_backward argument). --------------
+template <bool BWD, int V>
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+tv_hash_kernel(long long B, float* __restrict__ out, const float* __restrict__ go_, const float* __restrict__ query,
+               const float* __restrict__ feat, HashSpec h, int layout) {
+  __shared__ LevelTable tab;
+  build_table(tab, h);
+  const long long N = B * h.L;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += stride) {
+    int l = (int)(n / B);
+    long long b = n - (long long)l * B;
+    GridFrame g = level_frame(h, tab.G[l]);
+    unsigned T = (unsigned)tab.T[l];
+    const float* fl = feat + tab.off[l];
+    const float* q = query + b * 3;
+    Cell c = make_cell(g, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+    unsigned i000 = hash3(c.x0, c.y0, c.z0, T) * h.D, i001 = hash3(c.x0, c.y0, c.z1, T) * h.D;
+    unsigned i010 = hash3(c.x0, c.y1, c.z0, T) * h.D, i100 = hash3(c.x1, c.y0, c.z0, T) * h.D;
+    for (int d = 0; d < h.D; d += V) {
+      Vec<V> f000 = ldg_vec<V>(fl + i000 + d), f001 = ldg_vec<V>(fl + i001 + d);
+      Vec<V> f010 = ldg_vec<V>(fl + i010 + d), f100 = ldg_vec<V>(fl + i100 + d);
+      Vec<V> gx, gy, gz;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float dx = f100.v[j] - f000.v[j], dy = f010.v[j] - f000.v[j], dz = f001.v[j] - f000.v[j];
+        float s2 = dx * dx + dy * dy + dz * dz;
+        long long oi = out_index(layout, d + j, l, b, h.L, B, h.D);
+        if (!BWD) {
+          out[oi] = sqrtf(s2);
+        } else {
+          double common = (double)__ldg(go_ + oi) * rsqrt((double)s2 + 1e-12);
+          gx.v[j] = (float)(common * dx); gy.v[j] = (float)(common * dy); gz.v[j] = (float)(common * dz);
+        }
+      }
+      if (BWD) {
+        float* gl = out + tab.off[l];
+        red_vec<V>(gl + i100 + d, gx); red_vec<V>(gl + i010 + d, gy); red_vec<V>(gl + i001 + d, gz);
+      }
+    }
+  }
+}
+
 static int make_spec(HashSpec& h, int G0, float gf, int T0, int L, int D, const float* mn, const float* mx) {
   if (G0 <= 0 || T0 <= 0 || L <= 0 || L > NDJIR_HASH_MAX_LEVELS || D <= 0 || !mn || !mx) return NDJIR_ERR_ARG;
   h.G0 = G0; h.gf = gf; h.T0 = T0; h.L = L; h.D = D;
@@ -376,6 +545,149 @@ int ndjir_voxel_hash_grad_query_grad_feature(long long n_points, float* grad_fea
     return NDJIR_ERR_ARG;
   const float* gg = grad_grad_query;
   NDJIR_HASH_SCATTER(true);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+// ---- lanczos_voxel_hash_feature_cuda (csrc/grid_feature/lanczos_voxel_hash_feature_cuda.cu:959-976) -------------------
+// hash_index here hashes ONE integer cell per row (:54-66), not the 8 corners of a query.
+int ndjir_lanczos_voxel_hash_hash_index(long long n_points, float* output, const float* query, int T,
+                                        cudaStream_t st) {
+  if (n_points == 0) return NDJIR_OK;
+  if (n_points < 0 || T <= 0 || !output || !query) return NDJIR_ERR_ARG;
+  lz_hash_index_kernel<<<grid_for(n_points), NDJIR_BLOCK, 0, st>>>(n_points, output, query, (unsigned)T);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+#define NDJIR_LZ_HASH_GATHER(MODE, accum_)                                                                       \
+  do {                                                                                                           \
+    int V = hash_vec(h, feature);                                                                                \
+    int grid = grid_for(n_points * L);                                                                           \
+    if (V == 4) {                                                                                                \
+      if (accum_) lz_gather_kernel<MODE, 4, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout); \
+      else lz_gather_kernel<MODE, 4, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout);       \
+    } else if (V == 2) {                                                                                         \
+      if (accum_) lz_gather_kernel<MODE, 2, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout); \
+      else lz_gather_kernel<MODE, 2, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout);       \
+    } else {                                                                                                     \
+      if (accum_) lz_gather_kernel<MODE, 1, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout); \
+      else lz_gather_kernel<MODE, 1, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout);       \
+    }                                                                                                            \
+  } while (0)
+
+int ndjir_lanczos_voxel_hash_voxel_hash_feature(long long n_points, float* output, const float* query,
+                                                const float* feature, int G0, float growth_factor, int T0, int L,
+                                                int D, const float* min3, const float* max3, int layout, int accum,
+                                                cudaStream_t st) {
+  if (n_points == 0) return NDJIR_OK;
+  HashSpec h;
+  if (make_spec(h, G0, growth_factor, T0, L, D, min3, max3) || !output || !query || !feature || n_points < 0)
+    return NDJIR_ERR_ARG;
+  float* out = output; const float* a = nullptr; const float* gg = nullptr;
+  NDJIR_LZ_HASH_GATHER(FWD, accum);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_lanczos_voxel_hash_grad_query(long long n_points, float* grad_query, const float* grad_output,
+                                        const float* query, const float* feature, int G0, float growth_factor,
+                                        int T0, int L, int D, const float* min3, const float* max3, int layout,
+                                        int accum, cudaStream_t st) {
+  if (n_points == 0) return NDJIR_OK;
+  HashSpec h;
+  if (make_spec(h, G0, growth_factor, T0, L, D, min3, max3) || !grad_query || !grad_output || !query || !feature ||
+      n_points < 0)
+    return NDJIR_ERR_ARG;
+  if (!accum) fill_zero(grad_query, n_points * 3, st);
+  float* out = grad_query; const float* a = grad_output; const float* gg = nullptr;
+  NDJIR_LZ_HASH_GATHER(GRAD_QUERY, true);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_lanczos_voxel_hash_grad_query_grad_grad_output(long long n_points, float* grad_grad_output,
+                                                         const float* grad_grad_query, const float* query,
+                                                         const float* feature, int G0, float growth_factor, int T0,
+                                                         int L, int D, const float* min3, const float* max3,
+                                                         int layout, int accum, cudaStream_t st) {
+  if (n_points == 0) return NDJIR_OK;
+  HashSpec h;
+  if (make_spec(h, G0, growth_factor, T0, L, D, min3, max3) || !grad_grad_output || !grad_grad_query || !query ||
+      !feature || n_points < 0)
+    return NDJIR_ERR_ARG;
+  float* out = grad_grad_output; const float* a = nullptr; const float* gg = grad_grad_query;
+  NDJIR_LZ_HASH_GATHER(GGO, accum);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+#define NDJIR_LZ_HASH_SCATTER(SECOND)                                                                          \
+  do {                                                                                                         \
+    int V = hash_vec(h, grad_feature);                                                                         \
+    int grid = grid_for(n_points * L);                                                                         \
+    if (V == 4) lz_scatter_kernel<SECOND, 4><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout);      \
+    else if (V == 2) lz_scatter_kernel<SECOND, 2><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout); \
+    else lz_scatter_kernel<SECOND, 1><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout);             \
+  } while (0)
+
+int ndjir_lanczos_voxel_hash_grad_feature(long long n_points, float* grad_feature, const float* grad_output,
+                                          const float* query, int G0, float growth_factor, int T0, int L, int D,
+                                          const float* min3, const float* max3, int layout, int accum,
+                                          cudaStream_t st) {
+  HashSpec h;
+  if (make_spec(h, G0, growth_factor, T0, L, D, min3, max3) || !grad_feature || n_points < 0) return NDJIR_ERR_ARG;
+  if (!accum) fill_zero(grad_feature, ndjir_voxel_hash_num_params(G0, growth_factor, T0, L, D), st);
+  if (n_points == 0) NDJIR_RETURN_LAST_ERROR();
+  if (!grad_output || !query) return NDJIR_ERR_ARG;
+  const float* gg = nullptr;
+  NDJIR_LZ_HASH_SCATTER(false);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+// Always accumulates (lanczos_voxel_hash_feature_cuda.cu:708-735 has no zero-fill).
+int ndjir_lanczos_voxel_hash_grad_query_grad_feature(long long n_points, float* grad_feature,
+                                                     const float* grad_grad_query, const float* grad_output,
+                                                     const float* query, int G0, float growth_factor, int T0, int L,
+                                                     int D, const float* min3, const float* max3, int layout,
+                                                     cudaStream_t st) {
+  if (n_points == 0) return NDJIR_OK;
+  HashSpec h;
+  if (make_spec(h, G0, growth_factor, T0, L, D, min3, max3) || !grad_feature || !grad_grad_query || !grad_output ||
+      !query || n_points < 0)
+    return NDJIR_ERR_ARG;
+  const float* gg = grad_grad_query;
+  NDJIR_LZ_HASH_SCATTER(true);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+// ---- total_variation_loss_on_voxel_hash_cuda (csrc/grid_feature/total_variation_loss_on_voxel_hash_cuda.cu:229-234) ----
+int ndjir_tv_loss_on_voxel_hash(long long n_points, float* output, const float* query, const float* feature, int G0,
+                                float growth_factor, int T0, int L, int D, const float* min3, const float* max3,
+                                int layout, cudaStream_t st) {
+  if (n_points == 0) return NDJIR_OK;
+  HashSpec h;
+  if (make_spec(h, G0, growth_factor, T0, L, D, min3, max3) || !output || !query || !feature || n_points < 0)
+    return NDJIR_ERR_ARG;
+  int V = hash_vec(h, feature);
+  int grid = grid_for(n_points * L);
+  if (V == 4) tv_hash_kernel<false, 4><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, output, nullptr, query, feature, h, layout);
+  else if (V == 2) tv_hash_kernel<false, 2><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, output, nullptr, query, feature, h, layout);
+  else tv_hash_kernel<false, 1><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, output, nullptr, query, feature, h, layout);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+// Always accumulates (:198-216 has no zero-fill).
+int ndjir_tv_loss_on_voxel_hash_backward(long long n_points, float* grad_feature, const float* grad_output,
+                                         const float* query, const float* feature, int G0, float growth_factor,
+                                         int T0, int L, int D, const float* min3, const float* max3, int layout,
+                                         cudaStream_t st) {
+  if (n_points == 0) return NDJIR_OK;
+  HashSpec h;
+  if (make_spec(h, G0, growth_factor, T0, L, D, min3, max3) || !grad_feature || !grad_output || !query || !feature ||
+      n_points < 0)
+    return NDJIR_ERR_ARG;
+  int V = hash_vec(h, feature);
+  if (V > 1 && hash_vec(h, grad_feature) < V) V = hash_vec(h, grad_feature);
+  int grid = grid_for(n_points * L);
+  if (V == 4) tv_hash_kernel<true, 4><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, query, feature, h, layout);
+  else if (V == 2) tv_hash_kernel<true, 2><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, query, feature, h, layout);
+  else tv_hash_kernel<true, 1><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, query, feature, h, layout);
   NDJIR_RETURN_LAST_ERROR();
 }
 

@@ -32,18 +32,17 @@ SCOPED = [
     "grid_feature/cosine_triline_feature_cuda.cu",
     "grid_feature/lanczos_triplane_feature_cuda.cu",
     "grid_feature/lanczos_triline_feature_cuda.cu",
+    "grid_feature/lanczos_voxel_hash_feature_cuda.cu",
     "grid_feature/total_variation_loss_cuda.cu",
     "grid_feature/total_variation_loss_on_triplane_cuda.cu",
     "grid_feature/total_variation_loss_on_triline_cuda.cu",
+    "grid_feature/total_variation_loss_on_voxel_hash_cuda.cu",
     "intersection/ray_aabb_intersection_cuda.cu",
     "intersection/ray_sphere_intersection_cuda.cu",
     "sampling/inverse_transform_cuda.cu",
     "activation/squareplus_cuda.cu",
 ]
-EXTRA = [
-    "grid_feature/lanczos_voxel_hash_feature_cuda.cu",
-    "grid_feature/total_variation_loss_on_voxel_hash_cuda.cu",
-]
+EXTRA = []
 
 
 def _includes():

@@ -833,6 +833,111 @@ def voxel_hash_grad_query_grad_feature(grad_grad_query, grad_output_dlb, query, 
 
 
 # --------------------------------------------------------------------------------------
+# lanczos voxel hash: csrc/grid_feature/lanczos_voxel_hash_feature_cuda.cu (level table, offsets and (D,L,B)
+# layout of the trilinear hash family; per level the 4x4x4 clamped Lanczos taps, each hashed)
+# --------------------------------------------------------------------------------------
+def lanczos_hash_cell_index(cells, T):
+    """kernel_hash_index, lanczos_voxel_hash_feature_cuda.cu:54-66: one integer cell (as floats) per row."""
+    c = np.asarray(cells, dtype=f32).reshape(-1, 3).astype(np.uint32)
+    return hash_index3(c[:, 0], c[:, 1], c[:, 2], T)
+
+
+def _lz_hash_levels(query, G0, growth_factor, T0, L, D, min_, max_, Gs, w=2):
+    Gs, Ts, offs, total = hash_level_table(G0, growth_factor, T0, L, D, Gs)
+    for l in range(L):
+        taps, c, gc, s = _lanczos_taps(query, (Gs[l],) * 3, min_, max_, w)
+        yield l, Ts[l], offs[l], taps, c.astype(np.float64), gc.astype(np.float64), [float(v) for v in s], c
+    return
+
+
+def lanczos_voxel_hash_query(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None, w=2):
+    """kernel_voxel_hash_feature, lanczos_voxel_hash_feature_cuda.cu:131-195 -> (D,L,B)."""
+    feature = np.asarray(feature, dtype=f32).reshape(-1)
+    B, K = np.asarray(query).reshape(-1, 3).shape[0], 2 * w
+    out = np.zeros((D, L, B), dtype=f32)
+    for l, T, off, taps, _, _, _, c32 in _lz_hash_levels(query, G0, growth_factor, T0, L, D, min_, max_, Gs, w):
+        tab = feature[off: off + T * D].reshape(T, D)
+        acc = np.zeros((B, D), dtype=f32)
+        for i in range(K):
+            for j in range(K):
+                for k in range(K):
+                    cijk = ((c32[:, 0, i] * c32[:, 1, j]).astype(f32) * c32[:, 2, k]).astype(f32)
+                    acc = (acc + cijk[:, None] * tab[hash_index3(taps[:, 0, i], taps[:, 1, j], taps[:, 2, k], T)]).astype(f32)
+        out[:, l, :] = acc.T
+    return out
+
+
+def _lz_hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None, w=2):
+    """(D,L,B,3), lanczos_voxel_hash_feature_cuda.cu:262-287."""
+    feature = np.asarray(feature, dtype=f32).reshape(-1)
+    B, K = np.asarray(query).reshape(-1, 3).shape[0], 2 * w
+    g = np.zeros((D, L, B, 3), dtype=np.float64)
+    for l, T, off, taps, C, GC, s, _ in _lz_hash_levels(query, G0, growth_factor, T0, L, D, min_, max_, Gs, w):
+        tab = feature[off: off + T * D].reshape(T, D).astype(np.float64)
+        for i in range(K):
+            for j in range(K):
+                for k in range(K):
+                    f = tab[hash_index3(taps[:, 0, i], taps[:, 1, j], taps[:, 2, k], T)]      # (B,D)
+                    g[:, l, :, 0] += ((s[0] * GC[:, 0, i] * C[:, 1, j] * C[:, 2, k])[:, None] * f).T
+                    g[:, l, :, 1] += ((s[1] * C[:, 0, i] * GC[:, 1, j] * C[:, 2, k])[:, None] * f).T
+                    g[:, l, :, 2] += ((s[2] * C[:, 0, i] * C[:, 1, j] * GC[:, 2, k])[:, None] * f).T
+    return g
+
+
+def lanczos_voxel_hash_grad_query(grad_output_dlb, query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None):
+    """kernel_grad_query, lanczos_voxel_hash_feature_cuda.cu:222-300."""
+    g = _lz_hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs)
+    go = np.asarray(grad_output_dlb, dtype=np.float64).reshape(D, L, -1)
+    return (go[..., None] * g).sum(axis=(0, 1))
+
+
+def lanczos_voxel_hash_grad_feature(grad_output_dlb, query, G0, growth_factor, T0, L, D, min_, max_, out=None, Gs=None,
+                                    w=2):
+    """kernel_grad_feature, lanczos_voxel_hash_feature_cuda.cu:327-385."""
+    total = hash_level_table(G0, growth_factor, T0, L, D, Gs)[3]
+    go = np.asarray(grad_output_dlb, dtype=np.float64).reshape(D, L, -1)
+    gf = np.zeros(total, dtype=np.float64) if out is None else out
+    K = 2 * w
+    for l, T, off, taps, C, _, _, _ in _lz_hash_levels(query, G0, growth_factor, T0, L, D, min_, max_, Gs, w):
+        tab = gf[off: off + T * D].reshape(T, D)
+        for i in range(K):
+            for j in range(K):
+                for k in range(K):
+                    np.add.at(tab, hash_index3(taps[:, 0, i], taps[:, 1, j], taps[:, 2, k], T),
+                              go[:, l, :].T * (C[:, 0, i] * C[:, 1, j] * C[:, 2, k])[:, None])
+    return gf
+
+
+def lanczos_voxel_hash_grad_query_grad_grad_output(grad_grad_query, query, feature, G0, growth_factor, T0, L, D, min_,
+                                                   max_, Gs=None):
+    """kernel_grad_query_grad_grad_output, lanczos_voxel_hash_feature_cuda.cu:437-512 -> (D,L,B)."""
+    g = _lz_hash_dfdq(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs)
+    gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
+    return (g * gg[None, None, :, :]).sum(axis=-1)
+
+
+def lanczos_voxel_hash_grad_query_grad_feature(grad_grad_query, grad_output_dlb, query, G0, growth_factor, T0, L, D,
+                                               min_, max_, out=None, Gs=None, w=2):
+    """kernel_grad_query_grad_feature, lanczos_voxel_hash_feature_cuda.cu:649-705."""
+    total = hash_level_table(G0, growth_factor, T0, L, D, Gs)[3]
+    go = np.asarray(grad_output_dlb, dtype=np.float64).reshape(D, L, -1)
+    gg = np.asarray(grad_grad_query, dtype=np.float64).reshape(-1, 3)
+    gf = np.zeros(total, dtype=np.float64) if out is None else out
+    K = 2 * w
+    for l, T, off, taps, C, GC, s, _ in _lz_hash_levels(query, G0, growth_factor, T0, L, D, min_, max_, Gs, w):
+        tab = gf[off: off + T * D].reshape(T, D)
+        for i in range(K):
+            for j in range(K):
+                for k in range(K):
+                    coef = (gg[:, 0] * s[0] * GC[:, 0, i] * C[:, 1, j] * C[:, 2, k]
+                            + gg[:, 1] * s[1] * C[:, 0, i] * GC[:, 1, j] * C[:, 2, k]
+                            + gg[:, 2] * s[2] * C[:, 0, i] * C[:, 1, j] * GC[:, 2, k])
+                    np.add.at(tab, hash_index3(taps[:, 0, i], taps[:, 1, j], taps[:, 2, k], T),
+                              go[:, l, :].T * coef[:, None])
+    return gf
+
+
+# --------------------------------------------------------------------------------------
 # total variation: csrc/grid_feature/total_variation_loss{,_on_triplane,_on_triline}_cuda.cu
 # --------------------------------------------------------------------------------------
 def tv_voxel(query, feature, min_, max_):
@@ -864,6 +969,48 @@ def tv_voxel_backward(grad_output, query, feature, min_, max_, sym_backward, out
     np.add.at(gf, (i0[:, 0], i0[:, 1], i1[:, 2]), g001)
     if sym_backward:
         np.add.at(gf, (i0[:, 0], i0[:, 1], i0[:, 2]), -(g100 + g010 + g001))
+    return gf
+
+
+def tv_voxel_hash(query, feature, G0, growth_factor, T0, L, D, min_, max_, Gs=None):
+    """kernel_tv_loss_on_voxel_hash_forward, total_variation_loss_on_voxel_hash_cuda.cu:50-106 -> (D,L,B)."""
+    feature = np.asarray(feature, dtype=f32).reshape(-1)
+    Gs, Ts, offs, _ = hash_level_table(G0, growth_factor, T0, L, D, Gs)
+    B = np.asarray(query).reshape(-1, 3).shape[0]
+    out = np.zeros((D, L, B), dtype=f32)
+    for l in range(L):
+        i0, i1, _, _, _, _ = cell(query, (Gs[l],) * 3, min_, max_)
+        tab = feature[offs[l]: offs[l] + Ts[l] * D].reshape(Ts[l], D)
+        f000 = tab[hash_index3(i0[:, 0], i0[:, 1], i0[:, 2], Ts[l])]
+        dx = tab[hash_index3(i1[:, 0], i0[:, 1], i0[:, 2], Ts[l])] - f000
+        dy = tab[hash_index3(i0[:, 0], i1[:, 1], i0[:, 2], Ts[l])] - f000
+        dz = tab[hash_index3(i0[:, 0], i0[:, 1], i1[:, 2], Ts[l])] - f000
+        out[:, l, :] = np.sqrt((dx * dx + dy * dy + dz * dz).astype(f32)).astype(f32).T
+    return out
+
+
+def tv_voxel_hash_backward(grad_output_dlb, query, feature, G0, growth_factor, T0, L, D, min_, max_, out=None, Gs=None):
+    """kernel_tv_loss_on_voxel_hash_backward, :132-196: ograd * delta * rsqrt(sum + 1e-12) to the three upper neighbours;
+    the lower corner gets nothing (no sym_backward in this family)."""
+    feature = np.asarray(feature, dtype=f32).reshape(-1)
+    Gs, Ts, offs, total = hash_level_table(G0, growth_factor, T0, L, D, Gs)
+    go = np.asarray(grad_output_dlb, dtype=np.float64).reshape(D, L, -1)
+    gf = np.zeros(total, dtype=np.float64) if out is None else out
+    for l in range(L):
+        i0, i1, _, _, _, _ = cell(query, (Gs[l],) * 3, min_, max_)
+        tab = feature[offs[l]: offs[l] + Ts[l] * D].reshape(Ts[l], D)
+        gtab = gf[offs[l]: offs[l] + Ts[l] * D].reshape(Ts[l], D)
+        h000 = hash_index3(i0[:, 0], i0[:, 1], i0[:, 2], Ts[l])
+        hx = hash_index3(i1[:, 0], i0[:, 1], i0[:, 2], Ts[l])
+        hy = hash_index3(i0[:, 0], i1[:, 1], i0[:, 2], Ts[l])
+        hz = hash_index3(i0[:, 0], i0[:, 1], i1[:, 2], Ts[l])
+        f000 = tab[h000]
+        dx, dy, dz = tab[hx] - f000, tab[hy] - f000, tab[hz] - f000
+        s2 = (dx * dx + dy * dy + dz * dz).astype(f32).astype(np.float64)
+        common = go[:, l, :].T / np.sqrt(s2 + 1e-12)
+        np.add.at(gtab, hx, common * dx)
+        np.add.at(gtab, hy, common * dy)
+        np.add.at(gtab, hz, common * dz)
     return gf
 
 

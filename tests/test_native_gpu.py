@@ -210,6 +210,92 @@ def test_triplane_triline(B, G, D, spread, family):
     close(b1, getattr(R, f"{oname}_grad_query_grad_feature")(gg_np, go_np, q_np, G, D, MN, MX), 1e-4, "gq_gf vs oracle")
 
 
+@pytest.mark.parametrize("B,G0,L,D", [(2, 2, 1, 2), (8, 4, 4, 2), (5000, 16, 16, 2), (3001, 4, 6, 4), (1234, 3, 5, 1)])
+def test_tv_loss_on_voxel_hash(B, G0, L, D):
+    """total_variation_loss_on_voxel_hash_cuda against the reference kernels and the numpy oracle."""
+    ours, ref = compat.load("total_variation_loss_on_voxel_hash_cuda"), ref_mod("total_variation_loss_on_voxel_hash_cuda")
+    gf, T0 = 1.5, 2 ** 10 if B < 1000 else 2 ** 15
+    q_np, rng = queries(B, spread=1.1)
+    from ndjir_b200._lib import call as _call
+    gdev, tdev = torch.zeros(L, dtype=torch.int32).cuda(), torch.zeros(L, dtype=torch.int32).cuda()
+    _call("ndjir_voxel_hash_level_table_device", G0, gf, T0, L, D, gdev, tdev, 0)
+    Gdev = [int(v) for v in gdev.cpu()]
+    total = R.hash_level_table(G0, gf, T0, L, D, Gdev)[3]
+    f_np = (rng.randn(total) * 0.01).astype(np.float32)
+    go_np = rng.randn(D, L, B).astype(np.float32)
+    q, f, go = dev(q_np), dev(f_np), dev(go_np)
+    N = L * B
+    o1, o2 = torch.full((D, L, B), 7.0).cuda(), torch.full((D, L, B), 7.0).cuda()
+    ours.tv_loss_on_voxel_hash(N, o1.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
+    ref.tv_loss_on_voxel_hash(N, o2.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
+    close(o1, o2, 1e-6, "tv fwd vs reference kernel")
+    close(o1, R.tv_voxel_hash(q_np, f_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 1e-5, "tv fwd vs oracle")
+    g1, g2 = torch.full((total,), 0.25).cuda(), torch.full((total,), 0.25).cuda()
+    ours.tv_loss_on_voxel_hash_backward(N, g1.data_ptr(), go.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
+    ref.tv_loss_on_voxel_hash_backward(N, g2.data_ptr(), go.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
+    close(g1, g2, 1e-4, "tv bwd vs reference kernel")
+    close(g1 - 0.25, R.tv_voxel_hash_backward(go_np, q_np, f_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 1e-4, "tv bwd vs oracle")
+
+
+LZ_HASH_CASES = [(2, 2, 1, 2), (8, 4, 4, 2), (700, 16, 8, 2), (501, 4, 6, 4), (234, 3, 5, 1)]
+
+
+@pytest.mark.parametrize("B,G0,L,D", LZ_HASH_CASES)
+def test_lanczos_voxel_hash(B, G0, L, D):
+    """lanczos_voxel_hash_feature_cuda (6 exports) against the reference kernels and the numpy oracle; shapes follow the
+    trilinear hash test (gf = 1.5, T0 = 2^10)."""
+    ours, ref = compat.load("lanczos_voxel_hash_feature_cuda"), ref_mod("lanczos_voxel_hash_feature_cuda")
+    gf, T0 = 1.5, 2 ** 10
+    q_np, rng = queries(B, spread=1.1)
+    from ndjir_b200._lib import call as _call
+    gdev, tdev = torch.zeros(L, dtype=torch.int32).cuda(), torch.zeros(L, dtype=torch.int32).cuda()
+    _call("ndjir_voxel_hash_level_table_device", G0, gf, T0, L, D, gdev, tdev, 0)
+    Gdev = [int(v) for v in gdev.cpu()]
+    Gs, Ts, offs, total = R.hash_level_table(G0, gf, T0, L, D, Gdev)
+    f_np = (rng.randn(total) * 0.01).astype(np.float32)
+    go_np = rng.randn(D, L, B).astype(np.float32)
+    gg_np = rng.randn(B, 3).astype(np.float32)
+    q, f, go, gg = dev(q_np), dev(f_np), dev(go_np), dev(gg_np)
+    N = L * B
+    cells = rng.randint(0, 5000, (B, 3)).astype(np.float32)
+    h1, h2 = torch.zeros(B).cuda(), torch.zeros(B).cuda()
+    ours.hash_index(B, h1.data_ptr(), dev(cells).data_ptr(), Ts[-1], False)
+    ref.hash_index(B, h2.data_ptr(), dev(cells).data_ptr(), Ts[-1], False)
+    assert torch.equal(h1, h2), "cell hash differs from the reference kernel"
+    assert np.array_equal(h1.cpu().numpy().astype(np.uint32), R.lanczos_hash_cell_index(cells, Ts[-1]))
+    o1, o2 = torch.full((D, L, B), 7.0).cuda(), torch.full((D, L, B), 7.0).cuda()
+    ours.voxel_hash_feature(N, o1.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
+    ref.voxel_hash_feature(N, o2.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
+    close(o1, o2, 2e-5, "fwd vs reference kernel")
+    close(o1, R.lanczos_voxel_hash_query(q_np, f_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 2e-5, "fwd vs oracle")
+    for accum in (False, True):
+        g1, g2 = torch.full((B, 3), 0.5).cuda(), torch.full((B, 3), 0.5).cuda()
+        ours.grad_query(N, g1.data_ptr(), go.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False, accum)
+        ref.grad_query(N, g2.data_ptr(), go.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False, accum)
+        close(g1, g2, 1e-4, f"grad_query accum={accum}")
+    close(g1 - 0.5, R.lanczos_voxel_hash_grad_query(go_np, q_np, f_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 1e-4,
+          "grad_query vs oracle")
+    for accum in (False, True):
+        gf1, gf2 = torch.full((total,), 0.25).cuda(), torch.full((total,), 0.25).cuda()
+        ours.grad_feature(N, gf1.data_ptr(), go.data_ptr(), q.data_ptr(), G0, gf, T0, L, D, MN, MX, False, accum)
+        ref.grad_feature(N, gf2.data_ptr(), go.data_ptr(), q.data_ptr(), G0, gf, T0, L, D, MN, MX, False, accum)
+        close(gf1, gf2, 1e-4, f"grad_feature accum={accum}")
+    close(gf1 - 0.25, R.lanczos_voxel_hash_grad_feature(go_np, q_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 1e-4,
+          "grad_feature vs oracle")
+    a1, a2 = torch.zeros(D, L, B).cuda(), torch.zeros(D, L, B).cuda()
+    ours.grad_query_grad_grad_output(N, a1.data_ptr(), gg.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False, False)
+    ref.grad_query_grad_grad_output(N, a2.data_ptr(), gg.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False, False)
+    close(a1, a2, 1e-4, "gq_ggo")
+    close(a1, R.lanczos_voxel_hash_grad_query_grad_grad_output(gg_np, q_np, f_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 1e-4,
+          "gq_ggo vs oracle")
+    b1, b2 = torch.zeros(total).cuda(), torch.zeros(total).cuda()
+    ours.grad_query_grad_feature(N, b1.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), G0, gf, T0, L, D, MN, MX, False, False)
+    ref.grad_query_grad_feature(N, b2.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), G0, gf, T0, L, D, MN, MX, False, False)
+    close(b1, b2, 1e-4, "gq_gf")
+    close(b1, R.lanczos_voxel_hash_grad_query_grad_feature(gg_np, go_np, q_np, G0, gf, T0, L, D, MN, MX, Gs=Gdev), 1e-4,
+          "gq_gf vs oracle")
+
+
 HASH_CASES = [(2, 2, 1, 2), (8, 4, 4, 2), (8, 2, 4, 2), (5000, 16, 16, 2), (3001, 4, 6, 4), (1234, 3, 5, 1)]
 
 
