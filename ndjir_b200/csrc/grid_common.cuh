@@ -66,6 +66,15 @@ __device__ __forceinline__ void cell_axis_cosine(float q, float mn, float s, flo
   i1 = (unsigned)f1;
 }
 
+__device__ __forceinline__ Cell make_cell_linear(const GridFrame& g, float qx, float qy, float qz) {
+  Cell c;
+  cell_axis(qx, g.mnx, g.sx, g.gx1, c.x0, c.x1, c.p0, c.p1);
+  cell_axis(qy, g.mny, g.sy, g.gy1, c.y0, c.y1, c.q0, c.q1);
+  cell_axis(qz, g.mnz, g.sz, g.gz1, c.z0, c.z1, c.r0, c.r1);
+  c.sx = g.sx; c.sy = g.sy; c.sz = g.sz;
+  return c;
+}
+
 __device__ __forceinline__ Cell make_cell(const GridFrame& g, float qx, float qy, float qz) {
   Cell c;
   if (g.interp == INTERP_COSINE) {

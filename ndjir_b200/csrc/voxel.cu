@@ -387,14 +387,6 @@ int ndjir_set_option(const char* key, int value) {
   i = 0;
   while (k8[i] && key[i] == k8[i]) ++i;
   if (k8[i] == 0 && key[i] == 0) { ndjir::g_voxel_pair256 = value; return NDJIR_OK; }
-  const char* k9 = "voxel_prefetch";
-  i = 0;
-  while (k9[i] && key[i] == k9[i]) ++i;
-  if (k9[i] == 0 && key[i] == 0) { ndjir::g_voxel_prefetch = value; return NDJIR_OK; }
-  const char* k10 = "mlp_presplit";
-  i = 0;
-  while (k10[i] && key[i] == k10[i]) ++i;
-  if (k10[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_presplit = value; return NDJIR_OK; }
   const char* k7 = "voxel_bin_mb";
   i = 0;
   while (k7[i] && key[i] == k7[i]) ++i;

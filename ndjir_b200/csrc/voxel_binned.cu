@@ -25,14 +25,12 @@ namespace ndjir {
 
 int g_voxel_binned = -1;    // -1 auto, 0 never, 1 always (when the shape allows it)
 int g_voxel_bin_mb = 16;    // target brick size
-int g_voxel_prefetch = 0;   // gather sweep: 0 no software prefetch, 1 records, 2 records + table lines (measured: no gain)
 int g_voxel_pair256 = 0;    // 256-bit loads for z-neighbour pairs that share a sector
 
 namespace voxel_binned {
 
 constexpr int kMaxBins = 512;
 constexpr int kPlaceBlock = 256;
-constexpr int kPfRec = 3072, kPfTab = 1024;  // prefetch distances of the gather sweep, in CTAs (888 are resident)
 constexpr long long kHeaderBytes = 8192;  // kMaxBins cursors + padding; records start 16-byte aligned
 
 struct Bins {
@@ -216,7 +214,7 @@ __device__ __forceinline__ void ldg_pair256(const float* p, Vec<4>& a, Vec<4>& b
 template <int V, bool ACCUM, bool PAIR256>
 __global__ void __launch_bounds__(256, 6)
 gather_kernel(long long B, float* __restrict__ out, const float4* __restrict__ rec, const float* __restrict__ feat,
-              GridFrame g, Strides s, int D, int pf) {
+              GridFrame g, Strides s, int D) {
   const int sub = threadIdx.x & 3;
   const int cx = sub >> 1, cy = sub & 1;
   // NO grid-stride loop: CTA k owns records [128k, 128k+128), two per lane group (both issued before either is
@@ -225,41 +223,20 @@ gather_kernel(long long B, float* __restrict__ out, const float4* __restrict__ r
   // table; a persistent grid-stride sweep lets fast CTAs run many rounds ahead and the window (and with it the
   // L2 footprint) grows without bound (measured: 8.0 GB of DRAM reads instead of 2.9 GB).
   long long i0 = (long long)blockIdx.x * 128 + (threadIdx.x >> 2);
-  // Software prefetch into L2 for CTAs that start later (each CTA is one dependent chain record -> cells -> store
-  // and lives only a few microseconds, so without it every link of the chain is a DRAM-latency miss):
-  //   pf >= 1: the record block of CTA k + kPfRec;  pf >= 2: the table lines of CTA k + kPfTab's points (their
-  //   records were prefetched by CTA k + kPfTab - kPfRec).
-  if (pf >= 1 && threadIdx.x < 16) {
-    long long j = ((long long)blockIdx.x + kPfRec) * 128 + threadIdx.x * 8;
-    if (j < B) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + j));
-  }
   bool active[2];
-  float4 rc[2], rn[2];
+  float4 rc[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     long long i = i0 + 64 * u;
     active[u] = i < B;
     rc[u] = __ldg(rec + (active[u] ? i : B - 1));
-    long long in = i + (long long)kPfTab * 128;
-    if (pf >= 2) rn[u] = __ldg(rec + (in < B ? in : B - 1));
-  }
-  if (pf >= 2) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      Cell c = make_cell(g, rn[u].x, rn[u].y, rn[u].z);
-      const float* a0 = feat + ((cx ? c.x1 : c.x0) * s.sx + (cy ? c.y1 : c.y0) * s.sy + c.z0 * s.sz);
-      const float* a1 = a0 + (c.z1 - c.z0) * s.sz + (D - 1);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a0));
-      if ((reinterpret_cast<uintptr_t>(a0) ^ reinterpret_cast<uintptr_t>(a1)) >> 7)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a1));
-    }
   }
   for (int d = 0; d < D; d += V) {
     Vec<V> f0[2], f1[2];
     float w0[2], w1[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      Cell c = make_cell(g, rc[u].x, rc[u].y, rc[u].z);
+      Cell c = make_cell_linear(g, rc[u].x, rc[u].y, rc[u].z);
       unsigned base = (cx ? c.x1 : c.x0) * s.sx + (cy ? c.y1 : c.y0) * s.sy;
       float wxy = (cx ? c.p1 : c.p0) * (cy ? c.q1 : c.q0);
       w0[u] = wxy * c.r0; w1[u] = wxy * c.r1;
@@ -305,7 +282,7 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
     float4 rc = __ldg(rec + (WIDE ? 2 * i : i));
     float4 pay = WIDE ? __ldg(rec + 2 * i + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     long long p = (long long)__float_as_uint(rc.w);
-    Cell c = make_cell(g, rc.x, rc.y, rc.z);
+    Cell c = make_cell_linear(g, rc.x, rc.y, rc.z);
     float pw = cx ? c.p1 : c.p0, qw = cy ? c.q1 : c.q0, rw = cz ? c.r1 : c.r0;
     float coef;
     if (!SECOND) {
@@ -396,12 +373,12 @@ int query(long long B, float* out, const float* query_, const float* feat, const
   int V = pick_vec(D, feat, out);
   unsigned grid = (unsigned)((B + 127) / 128);
 #define NDJIR_LAUNCH(VV)                                                                        \
-  if (accum) gather_kernel<VV, true, false><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D, g_voxel_prefetch);  \
-  else gather_kernel<VV, false, false><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D, g_voxel_prefetch);
+  if (accum) gather_kernel<VV, true, false><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D);  \
+  else gather_kernel<VV, false, false><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D);
   bool pair256 = V == 4 && D == 4 && (G[2] & 1) == 0 && (reinterpret_cast<uintptr_t>(feat) & 31) == 0 && g_voxel_pair256;
   if (pair256) {
-    if (accum) gather_kernel<4, true, true><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D, g_voxel_prefetch);
-    else gather_kernel<4, false, true><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D, g_voxel_prefetch);
+    if (accum) gather_kernel<4, true, true><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D);
+    else gather_kernel<4, false, true><<<grid, 256, 0, st>>>(B, out, rec, feat, g, s, D);
   } else if (V == 4) { NDJIR_LAUNCH(4) } else if (V == 2) { NDJIR_LAUNCH(2) } else { NDJIR_LAUNCH(1) }
 #undef NDJIR_LAUNCH
   NDJIR_RETURN_LAST_ERROR();

@@ -6,7 +6,6 @@ namespace ndjir {
 
 extern int g_voxel_binned;  // -1 auto (large batch on a table far larger than L2), 0 never, 1 whenever possible
 extern int g_voxel_pair256;
-extern int g_voxel_prefetch;
 extern int g_voxel_bin_mb;  // target brick size in MiB
 
 namespace voxel_binned {

@@ -623,8 +623,8 @@ def test_voxel_binned_matches_direct_and_reference(B, G, D, spread, mb):
         call("ndjir_voxel_grad_query_grad_feature_binned", B, b1, gg, go, q, list(G), D, MN, MX, ws, wsb, 0)
         ref.grad_query_grad_feature(N, b2.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, False)
         close(b1, b2, 1e-4, "binned gq_gf")
-        # experiment switches of the gather sweep (L2 software prefetch, 256-bit z-pair loads) do not change results
-        for key, val in (("voxel_prefetch", 1), ("voxel_prefetch", 2), ("voxel_pair256", 1)):
+        # the experiment switch of the gather sweep (256-bit z-pair loads) does not change results
+        for key, val in (("voxel_pair256", 1),):
             call("ndjir_set_option", key, val)
             o4 = torch.empty((B, D)).cuda()
             call("ndjir_voxel_query_on_voxel_binned", B, o4, q, f, list(G), D, MN, MX, 0, ws, wsb, 0)

@@ -73,11 +73,10 @@ for mb in [int(x) for x in args.mbs.split(",")]:
          t(lambda: call("ndjir_voxel_grad_feature_binned", B, gf, go, q, [G] * 3, D, MN, MX, 1, ws, wsb, 0)), 284)
     print(f"    max-norm rel. diff vs direct: fwd {err:.2e}, grad_feature {err2:.2e}", flush=True)
 call("ndjir_set_option", "voxel_bin_mb", 16)
-for pf in (0, 1, 2):
-    call("ndjir_set_option", "voxel_prefetch", pf)
-    show(f"gather binned, 16 MiB, prefetch mode {pf}",
-         t(lambda: call("ndjir_voxel_query_on_voxel_binned", B, out, q, feat, [G] * 3, D, MN, MX, 0, ws, wsb, 0)), 156)
-    print("    diff", (out - ref_out).abs().max().item())
+call("ndjir_set_option", "voxel_pair256", 1)
+show("gather binned, 16 MiB, 256-bit z-pair loads",
+     t(lambda: call("ndjir_voxel_query_on_voxel_binned", B, out, q, feat, [G] * 3, D, MN, MX, 0, ws, wsb, 0)), 156)
+call("ndjir_set_option", "voxel_pair256", 0)
 call("ndjir_set_option", "voxel_binned", -1)
 show("gather auto (cudaMallocAsync scratch)", t(lambda: call("ndjir_voxel_query_on_voxel", B, out, q, feat, [G] * 3, D, MN, MX, 0, 0)), 156)
 show("scatter auto accum=0", t(lambda: call("ndjir_voxel_grad_feature", B, gf, go, q, [G] * 3, D, MN, MX, 0, 0)), 284)
