@@ -272,7 +272,7 @@ gather_kernel(long long B, float* __restrict__ out, const float4* __restrict__ r
 // Scatter over the records, EIGHT LANES PER POINT (one corner each), like voxel::scatter8_kernel.
 // WIDE (first order, D = 4): the record carries the grad_output row, nothing is read at `point index`.
 template <bool SECOND, int V, bool WIDE>
-__global__ void __launch_bounds__(256, 8)
+__global__ void __launch_bounds__(256, 6)
 scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go, const float* __restrict__ gg,
                const float4* __restrict__ rec, GridFrame g, Strides s, int D) {
   const int k = threadIdx.x & 7;
