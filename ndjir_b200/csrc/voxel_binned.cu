@@ -325,9 +325,10 @@ bool worthwhile(long long B, const int* G, int D) {
   return table >= (96ll << 20) && B >= (1ll << 21);
 }
 
-// Builds the brick-ordered records in `ws`; returns the record pointer through *rec_out.
-static int build_records(long long B, const float* query, const float* payload, const GridFrame& g, const int* G,
-                         int D, void* ws, long long ws_bytes, cudaStream_t st, const float4** rec_out) {
+// Builds the brick-ordered records in `ws`: 16-byte {q, point index}, or 32-byte {q, index | payload row (4 floats)}
+// when `payload` is given.  Also used by the Lanczos voxel family (lanczos_voxel.cu).
+int build_records(long long B, const float* query, const float* payload, const GridFrame& g, const int* G, int D,
+                  void* ws, long long ws_bytes, cudaStream_t st, const float4** rec_out) {
   if (!ws || ws_bytes < workspace_bytes(B) || (reinterpret_cast<uintptr_t>(ws) & 15)) return NDJIR_ERR_ARG;
   Bins b = make_bins(G, D, g_voxel_bin_mb);
   unsigned* cursors = reinterpret_cast<unsigned*>(ws);

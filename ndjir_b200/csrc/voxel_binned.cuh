@@ -1,6 +1,7 @@
 // Brick-ordered voxel gather / scatter (voxel_binned.cu): interface used by the dispatch in voxel.cu.
 #pragma once
 #include <cuda_runtime.h>
+#include "grid_common.cuh"
 
 namespace ndjir {
 
@@ -17,6 +18,8 @@ int query(long long B, float* out, const float* query, const float* feat, const 
           const float* mx, bool accum, void* ws, long long ws_bytes, cudaStream_t st);
 int scatter(bool second, long long B, float* gf, const float* go, const float* gg, const float* query, const int* G,
             int D, const float* mn, const float* mx, void* ws, long long ws_bytes, cudaStream_t st);
+int build_records(long long B, const float* query, const float* payload, const GridFrame& g, const int* G, int D,
+                  void* ws, long long ws_bytes, cudaStream_t st, const float4** rec_out);
 void* scratch_alloc(long long bytes, cudaStream_t st);
 void scratch_free(void* p, cudaStream_t st);
 

@@ -144,7 +144,13 @@ def main():
     if not only or "lanczos" in only:
         G, D = 256, 4
         feat = torch.randn(G, G, G, D, device="cuda") * 0.01
-        run_family("lanczos", "lanczos_voxel_feature_cuda", "query_on_voxel", feat, (G, G, G), D, D, 44, 44 + 16)
+        # default dispatch: brick-ordered (268 MB table, 2^24 points); then the direct kernels
+        run_family("lanczos", "lanczos_voxel_feature_cuda", "query_on_voxel", feat, (G, G, G), D, D, 44, 44 + 16,
+                   ours_label="ndjir_b200 (brick-ordered, default)", with_ref=False)
+        call("ndjir_set_option", "voxel_binned", 0)
+        run_family("lanczos", "lanczos_voxel_feature_cuda", "query_on_voxel", feat, (G, G, G), D, D, 44, 44 + 16,
+                   ours_label="ndjir_b200 (direct)")
+        call("ndjir_set_option", "voxel_binned", -1)
         del feat
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(results, open(args.out, "w"), indent=1)
