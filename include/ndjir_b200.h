@@ -29,7 +29,9 @@ extern "C" {
 #endif
 
 /* ---- library options ------------------------------------------------------------------------------- */
-/* "scatter_aggregate": 1 = warp-aggregated scatter reductions (coherent rays), 0 = plain vector reductions */
+/* "scatter_aggregate": 1 = warp-aggregated scatter reductions (coherent rays), 0 = plain vector reductions;
+ * "mlp_tensor_cores" (default 1; 0 = fp32 FFMA parity path), "mlp_presplit" (1), "mlp_cta_pair" (0), "voxel_binned"
+ * (-1 auto / 0 / 1), "voxel_bin_mb" (16), plus profiling switches; unknown keys return -1 */
 int ndjir_set_option(const char* key, int value);
 
 /* ---- voxel_feature_cuda (csrc/grid_feature/voxel_feature_cuda.cu:844-863) --------------------------- */

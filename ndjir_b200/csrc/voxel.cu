@@ -359,38 +359,23 @@ extern "C" {
 
 int ndjir_set_option(const char* key, int value) {
   if (!key) return NDJIR_ERR_ARG;
-  const char* k = "scatter_aggregate";
-  int i = 0;
-  while (k[i] && key[i] == k[i]) ++i;
-  if (k[i] == 0 && key[i] == 0) { g_scatter_aggregate = value; return NDJIR_OK; }
-  const char* k2 = "mlp_tensor_cores";
-  i = 0;
-  while (k2[i] && key[i] == k2[i]) ++i;
-  if (k2[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_tensor_cores = value; return NDJIR_OK; }
-  const char* k5 = "mlp_cta_pair";
-  i = 0;
-  while (k5[i] && key[i] == k5[i]) ++i;
-  if (k5[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_cta_pair = value; return NDJIR_OK; }
-  const char* k4 = "mlp_dbg";
-  i = 0;
-  while (k4[i] && key[i] == k4[i]) ++i;
-  if (k4[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_dbg = value; return NDJIR_OK; }
-  const char* k3 = "mlp_mask_hi";
-  i = 0;
-  while (k3[i] && key[i] == k3[i]) ++i;
-  if (k3[i] == 0 && key[i] == 0) { ndjir::gemm::g_mlp_mask_hi = value; return NDJIR_OK; }
-  const char* k6 = "voxel_binned";
-  i = 0;
-  while (k6[i] && key[i] == k6[i]) ++i;
-  if (k6[i] == 0 && key[i] == 0) { ndjir::g_voxel_binned = value; return NDJIR_OK; }
-  const char* k8 = "voxel_pair256";
-  i = 0;
-  while (k8[i] && key[i] == k8[i]) ++i;
-  if (k8[i] == 0 && key[i] == 0) { ndjir::g_voxel_pair256 = value; return NDJIR_OK; }
-  const char* k7 = "voxel_bin_mb";
-  i = 0;
-  while (k7[i] && key[i] == k7[i]) ++i;
-  if (k7[i] == 0 && key[i] == 0) { ndjir::g_voxel_bin_mb = value; return NDJIR_OK; }
+  struct Opt { const char* name; int* target; };
+  const Opt opts[] = {
+      {"scatter_aggregate", &g_scatter_aggregate},          // 1: warp-aggregated scatter reductions (coherent rays)
+      {"mlp_tensor_cores", &ndjir::gemm::g_mlp_tensor_cores},  // 0: fp32 FFMA parity path for every MLP product
+      {"mlp_cta_pair", &ndjir::gemm::g_mlp_cta_pair},       // 1: tcgen05 cta_group::2 product kernel (measured slower)
+      {"mlp_presplit", &ndjir::gemm::g_mlp_presplit},       // 0: ignore caller-supplied lo parts of the weight operand
+      {"mlp_dbg", &ndjir::gemm::g_mlp_dbg},                 // profiling switches of the tcgen05 kernel
+      {"mlp_mask_hi", &ndjir::gemm::g_mlp_mask_hi},
+      {"voxel_binned", &ndjir::g_voxel_binned},             // -1 auto, 0 never, 1 whenever possible (brick-ordered sweeps)
+      {"voxel_bin_mb", &ndjir::g_voxel_bin_mb},             // brick size in MiB
+      {"voxel_pair256", &ndjir::g_voxel_pair256},           // 256-bit z-pair loads in the binned gather (measured slower)
+  };
+  for (const Opt& o : opts) {
+    int i = 0;
+    while (o.name[i] && key[i] == o.name[i]) ++i;
+    if (o.name[i] == 0 && key[i] == 0) { *o.target = value; return NDJIR_OK; }
+  }
   return NDJIR_ERR_ARG;
 }
 

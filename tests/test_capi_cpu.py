@@ -105,3 +105,15 @@ def test_binned_sweep_kernels_do_not_spill():
             assert m and int(m.group(1)) == 0, f"{name}: {m.group(0) if m else 'no ptxas report'}"
             checked += 1
     assert checked >= 6
+
+
+def test_set_option_keys():
+    """Every documented option key is accepted (host-only call), unknown keys are an argument error."""
+    from ndjir_b200 import _lib
+    defaults = {"scatter_aggregate": 0, "mlp_tensor_cores": 1, "mlp_cta_pair": 0, "mlp_presplit": 1, "mlp_dbg": 0,
+                "mlp_mask_hi": 0, "voxel_binned": -1, "voxel_bin_mb": 16, "voxel_pair256": 0}
+    for k, v in defaults.items():
+        _lib.call("ndjir_set_option", k, v)
+    import pytest
+    with pytest.raises(_lib.NdjirError):
+        _lib.call("ndjir_set_option", "no_such_option", 1)
