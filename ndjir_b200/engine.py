@@ -715,7 +715,7 @@ class Engine:
     # total_loss forward + backward (python/loss.py:27-192 over python/renderer.py:32-209)
     # ------------------------------------------------------------------------------------------------
     def train_step(self, camloc, raydir, color_gt, rnd, cos_anneal_ratio=0.0, samples=None, zero_grad=True,
-                   backward=True, keep=False):
+                   backward=True, keep=False, inference=False):
         """One loss.forward() + loss.backward().  `rnd` holds the explicit random tensors (scene.make_randoms) on
         the device.  Returns the (N_LOSSES,) device tensor of loss terms; gradients accumulate in self.params.grad /
         grid_grad (all-reduced over the process group when world_size > 1)."""
@@ -793,7 +793,7 @@ class Engine:
         nhat = self.buf("nhat", NR, 3)
         self.call("ndjir_pixel_normal_forward", NR, P_(pix, Df + 3), LDO, float(r.eps_normal), P_(nhat))
         # ---------------- per-sample heads ----------------
-        RAW = self.buf("RAW", P, 16)
+        RAW = self.buf("RAW", P, 16, zero=inference)     # inference leaves column 13 (perturbed base colour) unset
         acts = {}
         acts["bc"] = self.mlp_forward("bc", "bc", P_(O), LDO, P, [(P_(RAW, 0), 16)])
         acts["ii"] = self.mlp_forward("ii", "ii", P_(O), LDO, P, [(P_(RAW, 3), 16)])
@@ -810,14 +810,18 @@ class Engine:
         self.call("ndjir_inv_sq_dist", P, R * N, P_(x_fg), P_(camloc), P_(Xpl, Df + 6 + npl), ldpl)
         acts["pl"] = self.mlp_forward("pl", "pl", P_(Xpl), ldpl, P, [(P_(RAW, 12), 16)])
         # ---------------- perturbed colour branch (renderer.py:187-193) ----------------
-        G = conf.geometric_network.voxel.grid_size
-        x_ptb = self.buf("x_ptb", P, 3)
-        self.copy2d(P, 3, P_(x_ptb), 3, P_(x_fg), 3)
-        self.copy2d(P, 3, P_(x_ptb), 3, P_(rnd["perturb"]), 3, alpha=math.sqrt(3) * 2 * self.rad / G, accum=1)
-        Op = self.buf("O_ptb", P, LDO)
-        Ap, _ = self.geo_forward(x_ptb, P, "ptb", store=True, O=Op)
-        self.copy2d(P, 3, P_(Op, Df), LDO, P_(x_ptb), 3)
-        acts["bcp"] = self.mlp_forward("bc", "bcp", P_(Op), LDO, P, [(P_(RAW, 13), 16)])
+        # It only feeds the base-colour prior of the loss: image rendering (inference=True, forward only) skips the
+        # second geometric-network evaluation and reads a zero base colour there.
+        assert not (inference and backward), "inference=True is forward only"
+        if not inference:
+            G = conf.geometric_network.voxel.grid_size
+            x_ptb = self.buf("x_ptb", P, 3)
+            self.copy2d(P, 3, P_(x_ptb), 3, P_(x_fg), 3)
+            self.copy2d(P, 3, P_(x_ptb), 3, P_(rnd["perturb"]), 3, alpha=math.sqrt(3) * 2 * self.rad / G, accum=1)
+            Op = self.buf("O_ptb", P, LDO)
+            Ap, _ = self.geo_forward(x_ptb, P, "ptb", store=True, O=Op)
+            self.copy2d(P, 3, P_(Op, Df), LDO, P_(x_ptb), 3)
+            acts["bcp"] = self.mlp_forward("bc", "bcp", P_(Op), LDO, P, [(P_(RAW, 13), 16)])
         # ---------------- material attributes + per-sample losses ----------------
         ro_c, sp_c = conf.roughness_network, conf.specular_reflectance_network
         cfg10 = [ro_c.lower_bound, ro_c.prior_value, sp_c.prior_value, sp_c.upper_bound_scale, ps.pl_gain,

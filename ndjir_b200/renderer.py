@@ -55,7 +55,7 @@ def render_image(pose, intrinsic, resolution, conf, n_rays=None, seed=0, rank=0,
                    perturb=torch.zeros((1, R, N, 3), device="cuda"))
         gt = torch.zeros((1, R, 3), device="cuda")
         eng.train_step(camloc_d, raydir_d[:, p0:p1].contiguous(), gt, rnd, cos_anneal_ratio=1.0, backward=False,
-                       zero_grad=False, keep=True)
+                       zero_grad=False, keep=True, inference=True)
         out[p0:p1] = eng.debug["color"][:R]
     return out.clamp_(0, 1).reshape(H, W, 3).permute(2, 0, 1)[None]
 

@@ -198,3 +198,27 @@ def test_render_image_is_chunk_invariant_and_sdf_volume_matches_oracle():
     pts = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), dim=-1).reshape(-1, 3)
     want = model.geometric_network(pts)[0].detach().reshape(9, 9, 9).numpy()
     np.testing.assert_allclose(vol.cpu().numpy(), want, atol=2e-5 * np.abs(want).max())
+
+
+def test_inference_mode_renders_the_same_pixels():
+    """train_step(backward=False, inference=True) skips the perturbed colour branch (it only feeds the base-colour prior):
+    pixel colours, normals and weights are bit-identical to the full forward pass."""
+    from ndjir_b200 import scene
+    from ndjir_b200.engine import Engine
+    from test_engine_gpu import small_conf, dev
+    conf = small_conf("default")
+    eng = Engine(conf)
+    eng.params.load_reference(scene.init_params(conf, seed=313, grid_std=0.05))
+    camloc, raydir, color_gt = scene.make_batch(conf, step=3, B=conf.train.batch_size, R=conf.train.n_rays)
+    rnd = {k: dev(v) for k, v in scene.make_randoms(conf, conf.train.batch_size, conf.train.n_rays, step=3).items()}
+    outs = []
+    for inference in (False, True):
+        eng.train_step(dev(camloc), dev(raydir), dev(color_gt), rnd, cos_anneal_ratio=1.0, backward=False, keep=True,
+                       inference=inference)
+        d = eng.debug
+        outs.append({k: d[k].clone() for k in ("color", "nhat", "w", "attpix")})
+    for k in outs[0]:
+        a, b = outs[0][k], outs[1][k]
+        if k == "attpix":          # column layout: only the rendered material attributes, not the prior terms
+            continue
+        assert torch.equal(a, b), k
