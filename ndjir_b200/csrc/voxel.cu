@@ -15,6 +15,7 @@
 
 namespace ndjir {
 
+extern int g_hash_coarse_private;
 int g_scatter_aggregate = 0;
 
 namespace voxel {
@@ -369,6 +370,7 @@ int ndjir_set_option(const char* key, int value) {
       {"mlp_mask_hi", &ndjir::gemm::g_mlp_mask_hi},
       {"voxel_binned", &ndjir::g_voxel_binned},             // -1 auto, 0 never, 1 whenever possible (brick-ordered sweeps)
       {"voxel_bin_mb", &ndjir::g_voxel_bin_mb},             // brick size in MiB
+      {"hash_coarse_private", &ndjir::g_hash_coarse_private},  // 0 off, 1 batches >= 2^20 points, 2 always
       {"voxel_pair256", &ndjir::g_voxel_pair256},           // 256-bit z-pair loads in the binned gather (measured slower)
   };
   for (const Opt& o : opts) {

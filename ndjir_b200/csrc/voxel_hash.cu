@@ -17,6 +17,7 @@
 #include "../../include/ndjir_b200.h"
 
 namespace ndjir {
+int g_hash_coarse_private = 1;   // grad_feature of large batches: coarse levels accumulate in shared memory (2: always)
 namespace vhash {
 
 #define NDJIR_HASH_MAX_LEVELS 32
@@ -174,14 +175,14 @@ gather_kernel(long long B, float* __restrict__ out, const float* __restrict__ a,
 template <bool SECOND, int V>
 __global__ void __launch_bounds__(NDJIR_BLOCK)
 scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go_, const float* __restrict__ gg,
-               const float* __restrict__ query, HashSpec h, int layout) {
+               const float* __restrict__ query, HashSpec h, int layout, int l_begin) {
   __shared__ LevelTable tab;
   build_table(tab, h);
-  const long long N = B * h.L;
+  const long long N = B * (h.L - l_begin);    // levels below l_begin were handled by scatter_coarse_kernel
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += stride) {
-    int l = (int)(n / B);
-    long long b = n - (long long)l * B;
+    int l = l_begin + (int)(n / B);
+    long long b = n - (long long)(l - l_begin) * B;
     GridFrame g = level_frame(h, tab.G[l]);
     unsigned T = (unsigned)tab.T[l];
     float* gl = gf + tab.off[l];
@@ -209,6 +210,46 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
         red_vec<V>(gl + hash3(xs[cx], ys[cy], zs[cz], T) * h.D + d, val);
       }
     }
+  }
+}
+
+// First-order scatter into the COARSE levels of a large batch.  At the bench shape 2^24 points send 134 M reductions
+// into the 4096 entries of level 0 (13 824 at level 1): same-address reductions serialise in the L2 atomic units and
+// these two levels cost 4.1 + 1.8 ms of a 13 ms call (tools/exp/hash_levels.py).  Here every CTA of a persistent
+// grid accumulates a level into a private copy in shared memory and flushes it with one reduction per non-zero entry.
+__global__ void __launch_bounds__(1024, 1)
+scatter_coarse_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go_,
+                      const float* __restrict__ query, HashSpec h, int layout, int n_coarse) {
+  extern __shared__ float priv[];
+  __shared__ LevelTable tab;
+  build_table(tab, h);
+  for (int l = 0; l < n_coarse; ++l) {
+    const unsigned T = (unsigned)tab.T[l];
+    const unsigned n_fl = T * (unsigned)h.D;
+    for (unsigned i = threadIdx.x; i < n_fl; i += blockDim.x) priv[i] = 0.f;
+    __syncthreads();
+    GridFrame g = level_frame(h, tab.G[l]);
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+      const float* q = query + b * 3;
+      Cell c = make_cell_linear(g, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+      const unsigned xs[2] = {c.x0, c.x1}, ys[2] = {c.y0, c.y1}, zs[2] = {c.z0, c.z1};
+      const float ps[2] = {c.p0, c.p1}, qs[2] = {c.q0, c.q1}, rs[2] = {c.r0, c.r1};
+      for (int d = 0; d < h.D; ++d) {
+        float go = __ldg(go_ + out_index(layout, d, l, b, h.L, B, h.D));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          int cx = (k >> 2) & 1, cy = (k >> 1) & 1, cz = k & 1;
+          atomicAdd(&priv[hash3(xs[cx], ys[cy], zs[cz], T) * h.D + d], go * (ps[cx] * qs[cy] * rs[cz]));
+        }
+      }
+    }
+    __syncthreads();
+    float* gl = gf + tab.off[l];
+    for (unsigned i = threadIdx.x; i < n_fl; i += blockDim.x) {
+      float v = priv[i];
+      if (v != 0.f) atomicAdd(gl + i, v);
+    }
+    __syncthreads();
   }
 }
 
@@ -513,10 +554,10 @@ int ndjir_voxel_hash_grad_query_grad_grad_output(long long n_points, float* grad
 #define NDJIR_HASH_SCATTER(SECOND)                                                                             \
   do {                                                                                                         \
     int V = hash_vec(h, grad_feature);                                                                         \
-    int grid = grid_for(n_points * L);                                                                         \
-    if (V == 4) scatter_kernel<SECOND, 4><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout);      \
-    else if (V == 2) scatter_kernel<SECOND, 2><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout); \
-    else scatter_kernel<SECOND, 1><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout);             \
+    int grid = grid_for(n_points * (L - l_begin));                                                             \
+    if (V == 4) scatter_kernel<SECOND, 4><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout, l_begin);      \
+    else if (V == 2) scatter_kernel<SECOND, 2><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout, l_begin); \
+    else scatter_kernel<SECOND, 1><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, grad_feature, grad_output, gg, query, h, layout, l_begin);             \
   } while (0)
 
 int ndjir_voxel_hash_grad_feature(long long n_points, float* grad_feature, const float* grad_output,
@@ -528,7 +569,25 @@ int ndjir_voxel_hash_grad_feature(long long n_points, float* grad_feature, const
   if (n_points == 0) NDJIR_RETURN_LAST_ERROR();
   if (!grad_output || !query) return NDJIR_ERR_ARG;
   const float* gg = nullptr;
-  NDJIR_HASH_SCATTER(false);
+  int l_begin = 0;
+  if (g_hash_coarse_private && n_points >= (g_hash_coarse_private == 2 ? 1 : (1ll << 20))) {
+    // coarse levels (private copy <= 160 KB of shared memory, a dense prefix of the level list) go through the
+    // shared-memory privatised kernel
+    long long max_fl = 0;
+    while (l_begin < L) {
+      long long fl = (long long)level_table_size(level_grid_size(G0, growth_factor, l_begin), T0) * D;
+      if (fl * 4 > 160 * 1024 || fl / D >= n_points) break;              // too large, or too few points to contend
+      if (fl > max_fl) max_fl = fl;
+      ++l_begin;
+    }
+    if (l_begin > 0) {
+      size_t smem = (size_t)max_fl * 4;
+      cudaError_t e = cudaFuncSetAttribute(scatter_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); l_begin = 0; }
+      else scatter_coarse_kernel<<<NDJIR_NUM_SMS, 1024, smem, st>>>(n_points, grad_feature, grad_output, query, h, layout, l_begin);
+    }
+  }
+  if (l_begin < L) { NDJIR_HASH_SCATTER(false); }
   NDJIR_RETURN_LAST_ERROR();
 }
 
@@ -544,6 +603,7 @@ int ndjir_voxel_hash_grad_query_grad_feature(long long n_points, float* grad_fea
       !query || n_points < 0)
     return NDJIR_ERR_ARG;
   const float* gg = grad_grad_query;
+  const int l_begin = 0;
   NDJIR_HASH_SCATTER(true);
   NDJIR_RETURN_LAST_ERROR();
 }

@@ -687,3 +687,33 @@ def test_lanczos_voxel_binned_matches_direct(B, G, D):
         close(res[1][1][a], res[0][1][a], 1e-4, f"binned vs direct grad_feature accum={accum}")
         if not accum:
             assert torch.equal(res[1][1][a] != 0.0, g2 != 0.0)
+
+
+@pytest.mark.parametrize("B,G0,L,D,T0", [(5000, 16, 16, 2, 2 ** 15), (3001, 4, 6, 4, 2 ** 12), (1234, 3, 5, 1, 2 ** 10),
+                                         (70000, 16, 16, 2, 2 ** 15)])
+def test_voxel_hash_grad_feature_coarse_levels_private(B, G0, L, D, T0):
+    """grad_feature with the coarse levels accumulated in shared memory (forced with hash_coarse_private=2) against the
+    all-global-reductions kernel and the reference kernel, both accumulate modes."""
+    from ndjir_b200._lib import call
+    ours, ref = compat.load("voxel_hash_feature_cuda"), ref_mod("voxel_hash_feature_cuda")
+    gf = 1.5
+    q_np, rng = queries(B, spread=1.1)
+    total = call("ndjir_voxel_hash_num_params", G0, gf, T0, L, D)
+    q, go = dev(q_np), dev(rng.randn(D, L, B).astype(np.float32))
+    N = L * B
+    for accum in (False, True):
+        g_ref = torch.full((total,), 0.25).cuda()
+        ref.grad_feature(N, g_ref.data_ptr(), go.data_ptr(), q.data_ptr(), G0, gf, T0, L, D, MN, MX, False, accum)
+        res = {}
+        for mode in (0, 2):
+            call("ndjir_set_option", "hash_coarse_private", mode)
+            try:
+                g1 = torch.full((total,), 0.25).cuda()
+                ours.grad_feature(N, g1.data_ptr(), go.data_ptr(), q.data_ptr(), G0, gf, T0, L, D, MN, MX, False, accum)
+                res[mode] = g1
+            finally:
+                call("ndjir_set_option", "hash_coarse_private", 1)
+        close(res[2], g_ref, 1e-4, f"private coarse levels vs reference kernel, accum={accum}")
+        close(res[2], res[0], 1e-4, f"private coarse levels vs global reductions, accum={accum}")
+        if not accum:
+            assert torch.equal(res[2] != 0, g_ref != 0), "touched entries differ"

@@ -23,3 +23,13 @@ for lvl in (0, 1, 2, 3, 4, 6, 8, 12, 15):
     b = t(lambda: call("ndjir_voxel_hash_grad_feature", B, gf, go, q, G, 1.0, T0, 1, D, MN, MX, 0, 1, 0))
     print(f"level {lvl:2d} G={G:5d} T={min(G**3, T0):6d}: fwd {f:.3f} ms  grad_feature {b:.3f} ms", flush=True)
 
+
+# full bench shape: grad_feature with / without the shared-memory privatised coarse levels
+G0, gf_, L = 16, 1.5, 16
+n = call("ndjir_voxel_hash_num_params", G0, gf_, T0, L, D)
+gfe = torch.zeros(n, device="cuda"); go = torch.ones(D * L * B, device="cuda")
+for mode in (0, 1, 0, 1):
+    call("ndjir_set_option", "hash_coarse_private", mode)
+    ms = t(lambda: call("ndjir_voxel_hash_grad_feature", B, gfe, go, q, G0, gf_, T0, L, D, MN, MX, 0, 0, 0))
+    print(f"bench shape grad_feature, hash_coarse_private={mode}: {ms:.3f} ms", flush=True)
+call("ndjir_set_option", "hash_coarse_private", 1)
