@@ -209,19 +209,26 @@ gather_fwd_chunk_kernel(long long B, float* __restrict__ out, const float* __res
   }
 }
 
-// Scatter with one thread per (point, plane|line, corner): 12 (6) threads per point, one vector reduction per
-// channel chunk each.
+// Scatter with one thread per (point, plane|line, corner, channel chunk of V): the chunks of a cell sit in ADJACENT
+// lanes, so one warp-wide reduction instruction carries whole 32-byte sectors (D = 8: two 16-byte halves side by side)
+// instead of issuing the halves of a cell from two instructions of the same lane - half as many L2 transactions on
+// tables whose reductions are contention-bound (triline: 49 152 cells for 2^24 points).
 template <bool PLANE, bool SECOND, int V>
 __global__ void __launch_bounds__(NDJIR_BLOCK)
 scatter_split_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go_, const float* __restrict__ gg,
                      const float* __restrict__ query, GridFrame g, int G, int D) {
   constexpr int NC = PLANE ? 4 : 2;
+  const int nchunk = D / V;
   long long stride = (long long)gridDim.x * blockDim.x;
   const long long plane_elems = PLANE ? (long long)G * G * D : (long long)G * D;
-  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < B * 3 * NC; w += stride) {
-    long long p = w / (3 * NC);
-    int rem = (int)(w - p * 3 * NC);
-    int i = rem / NC, k = rem - i * NC;
+  const long long per_point = 3ll * NC * nchunk;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < B * per_point; w += stride) {
+    long long p = w / per_point;
+    int rem = (int)(w - p * per_point);
+    int i = rem / (NC * nchunk);
+    rem -= i * NC * nchunk;
+    int k = rem / nchunk;
+    int d = (rem - k * nchunk) * V;
     const float* q = query + p * 3;
     Cell c = make_cell(g, __ldg(q), __ldg(q + 1), __ldg(q + 2));
     float ggx = 0.f, ggy = 0.f, ggz = 0.f;
@@ -239,13 +246,10 @@ scatter_split_kernel(long long B, float* __restrict__ gf, const float* __restric
       off = (long long)(k ? x.u1 : x.u0) * D;
     }
     const float* grow = go_ + p * 3 * D + i;
-    float* gi = gf + i * plane_elems + off;
-    for (int d = 0; d < D; d += V) {
-      Vec<V> val;
+    Vec<V> val;
 #pragma unroll
-      for (int j = 0; j < V; ++j) val.v[j] = __ldg(grow + (d + j) * 3) * coef;
-      red_vec<V>(gi + d, val);
-    }
+    for (int j = 0; j < V; ++j) val.v[j] = __ldg(grow + (d + j) * 3) * coef;
+    red_vec<V>(gf + i * plane_elems + off + d, val);
   }
 }
 
@@ -294,7 +298,7 @@ static int launch_scatter(long long B, float* gf, const float* go, const float* 
     // triline: the table is tiny (49 152 cells at G=2048) and the reductions are contention-bound (1.6 ms at 2^24
     // points; tried and rejected: scalar reductions 6.0 ms, a shared-memory private copy of the table 3.1 ms)
     int V2 = pick_vec(D, gf);
-    int gridc = grid_for(B * 3 * (PLANE ? 4 : 2));
+    int gridc = grid_for(B * 3 * (PLANE ? 4 : 2) * (D / V2));
     if (V2 == 4) scatter_split_kernel<PLANE, SECOND, 4><<<gridc, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, G, D);
     else if (V2 == 2) scatter_split_kernel<PLANE, SECOND, 2><<<gridc, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, G, D);
     else scatter_split_kernel<PLANE, SECOND, 1><<<gridc, NDJIR_BLOCK, 0, st>>>(B, gf, go, gg, query, g, G, D);
