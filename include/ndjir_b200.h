@@ -355,6 +355,12 @@ int ndjir_gemm(int M, int N, int K, const float* A, long long a_rs, long long a_
                const float* H, long long ldh, float hscale, const float* U, long long ldu, float* C2,
                long long ldc2, int split_k, int epilogue, cudaStream_t stream);
 
+/* Weight and bias gradient of one affine layer in one call (the backward of PF.affine, python/network.py:88-93):
+ * gW (K_in, N) += A(rows, K_in)^T dZ(rows, N), gb (N) += column sums of dZ (gb may be NULL).  On the tcgen05 path the
+ * column sums ride on the product's shared-memory pass over dZ; option "mlp_fused_colsum" = 0 runs them separately. */
+int ndjir_wgrad_bias(long long rows, int K_in, int N, const float* A, long long lda, const float* dZ, long long ldz,
+                     float* gW, long long ldw, float* gb, int split_k, cudaStream_t stream);
+
 /* ---- sample placement (python/sampler.py) ---- */
 /* :140-165  t = t_near + (t_far - t_near)/N0 * (i + xi) */
 int ndjir_stratified_dists(int n_rays, int N0, float* t, const float* t_near, const float* t_far, const float* xi,

@@ -186,6 +186,7 @@ static void dispatch_tile(const Args& a, cudaStream_t st) {
   }
 }
 
+int g_mlp_fused_colsum = 1;   // ndjir_wgrad_bias: bias gradient carried by the weight-gradient product's transform warps
 int g_mlp_tensor_cores = 1;   // 1: tcgen05 3xTF32 path where shapes allow (gemm_tc.cu), 0: fp32 FFMA everywhere
 
 int launch(const Args& a, int epi, cudaStream_t st) {
@@ -236,3 +237,25 @@ extern "C" int ndjir_gemm_presplit(int M, int N, int K, const float* A, long lon
   a.U = U; a.ldu = ldu; a.C2 = C2; a.ldc2 = ldc2; a.split_k = split_k;
   return ndjir::gemm::launch(a, epilogue, stream);
 }
+
+// Weight gradient and bias gradient of one layer in one call: gW (K_in, N) += A(rows, K_in)^T dZ(rows, N) (split-K with
+// atomic accumulation) and gb (N) += column sums of dZ.  On the tcgen05 path the transform warps, which read every dZ
+// tile anyway, carry the column sums (no second pass over dZ); otherwise the product is followed by ndjir_colsum.
+extern "C" int ndjir_colsum(long long rows, int cols, float* out, const float* src, long long ld_src, float alpha,
+                            cudaStream_t stream);
+extern "C" int ndjir_wgrad_bias(long long rows, int K_in, int N, const float* A, long long lda, const float* dZ,
+                                long long ldz, float* gW, long long ldw, float* gb, int split_k, cudaStream_t stream) {
+  if (rows == 0 || K_in <= 0 || N <= 0) return NDJIR_OK;
+  if (rows < 0 || rows > 0x7fffffffll || !A || !dZ || !gW) return NDJIR_ERR_ARG;
+  using namespace ndjir::gemm;
+  Args a = make_args(K_in, N, (int)rows);
+  a.A = A; a.a_rs = 1; a.a_cs = lda; a.B = dZ; a.b_rs = ldz; a.b_cs = 1; a.C = gW; a.ldc = ldw;
+  a.split_k = split_k > 1 ? split_k : 1;
+  const bool fused = gb && g_mlp_tensor_cores && g_mlp_fused_colsum && !skinny_eligible(a, EPI_ATOMIC) &&
+                     tc_eligible(a, EPI_ATOMIC);
+  if (fused) a.colsum = gb;
+  int rc = launch(a, EPI_ATOMIC, stream);
+  if (rc != NDJIR_OK || !gb || fused) return rc;
+  return ndjir_colsum(rows, N, gb, dZ, ldz, 1.0f, stream);
+}
+

@@ -38,6 +38,7 @@ struct Args {
   const float* U; long long ldu;         // EPI_MUL_S addend / EPI_ADJ factor
   float* C2; long long ldc2;             // EPI_ADJ second output
   int split_k;                           // >1: K is split over gridDim.z (EPI_ATOMIC only)
+  float* colsum;                         // optional [N]: += column sums of B over k (bias gradient of a wgrad product)
 };
 
 static inline Args make_args(int M, int N, int K) {
@@ -49,7 +50,7 @@ static inline Args make_args(int M, int N, int K) {
   a.alpha = 1.f; a.out_scale = 1.f; a.beta = 100.f;
   a.H = nullptr; a.ldh = 0; a.hscale = 1.f;
   a.U = nullptr; a.ldu = 0;
-  a.C2 = nullptr; a.ldc2 = 0; a.split_k = 1;
+  a.C2 = nullptr; a.ldc2 = 0; a.split_k = 1; a.colsum = nullptr;
   return a;
 }
 
@@ -101,6 +102,7 @@ int launch(const Args& a, int epi, cudaStream_t st);
 extern int g_mlp_tensor_cores;
 extern int g_mlp_cta_pair;
 extern int g_mlp_dbg;
+extern int g_mlp_fused_colsum;
 extern int g_mlp_presplit;    // 1: a B operand that comes with its lo part is fetched as raw + lo TMA tiles
 extern int g_mlp_mask_hi;     // 1: the transform warps also clear the low 13 mantissa bits of the raw tiles
 bool tc_eligible(const Args& a, int epi);

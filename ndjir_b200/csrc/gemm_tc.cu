@@ -166,6 +166,7 @@ struct TcParams {
   int mask_hi;
   int dbg;
   int a_3d, b_3d;        // MN-major operand loaded with ONE 3-D TMA request per K block (extent % 32 == 0)
+  int do_colsum;         // the transform warps also accumulate the column sums of the MN-major B tiles (a.colsum)
   int b_lo_tma;          // the lo part of B comes pre-split from global memory (registered weights): no B transform
   int vec_epi;           // every epilogue operand is 16-byte aligned with a row stride that is a multiple of 4
   int m_tiles, n_tiles, splits, kb_per_split, nkb_total;
@@ -218,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * TC_STAGES + 4];
   __shared__ uint32_t tmem_base_sh;
+  __shared__ float colsum_sh[TC_BN];
 
   const Args& a = p.a;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -368,11 +370,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===================== transform: lo = x - hi for both operand tiles =====================
     const int t = threadIdx.x - 64;   // 0..TC_XFORM_THREADS-1
     uint32_t it = 0;
+    // Column sums of B (the bias gradient that goes with a weight-gradient product): every thread meets the same
+    // four 16-byte pieces of the [chunk][k][32 n] tile in every K block, so it keeps four private float4 sums and
+    // folds them into the CTA's column vector once per work item.  Physical -> logical offset of a piece: the
+    // 128-byte rows are swizzled in 32-byte units, unit ^= (row & 3) (Swizzle<2,5,2>, the layout TMA wrote).
+    float4 cs[B_TILE_BYTES / (TC_XFORM_THREADS * 16)];
+#pragma unroll
+    for (int j = 0; j < B_TILE_BYTES / (TC_XFORM_THREADS * 16); ++j) cs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.do_colsum) {
+      for (int c = t; c < TC_BN; c += TC_XFORM_THREADS) colsum_sh[c] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_XFORM_THREADS) : "memory");
+    }
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int m0, n0, kb0, nkb;
       item_info(item, m0, n0, kb0, nkb);
       const int umma_n = (min(TC_BN, a.N - n0) + 15) & ~15;
       const int b_bytes = (p.b_mn && !p.b_3d) ? ((umma_n + 31) / 32) * TC_BK * 128 : B_TILE_BYTES;
+      const bool sum_b = p.do_colsum && m0 == 0;     // one m tile per (n tile, K split) carries the sums
       for (int i = 0; i < nkb; ++i, ++it) {
         int s = it % TC_STAGES;
         uint32_t ph = (it / TC_STAGES) & 1;
@@ -391,20 +405,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           sts128(st + A_TILE_BYTES + off, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
           if (p.mask_hi) sts128(st + off, h);
         }
-        if (!p.b_lo_tma)
-#pragma unroll 4
-        for (int off = t * 16; off < b_bytes; off += TC_XFORM_THREADS * 16) {
-          float4 x = lds128(st + 2 * A_TILE_BYTES + off);
-          float4 h;
-          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-          sts128(st + 2 * A_TILE_BYTES + B_TILE_BYTES + off, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
-          if (p.mask_hi) sts128(st + 2 * A_TILE_BYTES + off, h);
+        if (!p.b_lo_tma) {
+#pragma unroll
+          for (int j = 0; j < B_TILE_BYTES / (TC_XFORM_THREADS * 16); ++j) {
+            const int off = t * 16 + j * TC_XFORM_THREADS * 16;
+            if (off < b_bytes) {
+              float4 x = lds128(st + 2 * A_TILE_BYTES + off);
+              float4 h;
+              h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+              h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+              h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+              h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+              sts128(st + 2 * A_TILE_BYTES + B_TILE_BYTES + off, make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w));
+              if (p.mask_hi) sts128(st + 2 * A_TILE_BYTES + off, h);
+              if (sum_b) { cs[j].x += x.x; cs[j].y += x.y; cs[j].z += x.z; cs[j].w += x.w; }
+            }
+          }
         }
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(bar_ready(s));
+      }
+      if (sum_b) {
+#pragma unroll
+        for (int j = 0; j < B_TILE_BYTES / (TC_XFORM_THREADS * 16); ++j) {
+          const int off = t * 16 + j * TC_XFORM_THREADS * 16;
+          if (off < b_bytes) {
+            const int lof = off ^ (((off >> 7) & 3) << 5);                 // undo the 32-byte-unit swizzle
+            const int col = (lof >> 11) * 32 + ((lof & 127) >> 2);          // chunk * 32 + n inside the 128-byte row
+            atomicAdd(&colsum_sh[col], cs[j].x); atomicAdd(&colsum_sh[col + 1], cs[j].y);
+            atomicAdd(&colsum_sh[col + 2], cs[j].z); atomicAdd(&colsum_sh[col + 3], cs[j].w);
+          }
+          cs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_XFORM_THREADS) : "memory");
+        for (int c = t; c < TC_BN; c += TC_XFORM_THREADS) {
+          float v = colsum_sh[c];
+          colsum_sh[c] = 0.f;
+          if (v != 0.f && n0 + c < a.N) atomicAdd(a.colsum + n0 + c, v);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_XFORM_THREADS) : "memory");
       }
     }
   } else {
@@ -840,7 +879,7 @@ static int launch_tc2_epi(const Args& a, cudaStream_t st) {
   p.a = a;
   p.a_mn = 0;
   p.b_mn = (a.b_cs == 1);
-  p.mask_hi = 0; p.dbg = 0; p.a_3d = 0; p.b_lo_tma = 0;
+  p.mask_hi = 0; p.dbg = 0; p.a_3d = 0; p.b_lo_tma = 0; p.do_colsum = 0;
   auto ok16 = [](const void* q, long long ld) { return q == nullptr || (al16p(q) && ld % 4 == 0); };
   p.vec_epi = ok16(a.C, a.ldc) && ok16(a.H, a.ldh) && ok16(a.U, a.ldu) && ok16(a.C2, a.ldc2) && ok16(a.bias, 0);
   p.b_3d = p.b_mn && a.N % 64 == 0;
@@ -908,6 +947,7 @@ static int launch_tc_epi(const Args& a, cudaStream_t st) {
   CUtensorMap mapBlo = mapB;
   const float* blo = g_mlp_presplit ? a.B_lo : nullptr;
   p.b_lo_tma = (blo != nullptr && al16p(blo)) ? 1 : 0;
+  p.do_colsum = (a.colsum != nullptr && p.b_mn && EPI == EPI_ATOMIC && !p.b_lo_tma) ? 1 : 0;
   if (p.b_lo_tma) {
     if (p.b_3d) ok = ok && make_map3(&mapBlo, blo, a.N, a.K, a.b_rs, TC_BN / 32);
     else if (p.b_mn) ok = ok && make_map(&mapBlo, blo, a.N, a.K, a.b_rs, 32, TC_BK, true);

@@ -366,6 +366,7 @@ int ndjir_set_option(const char* key, int value) {
       {"mlp_tensor_cores", &ndjir::gemm::g_mlp_tensor_cores},  // 0: fp32 FFMA parity path for every MLP product
       {"mlp_cta_pair", &ndjir::gemm::g_mlp_cta_pair},       // 1: tcgen05 cta_group::2 product kernel (measured slower)
       {"mlp_presplit", &ndjir::gemm::g_mlp_presplit},       // 0: ignore caller-supplied lo parts of the weight operand
+      {"mlp_fused_colsum", &ndjir::gemm::g_mlp_fused_colsum},  // 0: bias gradients by a separate column-sum pass
       {"mlp_dbg", &ndjir::gemm::g_mlp_dbg},                 // profiling switches of the tcgen05 kernel
       {"mlp_mask_hi", &ndjir::gemm::g_mlp_mask_hi},
       {"voxel_binned", &ndjir::g_voxel_binned},             // -1 auto, 0 never, 1 whenever possible (brick-ordered sweeps)

@@ -292,11 +292,21 @@ class Engine:
             e1.record()
             self.prof_events.append((e0, e1, 2.0 * M * N * K, f"epi{epi} {M}x{N}x{K}"))
 
-    def wgrad(self, rows, K, N, A, lda, dZ, ldz, gW, ldw):
-        """gW (K,N) += A(rows,K)^T dZ(rows,N): split-K over the rows with atomic accumulation."""
+    def wgrad(self, rows, K, N, A, lda, dZ, ldz, gW, ldw, gb=0):
+        """gW (K,N) += A(rows,K)^T dZ(rows,N): split-K over the rows with atomic accumulation; gb (N) += column sums
+        of dZ (the bias gradient) in the same call when given."""
         tiles = ((K + 127) // 128) * ((N + 127) // 128 if N > 32 else 1)
         split = max(1, min(rows // 512, (148 * 4) // tiles))
-        self.gemm(K, N, rows, A, 1, lda, dZ, ldz, 1, gW, ldw, EPI_ATOMIC, split_k=split)
+        if not gb:
+            self.gemm(K, N, rows, A, 1, lda, dZ, ldz, 1, gW, ldw, EPI_ATOMIC, split_k=split)
+            return
+        if self.profile:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.call("ndjir_wgrad_bias", rows, K, N, A, lda, dZ, ldz, gW, ldw, gb, split)
+        if self.profile:
+            e1.record()
+            self.prof_events.append((e0, e1, 2.0 * K * N * rows, f"epi5 {K}x{N}x{rows}"))
 
     def copy2d(self, rows, cols, dst, ld_dst, src, ld_src, rep=1, alpha=1.0, accum=0):
         self.call("ndjir_copy2d", rows, cols, dst, ld_dst, src, ld_src, rep, alpha, accum)
@@ -506,8 +516,7 @@ class Engine:
         last = A[nl]
         pp = [self.buf("geo_dz0", rows, r4(self.Df)), self.buf("geo_dz1", rows, r4(self.Df))]
         # last layer
-        self.wgrad(rows, Lf.K, Lf.N, P_(last), last.shape[1], P_(dO), self.LDO, ps.gW(Lf), Lf.ldw)
-        self.call("ndjir_colsum", rows, Lf.N, ps.gb(Lf), P_(dO), self.LDO, 1.0)
+        self.wgrad(rows, Lf.K, Lf.N, P_(last), last.shape[1], P_(dO), self.LDO, ps.gW(Lf), Lf.ldw, gb=ps.gb(Lf))
         cur = pp[0]
         ldc = cur.shape[1]
         self.gemm(rows, Lf.K, Lf.N, P_(dO), self.LDO, 1, *ps.Bt(Lf), P_(cur), ldc, EPI_MUL_S, H=P_(last),
@@ -522,8 +531,7 @@ class Engine:
         for l in range(nl - 1, -1, -1):
             L = net[l]
             Al = A[l]
-            self.wgrad(rows, L.K, L.N, P_(Al), Al.shape[1], P_(cur), ldc, ps.gW(L), L.ldw)
-            self.call("ndjir_colsum", rows, L.N, ps.gb(L), P_(cur), ldc, 1.0)
+            self.wgrad(rows, L.K, L.N, P_(Al), Al.shape[1], P_(cur), ldc, ps.gW(L), L.ldw, gb=ps.gb(L))
             if l > 0:
                 is_skip = (l == self.skip)
                 n_prev = net[l - 1].N
@@ -577,8 +585,7 @@ class Engine:
         cur = pp[0]
         first = True
         for (dptr, ldd), L in zip(douts, net[nh:]):
-            self.wgrad(rows, L.K, L.N, lastA, lda, dptr, ldd, ps.gW(L), L.ldw)
-            self.call("ndjir_colsum", rows, L.N, ps.gb(L), dptr, ldd, 1.0)
+            self.wgrad(rows, L.K, L.N, lastA, lda, dptr, ldd, ps.gW(L), L.ldw, gb=ps.gb(L))
             if nh:
                 self.gemm(rows, L.K, L.N, dptr, ldd, 1, *ps.Bt(L), P_(cur), wmax, EPI_MUL_S, H=lastA, ldh=lda,
                           U=(0 if first else P_(cur)), ldu=(0 if first else wmax))
@@ -589,8 +596,7 @@ class Engine:
         for l in range(nh - 1, -1, -1):
             L = net[l]
             Aptr, lda = (P_(acts[l - 1]), acts[l - 1].shape[1]) if l > 0 else (X, ldx)
-            self.wgrad(rows, L.K, L.N, Aptr, lda, P_(cur), wmax, ps.gW(L), L.ldw)
-            self.call("ndjir_colsum", rows, L.N, ps.gb(L), P_(cur), wmax, 1.0)
+            self.wgrad(rows, L.K, L.N, Aptr, lda, P_(cur), wmax, ps.gW(L), L.ldw, gb=ps.gb(L))
             if l > 0:
                 nxt = pp[1] if cur is pp[0] else pp[0]
                 self.gemm(rows, L.K, L.N, P_(cur), wmax, 1, *ps.Bt(L), P_(nxt), wmax, EPI_MUL_S, H=Aptr,
