@@ -95,9 +95,11 @@ __global__ void __launch_bounds__(NDJIR_BLOCK) skinny_k_vec4_kernel(Args a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       if (EPI == EPI_BIAS) o[e] = a.alpha * acc[e] + bb[e];
-      else if (EPI == EPI_SOFTPLUS) o[e] = a.out_scale * softplus_beta(acc[e] + bb[e], a.beta);
+      // fast-math activations as in the tensor-core epilogue (these kernels only run on that path): the exact expm1f /
+      // log1pf made this memory-bound kernel compute-bound (0.23 ms for 268 M elements against a 0.08-0.12 ms HBM floor)
+      else if (EPI == EPI_SOFTPLUS) o[e] = a.out_scale * softplus_beta_fast(acc[e] + bb[e], a.beta);
       else if (EPI == EPI_ACCUM) o[e] = co[e] + a.alpha * acc[e];
-      else o[e] = a.alpha * acc[e] * sig_from_softplus(h[e] * a.hscale, a.beta) + u[e];
+      else o[e] = a.alpha * acc[e] * sig_from_softplus_fast(h[e] * a.hscale, a.beta) + u[e];
     }
     *reinterpret_cast<float4*>(a.C + m * a.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
   }
