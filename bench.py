@@ -385,6 +385,9 @@ def run_ours(args, conf):
         cfg = workload(conf)
         cfg["launch"] = ("one CUDA-graph replay per step (Engine.train_step_graphed)" if use_graph
                          else "eager: every kernel enqueued from the host")
+        if world > 1:
+            cfg["grid_gradient_exchange"] = ("sparse: all-gather of the per-sample scatter inputs, replicated scatter"
+                                             if eng._sparse_grid() else "dense all-reduce of the table gradient")
         cfg["parallelism"] = f"ray-sharded x{world}, replicated parameters, NCCL gradient all-reduce" if world > 1 else "1 GPU"
         line = {"metric": "train_rays_per_sec_fwd_bwd", "value": value, "unit": "rays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
