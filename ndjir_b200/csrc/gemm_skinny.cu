@@ -15,10 +15,14 @@ constexpr int SK_WARPS = 8;
 
 template <int NT, int EPI>
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_n_kernel(Args a, int vec) {
-  extern __shared__ float Bs[];   // [K][NT]
-  for (int i = threadIdx.x; i < a.K * NT; i += blockDim.x) {
-    int k = i / NT, n = i - k * NT;
-    Bs[i] = n < a.N ? __ldg(a.B + (long long)k * a.b_rs + (long long)n * a.b_cs) : 0.f;
+  // B staged as [NT][Kp] (k contiguous, Kp = K rounded up to 4): lane l reads the float4 at k = 4 l of every output's
+  // row, consecutive lanes consecutive 16 bytes - conflict-free.  (The first version staged [K][NT]: the lanes of a
+  // 128-bit shared load were 16 NT bytes apart, a 4-way bank conflict that made this one-pass kernel run at 1.6 TB/s.)
+  extern __shared__ __align__(16) float Bs[];
+  const int Kp = (a.K + 3) & ~3;
+  for (int i = threadIdx.x; i < Kp * NT; i += blockDim.x) {
+    int n = i / Kp, k = i - n * Kp;
+    Bs[i] = (n < a.N && k < a.K) ? __ldg(a.B + (long long)k * a.b_rs + (long long)n * a.b_cs) : 0.f;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -32,15 +36,16 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_n_kernel(Args a, int vec
     for (int n = 0; n < NT; ++n) acc[n] = 0.f;
     for (int k = lane * 4; k < K4; k += 128) {
       float4 x = __ldg(reinterpret_cast<const float4*>(row + k));
-      const float* b = Bs + k * NT;
 #pragma unroll
-      for (int n = 0; n < NT; ++n)
-        acc[n] += x.x * b[n] + x.y * b[NT + n] + x.z * b[2 * NT + n] + x.w * b[3 * NT + n];
+      for (int n = 0; n < NT; ++n) {
+        float4 b = *reinterpret_cast<const float4*>(Bs + n * Kp + k);
+        acc[n] += x.x * b.x + x.y * b.y + x.z * b.z + x.w * b.w;
+      }
     }
     for (int k = K4 + lane; k < a.K; k += 32) {
       float x = __ldg(row + k);
 #pragma unroll
-      for (int n = 0; n < NT; ++n) acc[n] += x * Bs[k * NT + n];
+      for (int n = 0; n < NT; ++n) acc[n] += x * Bs[n * Kp + k];
     }
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[n] = warp_sum(acc[n]);
@@ -154,7 +159,7 @@ static void launch_skinny_n(const Args& a, int epi, cudaStream_t st) {
   long long blocks = (a.M + SK_WARPS - 1) / SK_WARPS;
   long long cap = (long long)NDJIR_NUM_SMS * 16;
   int grid = (int)(blocks < cap ? blocks : cap);
-  size_t smem = (size_t)a.K * NT * sizeof(float);
+  size_t smem = (size_t)((a.K + 3) & ~3) * NT * sizeof(float);
   if (epi == EPI_BIAS) skinny_n_kernel<NT, EPI_BIAS><<<grid, SK_WARPS * 32, smem, st>>>(a, vec);
   else skinny_n_kernel<NT, EPI_ACCUM><<<grid, SK_WARPS * 32, smem, st>>>(a, vec);
 }
