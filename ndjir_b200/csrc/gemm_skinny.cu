@@ -25,16 +25,22 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_n_kernel(Args a, int vec
     Bs[i] = (n < a.N && k < a.K) ? __ldg(a.B + (long long)k * a.b_rs + (long long)n * a.b_cs) : 0.f;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * SK_WARPS + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * SK_WARPS;
+  // FOUR ROWS PER WARP, eight lanes per row: every lane has K/32 independent 16-byte loads in flight (one warp per row
+  // had two) and the reduction is three shuffle steps per output instead of five.
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const long long row0 = ((long long)blockIdx.x * SK_WARPS + (threadIdx.x >> 5)) * 4 + grp;
+  const long long row_stride = (long long)gridDim.x * SK_WARPS * 4;
   const int K4 = vec ? (a.K & ~3) : 0;
-  for (long long m = warp0; m < a.M; m += nwarps) {
-    const float* row = a.A + m * a.a_rs;
+  const long long rounds = (a.M + row_stride - 1) / row_stride;
+  for (long long r = 0; r < rounds; ++r) {
+    const long long m = row0 + r * row_stride;
+    const bool active = m < a.M;
+    const float* row = a.A + (active ? m : a.M - 1) * a.a_rs;
     float acc[NT];
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[n] = 0.f;
-    for (int k = lane * 4; k < K4; k += 128) {
+#pragma unroll 4
+    for (int k = sub * 4; k < K4; k += 32) {
       float4 x = __ldg(reinterpret_cast<const float4*>(row + k));
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
@@ -42,18 +48,22 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_n_kernel(Args a, int vec
         acc[n] += x.x * b.x + x.y * b.y + x.z * b.z + x.w * b.w;
       }
     }
-    for (int k = K4 + lane; k < a.K; k += 32) {
+    for (int k = K4 + sub; k < a.K; k += 8) {
       float x = __ldg(row + k);
 #pragma unroll
       for (int n = 0; n < NT; ++n) acc[n] += x * Bs[n * Kp + k];
     }
 #pragma unroll
-    for (int n = 0; n < NT; ++n) acc[n] = warp_sum(acc[n]);
-    if (lane < a.N) {
+    for (int n = 0; n < NT; ++n) {
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+    }
+    if (active && sub < a.N) {
       float v = 0.f;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) if (lane == n) v = acc[n];
-      epilogue_store<EPI>(a, (int)m, lane, v);
+      for (int n = 0; n < NT; ++n) if (sub == n) v = acc[n];
+      epilogue_store<EPI>(a, (int)m, sub, v);
     }
   }
 }
@@ -156,7 +166,7 @@ bool skinny_eligible(const Args& a, int epi) {
 template <int NT>
 static void launch_skinny_n(const Args& a, int epi, cudaStream_t st) {
   int vec = al16s(a.A) && a.a_rs % 4 == 0;
-  long long blocks = (a.M + SK_WARPS - 1) / SK_WARPS;
+  long long blocks = (a.M + SK_WARPS * 4 - 1) / (SK_WARPS * 4);
   long long cap = (long long)NDJIR_NUM_SMS * 16;
   int grid = (int)(blocks < cap ? blocks : cap);
   size_t smem = (size_t)((a.K + 3) & ~3) * NT * sizeof(float);
