@@ -115,14 +115,14 @@ enum Mode { FWD = 0, GRAD_QUERY = 1, GGO = 2 };
 template <int MODE, int V, bool ACCUM>
 __global__ void __launch_bounds__(NDJIR_BLOCK)
 gather_kernel(long long B, float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ gg,
-              const float* __restrict__ query, const float* __restrict__ feat, HashSpec h, int layout) {
+              const float* __restrict__ query, const float* __restrict__ feat, HashSpec h, int layout, int l_begin) {
   __shared__ LevelTable tab;
   build_table(tab, h);
-  const long long N = B * h.L;
+  const long long N = B * (h.L - l_begin);    // levels below l_begin were handled by fwd_coarse_kernel
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += stride) {
-    int l = (int)(n / B);
-    long long b = n - (long long)l * B;
+    int l = l_begin + (int)(n / B);
+    long long b = n - (long long)(l - l_begin) * B;
     GridFrame g = level_frame(h, tab.G[l]);
     unsigned T = (unsigned)tab.T[l];
     const float* fl = feat + tab.off[l];
@@ -208,6 +208,41 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
 #pragma unroll
         for (int j = 0; j < V; ++j) val.v[j] = o.v[j] * coef;
         red_vec<V>(gl + hash3(xs[cx], ys[cy], zs[cz], T) * h.D + d, val);
+      }
+    }
+  }
+}
+
+// Forward over the COARSE levels of a large batch with the level table staged in shared memory: the gathers of the
+// per-thread kernel above are bound by the L1 tag stage (one look-up per lane and clock, 0.26 ms per level at 2^24
+// points); a level that fits 160 KB is served from shared memory by a persistent grid instead.
+template <bool ACCUM>
+__global__ void __launch_bounds__(1024, 1)
+fwd_coarse_kernel(long long B, float* __restrict__ out, const float* __restrict__ query, const float* __restrict__ feat,
+                  HashSpec h, int layout, int n_coarse) {
+  extern __shared__ float tabs[];
+  __shared__ LevelTable tab;
+  build_table(tab, h);
+  for (int l = 0; l < n_coarse; ++l) {
+    const unsigned T = (unsigned)tab.T[l];
+    const unsigned n_fl = T * (unsigned)h.D;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n_fl; i += blockDim.x) tabs[i] = __ldg(feat + tab.off[l] + i);
+    __syncthreads();
+    GridFrame g = level_frame(h, tab.G[l]);
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+      const float* q = query + b * 3;
+      Cell c = make_cell_linear(g, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+      const float* e000 = tabs + hash3(c.x0, c.y0, c.z0, T) * h.D; const float* e001 = tabs + hash3(c.x0, c.y0, c.z1, T) * h.D;
+      const float* e010 = tabs + hash3(c.x0, c.y1, c.z0, T) * h.D; const float* e011 = tabs + hash3(c.x0, c.y1, c.z1, T) * h.D;
+      const float* e100 = tabs + hash3(c.x1, c.y0, c.z0, T) * h.D; const float* e101 = tabs + hash3(c.x1, c.y0, c.z1, T) * h.D;
+      const float* e110 = tabs + hash3(c.x1, c.y1, c.z0, T) * h.D; const float* e111 = tabs + hash3(c.x1, c.y1, c.z1, T) * h.D;
+      for (int d = 0; d < h.D; ++d) {
+        float f = c.p0 * c.q0 * c.r0 * e000[d] + c.p0 * c.q0 * c.r1 * e001[d] + c.p0 * c.q1 * c.r0 * e010[d] +
+                  c.p0 * c.q1 * c.r1 * e011[d] + c.p1 * c.q0 * c.r0 * e100[d] + c.p1 * c.q0 * c.r1 * e101[d] +
+                  c.p1 * c.q1 * c.r0 * e110[d] + c.p1 * c.q1 * c.r1 * e111[d];      // gather_kernel<FWD>'s expression
+        long long oi = out_index(layout, d, l, b, h.L, B, h.D);
+        out[oi] = ACCUM ? out[oi] + f : f;
       }
     }
   }
@@ -495,16 +530,16 @@ int ndjir_voxel_hash_hash_index(long long n_points, float* output, const float* 
 #define NDJIR_HASH_GATHER(MODE, accum_)                                                                          \
   do {                                                                                                           \
     int V = hash_vec(h, feature);                                                                                \
-    int grid = grid_for(n_points * L);                                                                           \
+    int grid = grid_for(n_points * (L - l_begin));                                                               \
     if (V == 4) {                                                                                                \
-      if (accum_) gather_kernel<MODE, 4, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout); \
-      else gather_kernel<MODE, 4, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout);       \
+      if (accum_) gather_kernel<MODE, 4, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout, l_begin); \
+      else gather_kernel<MODE, 4, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout, l_begin);       \
     } else if (V == 2) {                                                                                         \
-      if (accum_) gather_kernel<MODE, 2, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout); \
-      else gather_kernel<MODE, 2, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout);       \
+      if (accum_) gather_kernel<MODE, 2, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout, l_begin); \
+      else gather_kernel<MODE, 2, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout, l_begin);       \
     } else {                                                                                                     \
-      if (accum_) gather_kernel<MODE, 1, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout); \
-      else gather_kernel<MODE, 1, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout);       \
+      if (accum_) gather_kernel<MODE, 1, true><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout, l_begin); \
+      else gather_kernel<MODE, 1, false><<<grid, NDJIR_BLOCK, 0, st>>>(n_points, out, a, gg, query, feature, h, layout, l_begin);       \
     }                                                                                                            \
   } while (0)
 
@@ -517,7 +552,25 @@ int ndjir_voxel_hash_voxel_hash_feature(long long n_points, float* output, const
   if (make_spec(h, G0, growth_factor, T0, L, D, min3, max3) || !output || !query || !feature || n_points < 0)
     return NDJIR_ERR_ARG;
   float* out = output; const float* a = nullptr; const float* gg = nullptr;
-  NDJIR_HASH_GATHER(FWD, accum);
+  int l_begin = 0;
+  if (g_hash_coarse_private && n_points >= (g_hash_coarse_private == 2 ? 1 : (1ll << 20))) {
+    long long max_fl = 0;
+    while (l_begin < L) {       // the dense prefix of levels whose table fits 160 KB of shared memory
+      long long fl = (long long)level_table_size(level_grid_size(G0, growth_factor, l_begin), T0) * D;
+      if (fl * 4 > 160 * 1024) break;
+      if (fl > max_fl) max_fl = fl;
+      ++l_begin;
+    }
+    if (l_begin > 0) {
+      size_t smem = (size_t)max_fl * 4;
+      cudaError_t e = accum ? cudaFuncSetAttribute(fwd_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(fwd_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); l_begin = 0; }
+      else if (accum) fwd_coarse_kernel<true><<<NDJIR_NUM_SMS, 1024, smem, st>>>(n_points, output, query, feature, h, layout, l_begin);
+      else fwd_coarse_kernel<false><<<NDJIR_NUM_SMS, 1024, smem, st>>>(n_points, output, query, feature, h, layout, l_begin);
+    }
+  }
+  if (l_begin < L) { NDJIR_HASH_GATHER(FWD, accum); }
   NDJIR_RETURN_LAST_ERROR();
 }
 
@@ -532,6 +585,7 @@ int ndjir_voxel_hash_grad_query(long long n_points, float* grad_query, const flo
     return NDJIR_ERR_ARG;
   if (!accum) fill_zero(grad_query, n_points * 3, st);
   float* out = grad_query; const float* a = grad_output; const float* gg = nullptr;
+  const int l_begin = 0;
   NDJIR_HASH_GATHER(GRAD_QUERY, true);
   NDJIR_RETURN_LAST_ERROR();
 }
@@ -547,6 +601,7 @@ int ndjir_voxel_hash_grad_query_grad_grad_output(long long n_points, float* grad
       !feature || n_points < 0)
     return NDJIR_ERR_ARG;
   float* out = grad_grad_output; const float* a = nullptr; const float* gg = grad_grad_query;
+  const int l_begin = 0;
   NDJIR_HASH_GATHER(GGO, accum);
   NDJIR_RETURN_LAST_ERROR();
 }

@@ -701,6 +701,24 @@ def test_voxel_hash_grad_feature_coarse_levels_private(B, G0, L, D, T0):
     total = call("ndjir_voxel_hash_num_params", G0, gf, T0, L, D)
     q, go = dev(q_np), dev(rng.randn(D, L, B).astype(np.float32))
     N = L * B
+    # forward: the same coarse levels are served from shared memory (fwd_coarse_kernel)
+    f = dev((rng.randn(total) * 0.01).astype(np.float32))
+    o_ref = torch.zeros(D, L, B).cuda()
+    ref.voxel_hash_feature(N, o_ref.data_ptr(), q.data_ptr(), f.data_ptr(), G0, gf, T0, L, D, MN, MX, False)
+    fw = {}
+    for mode in (0, 2):
+        call("ndjir_set_option", "hash_coarse_private", mode)
+        try:
+            o0 = torch.full((D, L, B), 7.0).cuda()
+            call("ndjir_voxel_hash_voxel_hash_feature", B, o0, q, f, G0, gf, T0, L, D, MN, MX, 0, 0, 0)
+            o1 = torch.full((B, D * L), 7.0).cuda()
+            call("ndjir_voxel_hash_voxel_hash_feature", B, o1, q, f, G0, gf, T0, L, D, MN, MX, 1, 1, 0)
+            fw[mode] = (o0, o1)
+        finally:
+            call("ndjir_set_option", "hash_coarse_private", 1)
+    close(fw[2][0], o_ref, 1e-5, "shared-memory coarse levels, forward vs reference kernel")
+    close(fw[2][0], fw[0][0], 1e-6, "shared-memory coarse levels vs per-thread kernel")
+    close(fw[2][1], fw[0][1], 1e-6, "(B, D*L) layout with accumulate")
     for accum in (False, True):
         g_ref = torch.full((total,), 0.25).cuda()
         ref.grad_feature(N, g_ref.data_ptr(), go.data_ptr(), q.data_ptr(), G0, gf, T0, L, D, MN, MX, False, accum)
