@@ -4,9 +4,15 @@ sample placement, the SDF / colour / illumination MLPs, NeuS alpha compositing, 
 TEST INFRASTRUCTURE ONLY (see oracle/cpu_ref.py header): imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs, never by ndjir_b200/.
 
-PARITY UNPINNED at this boundary: the reference keeps no test, golden vector or fixture for sampler.py's
-SamplePoints, network.py, renderer.py, specular_brdf.py or loss.py, and nnabla is not
-installable here, so this restatement is the definition of the expected results.  It follows, line by line:
+PINNED on the reference's own Python: tests/golden/make_golden.py::golden_render EXECUTES python/sampler.py,
+network.py, renderer.py, specular_brdf.py and loss.py where they lie under /root/reference - through a torch-backed
+stand-in for the slice of nnabla they use (tests/golden/nnabla_standin.py; nnabla 1.29 is not installable here) - on
+the seeded cases of tests/golden/cases.py (the real per-ray shapes: 64 + 4 x 16 samples, 32 background samples, 128
+light directions; default widths incl. the 213 + 43 skip layer) and stores sample_points / pb_render / total_loss
+outputs and every parameter gradient in tests/golden/render_*.npz; tests/test_render_golden.py holds this file to
+those vectors at 1e-9 (float64 on both sides).  What the stand-in cannot pin is nnabla's own kernel arithmetic
+(float32 rounding inside cuBLAS / its elementwise kernels) and its RNG streams: random tensors are explicit inputs.
+It follows, line by line:
   python/sampler.py:140-165 (stratified), :167-242 (hierarchical), :244-254,:282-291 (background),
   python/network.py:96-117 (positional encoding), :154-232 (geometric), :235-561 (heads, background),
   python/renderer.py:32-209 (pb_render), python/specular_brdf.py:23-118 (filament), python/loss.py:27-192.

@@ -3,8 +3,10 @@ S.Adam, in the call order of python/train.py:135-148.
 
 TEST INFRASTRUCTURE ONLY (see oracle/cpu_ref.py header): imported by tests/, never by ndjir_b200/.
 
-PARITY UNPINNED: solver.py cannot be imported here (it imports nnabla, which is not installable) and the reference
-has no test for it.  The Adam arithmetic is nnabla's published update rule (nnabla.solvers.Adam docs, v1.29):
+Schedules and call order are PINNED on the reference's own solver.py, executed through tests/golden/nnabla_standin.py
+(tests/golden/solver.npz, tests/test_render_golden.py::test_solver_schedules_and_adam_equal_reference).  The Adam
+arithmetic itself lives in nnabla (S.Adam), which is not installable here: it is nnabla's published update rule
+(nnabla.solvers.Adam docs, v1.29), restated in the stand-in and here:
     m_t = beta1 m_{t-1} + (1 - beta1) g_t,   v_t = beta2 v_{t-1} + (1 - beta2) g_t^2,
     alpha_t = alpha sqrt(1 - beta2^t) / (1 - beta1^t),   w_t = w_{t-1} - alpha_t m_t / (sqrt(v_t) + eps),
 defaults beta1 = 0.9, beta2 = 0.999, eps = 1e-8; Solver.weight_decay(r): g += r w; Solver.check_inf_or_nan_grad():

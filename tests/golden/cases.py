@@ -1,0 +1,71 @@
+"""Seeded inputs of the render-path golden vectors (tests/golden/render_*.npz): shared by the generator
+(make_golden.py, which runs the reference's own Python on them) and by the tests (which run the oracle and the CUDA
+path on the same inputs).  Parameters and inputs are rebuilt from seeds, so only OUTPUTS are stored in the fixtures.
+
+  small_<kind>   reduced widths (64 / 32), the REAL per-ray shapes of default.yaml: 64 + 4 x 16 foreground samples,
+                 32 background samples, n_thetas 8 (128 light directions), skip layer at 4; 2 views x 4 rays; every
+                 gradient is stored
+  full_default   default.yaml widths (256 / 128, skip 213 + 43), voxel 32^3 x 4, 1 view x 8 rays; large gradient
+                 tensors are stored as norms + sampled entries (sampled_view)
+"""
+import numpy as np
+
+from ndjir_b200 import scene
+from ndjir_b200.config import make_conf
+
+CASES = {
+    "small_default": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.3, G=16),
+    "small_triplaneline": dict(kind="triplaneline", small=True, B=2, R=4, cos_anneal=0.0, G=32),
+    "small_no_voxel": dict(kind="no_voxel", small=True, B=2, R=4, cos_anneal=1.0, G=None),
+    "full_default": dict(kind="default", small=False, B=1, R=8, cos_anneal=0.5, G=32),
+}
+
+
+def case_conf(name):
+    c = CASES[name]
+    over = dict(train={"batch_size": c["B"], "n_rays": c["R"]})
+    if c["small"]:
+        over.update(
+            geometric_network={"feature_size": 64},
+            base_color_network={"feature_size": 32}, environment_light_network={"feature_size": 32},
+            soft_visibility_light_network={"feature_size": 32}, implicit_illumination_network={"feature_size": 32},
+            photogrammetric_light_network={"feature_size": 32}, roughness_network={"feature_size": 32},
+            specular_reflectance_network={"feature_size": 32},
+            background_network={"feature_size0": 32, "feature_size1": 32})
+    if c["G"] is not None:
+        vox = {"grid_size": c["G"]}
+        if c["kind"] == "triplaneline":
+            vox["feature_size"] = 2
+        over.setdefault("geometric_network", {})["voxel"] = vox
+    return make_conf(c["kind"], **over)
+
+
+def build_case(name):
+    """-> conf, P (numpy parameters, reference layout), camloc, raydir, color_gt, rnd, cos_anneal"""
+    c = CASES[name]
+    conf = case_conf(name)
+    P = scene.init_params(conf, seed=313, grid_std=0.05)
+    rng = np.random.RandomState(7)       # make heads / SDF non-degenerate: perturb zero-initialised rows and biases
+    for net, layers in P.items():
+        if isinstance(layers, list):
+            for (W, b) in layers:
+                W += (rng.randn(*W.shape) * 0.02).astype(np.float32)
+                b += (rng.randn(*b.shape) * 0.02).astype(np.float32)
+    camloc, raydir, color_gt = scene.make_batch(conf, step=3, B=c["B"], R=c["R"])
+    raydir[0, 0] = -raydir[0, 0]          # one ray that misses the box (mask 0)
+    rnd = scene.make_randoms(conf, c["B"], c["R"], step=3)
+    return conf, P, camloc, raydir, color_gt, rnd, c["cos_anneal"]
+
+
+BIG = 16384
+
+
+def sampled_view(a, key):
+    """What the fixtures keep of a large gradient tensor: its L2 norm, its sum, 1024 entries at seeded positions and the
+    256 entries of largest magnitude (with their positions)."""
+    flat = np.asarray(a, dtype=np.float64).reshape(-1)
+    rng = np.random.RandomState(sum(map(ord, key)))
+    pos = rng.randint(0, flat.size, 1024)
+    top = np.argsort(-np.abs(flat))[:256]
+    return dict(norm=np.float64(np.linalg.norm(flat)), sum=np.float64(flat.sum()), pos=pos, val=flat[pos], top=top,
+                topval=flat[top])

@@ -257,3 +257,106 @@ if __name__ == "__main__":
     a = golden_intersection(); print("intersection.npz", len(a))
     b = golden_directions(); print("directions.npz", len(b))
     c = golden_grids(); print("grids.npz", len(c))
+    print("render_*.npz / solver.npz", golden_render())
+
+
+# ----------------------------------------------------------------------------------------------------
+# the nnabla-composed part of the path: the reference's sampler.py / network.py / renderer.py / specular_brdf.py /
+# loss.py / solver.py EXECUTED through tests/golden/nnabla_standin.py on the seeded cases of tests/golden/cases.py
+# ----------------------------------------------------------------------------------------------------
+def golden_render():
+    sys.path.insert(0, OUT)
+    import cases
+    import nnabla_standin as S
+    from ndjir_b200 import nnabla_names
+    mods = S.load_reference_modules()
+    done = {}
+    for name in cases.CASES:
+        conf, P, camloc, raydir, color_gt, rnd, cos_anneal = cases.build_case(name)
+        S.set_parameters(nnabla_names.to_nnabla(conf, P))
+        r, tr = conf.renderer, conf.train
+        S.set_randoms(
+            {r.stratified_sample_seed: [rnd["stratified"]], r.background_sample_seed: [rnd["background"]],
+             r.diffuse_cdf_the_seed: [rnd["diffuse_cdf_the"]], r.diffuse_cdf_phi_seed: [rnd["diffuse_cdf_phi"]],
+             r.specular_cdf_the_seed: [rnd["specular_cdf_the"]], r.specular_cdf_phi_seed: [rnd["specular_cdf_phi"]]},
+            {tr.base_color_perturb_seed: [rnd["perturb"]]})
+        cam, ray, gt = S.V(camloc), S.V(raydir), S.V(color_gt)
+        car = S.V(np.asarray([cos_anneal]))
+        out = {}
+        # sample_points (sampler.py:311-314) on its own, then pb_render (renderer.py:32) on those samples
+        x_fg, t_fg, x_bg, t_bg, mask = mods["sampler"].sample_points(cam, ray, S.V(rnd["stratified"]),
+                                                                     S.V(rnd["background"]), conf)
+        for k, v in dict(x_fg=x_fg, t_fg=t_fg, x_bg=x_bg, t_bg=t_bg, mask=mask).items():
+            out[f"samples.{k}"] = v.detach().numpy().copy()
+        x_fg.apply(need_grad=True)
+        res = mods["renderer"].pb_render(x_fg, t_fg, x_bg, t_bg, cam, ray, mask, car, conf)
+        for k, v in res.items():
+            out[f"render.{k}"] = v.detach().numpy().copy()
+        # total_loss (loss.py:27) forward + backward (train.py:135-140): runs sample_points + pb_render again inside
+        for p in S.get_parameters().values():
+            p.grad = None
+        losses = mods["loss"].total_loss(cam, ray, gt, None, car, conf)
+        for k, v in losses.items():
+            out[f"loss.{k}"] = np.float64(v.detach().numpy())
+        losses["loss"].backward()
+        asked = set(S._STATE.asked)
+        table = dict(nnabla_names.parameter_names(conf))
+        missing = [n for n in table if n not in asked]
+        assert not missing, f"names in nnabla_names the reference never asked for: {missing}"
+        for nn_name, p in S.get_parameters().items():
+            key = table[nn_name]
+            okey = ({"geo_gain": "geo_gain", "pl_gain": None}.get(key[0]) if key[0] in ("geo_gain", "pl_gain")
+                    else f"grid.{key[1]}" if key[0] == "grid" else f"{key[0]}.{key[2]}{key[1]}")
+            if okey is None:
+                continue
+            g = p.grad.detach().numpy() if p.grad is not None else np.zeros(tuple(p.shape))
+            if g.size > cases.BIG:
+                for kk, vv in cases.sampled_view(g, okey).items():
+                    out[f"gradS.{okey}.{kk}"] = vv
+            else:
+                out[f"grad.{okey}"] = g
+        np.savez_compressed(os.path.join(OUT, f"render_{name}.npz"), **out)
+        done[name] = len(out)
+    # solver.py: schedules + one Solvers iteration in the order of train.py:135-148 over a tiny parameter set
+    out = {}
+    conf = cases.case_conf("small_default")
+    Sol = mods["solver"].Solvers
+    for tag, over in (("default", {}), ("short", {"epoch": 40, "warmup_term_ratio": 0.1, "sigmoid_gain_lv_end": 3})):
+        for k, v in over.items():
+            setattr(conf.train, k, v)
+        S._STATE.strict = False
+        S.set_parameters({"net/affine/W": np.linspace(-1, 1, 12).reshape(3, 4), "net/affine/b": np.zeros(4),
+                          "geo/voxel_feature/F": np.linspace(0.1, 0.5, 8).reshape(2, 4)},
+                         trainable=lambda n: True)
+        sol = Sol(conf)
+        sol.set_parameters()
+        E = conf.train.epoch
+        its = sorted(set([0, 1, 2, 5, E // 10, E // 4, E // 2, E - 1]))
+        lrs, car_, gain_ = [], [], []
+        for i in its:
+            sol.update_learning_rate(i)
+            lrs.append([sol.solver_weight.learning_rate(), sol.solver_feat.learning_rate()])
+            car_.append(float(S._STATE.params["cos_anneal_ratio"].detach()))
+            gain_.append(float(S._STATE.params["photogrammetric-light-network/gain"].detach()))
+        out[f"{tag}.iters"], out[f"{tag}.lr"] = np.asarray(its), np.asarray(lrs)
+        out[f"{tag}.cos_anneal_ratio"], out[f"{tag}.pl_gain"] = np.asarray(car_), np.asarray(gain_)
+        # three iterations: zero_grad, weight_decay, backward (accumulate a fixed gradient), check, update
+        sol.update_learning_rate(E // 4)
+        rng = np.random.RandomState(5)
+        names = ["net/affine/W", "net/affine/b", "geo/voxel_feature/F"]
+        for it in range(3):
+            sol.zero_grad()
+            sol.weight_decay()
+            for n in names:
+                p = S._STATE.params[n]
+                g = rng.randn(*p.shape)
+                out[f"{tag}.it{it}.g.{n}"] = g
+                p.grad = p.grad + torch.as_tensor(g)
+            assert not sol.check_inf_or_nan_grad()
+            sol.update()
+            for n in names:
+                out[f"{tag}.it{it}.w.{n}"] = S._STATE.params[n].detach().numpy().copy()
+        S._STATE.strict = True
+    np.savez_compressed(os.path.join(OUT, "solver.npz"), **out)
+    done["solver"] = len(out)
+    return done
