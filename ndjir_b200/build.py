@@ -24,6 +24,10 @@ NVCC_FLAGS = [
 ]
 
 
+# per-file flags: sample placement keeps every multiply / add individually rounded (see csrc/sampler.cu)
+EXTRA_FLAGS = {"sampler.cu": ["-fmad=false"]}
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -46,10 +50,10 @@ def _headers():
 def _compile_one(src, verbose):
     obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
     stamp = obj + ".sha1"
-    dig = _digest([os.path.join(CSRC, src)] + _headers())
+    dig = _digest([os.path.join(CSRC, src)] + _headers()) + "".join(EXTRA_FLAGS.get(src, []))
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False
-    cmd = [NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, capture_output=True, text=True)

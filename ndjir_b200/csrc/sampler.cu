@@ -7,6 +7,9 @@
 // transmittance, an additive warp scan for the CDF, a per-quantile binary search (searchsorted, right=False) and
 // a bitonic sort of the merged distances in shared memory.  No gradient flows through any of this
 // (SamplePoints.backward_impl is empty, sampler.py:301).
+// This file is compiled with -fmad=false (ndjir_b200/build.py): the reference evaluates every multiply and add of the
+// placement as a separate, individually rounded nnabla op, and the placement is ill-conditioned where section weights
+// are ~1e-5, so no a*b+c is contracted into an FMA here.
 #include "common.cuh"
 #include "../../include/ndjir_b200.h"
 
@@ -206,7 +209,7 @@ importance_round_kernel(int NR, int Nt, int M, const float* t_in, long long ld_i
     float ratio = (u - lower) / ws[idx_w];
     float step = (idx < Nt - 1) ? (ts[idx + 1] - ts[idx]) : (tf - ts[Nt - 1]);
     float tnew = ts[idx] + step * ratio;
-    tnew = fmaxf(fminf(tnew, tf), tn);
+    tnew = fminf(fmaxf(tnew, tn), tf);               // clip_by_value = minimum2(maximum2(t, t_near), t_far)
     newv[nslot++] = tnew;
     if (t_new_out) t_new_out[(long long)r * M + k] = tnew;
     if (idx_out) idx_out[(long long)r * M + k] = idx;

@@ -312,7 +312,7 @@ def importance_round(t, sdf, t_near, t_far, gain, M):
     steps_idx = torch.gather(steps[..., 0], 2, idx)[..., None]
     ts_idx = torch.gather(t[..., 0], 2, idx)[..., None]
     t_new = ts_idx + steps_idx * ratio
-    t_new = torch.maximum(torch.minimum(t_new, t_far), t_near)
+    t_new = torch.minimum(torch.maximum(t_new, t_near), t_far)     # clip_by_value = minimum2(maximum2(x, lo), hi)
     t_all, _ = torch.sort(torch.cat([t, t_new], dim=2), dim=2)
     return t_all, t_new, idx
 

@@ -10,8 +10,14 @@ Bars (BASELINE.json north_star), max-norm relative per tensor:
     tensor core accumulates ~100 partial products per output in fp32 with truncation, measured 2-8e-6 per product
     in tests/test_gemm_gpu.py, which an 8-layer double-backward chain amplifies);
   * where the oracle's own float32 evaluation deviates from its float64 evaluation by more than the bar
-    (ill-conditioned quantities: a normalised near-zero pixel normal, inverse-CDF steps through 1e-5 weights) the bar
-    is 4x that deviation (Report.check).
+    (a normalised near-zero pixel normal) the bar is 4x that deviation, CAPPED at 10x the base bar (Report.check):
+    nothing passes above 1e-3.
+Two shapes per configuration: `small` (2 x 8 rays, 16 + 4 samples, 64 / 32-wide networks) and `full` - the per-ray shapes
+of BASELINE's configs: 64 + 4 x 16 foreground and 32 background samples (160 composited samples = 5 scan chunks), 128
+light directions, 256 / 128-wide networks with the 213 + 43 skip layer, a 64^3 voxel grid; 1 view x 32 rays.
+Sample placement is checked stage by stage on the ENGINE's own SDF values (float32 restatement of sampler.py:196-240 in
+tests/test_stage_kernels_gpu.py) so that the ill-conditioned inverse CDF does not need a tolerance escape; the SDF
+network itself is compared with the oracle at identical sample positions.
 Every check is evaluated and reported (gpurun_out/engine_parity_*.json) before the test asserts."""
 import json
 import os
@@ -47,6 +53,17 @@ def small_conf(kind="default", **over):
     return conf
 
 
+def full_conf(kind="default"):
+    """BASELINE per-ray shapes and network widths (default.yaml / triplaneline.yaml / no_voxel.yaml); only the grid
+    resolution and the ray count are reduced so that the float64 CPU oracle finishes in seconds."""
+    over = dict(train={"batch_size": 1, "n_rays": 32})
+    if kind == "default":
+        over["geometric_network"] = {"voxel": {"grid_size": 64}}
+    elif kind == "triplaneline":
+        over["geometric_network"] = {"voxel": {"grid_size": 128}}
+    return make_conf(kind, **over)
+
+
 def relerr(a, b):
     a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
     b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
@@ -75,13 +92,13 @@ class Report:
         normalised near-zero pixel normal) the bar is 4x the oracle's own fp32-vs-fp64 deviation."""
         e = relerr(a, b)
         if b32 is not None:
-            tol = max(tol, 4.0 * relerr(b32, b))
+            tol = min(max(tol, 4.0 * relerr(b32, b)), 10.0 * tol)
         ok = bool(np.isfinite(e) and e <= tol)
         row = dict(what=what, err=e, tol=tol, ok=ok)
         if l2_tol is not None:
             e2 = rel_l2(a, b)
             if b32 is not None:
-                l2_tol = max(l2_tol, 4.0 * rel_l2(b32, b))
+                l2_tol = min(max(l2_tol, 4.0 * rel_l2(b32, b)), 10.0 * l2_tol)
             row.update(l2_err=e2, l2_tol=l2_tol)
             ok = ok and bool(np.isfinite(e2) and e2 <= l2_tol)
             row["ok"] = ok
@@ -99,9 +116,9 @@ class Report:
         assert not self.bad, "\n".join(self.bad)
 
 
-def setup(kind, seed=0, miss=True, grid_std=0.05):
+def setup(kind, seed=0, miss=True, grid_std=0.05, shape="small"):
     from ndjir_b200.engine import Engine
-    conf = small_conf(kind)
+    conf = small_conf(kind) if shape == "small" else full_conf(kind)
     P = scene.init_params(conf, seed=313, grid_std=grid_std)
     # make the heads and the SDF non-degenerate: perturb zero-initialised rows / biases
     rng = np.random.RandomState(7)
@@ -114,7 +131,7 @@ def setup(kind, seed=0, miss=True, grid_std=0.05):
     camloc, raydir, color_gt = scene.make_batch(conf, step=seed, B=tr.batch_size, R=tr.n_rays)
     if miss:   # a few rays that miss the box, and one camera-inside-the-box view is covered by test_native_gpu
         raydir[0, 0] = -raydir[0, 0]
-        raydir[1, 3] = np.array([0.0, 0.0, 1.0], np.float32)
+        raydir[-1, 3] = np.array([0.0, 0.0, 1.0], np.float32)
     rnd = scene.make_randoms(conf, tr.batch_size, tr.n_rays, step=seed)
     eng = Engine(conf)
     eng.params.load_reference(P)
@@ -122,33 +139,81 @@ def setup(kind, seed=0, miss=True, grid_std=0.05):
     return conf, P, camloc, raydir, color_gt, rnd, eng, model
 
 
-@pytest.mark.parametrize("kind", ["default", "triplaneline", "no_voxel"])
-def test_sample_points_matches_oracle(kind):
-    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind)
-    rep = Report(f"sampler_{kind}")
-    x_fg, t_fg, x_bg, t_bg, mask, dbg = CR.sample_points(model, camloc, raydir, rnd["stratified"], rnd["background"],
-                                                         return_debug=True)
+@pytest.mark.parametrize("kind,shape", [("default", "small"), ("triplaneline", "small"), ("no_voxel", "small"),
+                                        ("default", "full"), ("triplaneline", "full")])
+def test_sample_points_stage_by_stage(kind, shape):
+    """sample_points (sampler.py:256-299) checked stage by stage, each stage on the inputs the ENGINE gave it:
+      hit mask                  bit-exact vs the oracle
+      stratified distances      float32 formula of sampler.py:159-163, 1e-6
+      SDF of every round        the oracle's geometric network (float64) at the engine's own sample positions, 2e-5
+      placement of every round  float32 restatement of sampler.py:196-240 fed the engine's SDF: sample indices exact where
+                                the CDF decision is outside float32 rounding (>= 99.9 % overall), new distances within the
+                                conditioning bound, sorted union exact
+      background samples        vs the oracle, 1e-5 (t_bg 1e-6)."""
+    from test_stage_kernels_gpu import importance_round_f32
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind, shape=shape)
+    rep = Report(f"sampler_{kind}_{shape}")
+    r = conf.renderer
+    x_fg, t_fg, x_bg, t_bg, mask = CR.sample_points(model, camloc, raydir, rnd["stratified"], rnd["background"])
     ox, ot, obx, obt, om = eng.sample_points(dev(camloc), dev(raydir), dev(rnd["stratified"]), dev(rnd["background"]),
                                              debug=True)
     torch.cuda.synchronize()
     assert np.array_equal(om.cpu().numpy().reshape(-1), mask.numpy().reshape(-1).astype(np.float32)), "hit mask"
-    # the oracle in float32 measures how ill-conditioned the inverse-CDF placement is on this input: the new distances
-    # are (u - cdf[i-1]) / w[i] with w[i] as small as 1e-5, so fp32 rounding of the cumulative sums is amplified
-    model32 = CR.Model(conf, P, dtype=torch.float32)
-    x32, t32, xb32, tb32, m32, dbg32 = CR.sample_points(model32, camloc, raydir, rnd["stratified"], rnd["background"],
-                                                        return_debug=True)
-    for u, (d_or, d_us, d_32) in enumerate(zip(dbg, eng.debug["sampler"], dbg32)):
-        rep.check(f"round{u}.sdf", d_us["sdf"], d_or["sdf"], 2e-5, d_32["sdf"])
-        rep.check(f"round{u}.t_new", d_us["t_new"], d_or["t_new"], 1e-5, d_32["t_new"])
-        rep.check(f"round{u}.t_out", d_us["t_out"], d_or["t_out"], 1e-5, d_32["t_out"])
-        same = (d_us["idx"].cpu().numpy().reshape(-1) == d_or["idx"].numpy().reshape(-1)).mean()
-        rep.rows.append(dict(what=f"round{u}.idx_equal_fraction", err=1 - float(same), tol=0.02, ok=bool(same > 0.98)))
-        if same <= 0.98:
-            rep.bad.append(f"round{u}.idx equal fraction {same}")
-    rep.check("t_fg", ot, t_fg, 1e-5, t32)
-    rep.check("x_fg", ox, x_fg, 1e-5, x32)
-    rep.check("t_bg", obt, t_bg, 1e-5, tb32)
-    rep.check("x_bg", obx, x_bg, 1e-5, xb32)
+    B, Rr, _ = raydir.shape
+    NR, N0, M = B * Rr, r.n_samples0, r.n_samples1
+    tn, tf = eng.buf("t_near", NR, 1)[:NR, 0].cpu().numpy(), eng.buf("t_far", NR, 1)[:NR, 0].cpu().numpy()
+    o = np.repeat(camloc, Rr, axis=0).astype(np.float32)
+    d = raydir.reshape(NR, 3)
+    dbg = eng.debug["sampler"]
+    assert len(dbg) == r.n_upsamples
+    f32 = np.float32
+    strat = tn[:, None] + (tf - tn)[:, None] / f32(N0) * (np.arange(N0, dtype=f32)[None] + rnd["stratified"].reshape(NR, N0))
+    rep.check("stratified (sorted)", np.sort(strat, axis=1), dbg[0]["t_in"].cpu().numpy(), 1e-6)
+    for u, dd in enumerate(dbg):
+        t_in, sdf = dd["t_in"].cpu().numpy(), dd["sdf"].cpu().numpy()
+        Nt = t_in.shape[1]
+        assert Nt == N0 + u * M
+        x = o[:, None, :].astype(np.float64) + t_in[:, :, None].astype(np.float64) * d[:, None, :].astype(np.float64)
+        with torch.no_grad():
+            want_sdf = model.geometric_network(torch.as_tensor(x))[0][..., 0].numpy()
+        rep.check(f"round{u}.sdf (same positions)", sdf, want_sdf, 2e-5)
+        gain = r.sampling_sigmoid_gain * 2 ** u
+        r_idx, r_new, cdf, w, uq, steps = importance_round_f32(t_in, sdf, tn, tf, gain, M)
+        g_idx, g_new = dd["idx"].cpu().numpy(), dd["t_new"].cpu().numpy()
+        rows, S = np.arange(NR)[:, None], Nt - 1
+        below = np.where(r_idx > 0, cdf[rows, np.maximum(r_idx - 1, 0)], -1.0)
+        at = cdf[rows, np.minimum(r_idx, S - 1)]
+        margin = np.minimum(np.abs(uq[None] - below), np.where(r_idx < S, np.abs(at - uq[None]), 1.0))
+        hit = (tf > tn)[:, None] & np.ones_like(r_idx, bool)      # rays that miss have t_near = t_far = 0: 0/0 weights
+        decided = (margin > 2e-5) & hit
+        n_bad = int((g_idx[decided] != r_idx[decided]).sum())
+        eq = float((g_idx[hit] == r_idx[hit]).mean())
+        rep.rows.append(dict(what=f"round{u}.idx (decided: exact; overall {eq:.5f})", err=float(n_bad), tol=0.0,
+                             ok=bool(n_bad == 0 and eq >= 0.999)))
+        if n_bad or eq < 0.999:
+            rep.bad.append(f"round{u}.idx: {n_bad} decided entries differ, overall equal {eq}")
+        same = (g_idx == r_idx) & hit
+        wsel = w[rows, np.minimum(r_idx, S - 1)]
+        bound = 1e-6 * np.abs(r_new).max() + 2e-6 * np.abs(steps[rows, np.minimum(r_idx, Nt - 1)]) / np.maximum(wsel, 1e-30)
+        worst = float((np.abs(g_new - r_new)[same] / bound[same]).max())
+        rep.rows.append(dict(what=f"round{u}.t_new / conditioning bound", err=worst, tol=1.0, ok=bool(worst <= 1.0)))
+        if worst > 1.0:
+            rep.bad.append(f"round{u}.t_new exceeds its bound x{worst}")
+        well = same & (wsel > 1e-2)
+        if well.any():
+            rep.check(f"round{u}.t_new (well conditioned)", g_new[well], r_new[well], 3e-6)
+        union = np.sort(np.concatenate([t_in, g_new], axis=1), axis=1)
+        ok = np.array_equal(dd["t_out"].cpu().numpy()[hit[:, 0]], union[hit[:, 0]])
+        rep.rows.append(dict(what=f"round{u}.t_out == sort(t, t_new)", err=0.0 if ok else 1.0, tol=0.0, ok=bool(ok)))
+        if not ok:
+            rep.bad.append(f"round{u}.t_out is not the sorted union")
+    N = N0 + r.n_upsamples * M
+    got_t = ot.reshape(NR, N + 1).cpu().numpy()
+    rep.check("t_fg[-1] == t_far", got_t[:, N], tf, 0.0)
+    xo = o[:, None, :] + got_t[:, :N, None] * d[:, None, :]
+    rep.check("x_fg = o + t d", ox.reshape(NR, N, 3), xo, 1e-6)
+    rep.check("t_bg", obt, t_bg, 1e-6)
+    rep.check("x_bg", obx, x_bg, 1e-5)
     rep.finish()
 
 
@@ -160,11 +225,13 @@ def mlp_path(request):
     _lib.call("ndjir_set_option", "mlp_tensor_cores", 1)
 
 
-@pytest.mark.parametrize("kind,cos_anneal", [("default", 0.0), ("default", 0.7), ("triplaneline", 0.3),
-                                              ("no_voxel", 1.0)])
-def test_train_step_matches_oracle(kind, cos_anneal, mlp_path):
-    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind)
-    rep = Report(f"train_{kind}_{cos_anneal}_{'tc' if mlp_path else 'ffma'}")
+@pytest.mark.parametrize("kind,cos_anneal,shape", [("default", 0.0, "small"), ("default", 0.7, "small"),
+                                                    ("triplaneline", 0.3, "small"), ("no_voxel", 1.0, "small"),
+                                                    ("default", 0.5, "full"), ("triplaneline", 0.2, "full"),
+                                                    ("no_voxel", 1.0, "full")])
+def test_train_step_matches_oracle(kind, cos_anneal, shape, mlp_path):
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind, shape=shape)
+    rep = Report(f"train_{kind}_{cos_anneal}_{shape}_{'tc' if mlp_path else 'ffma'}")
     g_tol = 2e-4 if mlp_path else 1e-4
     # identical sample placement on both sides (placement itself is covered by the test above)
     samples = CR.sample_points(model, camloc, raydir, rnd["stratified"], rnd["background"])
