@@ -507,6 +507,60 @@ int ndjir_loss_inv_denorm(const float* mask_sum, int N, float* inv_denorm, cudaS
 int ndjir_finalize_losses(float* losses, const float* mask_sum, int N, float inv_rays, float w_eik, float w_tv,
                           float w_bc, float w_ro, float w_sp, cudaStream_t stream);
 
+/* ==== split-fp16 MLP engine (csrc/gemm_h.cu, csrc/h16_ops.cu) ==============================================
+ * The hidden activations and gradients of the MLPs (nnabla PF.affine + F.softplus chains, python/network.py:84-93,
+ * 154-232) are STORED as two fp16 planes, value = (hi + lo) / scale with hi = fp16(x*scale), lo = fp16(x*scale - hi):
+ * 22 mantissa bits in the same 4 bytes per element as fp32, and both planes are ready-made tcgen05 kind::f16 operands
+ * (TMA-loaded, no in-kernel conversion).  A product is three tensor-core products  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi
+ * at the fp16 rate; with `precise` the two correction products of the WHOLE contraction are accumulated first and the
+ * main product last, so that the tensor core's truncating fp32 accumulation only sees 16 full-magnitude partial sums
+ * per 256-long contraction.  `scale` is a per-tensor power of two kept on the device (ndjir_scale_update derives it from
+ * the running max of the tensor's previous use, ndjir_hmat.amax); writers clamp to the fp16 range. */
+typedef struct ndjir_hmat {
+  void* hi;            /* fp16 plane, rows x ld */
+  void* lo;            /* fp16 plane, same shape */
+  long long ld;        /* row stride in halfs; a multiple of 8 */
+  const float* scale;  /* DEVICE scalar, a power of two; NULL = 1 */
+  float* amax;         /* DEVICE scalar: writers fold max|value| into it; NULL = not tracked */
+} ndjir_hmat;
+
+typedef struct ndjir_gemm_h_desc {
+  int M, N, K;
+  int mn_major;        /* 0: A (M x K) and B (N x K) row-major planes (both K-major);
+                          1: A (K x M) and B (K x N) row-major planes: C (M x N) += A^T B, the weight gradient */
+  int epilogue;        /* csrc/gemm.cuh Epi */
+  int precise;         /* 1: corrections first, main product last (forward-accuracy passes) */
+  int split_k;         /* mn_major only: K (the sample rows) split over this many work items, atomic epilogue */
+  float alpha, out_scale, beta, hscale;
+  ndjir_hmat A, B;     /* tensor-core operands */
+  const float* A32; long long a_rs, a_cs;   /* fp32 A for the memory-bound corner shapes (K <= 8) */
+  const float* B32; long long b_rs, b_cs;   /* fp32 B(k,n) = B32[k*b_rs + n*b_cs] for the corner shapes (N <= 8, K <= 8) */
+  float* C; long long ldc;                  /* fp32 output, used when Ch.hi == NULL */
+  ndjir_hmat Ch;                            /* split-fp16 output */
+  float* C2; long long ldc2; ndjir_hmat C2h;        /* EPI_ADJ second output */
+  const float* bias;
+  const float* H; long long ldh; ndjir_hmat Hh;     /* activation the sigmoid factor is derived from (either form) */
+  const float* U; long long ldu; ndjir_hmat Uh;     /* EPI_MUL_S addend / EPI_ADJ factor (either form) */
+} ndjir_gemm_h_desc;
+
+int ndjir_gemm_h(const ndjir_gemm_h_desc* d, cudaStream_t stream);
+/* dst[r,c] = split(alpha * src[r / rep, c]) for c < cols (fp32 -> split fp16, dst->scale applied, dst->amax updated) */
+int ndjir_pack_h(long long rows, int cols, const float* src, long long ld_src, int rep, float alpha,
+                 const ndjir_hmat* dst, cudaStream_t stream);
+/* dst[r,c] = value of src[r,c] as fp32 */
+int ndjir_unpack_h(long long rows, int cols, const ndjir_hmat* src, float* dst, long long ld_dst, cudaStream_t stream);
+/* plane copy dst[r,c] = src[r / rep, c]; both must carry the same scale */
+int ndjir_copy2d_h(long long rows, int cols, const ndjir_hmat* dst, const ndjir_hmat* src, int rep,
+                   cudaStream_t stream);
+/* out[c] += alpha * sum_r src[r,c] */
+int ndjir_colsum_h(long long rows, int cols, float* out, const ndjir_hmat* src, float alpha, cudaStream_t stream);
+/* amax[0] = max(amax[0], max|x|) */
+int ndjir_amax(long long n, const float* x, float* amax, cudaStream_t stream);
+/* per slot i: if amax[i] is finite and > 0: scales[i] = 2^(target_log2 - 1 - floor(log2(amax[i]))), i.e. the tensor's
+ * largest value lands in [2^(target_log2-1), 2^target_log2); amax[i] = 0 afterwards.  flags[0] |= 1 if a slot's
+ * amax * old scale exceeded the fp16 range (values were clamped), |= 2 if a scale changed. */
+int ndjir_scale_update(int n_slots, float* scales, float* amax, int* flags, int target_log2, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

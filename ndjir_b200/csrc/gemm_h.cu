@@ -1,0 +1,585 @@
+// MLP products of the split-fp16 engine on the 5th-generation tensor cores (sm_100a).
+//
+// Operands are stored in HBM as two fp16 planes per matrix (hi, lo; include/ndjir_b200.h), so a 128 x 64 operand tile
+// of either plane is fetched by ONE TMA request straight into the 128-byte-swizzled layout tcgen05.mma reads: there is
+// no in-kernel conversion pass (the 3xTF32 kernel of csrc/gemm_tc.cu spends a third of its shared-memory bandwidth on
+// one).  A product is  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (kind::f16, fp32 accumulation in TMEM; the dropped lo*lo term
+// is 2^-22 relative) at twice the tf32 rate and half the operand bytes.
+//
+// Persistent kernel, one CTA per SM, 10 warps:
+//   warp 0      TMA producer: ring of 4 slots of 48 KB, a slot = one (A piece, B piece) pair of one 64-wide K block
+//   warp 1      one elected thread issues tcgen05.mma 128 x N x 16 into one of two 256-column TMEM accumulators
+//   warps 2-9   epilogue straight from TMEM (tcgen05.ld, one output row per thread): bias / softplus / sigmoid factor /
+//               second-order term / accumulate / atomics, reading and writing fp32 rows or split-fp16 planes; the
+//               epilogue of item i overlaps the main loop of item i+1
+// Accumulation order.  The tensor core adds every 128 x N x 16 partial product into the fp32 accumulator with
+// truncation, ~2^-24 relative per instruction; 96 instructions per output (3xTF32, K = 256) measured 1.6e-5 on the
+// SDF after eight layers, above the 1e-5 forward bar.  `precise` walks the K blocks twice: first the two correction
+// products of ALL blocks (their partial sums are 2^-11 of the result, so their truncation is invisible), then the
+// hi*hi products: only K/16 accumulations happen at full magnitude.  The hi tiles are fetched twice (L2 hits).
+//   K-major mode : A (M x K), B (N x K) row-major planes  -> forward and input-gradient products (B = W^T resp. W)
+//   MN-major mode: A (K x M), B (K x N) row-major planes  -> weight gradients A^T dZ, contraction over the sample
+//                  rows, split over work items, atomic fp32 epilogue
+#include <cudaTypedefs.h>
+#include "gemm_h.cuh"
+#include "tc_ptx.cuh"
+
+namespace ndjir {
+namespace gemmh {
+
+using namespace tcp;
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;                          // halfs per K block: 128-byte rows, SWIZZLE_128B
+constexpr int A_BYTES = BM * BK * 2;            // 16 KB
+constexpr int B_BYTES = BN * BK * 2;            // 32 KB
+constexpr int SLOT_BYTES = A_BYTES + B_BYTES;   // 48 KB
+constexpr int NSLOT = 4;
+constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + 1024;
+constexpr int EPI_WARP0 = 2;
+constexpr int EPI_THREADS = 256;
+constexpr int THREADS = 64 + EPI_THREADS;
+constexpr int TMEM_COLS = 512;
+constexpr int CHUNK_BYTES = BK * 128;           // MN-major tiles: [chunk of 64 mn][k row][128 B]
+
+int g_h_dbg = 0;   // profiling switches: 1 = skip the epilogue's global traffic, 2 = one MMA per K step
+
+struct HParams {
+  HArgs a;
+  int m_tiles, n_tiles, splits, kb_per_split, nkb_total;
+  int a3d, b3d;          // MN-major operand fetched as one 3-D box per slot
+  int b_box_rows;        // rows (K-major) / columns (MN-major) of B staged per slot: 64, 128 or 256
+  int vec_epi;           // every epilogue operand allows 16-byte accesses at 16-column granularity
+  int dbg;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+              const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, HParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * NSLOT + 4];
+  __shared__ uint32_t tmem_base_sh;
+
+  const HArgs& a = p.a;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  auto bar_full = [&](int s) { return smem_u32(&bars[s]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[NSLOT + s]); };
+  auto bar_acc_full = [&](int b) { return smem_u32(&bars[2 * NSLOT + b]); };
+  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[2 * NSLOT + 2 + b]); };
+  auto a_dst = [&](int s) { return smem_base + s * SLOT_BYTES; };
+  auto b_dst = [&](int s) { return smem_base + s * SLOT_BYTES + A_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);
+      mbar_init(bar_acc_empty(b), EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapAhi); prefetch_tmap(&mapAlo); prefetch_tmap(&mapBhi); prefetch_tmap(&mapBlo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  const int n_items = p.m_tiles * p.n_tiles * p.splits;
+  // work item -> (m0, n0, kb0, nkb); m tiles vary fastest so co-running CTAs share the same B tile in L2
+  auto item_info = [&](int item, int& m0, int& n0, int& kb0, int& nkb) {
+    int mt = item % p.m_tiles;
+    int rest = item / p.m_tiles;
+    int ntile = rest % p.n_tiles;
+    int sp = rest / p.n_tiles;
+    m0 = mt * BM;
+    n0 = ntile * BN;
+    kb0 = sp * p.kb_per_split;
+    int kb1 = min(p.nkb_total, kb0 + p.kb_per_split);
+    nkb = max(0, kb1 - kb0);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int b_chunks = p.b_box_rows / 64;
+      const uint32_t tx_bytes = A_BYTES + (uint32_t)p.b_box_rows * 128u;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        item_info(item, m0, n0, kb0, nkb);
+        auto load = [&](int piece, int kb) {
+          const int s = it % NSLOT;
+          const uint32_t ph = (it / NSLOT) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          mbar_expect_tx(bar_full(s), tx_bytes);
+          const CUtensorMap* ma = piece ? &mapAlo : &mapAhi;
+          const CUtensorMap* mb = piece ? &mapBlo : &mapBhi;
+          const int k0 = kb * BK;
+          if (!a.mn) {
+            tma_load_2d(a_dst(s), ma, k0, m0, bar_full(s));
+            tma_load_2d(b_dst(s), mb, k0, n0, bar_full(s));
+          } else {
+            if (p.a3d) {
+              tma_load_3d(a_dst(s), ma, 0, k0, m0 / 64, bar_full(s));
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst(s) + c * CHUNK_BYTES, ma, m0 + c * 64, k0, bar_full(s));
+            }
+            if (p.b3d) {
+              tma_load_3d(b_dst(s), mb, 0, k0, n0 / 64, bar_full(s));
+            } else {
+              for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_dst(s) + c * CHUNK_BYTES, mb, n0 + c * 64, k0, bar_full(s));
+            }
+          }
+          ++it;
+        };
+        for (int i = 0; i < nkb; ++i) {
+          load(0, kb0 + i);
+          load(1, kb0 + i);
+        }
+        if (a.precise)
+          for (int i = 0; i < nkb; ++i) load(0, kb0 + i);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO), a K step of 16 halfs = +32 B.
+      // MN-major (SWIZZLE_128B): k rows of 128 B (64 mn halfs), 8-row k groups 1024 B apart (SBO), 64-wide mn chunks
+      // CHUNK_BYTES apart (LBO), a K step of 16 rows = +2048 B.
+      const uint32_t lbo = a.mn ? CHUNK_BYTES : 16, sbo = 1024, kstep = a.mn ? 2048 : 32;
+      const uint64_t da0 = make_desc(a_dst(0), lbo, sbo, 2), db0 = make_desc(b_dst(0), lbo, sbo, 2);
+      const int k_total = a.K;
+      uint32_t it = 0, tile_it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        item_info(item, m0, n0, kb0, nkb);
+        if (nkb == 0) continue;
+        const int umma_n = (min(BN, a.N - n0) + 15) & ~15;
+        const uint32_t idesc = (1u << 4) | ((uint32_t)a.mn << 15) | ((uint32_t)a.mn << 16) |
+                               ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const int buf = tile_it & 1;
+        mbar_wait(bar_acc_empty(buf), ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * BN;
+        uint32_t first = 0;   // accumulate flag of the next instruction
+        for (int i = 0; i < nkb; ++i) {
+          const int sx = it % NSLOT, sy = (it + 1) % NSLOT;
+          mbar_wait(bar_full(sx), (it / NSLOT) & 1);
+          mbar_wait(bar_full(sy), ((it + 1) / NSLOT) & 1);
+          tc_fence_after();
+          const int ksteps = min(BK / 16, (k_total - (kb0 + i) * BK + 15) / 16);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ox = (uint64_t)((sx * SLOT_BYTES + ks * kstep) >> 4);
+            const uint64_t oy = (uint64_t)((sy * SLOT_BYTES + ks * kstep) >> 4);
+            if (p.dbg & 2) {
+              umma_f16(tacc, da0 + ox, db0 + ox, idesc, first);
+              first = 1;
+            } else {
+              umma_f16(tacc, da0 + oy, db0 + ox, idesc, first);   // lo * hi   (small terms first)
+              first = 1;
+              umma_f16(tacc, da0 + ox, db0 + oy, idesc, 1u);      // hi * lo
+              if (!a.precise) umma_f16(tacc, da0 + ox, db0 + ox, idesc, 1u);   // hi * hi
+            }
+          }
+          umma_commit(bar_empty(sx));
+          umma_commit(bar_empty(sy));
+          it += 2;
+        }
+        if (a.precise) {
+          for (int i = 0; i < nkb; ++i, ++it) {
+            const int s = it % NSLOT;
+            mbar_wait(bar_full(s), (it / NSLOT) & 1);
+            tc_fence_after();
+            const int ksteps = min(BK / 16, (k_total - (kb0 + i) * BK + 15) / 16);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t o = (uint64_t)((s * SLOT_BYTES + ks * kstep) >> 4);
+              umma_f16(tacc, da0 + o, db0 + o, idesc, 1u);         // hi * hi at full magnitude, last
+            }
+            umma_commit(bar_empty(s));
+          }
+        }
+        umma_commit(bar_acc_full(buf));
+        ++tile_it;
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global, one output row per thread =====================
+    const int q = warp & 3;                       // TMEM sub-partition of this warp: lanes 32q .. 32q+31
+    const int chalf = (warp - EPI_WARP0) >> 2;    // 0: even 16-column chunks, 1: odd chunks
+    constexpr bool NEED_H = (EPI == EPI_MUL_S || EPI == EPI_ADJ);
+    constexpr bool NEED_C = (EPI == EPI_ACCUM);
+    const bool need_u = (EPI == EPI_ADJ) || (EPI == EPI_MUL_S && (a.U.f != nullptr || a.U.hi != nullptr));
+    const bool need_b = (EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias != nullptr;
+    const float inv_ab = 1.f / (dev_scalar(a.a_scale) * dev_scalar(a.b_scale));
+    const float sc = dev_scalar(a.C.scale), sc2 = dev_scalar(a.C2.scale);
+    const float inv_h = 1.f / dev_scalar(a.H.scale), inv_u = 1.f / dev_scalar(a.U.scale);
+    float mx = 0.f, mx2 = 0.f;
+    uint32_t tile_it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int m0, n0, kb0, nkb;
+      item_info(item, m0, n0, kb0, nkb);
+      if (nkb == 0) continue;
+      const int n_valid = min(BN, a.N - n0);
+      const int buf = tile_it & 1;
+      const long long m = m0 + q * 32 + lane;
+      const bool row_ok = m < a.M;
+      const int n_vec = p.vec_epi ? (n_valid & ~15) : 0;     // whole 16-column chunks take the vector path
+      mbar_wait(bar_acc_full(buf), (tile_it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      for (int c0 = chalf * 16; c0 < n_valid; c0 += 32) {
+        const bool vec = row_ok && c0 < n_vec;
+        const int n = n0 + c0;
+        // operands of the fused epilogue for this thread's 16 columns, issued before the accumulator is read
+        uint4 hr[4], ur[4], cr[4];
+        float4 bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hr[j] = ur[j] = cr[j] = make_uint4(0u, 0u, 0u, 0u);
+          bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (vec && !(p.dbg & 1)) {
+          if (NEED_H) {
+            if (a.H.hi) {
+              const uint4* ph = reinterpret_cast<const uint4*>(a.H.hi + m * a.H.ldh + n);
+              const uint4* pl = reinterpret_cast<const uint4*>(a.H.lo + m * a.H.ldh + n);
+              hr[0] = __ldg(ph); hr[1] = __ldg(ph + 1); hr[2] = __ldg(pl); hr[3] = __ldg(pl + 1);
+            } else {
+              const uint4* pf = reinterpret_cast<const uint4*>(a.H.f + m * a.H.ldf + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) hr[j] = __ldg(pf + j);
+            }
+          }
+          if (need_u) {
+            if (a.U.hi) {
+              const uint4* ph = reinterpret_cast<const uint4*>(a.U.hi + m * a.U.ldh + n);
+              const uint4* pl = reinterpret_cast<const uint4*>(a.U.lo + m * a.U.ldh + n);
+              ur[0] = ph[0]; ur[1] = ph[1]; ur[2] = pl[0]; ur[3] = pl[1];
+            } else {
+              const uint4* pf = reinterpret_cast<const uint4*>(a.U.f + m * a.U.ldf + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ur[j] = pf[j];
+            }
+          }
+          if (NEED_C) {
+            const uint4* pf = reinterpret_cast<const uint4*>(a.C.f + m * a.C.ldf + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cr[j] = pf[j];
+          }
+          if (need_b) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(a.bias + n) + j);
+          }
+        }
+        float v[16];
+        tmem_ld16(tacc + (uint32_t)c0, v);
+        if (p.dbg & 1) { if (v[0] == 1.2345e-30f && row_ok) a.C.f[0] = v[1]; continue; }
+        if (vec) {
+          float h[16], u[16], cp[16], o[16], o2[16];
+          const float* bb = reinterpret_cast<const float*>(bv);
+          // decode the raw operand registers
+          if (NEED_H) {
+            if (a.H.hi) {
+              const uint32_t* hh = reinterpret_cast<const uint32_t*>(hr);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float2 t = join2(hh[e], hh[8 + e]);
+                h[2 * e] = t.x * inv_h; h[2 * e + 1] = t.y * inv_h;
+              }
+            } else {
+              const float* hf = reinterpret_cast<const float*>(hr);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) h[e] = hf[e];
+            }
+          }
+          if (need_u) {
+            if (a.U.hi) {
+              const uint32_t* uu = reinterpret_cast<const uint32_t*>(ur);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float2 t = join2(uu[e], uu[8 + e]);
+                u[2 * e] = t.x * inv_u; u[2 * e + 1] = t.y * inv_u;
+              }
+            } else {
+              const float* uf = reinterpret_cast<const float*>(ur);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) u[e] = uf[e];
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) u[e] = 0.f;
+          }
+          if (NEED_C) {
+            const float* cf = reinterpret_cast<const float*>(cr);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) cp[e] = cf[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            epi_math<EPI>(a, v[e] * inv_ab, NEED_H ? h[e] : 0.f, u[e], NEED_C ? cp[e] : 0.f, bb[e], o[e], o2[e]);
+            mx = fmaxf(mx, fabsf(o[e]));
+            if (EPI == EPI_ADJ) mx2 = fmaxf(mx2, fabsf(o2[e]));
+          }
+          // store
+          if (EPI == EPI_ATOMIC) {
+            float* cp_ = a.C.f + m * a.C.ldf + n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(cp_ + 4 * j), "f"(o[4 * j]),
+                           "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
+                           : "memory");
+          } else if (a.C.hi) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split2(o[2 * e] * sc, o[2 * e + 1] * sc, hi[e], lo[e]);
+            uint4* ph = reinterpret_cast<uint4*>(a.C.hi + m * a.C.ldh + n);
+            uint4* pl = reinterpret_cast<uint4*>(a.C.lo + m * a.C.ldh + n);
+            ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          } else {
+            float4* pf = reinterpret_cast<float4*>(a.C.f + m * a.C.ldf + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pf[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          if (EPI == EPI_ADJ) {
+            if (a.C2.hi) {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) split2(o2[2 * e] * sc2, o2[2 * e + 1] * sc2, hi[e], lo[e]);
+              uint4* ph = reinterpret_cast<uint4*>(a.C2.hi + m * a.C2.ldh + n);
+              uint4* pl = reinterpret_cast<uint4*>(a.C2.lo + m * a.C2.ldh + n);
+              ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            } else {
+              float4* pf = reinterpret_cast<float4*>(a.C2.f + m * a.C2.ldf + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pf[j] = make_float4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
+            }
+          }
+        } else if (row_ok) {
+          // ragged chunk / unaligned operands: one element at a time
+#pragma unroll 1
+          for (int e = 0; e < 16; ++e) {
+            const int c = c0 + e;
+            if (c >= n_valid) break;
+            const int nn = n0 + c;
+            float h = 0.f, u = 0.f, cpv = 0.f, b = 0.f, o, o2;
+            if (NEED_H) h = op_load(a.H, inv_h, m, nn);
+            if (need_u) u = op_load(a.U, inv_u, m, nn);
+            if (NEED_C) cpv = a.C.f[m * a.C.ldf + nn];
+            if (need_b) b = __ldg(a.bias + nn);
+            epi_math<EPI>(a, v[e] * inv_ab, h, u, cpv, b, o, o2);
+            mx = fmaxf(mx, fabsf(o));
+            if (EPI == EPI_ATOMIC) atomicAdd(a.C.f + m * a.C.ldf + nn, o);
+            else op_store(a.C, sc, m, nn, o);
+            if (EPI == EPI_ADJ) {
+              mx2 = fmaxf(mx2, fabsf(o2));
+              op_store(a.C2, sc2, m, nn, o2);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty(buf));
+      ++tile_it;
+    }
+    if (EPI != EPI_ATOMIC) {
+      amax_commit(a.C.amax, mx);
+      if (EPI == EPI_ADJ) amax_commit(a.C2.amax, mx2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled get_encode() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+  }
+  return fn;
+}
+
+static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// K-major plane: `rows` rows of `k` halfs (row stride ld); box = 64 halfs x box_rows rows
+static bool map_kmajor(CUtensorMap* map, const __half* base, long long k, long long rows, long long ld, int box_rows) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// MN-major plane: `krows` rows (the contraction index) of `mn` halfs.  3-D form (64 contiguous halfs, k rows, 64-wide
+// chunks): one request fills the whole [chunk][k][64] tile; needs ld % 64 == 0 (columns beyond mn up to ld are padding
+// inside the allocation and only reach outputs that are never stored).
+static bool map_mnmajor3(CUtensorMap* map, const __half* base, long long krows, long long ld, int box_chunks) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {64, (cuuint64_t)krows, (cuuint64_t)(ld / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)BK, (cuuint32_t)box_chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool map_mnmajor2(CUtensorMap* map, const __half* base, long long mn, long long krows, long long ld) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)krows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int EPI>
+static int launch_epi(const HArgs& a, cudaStream_t st) {
+  HParams p;
+  p.a = a;
+  p.dbg = g_h_dbg;
+  const int ncap = a.N < BN ? a.N : BN;
+  p.b_box_rows = ncap <= 64 ? 64 : (ncap <= 128 ? 128 : 256);
+  auto ok_op = [](const Op& o) {
+    if (o.hi) return al16p(o.hi) && al16p(o.lo) && o.ldh % 8 == 0;
+    if (o.f) return al16p(o.f) && o.ldf % 4 == 0;
+    return true;
+  };
+  p.vec_epi = ok_op(a.C) && ok_op(a.C2) && ok_op(a.H) && ok_op(a.U) && (a.bias == nullptr || al16p(a.bias));
+  CUtensorMap mAh, mAl, mBh, mBl;
+  bool ok = true;
+  p.a3d = p.b3d = 0;
+  if (!a.mn) {
+    ok = ok && map_kmajor(&mAh, a.Ahi, a.K, a.M, a.lda, BM) && map_kmajor(&mAl, a.Alo, a.K, a.M, a.lda, BM);
+    ok = ok && map_kmajor(&mBh, a.Bhi, a.K, a.N, a.ldb, p.b_box_rows) && map_kmajor(&mBl, a.Blo, a.K, a.N, a.ldb, p.b_box_rows);
+  } else {
+    p.a3d = a.lda % 64 == 0;
+    p.b3d = a.ldb % 64 == 0;
+    if (p.a3d) ok = ok && map_mnmajor3(&mAh, a.Ahi, a.K, a.lda, BM / 64) && map_mnmajor3(&mAl, a.Alo, a.K, a.lda, BM / 64);
+    else ok = ok && map_mnmajor2(&mAh, a.Ahi, a.M, a.K, a.lda) && map_mnmajor2(&mAl, a.Alo, a.M, a.K, a.lda);
+    if (p.b3d) ok = ok && map_mnmajor3(&mBh, a.Bhi, a.K, a.ldb, p.b_box_rows / 64) && map_mnmajor3(&mBl, a.Blo, a.K, a.ldb, p.b_box_rows / 64);
+    else ok = ok && map_mnmajor2(&mBh, a.Bhi, a.N, a.K, a.ldb) && map_mnmajor2(&mBl, a.Blo, a.N, a.K, a.ldb);
+  }
+  if (!ok) return NDJIR_ERR_ARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  p.m_tiles = (a.M + BM - 1) / BM;
+  p.n_tiles = (a.N + BN - 1) / BN;
+  p.nkb_total = (a.K + BK - 1) / BK;
+  int splits = (a.mn && a.split_k > 1) ? a.split_k : 1;
+  p.kb_per_split = (p.nkb_total + splits - 1) / splits;
+  p.splits = (p.nkb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+  int n_items = p.m_tiles * p.n_tiles * p.splits;
+  int grid = n_items < NDJIR_NUM_SMS ? n_items : NDJIR_NUM_SMS;
+  gemm_h_kernel<EPI><<<grid, THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int launch_tc(const HArgs& a, cudaStream_t st) {
+  if (!get_encode()) return NDJIR_ERR_ARG;
+  if (!a.Ahi || !a.Alo || !a.Bhi || !a.Blo) return NDJIR_ERR_ARG;
+  if (!al16p(a.Ahi) || !al16p(a.Alo) || !al16p(a.Bhi) || !al16p(a.Blo) || a.lda % 8 != 0 || a.ldb % 8 != 0)
+    return NDJIR_ERR_ARG;
+  if (a.mn && a.epi != EPI_ATOMIC) return NDJIR_ERR_ARG;
+  if (a.epi == EPI_ATOMIC && (a.C.hi || !a.C.f)) return NDJIR_ERR_ARG;
+  if (a.epi == EPI_ACCUM && (a.C.hi || !a.C.f)) return NDJIR_ERR_ARG;
+  switch (a.epi) {
+    case EPI_BIAS: return launch_epi<EPI_BIAS>(a, st);
+    case EPI_SOFTPLUS: return launch_epi<EPI_SOFTPLUS>(a, st);
+    case EPI_ACCUM: return launch_epi<EPI_ACCUM>(a, st);
+    case EPI_MUL_S: if (!a.H.f && !a.H.hi) return NDJIR_ERR_ARG; return launch_epi<EPI_MUL_S>(a, st);
+    case EPI_ADJ:
+      if ((!a.H.f && !a.H.hi) || (!a.U.f && !a.U.hi) || (!a.C2.f && !a.C2.hi)) return NDJIR_ERR_ARG;
+      return launch_epi<EPI_ADJ>(a, st);
+    case EPI_ATOMIC: return launch_epi<EPI_ATOMIC>(a, st);
+    default: return NDJIR_ERR_ARG;
+  }
+}
+
+}  // namespace gemmh
+}  // namespace ndjir
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+using ndjir::gemmh::Op;
+Op make_op(float* f, long long ldf, const ndjir_hmat& h) {
+  Op o;
+  o.f = h.hi ? nullptr : f;
+  o.ldf = ldf;
+  o.hi = reinterpret_cast<__half*>(h.hi);
+  o.lo = reinterpret_cast<__half*>(h.lo);
+  o.ldh = h.ld;
+  o.scale = h.hi ? h.scale : nullptr;
+  o.amax = h.hi ? h.amax : nullptr;
+  return o;
+}
+}  // namespace
+
+extern "C" int ndjir_gemm_h(const ndjir_gemm_h_desc* d, cudaStream_t stream) {
+  using namespace ndjir::gemmh;
+  if (!d) return NDJIR_ERR_ARG;
+  if (d->M <= 0 || d->N <= 0) return NDJIR_OK;
+  if (d->K < 0) return NDJIR_ERR_ARG;
+  HArgs a;
+  a.M = d->M; a.N = d->N; a.K = d->K;
+  a.mn = d->mn_major ? 1 : 0; a.epi = d->epilogue; a.precise = d->precise ? 1 : 0;
+  a.split_k = d->split_k > 1 ? d->split_k : 1;
+  a.alpha = d->alpha; a.out_scale = d->out_scale; a.beta = d->beta; a.hscale = d->hscale;
+  a.a_scale = d->A.hi ? d->A.scale : nullptr;
+  a.b_scale = d->B.hi ? d->B.scale : nullptr;
+  a.Ahi = reinterpret_cast<const __half*>(d->A.hi); a.Alo = reinterpret_cast<const __half*>(d->A.lo); a.lda = d->A.ld;
+  a.Bhi = reinterpret_cast<const __half*>(d->B.hi); a.Blo = reinterpret_cast<const __half*>(d->B.lo); a.ldb = d->B.ld;
+  a.A32 = d->A32; a.a_rs = d->a_rs; a.a_cs = d->a_cs;
+  a.B32 = d->B32; a.b_rs = d->b_rs; a.b_cs = d->b_cs;
+  a.C = make_op(d->C, d->ldc, d->Ch);
+  a.C2 = make_op(d->C2, d->ldc2, d->C2h);
+  a.H = make_op(const_cast<float*>(d->H), d->ldh, d->Hh);
+  a.U = make_op(const_cast<float*>(d->U), d->ldu, d->Uh);
+  a.bias = d->bias;
+  if (!a.C.f && !a.C.hi) return NDJIR_ERR_ARG;
+  if (corner_shape(a)) return launch_corner(a, stream);
+  return launch_tc(a, stream);
+}

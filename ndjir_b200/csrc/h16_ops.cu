@@ -1,0 +1,479 @@
+// Split-fp16 MLP engine: everything that is not a tensor-core product (sm_100a).
+//   * the memory-bound corner shapes of the MLP passes with split-fp16 activations (one pass over the large operand):
+//       skinny_n_h  C (M x N<=8)  = A(split) B32          last layers (sdf, colours ...), grid-feature gradient
+//       skinny_k_h  C (M x N)     = A32 (M x K<=8) B32    rank-1..8 updates with the full fused epilogue in either form
+//       skinny_w_h  C (M x N<=8) += A(split, K x M)^T B32 weight gradients of those last layers
+//   * format conversion: pack (fp32 -> split), unpack, plane copies, column sums (bias gradients)
+//   * the per-tensor power-of-two scales: running max -> scale (delayed by one use of the tensor)
+#include "gemm_h.cuh"
+
+namespace ndjir {
+namespace gemmh {
+
+constexpr int SK_WARPS = 8;
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT, int EPI>
+__global__ void __launch_bounds__(SK_WARPS * 32) skinny_n_h_kernel(HArgs a, int vec) {
+  // B staged as [NT][Kp] (k contiguous): the eight lanes of a row read consecutive 32-byte pieces, the four row groups
+  // of a warp the same addresses (broadcast): conflict-free
+  extern __shared__ __align__(16) float Bs[];
+  const int Kp = (a.K + 7) & ~7;
+  for (int i = threadIdx.x; i < Kp * NT; i += blockDim.x) {
+    int n = i / Kp, k = i - n * Kp;
+    Bs[i] = (n < a.N && k < a.K) ? __ldg(a.B32 + (long long)k * a.b_rs + (long long)n * a.b_cs) : 0.f;
+  }
+  __syncthreads();
+  const float inv_a = 1.f / dev_scalar(a.a_scale);
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const long long row0 = ((long long)blockIdx.x * SK_WARPS + (threadIdx.x >> 5)) * 4 + grp;
+  const long long row_stride = (long long)gridDim.x * SK_WARPS * 4;
+  const int K8 = vec ? (a.K & ~7) : 0;
+  const long long rounds = (a.M + row_stride - 1) / row_stride;
+  for (long long r = 0; r < rounds; ++r) {
+    const long long m = row0 + r * row_stride;
+    const bool active = m < a.M;
+    const long long mm = active ? m : a.M - 1;
+    const __half* rh = a.Ahi + mm * a.lda;
+    const __half* rl = a.Alo + mm * a.lda;
+    float acc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+#pragma unroll 2
+    for (int k = sub * 8; k < K8; k += 64) {
+      uint4 xh = __ldg(reinterpret_cast<const uint4*>(rh + k));
+      uint4 xl = __ldg(reinterpret_cast<const uint4*>(rl + k));
+      float2 x0 = join2(xh.x, xl.x), x1 = join2(xh.y, xl.y), x2 = join2(xh.z, xl.z), x3 = join2(xh.w, xl.w);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        float4 b0 = *reinterpret_cast<const float4*>(Bs + n * Kp + k);
+        float4 b1 = *reinterpret_cast<const float4*>(Bs + n * Kp + k + 4);
+        acc[n] += x0.x * b0.x + x0.y * b0.y + x1.x * b0.z + x1.y * b0.w + x2.x * b1.x + x2.y * b1.y + x3.x * b1.z +
+                  x3.y * b1.w;
+      }
+    }
+    for (int k = K8 + sub; k < a.K; k += 8) {
+      float x = __half2float(rh[k]) + __half2float(rl[k]);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) acc[n] += x * Bs[n * Kp + k];
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
+      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
+    }
+    if (active && sub < a.N) {
+      float v = 0.f;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) if (sub == n) v = acc[n];
+      v *= inv_a;
+      float* cp = a.C.f + m * a.C.ldf + sub;
+      if (EPI == EPI_BIAS) *cp = a.alpha * v + (a.bias ? __ldg(a.bias + sub) : 0.f);
+      else *cp += a.alpha * v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 8 columns per thread, 16-byte accesses in either operand form
+template <int EPI>
+__global__ void __launch_bounds__(NDJIR_BLOCK) skinny_k_h_kernel(HArgs a, int vec) {
+  const int CPT = vec ? 8 : 1;
+  const int ncol = (a.N + CPT - 1) / CPT;
+  const long long total = (long long)a.M * ncol;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float sc = dev_scalar(a.C.scale);
+  const float inv_h = 1.f / dev_scalar(a.H.scale), inv_u = 1.f / dev_scalar(a.U.scale);
+  const bool need_h = (EPI == EPI_MUL_S);
+  const bool need_u = (EPI == EPI_MUL_S) && (a.U.f || a.U.hi);
+  float mx = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long m = i / ncol;
+    const int n = (int)(i - m * ncol) * CPT;
+    float xa[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xa[k] = k < a.K ? __ldg(a.A32 + m * a.a_rs + (long long)k * a.a_cs) : 0.f;
+    float h[8], u[8], cp[8], b[8], o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = u[e] = cp[e] = b[e] = 0.f;
+    if (vec) {
+      if (need_h) {
+        if (a.H.hi) {
+          uint4 xh = __ldg(reinterpret_cast<const uint4*>(a.H.hi + m * a.H.ldh + n));
+          uint4 xl = __ldg(reinterpret_cast<const uint4*>(a.H.lo + m * a.H.ldh + n));
+          float2 t0 = join2(xh.x, xl.x), t1 = join2(xh.y, xl.y), t2 = join2(xh.z, xl.z), t3 = join2(xh.w, xl.w);
+          h[0] = t0.x; h[1] = t0.y; h[2] = t1.x; h[3] = t1.y; h[4] = t2.x; h[5] = t2.y; h[6] = t3.x; h[7] = t3.y;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] *= inv_h;
+        } else {
+          float4 t0 = __ldg(reinterpret_cast<const float4*>(a.H.f + m * a.H.ldf + n));
+          float4 t1 = __ldg(reinterpret_cast<const float4*>(a.H.f + m * a.H.ldf + n + 4));
+          h[0] = t0.x; h[1] = t0.y; h[2] = t0.z; h[3] = t0.w; h[4] = t1.x; h[5] = t1.y; h[6] = t1.z; h[7] = t1.w;
+        }
+      }
+      if (need_u) {
+        if (a.U.hi) {
+          uint4 xh = *reinterpret_cast<const uint4*>(a.U.hi + m * a.U.ldh + n);
+          uint4 xl = *reinterpret_cast<const uint4*>(a.U.lo + m * a.U.ldh + n);
+          float2 t0 = join2(xh.x, xl.x), t1 = join2(xh.y, xl.y), t2 = join2(xh.z, xl.z), t3 = join2(xh.w, xl.w);
+          u[0] = t0.x; u[1] = t0.y; u[2] = t1.x; u[3] = t1.y; u[4] = t2.x; u[5] = t2.y; u[6] = t3.x; u[7] = t3.y;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) u[e] *= inv_u;
+        } else {
+          float4 t0 = *reinterpret_cast<const float4*>(a.U.f + m * a.U.ldf + n);
+          float4 t1 = *reinterpret_cast<const float4*>(a.U.f + m * a.U.ldf + n + 4);
+          u[0] = t0.x; u[1] = t0.y; u[2] = t0.z; u[3] = t0.w; u[4] = t1.x; u[5] = t1.y; u[6] = t1.z; u[7] = t1.w;
+        }
+      }
+      if (EPI == EPI_ACCUM) {
+        float4 t0 = *reinterpret_cast<const float4*>(a.C.f + m * a.C.ldf + n);
+        float4 t1 = *reinterpret_cast<const float4*>(a.C.f + m * a.C.ldf + n + 4);
+        cp[0] = t0.x; cp[1] = t0.y; cp[2] = t0.z; cp[3] = t0.w; cp[4] = t1.x; cp[5] = t1.y; cp[6] = t1.z; cp[7] = t1.w;
+      }
+      if ((EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias) {
+        float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+        float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
+        b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
+      }
+    } else {
+      if (need_h) h[0] = op_load(a.H, inv_h, m, n);
+      if (need_u) u[0] = op_load(a.U, inv_u, m, n);
+      if (EPI == EPI_ACCUM) cp[0] = a.C.f[m * a.C.ldf + n];
+      if ((EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias) b[0] = __ldg(a.bias + n);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (e < CPT) {
+        float acc = 0.f;
+        const float* bp = a.B32 + (long long)(n + e) * a.b_cs;      // small operand: L1-resident
+        for (int k = 0; k < a.K; ++k) acc += xa[k] * __ldg(bp + (long long)k * a.b_rs);
+        float o2;
+        epi_math<EPI>(a, acc, h[e], u[e], cp[e], b[e], o[e], o2);
+        mx = fmaxf(mx, fabsf(o[e]));
+      }
+    }
+    if (vec) {
+      if (a.C.hi) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2(o[2 * e] * sc, o[2 * e + 1] * sc, hi[e], lo[e]);
+        *reinterpret_cast<uint4*>(a.C.hi + m * a.C.ldh + n) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a.C.lo + m * a.C.ldh + n) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      } else {
+        *reinterpret_cast<float4*>(a.C.f + m * a.C.ldf + n) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(a.C.f + m * a.C.ldf + n + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    } else {
+      op_store(a.C, sc, m, n, o[0]);
+    }
+  }
+  amax_commit(a.C.amax, mx);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C[m, n] += alpha * sum_k A(k, m) * B32(k, n): a thread owns two adjacent m, a block walks a slice of the k rows
+template <int NT>
+__global__ void __launch_bounds__(NDJIR_BLOCK) skinny_w_h_kernel(HArgs a) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const long long per = (a.K + gridDim.y - 1) / gridDim.y;
+  const long long k0 = (long long)blockIdx.y * per, k1 = k0 + per < a.K ? k0 + per : a.K;
+  const float inv_a = 1.f / dev_scalar(a.a_scale);
+  float acc0[NT], acc1[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) acc0[n] = acc1[n] = 0.f;
+  if (m < a.M) {
+    const bool pair = (m + 1 < a.M) && (a.lda % 2 == 0);
+#pragma unroll 4
+    for (long long k = k0; k < k1; ++k) {
+      float x0, x1 = 0.f;
+      if (pair) {
+        uint32_t xh = __ldg(reinterpret_cast<const uint32_t*>(a.Ahi + k * a.lda + m));
+        uint32_t xl = __ldg(reinterpret_cast<const uint32_t*>(a.Alo + k * a.lda + m));
+        float2 t = join2(xh, xl);
+        x0 = t.x; x1 = t.y;
+      } else {
+        x0 = __half2float(a.Ahi[k * a.lda + m]) + __half2float(a.Alo[k * a.lda + m]);
+        if (m + 1 < a.M) x1 = __half2float(a.Ahi[k * a.lda + m + 1]) + __half2float(a.Alo[k * a.lda + m + 1]);
+      }
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        if (n < a.N) {
+          float b = __ldg(a.B32 + k * a.b_rs + (long long)n * a.b_cs);
+          acc0[n] += x0 * b;
+          acc1[n] += x1 * b;
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      if (n < a.N) {
+        if (acc0[n] != 0.f) atomicAdd(a.C.f + (long long)m * a.C.ldf + n, a.alpha * inv_a * acc0[n]);
+        if (m + 1 < a.M && acc1[n] != 0.f) atomicAdd(a.C.f + (long long)(m + 1) * a.C.ldf + n, a.alpha * inv_a * acc1[n]);
+      }
+    }
+  }
+}
+
+static inline bool al16s(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int which_corner(const HArgs& a) {
+  if (!a.mn && a.N <= 8 && a.K >= 8 && a.K <= 2048 && a.Ahi && a.B32 && a.C.f && (a.epi == EPI_BIAS || a.epi == EPI_ACCUM))
+    return 1;
+  if (!a.mn && a.K <= 8 && a.A32 && a.B32 && a.epi != EPI_ATOMIC && a.epi != EPI_ADJ) return 2;
+  if (a.mn && a.N <= 8 && a.Ahi && a.B32 && a.C.f && a.epi == EPI_ATOMIC) return 3;
+  return 0;
+}
+
+bool corner_shape(const HArgs& a) { return which_corner(a) != 0; }
+
+template <int NT>
+static void launch_skinny_n(const HArgs& a, cudaStream_t st) {
+  int vec = al16s(a.Ahi) && al16s(a.Alo) && a.lda % 8 == 0;
+  long long blocks = (a.M + SK_WARPS * 4 - 1) / (SK_WARPS * 4);
+  long long cap = (long long)NDJIR_NUM_SMS * 16;
+  int grid = (int)(blocks < cap ? blocks : cap);
+  size_t smem = (size_t)((a.K + 7) & ~7) * NT * sizeof(float);
+  if (a.epi == EPI_BIAS) skinny_n_h_kernel<NT, EPI_BIAS><<<grid, SK_WARPS * 32, smem, st>>>(a, vec);
+  else skinny_n_h_kernel<NT, EPI_ACCUM><<<grid, SK_WARPS * 32, smem, st>>>(a, vec);
+}
+
+int launch_corner(const HArgs& a, cudaStream_t st) {
+  const int w = which_corner(a);
+  if (w == 1) {
+    if (a.N == 1) launch_skinny_n<1>(a, st);
+    else if (a.N == 2) launch_skinny_n<2>(a, st);
+    else if (a.N <= 4) launch_skinny_n<4>(a, st);
+    else launch_skinny_n<8>(a, st);
+  } else if (w == 2) {
+    auto ok_op = [](const Op& o) {
+      if (o.hi) return al16s(o.hi) && al16s(o.lo) && o.ldh % 8 == 0;
+      if (o.f) return al16s(o.f) && o.ldf % 4 == 0;
+      return true;
+    };
+    int vec = a.N % 8 == 0 && ok_op(a.C) && ok_op(a.H) && ok_op(a.U) && (a.bias == nullptr || al16s(a.bias));
+    int grid = grid_for((long long)a.M * (vec ? a.N / 8 : a.N));
+    switch (a.epi) {
+      case EPI_BIAS: skinny_k_h_kernel<EPI_BIAS><<<grid, NDJIR_BLOCK, 0, st>>>(a, vec); break;
+      case EPI_SOFTPLUS: skinny_k_h_kernel<EPI_SOFTPLUS><<<grid, NDJIR_BLOCK, 0, st>>>(a, vec); break;
+      case EPI_ACCUM:
+        if (!a.C.f) return NDJIR_ERR_ARG;
+        skinny_k_h_kernel<EPI_ACCUM><<<grid, NDJIR_BLOCK, 0, st>>>(a, vec);
+        break;
+      case EPI_MUL_S:
+        if (!a.H.f && !a.H.hi) return NDJIR_ERR_ARG;
+        skinny_k_h_kernel<EPI_MUL_S><<<grid, NDJIR_BLOCK, 0, st>>>(a, vec);
+        break;
+      default: return NDJIR_ERR_ARG;
+    }
+  } else if (w == 3) {
+    int gx = ((a.M + 1) / 2 + NDJIR_BLOCK - 1) / NDJIR_BLOCK;
+    long long want = (long long)NDJIR_NUM_SMS * 8 / gx;
+    long long maxy = (a.K + 63) / 64;
+    int gy = (int)(want < 1 ? 1 : (want > maxy ? maxy : want));
+    dim3 grid(gx, gy);
+    if (a.N == 1) skinny_w_h_kernel<1><<<grid, NDJIR_BLOCK, 0, st>>>(a);
+    else if (a.N == 2) skinny_w_h_kernel<2><<<grid, NDJIR_BLOCK, 0, st>>>(a);
+    else if (a.N <= 4) skinny_w_h_kernel<4><<<grid, NDJIR_BLOCK, 0, st>>>(a);
+    else skinny_w_h_kernel<8><<<grid, NDJIR_BLOCK, 0, st>>>(a);
+  } else {
+    return NDJIR_ERR_ARG;
+  }
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+}  // namespace gemmh
+}  // namespace ndjir
+
+// ---------------------------------------------------------------------------------------------------------------
+// format conversion and scales
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+using namespace ndjir::gemmh;
+
+struct HM {
+  __half* hi; __half* lo; long long ld; const float* scale; float* amax;
+};
+HM to_hm(const ndjir_hmat* h) {
+  HM m;
+  m.hi = reinterpret_cast<__half*>(h->hi); m.lo = reinterpret_cast<__half*>(h->lo); m.ld = h->ld;
+  m.scale = h->scale; m.amax = h->amax;
+  return m;
+}
+
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+pack_h_kernel(long long rows, int cols, const float* __restrict__ src, long long ld_src, int rep, float alpha, HM d,
+              int vec) {
+  const int CPT = vec ? 8 : 1;
+  const int ncol = (cols + CPT - 1) / CPT;
+  const long long total = rows * ncol;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float sc = dev_scalar(d.scale);
+  float mx = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / ncol;
+    const int c = (int)(i - r * ncol) * CPT;
+    const float* sp = src + (r / rep) * ld_src + c;
+    if (vec) {
+      float4 t0 = __ldg(reinterpret_cast<const float4*>(sp)), t1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
+      float x[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { x[e] *= alpha; mx = fmaxf(mx, fabsf(x[e])); }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split2(x[2 * e] * sc, x[2 * e + 1] * sc, hi[e], lo[e]);
+      *reinterpret_cast<uint4*>(d.hi + r * d.ld + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(d.lo + r * d.ld + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+      float x = alpha * __ldg(sp);
+      mx = fmaxf(mx, fabsf(x));
+      __half h, l;
+      split1(x * sc, h, l);
+      d.hi[r * d.ld + c] = h;
+      d.lo[r * d.ld + c] = l;
+    }
+  }
+  amax_commit(d.amax, mx);
+}
+
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+unpack_h_kernel(long long rows, int cols, HM s, float* __restrict__ dst, long long ld_dst) {
+  const long long total = rows * cols;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float inv = 1.f / dev_scalar(s.scale);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dst[r * ld_dst + c] = (__half2float(s.hi[r * s.ld + c]) + __half2float(s.lo[r * s.ld + c])) * inv;
+  }
+}
+
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+copy2d_h_kernel(long long rows, int cols, HM d, HM s, int rep, int vec) {
+  const int CPT = vec ? 8 : 1;
+  const int ncol = (cols + CPT - 1) / CPT;
+  const long long total = rows * ncol;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / ncol;
+    const int c = (int)(i - r * ncol) * CPT;
+    const long long so = (r / rep) * s.ld + c, dof = r * d.ld + c;
+    if (vec) {
+      *reinterpret_cast<uint4*>(d.hi + dof) = __ldg(reinterpret_cast<const uint4*>(s.hi + so));
+      *reinterpret_cast<uint4*>(d.lo + dof) = __ldg(reinterpret_cast<const uint4*>(s.lo + so));
+    } else {
+      d.hi[dof] = s.hi[so];
+      d.lo[dof] = s.lo[so];
+    }
+  }
+}
+
+// out[c] += alpha * sum_r src[r, c]: a thread owns two adjacent columns, blockIdx.y a slab of rows
+__global__ void __launch_bounds__(128)
+colsum_h_kernel(long long rows, int cols, float* __restrict__ out, HM s, float alpha) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+  if (c >= cols) return;
+  const bool pair = c + 1 < cols;
+  float a0 = 0.f, a1 = 0.f;
+  if (pair && s.ld % 2 == 0) {
+#pragma unroll 8
+    for (long long r = r0; r < r1; ++r) {
+      uint32_t xh = __ldg(reinterpret_cast<const uint32_t*>(s.hi + r * s.ld + c));
+      uint32_t xl = __ldg(reinterpret_cast<const uint32_t*>(s.lo + r * s.ld + c));
+      float2 t = join2(xh, xl);
+      a0 += t.x; a1 += t.y;
+    }
+  } else {
+    for (long long r = r0; r < r1; ++r) {
+      a0 += __half2float(s.hi[r * s.ld + c]) + __half2float(s.lo[r * s.ld + c]);
+      if (pair) a1 += __half2float(s.hi[r * s.ld + c + 1]) + __half2float(s.lo[r * s.ld + c + 1]);
+    }
+  }
+  const float f = alpha / dev_scalar(s.scale);
+  if (a0 != 0.f) atomicAdd(out + c, f * a0);
+  if (pair && a1 != 0.f) atomicAdd(out + c + 1, f * a1);
+}
+
+__global__ void __launch_bounds__(NDJIR_BLOCK) amax_kernel(long long n, const float* __restrict__ x, float* amax) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float mx = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mx = fmaxf(mx, fabsf(__ldg(x + i)));
+  amax_commit(amax, mx);
+}
+
+__global__ void scale_update_kernel(int n, float* scales, float* amax, int* flags, int target_log2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float m = amax[i];
+  amax[i] = 0.f;
+  if (!(m > 0.f) || !isfinite(m)) return;
+  float old = scales[i];
+  int fl = 0;
+  if (m * old > H16_MAX) fl |= 1;
+  int e;
+  frexpf(m, &e);                   // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(target - e) in [2^(target-1), 2^target)
+  float s = ldexpf(1.f, target_log2 - e);
+  if (s != old) fl |= 2;
+  scales[i] = s;
+  if (fl && flags) atomicOr(flags, fl);
+}
+}  // namespace
+
+extern "C" {
+
+int ndjir_pack_h(long long rows, int cols, const float* src, long long ld_src, int rep, float alpha,
+                 const ndjir_hmat* dst, cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return NDJIR_OK;
+  if (rows < 0 || cols < 0 || !src || !dst || !dst->hi || !dst->lo || rep < 1) return NDJIR_ERR_ARG;
+  HM d = to_hm(dst);
+  int vec = cols % 8 == 0 && al16s(src) && ld_src % 4 == 0 && al16s(d.hi) && al16s(d.lo) && d.ld % 8 == 0;
+  pack_h_kernel<<<ndjir::grid_for(rows * (vec ? cols / 8 : cols)), NDJIR_BLOCK, 0, stream>>>(rows, cols, src, ld_src, rep,
+                                                                                           alpha, d, vec);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_unpack_h(long long rows, int cols, const ndjir_hmat* src, float* dst, long long ld_dst, cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return NDJIR_OK;
+  if (rows < 0 || cols < 0 || !src || !src->hi || !src->lo || !dst) return NDJIR_ERR_ARG;
+  unpack_h_kernel<<<ndjir::grid_for(rows * cols), NDJIR_BLOCK, 0, stream>>>(rows, cols, to_hm(src), dst, ld_dst);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_copy2d_h(long long rows, int cols, const ndjir_hmat* dst, const ndjir_hmat* src, int rep,
+                   cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return NDJIR_OK;
+  if (rows < 0 || cols < 0 || !src || !dst || !src->hi || !dst->hi || rep < 1) return NDJIR_ERR_ARG;
+  HM d = to_hm(dst), s = to_hm(src);
+  int vec = cols % 8 == 0 && al16s(d.hi) && al16s(d.lo) && al16s(s.hi) && al16s(s.lo) && d.ld % 8 == 0 && s.ld % 8 == 0;
+  copy2d_h_kernel<<<ndjir::grid_for(rows * (vec ? cols / 8 : cols)), NDJIR_BLOCK, 0, stream>>>(rows, cols, d, s, rep, vec);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_colsum_h(long long rows, int cols, float* out, const ndjir_hmat* src, float alpha, cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return NDJIR_OK;
+  if (rows < 0 || cols < 0 || !src || !src->hi || !out) return NDJIR_ERR_ARG;
+  int gx = ((cols + 1) / 2 + 127) / 128;
+  long long want = (long long)NDJIR_NUM_SMS * 16 / gx;
+  long long maxy = (rows + 63) / 64;
+  int gy = (int)(want < 1 ? 1 : (want > maxy ? maxy : want));
+  colsum_h_kernel<<<dim3(gx, gy), 128, 0, stream>>>(rows, cols, out, to_hm(src), alpha);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_amax(long long n, const float* x, float* amax, cudaStream_t stream) {
+  if (n == 0) return NDJIR_OK;
+  if (n < 0 || !x || !amax) return NDJIR_ERR_ARG;
+  amax_kernel<<<ndjir::grid_for(n, NDJIR_BLOCK, 8), NDJIR_BLOCK, 0, stream>>>(n, x, amax);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_scale_update(int n_slots, float* scales, float* amax, int* flags, int target_log2, cudaStream_t stream) {
+  if (n_slots == 0) return NDJIR_OK;
+  if (n_slots < 0 || !scales || !amax) return NDJIR_ERR_ARG;
+  scale_update_kernel<<<(n_slots + 255) / 256, 256, 0, stream>>>(n_slots, scales, amax, flags, target_log2);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+}  // extern "C"

@@ -10,6 +10,7 @@
 // grad_feature 12+16+2*8*16 = 284 B.
 #include "grid_common.cuh"
 #include "gemm.cuh"
+#include "gemm_h.cuh"
 #include "voxel_binned.cuh"
 #include "../../include/ndjir_b200.h"
 
@@ -369,6 +370,7 @@ int ndjir_set_option(const char* key, int value) {
       {"mlp_fused_colsum", &ndjir::gemm::g_mlp_fused_colsum},  // 0: bias gradients by a separate column-sum pass
       {"mlp_dbg", &ndjir::gemm::g_mlp_dbg},                 // profiling switches of the tcgen05 kernel
       {"mlp_mask_hi", &ndjir::gemm::g_mlp_mask_hi},
+      {"mlp_h_dbg", &ndjir::gemmh::g_h_dbg},                // profiling switches of the split-fp16 tcgen05 kernel
       {"voxel_binned", &ndjir::g_voxel_binned},             // -1 auto, 0 never, 1 whenever possible (brick-ordered sweeps)
       {"voxel_bin_mb", &ndjir::g_voxel_bin_mb},             // brick size in MiB
       {"hash_coarse_private", &ndjir::g_hash_coarse_private},  // 0 off, 1 batches >= 2^20 points, 2 always
