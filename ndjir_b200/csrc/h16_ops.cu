@@ -76,116 +76,140 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_n_h_kernel(HArgs a, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 8 columns per thread, 16-byte accesses in either operand form
-template <int EPI>
-__global__ void __launch_bounds__(NDJIR_BLOCK) skinny_k_h_kernel(HArgs a, int vec) {
-  const int CPT = vec ? 8 : 1;
-  const int ncol = (a.N + CPT - 1) / CPT;
-  const long long total = (long long)a.M * ncol;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+// Rank-K update (K <= 8) with the fused epilogue.  Vector form: a thread owns ONE group of 8 adjacent columns for the
+// whole kernel (its K x 8 block of B lives in registers) and walks the rows with the block: every access to the
+// epilogue operands is a 16-byte piece of a 512-byte contiguous row segment.  Needs N % 8 == 0, blockDim % (N/8) == 0.
+template <int EPI, int KT>
+__global__ void __launch_bounds__(NDJIR_BLOCK) skinny_k_h_vec_kernel(HArgs a) {
+  const int ncol = a.N / 8;
+  const int g = threadIdx.x % ncol;
+  const int rows_per_block = blockDim.x / ncol;
+  const int n = g * 8;
   const float sc = dev_scalar(a.C.scale);
   const float inv_h = 1.f / dev_scalar(a.H.scale), inv_u = 1.f / dev_scalar(a.U.scale);
   const bool need_h = (EPI == EPI_MUL_S);
   const bool need_u = (EPI == EPI_MUL_S) && (a.U.f || a.U.hi);
+  float bw[KT][8];
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      bw[k][e] = k < a.K ? __ldg(a.B32 + (long long)k * a.b_rs + (long long)(n + e) * a.b_cs) : 0.f;
+  float b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) b[e] = ((EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias) ? __ldg(a.bias + n + e) : 0.f;
   float mx = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long m = i / ncol;
-    const int n = (int)(i - m * ncol) * CPT;
-    float xa[8];
+  const long long row_stride = (long long)gridDim.x * rows_per_block;
+  for (long long m = (long long)blockIdx.x * rows_per_block + threadIdx.x / ncol; m < a.M; m += row_stride) {
+    float xa[KT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) xa[k] = k < a.K ? __ldg(a.A32 + m * a.a_rs + (long long)k * a.a_cs) : 0.f;
-    float h[8], u[8], cp[8], b[8], o[8];
+    for (int k = 0; k < KT; ++k) xa[k] = k < a.K ? __ldg(a.A32 + m * a.a_rs + (long long)k * a.a_cs) : 0.f;
+    float h[8], u[8], cp[8], o[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) h[e] = u[e] = cp[e] = b[e] = 0.f;
-    if (vec) {
-      if (need_h) {
-        if (a.H.hi) {
-          uint4 xh = __ldg(reinterpret_cast<const uint4*>(a.H.hi + m * a.H.ldh + n));
-          uint4 xl = __ldg(reinterpret_cast<const uint4*>(a.H.lo + m * a.H.ldh + n));
-          float2 t0 = join2(xh.x, xl.x), t1 = join2(xh.y, xl.y), t2 = join2(xh.z, xl.z), t3 = join2(xh.w, xl.w);
-          h[0] = t0.x; h[1] = t0.y; h[2] = t1.x; h[3] = t1.y; h[4] = t2.x; h[5] = t2.y; h[6] = t3.x; h[7] = t3.y;
+    for (int e = 0; e < 8; ++e) h[e] = u[e] = cp[e] = 0.f;
+    if (need_h) {
+      if (a.H.hi) {
+        uint4 xh = __ldg(reinterpret_cast<const uint4*>(a.H.hi + m * a.H.ldh + n));
+        uint4 xl = __ldg(reinterpret_cast<const uint4*>(a.H.lo + m * a.H.ldh + n));
+        float2 t0 = join2(xh.x, xl.x), t1 = join2(xh.y, xl.y), t2 = join2(xh.z, xl.z), t3 = join2(xh.w, xl.w);
+        h[0] = t0.x; h[1] = t0.y; h[2] = t1.x; h[3] = t1.y; h[4] = t2.x; h[5] = t2.y; h[6] = t3.x; h[7] = t3.y;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) h[e] *= inv_h;
-        } else {
-          float4 t0 = __ldg(reinterpret_cast<const float4*>(a.H.f + m * a.H.ldf + n));
-          float4 t1 = __ldg(reinterpret_cast<const float4*>(a.H.f + m * a.H.ldf + n + 4));
-          h[0] = t0.x; h[1] = t0.y; h[2] = t0.z; h[3] = t0.w; h[4] = t1.x; h[5] = t1.y; h[6] = t1.z; h[7] = t1.w;
-        }
+        for (int e = 0; e < 8; ++e) h[e] *= inv_h;
+      } else {
+        float4 t0 = __ldg(reinterpret_cast<const float4*>(a.H.f + m * a.H.ldf + n));
+        float4 t1 = __ldg(reinterpret_cast<const float4*>(a.H.f + m * a.H.ldf + n + 4));
+        h[0] = t0.x; h[1] = t0.y; h[2] = t0.z; h[3] = t0.w; h[4] = t1.x; h[5] = t1.y; h[6] = t1.z; h[7] = t1.w;
       }
-      if (need_u) {
-        if (a.U.hi) {
-          uint4 xh = *reinterpret_cast<const uint4*>(a.U.hi + m * a.U.ldh + n);
-          uint4 xl = *reinterpret_cast<const uint4*>(a.U.lo + m * a.U.ldh + n);
-          float2 t0 = join2(xh.x, xl.x), t1 = join2(xh.y, xl.y), t2 = join2(xh.z, xl.z), t3 = join2(xh.w, xl.w);
-          u[0] = t0.x; u[1] = t0.y; u[2] = t1.x; u[3] = t1.y; u[4] = t2.x; u[5] = t2.y; u[6] = t3.x; u[7] = t3.y;
+    }
+    if (need_u) {
+      if (a.U.hi) {
+        uint4 xh = *reinterpret_cast<const uint4*>(a.U.hi + m * a.U.ldh + n);
+        uint4 xl = *reinterpret_cast<const uint4*>(a.U.lo + m * a.U.ldh + n);
+        float2 t0 = join2(xh.x, xl.x), t1 = join2(xh.y, xl.y), t2 = join2(xh.z, xl.z), t3 = join2(xh.w, xl.w);
+        u[0] = t0.x; u[1] = t0.y; u[2] = t1.x; u[3] = t1.y; u[4] = t2.x; u[5] = t2.y; u[6] = t3.x; u[7] = t3.y;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) u[e] *= inv_u;
-        } else {
-          float4 t0 = *reinterpret_cast<const float4*>(a.U.f + m * a.U.ldf + n);
-          float4 t1 = *reinterpret_cast<const float4*>(a.U.f + m * a.U.ldf + n + 4);
-          u[0] = t0.x; u[1] = t0.y; u[2] = t0.z; u[3] = t0.w; u[4] = t1.x; u[5] = t1.y; u[6] = t1.z; u[7] = t1.w;
-        }
+        for (int e = 0; e < 8; ++e) u[e] *= inv_u;
+      } else {
+        float4 t0 = *reinterpret_cast<const float4*>(a.U.f + m * a.U.ldf + n);
+        float4 t1 = *reinterpret_cast<const float4*>(a.U.f + m * a.U.ldf + n + 4);
+        u[0] = t0.x; u[1] = t0.y; u[2] = t0.z; u[3] = t0.w; u[4] = t1.x; u[5] = t1.y; u[6] = t1.z; u[7] = t1.w;
       }
-      if (EPI == EPI_ACCUM) {
-        float4 t0 = *reinterpret_cast<const float4*>(a.C.f + m * a.C.ldf + n);
-        float4 t1 = *reinterpret_cast<const float4*>(a.C.f + m * a.C.ldf + n + 4);
-        cp[0] = t0.x; cp[1] = t0.y; cp[2] = t0.z; cp[3] = t0.w; cp[4] = t1.x; cp[5] = t1.y; cp[6] = t1.z; cp[7] = t1.w;
-      }
-      if ((EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias) {
-        float4 t0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-        float4 t1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
-        b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
-      }
-    } else {
-      if (need_h) h[0] = op_load(a.H, inv_h, m, n);
-      if (need_u) u[0] = op_load(a.U, inv_u, m, n);
-      if (EPI == EPI_ACCUM) cp[0] = a.C.f[m * a.C.ldf + n];
-      if ((EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias) b[0] = __ldg(a.bias + n);
+    }
+    if (EPI == EPI_ACCUM) {
+      float4 t0 = *reinterpret_cast<const float4*>(a.C.f + m * a.C.ldf + n);
+      float4 t1 = *reinterpret_cast<const float4*>(a.C.f + m * a.C.ldf + n + 4);
+      cp[0] = t0.x; cp[1] = t0.y; cp[2] = t0.z; cp[3] = t0.w; cp[4] = t1.x; cp[5] = t1.y; cp[6] = t1.z; cp[7] = t1.w;
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (e < CPT) {
-        float acc = 0.f;
-        const float* bp = a.B32 + (long long)(n + e) * a.b_cs;      // small operand: L1-resident
-        for (int k = 0; k < a.K; ++k) acc += xa[k] * __ldg(bp + (long long)k * a.b_rs);
-        float o2;
-        epi_math<EPI>(a, acc, h[e], u[e], cp[e], b[e], o[e], o2);
-        mx = fmaxf(mx, fabsf(o[e]));
-      }
-    }
-    if (vec) {
-      if (a.C.hi) {
-        uint32_t hi[4], lo[4];
+      float acc = 0.f, o2;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split2(o[2 * e] * sc, o[2 * e + 1] * sc, hi[e], lo[e]);
-        *reinterpret_cast<uint4*>(a.C.hi + m * a.C.ldh + n) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(a.C.lo + m * a.C.ldh + n) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      } else {
-        *reinterpret_cast<float4*>(a.C.f + m * a.C.ldf + n) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(a.C.f + m * a.C.ldf + n + 4) = make_float4(o[4], o[5], o[6], o[7]);
-      }
+      for (int k = 0; k < KT; ++k) acc += xa[k] * bw[k][e];
+      epi_math<EPI>(a, acc, h[e], u[e], cp[e], b[e], o[e], o2);
+      mx = fmaxf(mx, fabsf(o[e]));
+    }
+    if (a.C.hi) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split2(o[2 * e] * sc, o[2 * e + 1] * sc, hi[e], lo[e]);
+      *reinterpret_cast<uint4*>(a.C.hi + m * a.C.ldh + n) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(a.C.lo + m * a.C.ldh + n) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     } else {
-      op_store(a.C, sc, m, n, o[0]);
+      *reinterpret_cast<float4*>(a.C.f + m * a.C.ldf + n) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(a.C.f + m * a.C.ldf + n + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
   }
   amax_commit(a.C.amax, mx);
 }
 
+// scalar form: any N, unaligned operands
+template <int EPI>
+__global__ void __launch_bounds__(NDJIR_BLOCK) skinny_k_h_kernel(HArgs a) {
+  const long long total = (long long)a.M * a.N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float sc = dev_scalar(a.C.scale);
+  const float inv_h = 1.f / dev_scalar(a.H.scale), inv_u = 1.f / dev_scalar(a.U.scale);
+  const bool need_u = (EPI == EPI_MUL_S) && (a.U.f || a.U.hi);
+  float mx = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long m = i / a.N;
+    const int n = (int)(i - m * a.N);
+    float acc = 0.f;
+    for (int k = 0; k < a.K; ++k)
+      acc += __ldg(a.A32 + m * a.a_rs + (long long)k * a.a_cs) * __ldg(a.B32 + (long long)k * a.b_rs + (long long)n * a.b_cs);
+    float h = 0.f, u = 0.f, cp = 0.f, b = 0.f, o, o2;
+    if (EPI == EPI_MUL_S) h = op_load(a.H, inv_h, m, n);
+    if (need_u) u = op_load(a.U, inv_u, m, n);
+    if (EPI == EPI_ACCUM) cp = a.C.f[m * a.C.ldf + n];
+    if ((EPI == EPI_BIAS || EPI == EPI_SOFTPLUS) && a.bias) b = __ldg(a.bias + n);
+    epi_math<EPI>(a, acc, h, u, cp, b, o, o2);
+    mx = fmaxf(mx, fabsf(o));
+    op_store(a.C, sc, m, n, o);
+  }
+  amax_commit(a.C.amax, mx);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// C[m, n] += alpha * sum_k A(k, m) * B32(k, n): a thread owns two adjacent m, a block walks a slice of the k rows
+// C[m, n] += alpha * sum_k A(k, m) * B32(k, n), N <= 8.  A block walks a slab of the k rows; its 256 threads are
+// (row lane, pair of adjacent m): a warp reads 128 contiguous bytes of each plane per row.  Row lanes are folded through
+// shared memory, then one atomic per (m, n) and block.
 template <int NT>
 __global__ void __launch_bounds__(NDJIR_BLOCK) skinny_w_h_kernel(HArgs a) {
-  const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  const long long per = (a.K + gridDim.y - 1) / gridDim.y;
-  const long long k0 = (long long)blockIdx.y * per, k1 = k0 + per < a.K ? k0 + per : a.K;
+  __shared__ float red[NDJIR_BLOCK * 2 * NT];
+  const int pairs = (a.M + 1) / 2;                     // <= blockDim.x (checked by the launcher)
+  const int lanes = blockDim.x / pairs;
+  const int pr = threadIdx.x % pairs, rl = threadIdx.x / pairs;
+  const int m = pr * 2;
+  const long long per = (a.K + gridDim.x - 1) / gridDim.x;
+  const long long k0 = (long long)blockIdx.x * per, k1 = k0 + per < a.K ? k0 + per : a.K;
   const float inv_a = 1.f / dev_scalar(a.a_scale);
   float acc0[NT], acc1[NT];
 #pragma unroll
   for (int n = 0; n < NT; ++n) acc0[n] = acc1[n] = 0.f;
-  if (m < a.M) {
+  if (rl < lanes) {
     const bool pair = (m + 1 < a.M) && (a.lda % 2 == 0);
 #pragma unroll 4
-    for (long long k = k0; k < k1; ++k) {
+    for (long long k = k0 + rl; k < k1; k += lanes) {
       float x0, x1 = 0.f;
       if (pair) {
         uint32_t xh = __ldg(reinterpret_cast<const uint32_t*>(a.Ahi + k * a.lda + m));
@@ -205,11 +229,24 @@ __global__ void __launch_bounds__(NDJIR_BLOCK) skinny_w_h_kernel(HArgs a) {
         }
       }
     }
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    red[(threadIdx.x * 2) * NT + n] = acc0[n];
+    red[(threadIdx.x * 2 + 1) * NT + n] = acc1[n];
+  }
+  __syncthreads();
+  if (rl == 0) {
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
       if (n < a.N) {
-        if (acc0[n] != 0.f) atomicAdd(a.C.f + (long long)m * a.C.ldf + n, a.alpha * inv_a * acc0[n]);
-        if (m + 1 < a.M && acc1[n] != 0.f) atomicAdd(a.C.f + (long long)(m + 1) * a.C.ldf + n, a.alpha * inv_a * acc1[n]);
+        float s0 = 0.f, s1 = 0.f;
+        for (int l = 0; l < lanes; ++l) {
+          s0 += red[((l * pairs + pr) * 2) * NT + n];
+          s1 += red[((l * pairs + pr) * 2 + 1) * NT + n];
+        }
+        if (s0 != 0.f) atomicAdd(a.C.f + (long long)m * a.C.ldf + n, a.alpha * inv_a * s0);
+        if (m + 1 < a.M && s1 != 0.f) atomicAdd(a.C.f + (long long)(m + 1) * a.C.ldf + n, a.alpha * inv_a * s1);
       }
     }
   }
@@ -221,7 +258,7 @@ static int which_corner(const HArgs& a) {
   if (!a.mn && a.N <= 8 && a.K >= 8 && a.K <= 2048 && a.Ahi && a.B32 && a.C.f && (a.epi == EPI_BIAS || a.epi == EPI_ACCUM))
     return 1;
   if (!a.mn && a.K <= 8 && a.A32 && a.B32 && a.epi != EPI_ATOMIC && a.epi != EPI_ADJ) return 2;
-  if (a.mn && a.N <= 8 && a.Ahi && a.B32 && a.C.f && a.epi == EPI_ATOMIC) return 3;
+  if (a.mn && a.N <= 8 && a.M <= 2 * NDJIR_BLOCK && a.Ahi && a.B32 && a.C.f && a.epi == EPI_ATOMIC) return 3;
   return 0;
 }
 
@@ -251,27 +288,43 @@ int launch_corner(const HArgs& a, cudaStream_t st) {
       if (o.f) return al16s(o.f) && o.ldf % 4 == 0;
       return true;
     };
-    int vec = a.N % 8 == 0 && ok_op(a.C) && ok_op(a.H) && ok_op(a.U) && (a.bias == nullptr || al16s(a.bias));
-    int grid = grid_for((long long)a.M * (vec ? a.N / 8 : a.N));
-    switch (a.epi) {
-      case EPI_BIAS: skinny_k_h_kernel<EPI_BIAS><<<grid, NDJIR_BLOCK, 0, st>>>(a, vec); break;
-      case EPI_SOFTPLUS: skinny_k_h_kernel<EPI_SOFTPLUS><<<grid, NDJIR_BLOCK, 0, st>>>(a, vec); break;
-      case EPI_ACCUM:
-        if (!a.C.f) return NDJIR_ERR_ARG;
-        skinny_k_h_kernel<EPI_ACCUM><<<grid, NDJIR_BLOCK, 0, st>>>(a, vec);
-        break;
-      case EPI_MUL_S:
-        if (!a.H.f && !a.H.hi) return NDJIR_ERR_ARG;
-        skinny_k_h_kernel<EPI_MUL_S><<<grid, NDJIR_BLOCK, 0, st>>>(a, vec);
-        break;
-      default: return NDJIR_ERR_ARG;
+    if (a.epi == EPI_ACCUM && !a.C.f) return NDJIR_ERR_ARG;
+    if (a.epi == EPI_MUL_S && !a.H.f && !a.H.hi) return NDJIR_ERR_ARG;
+    const bool vec = a.N % 8 == 0 && NDJIR_BLOCK % (a.N / 8) == 0 && ok_op(a.C) && ok_op(a.H) && ok_op(a.U);
+    if (vec) {
+      const int rows_per_block = NDJIR_BLOCK / (a.N / 8);
+      long long blocks = (a.M + rows_per_block - 1) / rows_per_block;
+      long long cap = (long long)NDJIR_NUM_SMS * 16;
+      int grid = (int)(blocks < cap ? blocks : cap);
+#define NDJIR_SK(E, KT) skinny_k_h_vec_kernel<E, KT><<<grid, NDJIR_BLOCK, 0, st>>>(a)
+#define NDJIR_SK_K(E)                                     \
+  if (a.K <= 1) NDJIR_SK(E, 1); else if (a.K <= 2) NDJIR_SK(E, 2); else if (a.K <= 3) NDJIR_SK(E, 3); \
+  else if (a.K <= 4) NDJIR_SK(E, 4); else if (a.K <= 6) NDJIR_SK(E, 6); else NDJIR_SK(E, 8)
+      switch (a.epi) {
+        case EPI_BIAS: NDJIR_SK_K(EPI_BIAS); break;
+        case EPI_SOFTPLUS: NDJIR_SK_K(EPI_SOFTPLUS); break;
+        case EPI_ACCUM: NDJIR_SK_K(EPI_ACCUM); break;
+        case EPI_MUL_S: NDJIR_SK_K(EPI_MUL_S); break;
+        default: return NDJIR_ERR_ARG;
+      }
+#undef NDJIR_SK_K
+#undef NDJIR_SK
+    } else {
+      int grid = grid_for((long long)a.M * a.N);
+      switch (a.epi) {
+        case EPI_BIAS: skinny_k_h_kernel<EPI_BIAS><<<grid, NDJIR_BLOCK, 0, st>>>(a); break;
+        case EPI_SOFTPLUS: skinny_k_h_kernel<EPI_SOFTPLUS><<<grid, NDJIR_BLOCK, 0, st>>>(a); break;
+        case EPI_ACCUM: skinny_k_h_kernel<EPI_ACCUM><<<grid, NDJIR_BLOCK, 0, st>>>(a); break;
+        case EPI_MUL_S: skinny_k_h_kernel<EPI_MUL_S><<<grid, NDJIR_BLOCK, 0, st>>>(a); break;
+        default: return NDJIR_ERR_ARG;
+      }
     }
   } else if (w == 3) {
-    int gx = ((a.M + 1) / 2 + NDJIR_BLOCK - 1) / NDJIR_BLOCK;
-    long long want = (long long)NDJIR_NUM_SMS * 8 / gx;
-    long long maxy = (a.K + 63) / 64;
-    int gy = (int)(want < 1 ? 1 : (want > maxy ? maxy : want));
-    dim3 grid(gx, gy);
+    if ((a.M + 1) / 2 > NDJIR_BLOCK) return NDJIR_ERR_ARG;
+    long long maxg = (a.K + 63) / 64;
+    long long want = (long long)NDJIR_NUM_SMS * 8;
+    int grid = (int)(want > maxg ? maxg : want);
+    if (grid < 1) grid = 1;
     if (a.N == 1) skinny_w_h_kernel<1><<<grid, NDJIR_BLOCK, 0, st>>>(a);
     else if (a.N == 2) skinny_w_h_kernel<2><<<grid, NDJIR_BLOCK, 0, st>>>(a);
     else if (a.N <= 4) skinny_w_h_kernel<4><<<grid, NDJIR_BLOCK, 0, st>>>(a);

@@ -18,6 +18,8 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import h16
+from .h16 import HMat
 from .config import grid_channels
 from .parallel import allgather_rows, allreduce_gradients, allreduce_mask_sum
 from .scene import network_dims, pe_dim, NET_ORDER
@@ -32,6 +34,10 @@ def r4(n):
     return (n + 3) // 4 * 4
 
 
+def r8(n):
+    return (n + 7) // 8 * 8
+
+
 class Layer:
     """One affine layer in INTERNAL layout: W (K, ldw) row-major with ldw = round4(N); `rowmap[i]` is the internal
     row of reference input row i (the engine keeps head inputs as [feature | x | normal | ...] so the geometric
@@ -39,11 +45,11 @@ class Layer:
 
     def __init__(self, K, N, rowmap=None, col0=0, Nref=None):
         self.K, self.N = K, N
-        self.ldw = r4(N)
+        self.ldw = r8(N)
         self.rowmap = np.arange(K) if rowmap is None else np.asarray(rowmap)
         self.col0 = col0            # first reference output column held by this layer (split last layers)
         self.w_off = self.b_off = self.t_off = -1
-        self.ldt = r4(K)            # row stride of the transposed copy W^T (N, ldt)
+        self.ldt = r8(K)            # row stride of the transposed copy W^T (N, ldt)
 
 
 class ParamStore:
@@ -101,13 +107,13 @@ class ParamStore:
         for name in NET_ORDER:
             for L in self.nets[name]:
                 L.w_off = n; n += L.K * L.ldw
-                L.b_off = n; n += r4(L.N)
-        self.gain_off = n; n += 4
+                L.b_off = n; n += r8(L.N)
+        self.gain_off = n; n += 8
         self.n_mlp = n
         nt = 0
         for name in NET_ORDER:
             for L in self.nets[name]:
-                L.t_off = nt; nt += r4(L.N) * L.ldt
+                L.t_off = nt; nt += r8(L.N) * L.ldt
         # The skip layer's input block (rows [n_prev, K) of its W: the 43 network inputs re-entering at layer 4) starts at
         # row 213, which is not 16-byte aligned inside the transposed copy: it gets a transposed copy of its own so that
         # its input-gradient product also sees a TMA-friendly MN-major operand (K-major fallback: 0.36 ms, this: 0.16 ms)
@@ -119,15 +125,22 @@ class ParamStore:
                 rows = L.K - Lp.N
                 if rows > 0 and Lp.N % 4 != 0:
                     self.skip_t[id(L)] = (Lp.N, rows, nt, r4(rows))
-                    nt += r4(L.N) * r4(rows)
+                    nt += r8(r4(L.N) * r4(rows))
         # transposed weight copies for the input-gradient products (refreshed once per step, engine.refresh_transposes)
-        self.data_t = torch.zeros(max(nt, 4), dtype=torch.float32, device=device)
+        self.data_t = torch.zeros(max(r8(nt), 8), dtype=torch.float32, device=device)
         self.data = torch.zeros(n, dtype=torch.float32, device=device)
         # lo parts (x - tf32(x)) of both weight buffers for the tensor-core products (registered with the library in
         # Engine.__init__, refreshed together with the transposes)
         self.data_lo = torch.zeros_like(self.data)
         self.data_t_lo = torch.zeros_like(self.data_t)
         self.grad = torch.zeros(n, dtype=torch.float32, device=device)
+        # split-fp16 copies of both weight buffers (same element offsets; planes [2, n]) and their common power-of-two
+        # scale: the B operands of the split-fp16 engine (W^T for forward products, W for input-gradient products),
+        # refreshed with the transposes
+        self.w16 = torch.zeros((2, n), dtype=torch.float16, device=device)
+        self.wt16 = torch.zeros((2, self.data_t.numel()), dtype=torch.float16, device=device)
+        self.wscale = torch.ones(4, dtype=torch.float32, device=device)      # [scale, amax, -, -]
+        self.wflags = torch.zeros(4, dtype=torch.int32, device=device)
         self.grid = {}        # name -> tensor
         self.grid_grad = {}
         self.pl_gain = float(conf.train.sigmoid_gain_lv_start)
@@ -222,6 +235,22 @@ class ParamStore:
             return self.data_t.data_ptr() + 4 * sk[2], sk[3], 1
         return self.W(L, row0), 1, L.ldw
 
+    def W16(self, L, row0=0):
+        """rows [row0, ...) of W_L as split-fp16 planes (K_in rows x N): the K-major B operand of input-gradient products"""
+        off = 2 * (L.w_off + row0 * L.ldw)
+        return HMat(self.w16.data_ptr() + off, self.w16.data_ptr() + 2 * self.w16.shape[1] + off, L.ldw,
+                    self.wscale.data_ptr(), None)
+
+    def WT16(self, L):
+        """W_L^T as split-fp16 planes (N rows x K_in): the K-major B operand of forward products"""
+        off = 2 * L.t_off
+        return HMat(self.wt16.data_ptr() + off, self.wt16.data_ptr() + 2 * self.wt16.shape[1] + off, L.ldt,
+                    self.wscale.data_ptr(), None)
+
+    def Bt32(self, L, row0=0):
+        """fp32 operand B(k, j) = W[row0 + j, k] of the memory-bound input-gradient products as (pointer, b_rs, b_cs)"""
+        return self.W(L, row0), 1, L.ldw
+
     def gW(self, L, row=0):
         return self.grad.data_ptr() + 4 * (L.w_off + row * L.ldw)
 
@@ -245,8 +274,28 @@ def P_(t, off=0):
     return t.data_ptr() + 4 * off
 
 
+class Mat:
+    """A matrix the MLP passes read or write: fp32 rows (`f`, a (rows_alloc, ldf) tensor) and / or split-fp16 planes
+    (`h`, an h16.HBuf).  `rs` overrides the fp32 row stride (0 = one row broadcast to every sample)."""
+    __slots__ = ("f", "h", "cols", "rows", "rs")
+
+    def __init__(self, f=None, h=None, cols=0, rows=None, rs=None):
+        self.f, self.h, self.cols, self.rs = f, h, cols, rs
+        self.rows = rows if rows is not None else (f.shape[0] if f is not None else (h.rows if h is not None else 0))
+
+    @property
+    def ldf(self):
+        return self.rs if self.rs is not None else self.f.shape[1]
+
+    def fptr(self, col=0, row=0):
+        return self.f.data_ptr() + 4 * (row * self.ldf + col)
+
+    def hmat(self, col=0, track=True, row=0):
+        return self.h.hmat(col, row=row, track=track)
+
+
 class Engine:
-    def __init__(self, conf, device="cuda", world_size=1, process_group=None, grid_exchange="auto"):
+    def __init__(self, conf, device="cuda", world_size=1, process_group=None, grid_exchange="auto", mlp="h16"):
         if not torch.cuda.is_available():
             raise _lib.NdjirError("ndjir_b200 needs a CUDA device (there is no CPU fallback)")
         _lib.lib()   # raises if the CUDA library is missing
@@ -274,6 +323,14 @@ class Engine:
         self._graphs = {}
         self._reserve = 0
         self.one = torch.ones(4, dtype=torch.float32, device=self.device)
+        self.ones_col = Mat(f=self.one.view(1, 4), rs=0)     # a column of ones (rank-1 products with w_sdf)
+        # MLP engine: "h16" = split-fp16 storage + tcgen05 kind::f16 products (csrc/gemm_h.cu); "fp32" = fp32 storage,
+        # 3xTF32 tcgen05 products or, with ndjir_set_option("mlp_tensor_cores", 0), the exact FFMA parity path
+        assert mlp in ("h16", "fp32")
+        self.h16 = mlp == "h16"
+        self.scales = h16.Scales(self.device) if self.h16 else None
+        self._calibrated = not self.h16
+        self.precise_fwd = True
         self.rad = float(conf.renderer.bounding_sphere_radius)
         self.debug = {}
         self.profile, self.prof_events, self.n_launches = False, [], 0
@@ -296,6 +353,61 @@ class Engine:
             t[:rows].zero_()
         return t
 
+    # ------------------------------------------------------------------------------------------------
+    # matrices of the MLP passes: fp32 rows and / or split-fp16 planes (class Mat), products in either engine
+    # ------------------------------------------------------------------------------------------------
+    def mat(self, name, rows, cols, kind="a", zero=False, slot=None, grad=False):
+        """kind 'f': fp32 rows (row stride round4(cols)); 'a': the MLP activation format (split-fp16 planes in h16 mode,
+        fp32 rows otherwise); 'fa': fp32 rows plus, in h16 mode, planes that sync_h() refreshes from them.
+        grad=True marks a gradient-magnitude tensor (initial power-of-two scale 2^24 instead of 2^4)."""
+        key = ("mat", name, cols, kind)
+        m = self._bufs.get(key)
+        if m is None or m.rows < rows:
+            need = max(rows, self._reserve)
+            f = h = None
+            if kind in ("f", "fa") or not self.h16:
+                f = torch.empty((need, r4(cols)), dtype=torch.float32, device=self.device)
+            if self.h16 and kind in ("a", "fa"):
+                h = h16.HBuf(need, cols, self.device, self.scales, slot or name, init=2.0 ** 24 if grad else 16.0)
+            m = Mat(f, h, cols, need)
+            self._bufs[key] = m
+        if zero:
+            if m.f is not None:
+                m.f[:rows].zero_()
+            if m.h is not None:
+                m.h.t[:, :rows].zero_()
+        return m
+
+    def sync_h(self, m, cols, rows, col=0):
+        """planes of a 'fa' matrix <- its fp32 rows (columns [col, col + cols)); nothing to do in fp32 mode"""
+        if self.h16 and m.h is not None:
+            self._pack(rows, cols, m.fptr(col), m.ldf, 1, 1.0, m, col, 0)
+
+    def _pack(self, rows, ncols, src, ld_src, rep, alpha, dst, dcol, drow):
+        """ndjir_pack_h with the 16-byte-aligned bulk of the columns on the vector path and the ragged tail separately"""
+        bulk = (ncols // 8) * 8 if (dcol % 8 == 0 and ncols >= 16 and ncols % 8) else 0
+        if bulk:
+            self.call("ndjir_pack_h", rows, bulk, src, ld_src, rep, alpha, dst.hmat(dcol, row=drow))
+            self.call("ndjir_pack_h", rows, ncols - bulk, src + 4 * bulk, ld_src, rep, alpha,
+                      dst.hmat(dcol + bulk, row=drow))
+        else:
+            self.call("ndjir_pack_h", rows, ncols, src, ld_src, rep, alpha, dst.hmat(dcol, row=drow))
+
+    def fill_cols(self, dst, dcol, src, ld_src, ncols, rows, rep=1, alpha=1.0, drow=0):
+        """dst[drow + r, dcol:dcol+ncols] = alpha * src[r // rep, :ncols]   (src: fp32 device address)"""
+        if dst.f is not None:
+            self.copy2d(rows, ncols, dst.fptr(dcol, drow), dst.ldf, src, ld_src, rep=rep, alpha=alpha)
+        else:
+            self._pack(rows, ncols, src, ld_src, rep, alpha, dst, dcol, drow)
+
+    def copy_cols(self, dst, src, ncols, rows):
+        """dst[:, :ncols] = src[:, :ncols] between two matrices of the activation format (same scale slot in h16 mode)"""
+        if self.h16:
+            n8 = r8(ncols) if (r8(ncols) <= dst.h.ld and r8(ncols) <= src.h.ld) else ncols
+            self.call("ndjir_copy2d_h", rows, n8, dst.hmat(0, track=False), src.hmat(0, track=False), 1)
+        else:
+            self.copy2d(rows, ncols, dst.fptr(), dst.ldf, src.fptr(), src.ldf)
+
     def gemm(self, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, epi, bias=0, alpha=1.0, out_scale=1.0, H=0, ldh=0,
              hscale=1.0, U=0, ldu=0, C2=0, ldc2=0, split_k=1):
         if self.profile:
@@ -306,6 +418,18 @@ class Engine:
         if self.profile:
             e1.record()
             self.prof_events.append((e0, e1, 2.0 * M * N * K, f"epi{epi} {M}x{N}x{K}"))
+
+    def gemm_h(self, M, N, K, epi, **kw):
+        """one product of the split-fp16 engine (ndjir_gemm_h)"""
+        if self.profile:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.n_launches += 1
+        h16.gemm_h(self.stream(), M, N, K, epi, **kw)
+        if self.profile:
+            e1.record()
+            mn = kw.get("mn_major", False)
+            self.prof_events.append((e0, e1, 2.0 * M * N * K, f"epi{epi} {M}x{N}x{K}" + (" mn" if mn else "")))
 
     def wgrad(self, rows, K, N, A, lda, dZ, ldz, gW, ldw, gb=0):
         """gW (K,N) += A(rows,K)^T dZ(rows,N): split-K over the rows with atomic accumulation; gb (N) += column sums
@@ -325,6 +449,74 @@ class Engine:
 
     def copy2d(self, rows, cols, dst, ld_dst, src, ld_src, rep=1, alpha=1.0, accum=0):
         self.call("ndjir_copy2d", rows, cols, dst, ld_dst, src, ld_src, rep, alpha, accum)
+
+    @staticmethod
+    def _out(Y, col, key="C"):
+        """keyword arguments of ndjir_gemm_h for an output / epilogue operand in whichever form the matrix has"""
+        if Y is None:
+            return {}
+        if key in ("C", "C2"):
+            if Y.f is not None:
+                return {key: Y.fptr(col), "ld" + key.lower(): Y.ldf}
+            return {key + "h": Y.hmat(col)}
+        if Y.h is not None:
+            return {key + "h": Y.hmat(col, track=False)}
+        return {key: Y.fptr(col), "ld" + key.lower(): Y.ldf}
+
+    def fwd(self, rows, L, X, Y, ycol, epi, out_scale=1.0):
+        """Y[:, ycol:ycol+N] = epi(X[:, :K] W_L + b_L)   (PF.affine [+ softplus], python/network.py:84-93)"""
+        ps = self.params
+        if not self.h16:
+            self.gemm(rows, L.N, L.K, X.fptr(), X.ldf, 1, ps.W(L), L.ldw, 1, Y.fptr(ycol), Y.ldf, epi, bias=ps.b(L),
+                      out_scale=out_scale)
+        elif L.N <= 8:     # one pass over the activations (sdf, colours, ...): fp32 weights, fp32 output
+            self.gemm_h(rows, L.N, L.K, epi, A=X.hmat(0, track=False), B32=ps.W(L), b_rs=L.ldw, b_cs=1, bias=ps.b(L),
+                        C=Y.fptr(ycol), ldc=Y.ldf)
+        else:
+            self.gemm_h(rows, L.N, L.K, epi, A=X.hmat(0, track=False), B=ps.WT16(L), precise=self.precise_fwd,
+                        bias=ps.b(L), out_scale=out_scale, **self._out(Y, ycol))
+
+    def dgrad(self, rows, L, dY, dycol, dX, dxcol, epi, row0=0, ncols=None, alpha=1.0, H=None, hscale=1.0, U=None,
+              precise=False):
+        """dX[:, dxcol:dxcol+ncols] = epi(alpha * dY[:, dycol:dycol+N] W_L[row0:row0+ncols, :]^T)"""
+        ps = self.params
+        ncols = L.K if ncols is None else ncols
+        if not self.h16:
+            self.gemm(rows, ncols, L.N, dY.fptr(dycol), dY.ldf, 1, *ps.Bt(L, row0), dX.fptr(dxcol), dX.ldf, epi,
+                      alpha=alpha, H=(H.fptr() if H is not None else 0), ldh=(H.ldf if H is not None else 0),
+                      hscale=hscale, U=(U.fptr() if U is not None else 0), ldu=(U.ldf if U is not None else 0))
+            return
+        kw = dict(alpha=alpha, hscale=hscale, **self._out(dX, dxcol), **self._out(H, 0, "H"), **self._out(U, 0, "U"))
+        b32, b_rs, b_cs = ps.Bt32(L, row0)
+        if dY.h is None:       # narrow fp32 gradient (<= 8 columns): rank-N update with the fused epilogue
+            self.gemm_h(rows, ncols, L.N, epi, A32=dY.fptr(dycol), a_rs=dY.ldf, a_cs=1, B32=b32, b_rs=b_rs, b_cs=b_cs,
+                        **kw)
+        elif ncols <= 8:       # narrow fp32 result (grid-feature gradient)
+            self.gemm_h(rows, ncols, L.N, epi, A=dY.hmat(dycol, track=False), B32=b32, b_rs=b_rs, b_cs=b_cs, **kw)
+        else:
+            self.gemm_h(rows, ncols, L.N, epi, A=dY.hmat(dycol, track=False), B=ps.W16(L, row0), precise=precise,
+                        **kw)
+
+    def wgrad_(self, rows, L, X, dY, dycol, kin=None, bias=True):
+        """gW_L[:kin, :] += X[:, :kin]^T dY[:, dycol:dycol+N];  gb_L += column sums of dY"""
+        ps = self.params
+        kin = L.K if kin is None else kin
+        if not self.h16:
+            self.wgrad(rows, kin, L.N, X.fptr(), X.ldf, dY.fptr(dycol), dY.ldf, ps.gW(L), L.ldw,
+                       gb=(ps.gb(L) if bias else 0))
+            return
+        if dY.h is None:
+            self.gemm_h(kin, L.N, rows, EPI_ATOMIC, A=X.hmat(0, track=False), mn_major=True, B32=dY.fptr(dycol),
+                        b_rs=dY.ldf, b_cs=1, C=ps.gW(L), ldc=L.ldw)
+            if bias:
+                self.call("ndjir_colsum", rows, L.N, ps.gb(L), dY.fptr(dycol), dY.ldf, 1.0)
+            return
+        tiles = ((kin + 127) // 128) * ((L.N + 255) // 256)
+        split = max(1, min(rows // 256, (148 * 2) // tiles))
+        self.gemm_h(kin, L.N, rows, EPI_ATOMIC, A=X.hmat(0, track=False), B=dY.hmat(dycol, track=False), mn_major=True,
+                    split_k=split, C=ps.gW(L), ldc=L.ldw)
+        if bias:
+            self.call("ndjir_colsum_h", rows, L.N, ps.gb(L), dY.hmat(dycol, track=False), 1.0)
 
     def _sparse_grid(self):
         if self.world_size <= 1:
@@ -357,14 +549,25 @@ class Engine:
         self._grid_call(kind, part, rows, P_(self.params.grid_grad[part]), *[P_(a) for a in arrays], P_(x), *tail)
 
     def refresh_transposes(self):
-        """W^T copies used by every input-gradient product; call after the parameters change (once per step)."""
+        """W^T copies used by the input-gradient products (fp32 engine) / forward products (split-fp16 engine), and the
+        low-order / split-fp16 copies of the weights; call after the parameters change (once per step)."""
         ps = self.params
         for name in NET_ORDER:
             for L in ps.nets[name]:
                 self.call("ndjir_transpose", L.K, L.N, ps.data_t.data_ptr() + 4 * L.t_off, L.ldt, ps.W(L), L.ldw)
                 sk = ps.skip_t.get(id(L))
-                if sk is not None:      # rows [row0, row0 + rows) of W -> their own (N, r4(rows)) transposed block
+                if sk is not None and not self.h16:   # rows [row0, row0 + rows) of W -> their own transposed block
                     self.call("ndjir_transpose", sk[1], L.N, ps.data_t.data_ptr() + 4 * sk[2], sk[3], ps.W(L, sk[0]), L.ldw)
+        if self.h16:
+            # one power-of-two scale for all weights from their current maximum, then both buffers as fp16 planes
+            n, nt = ps.data.numel(), ps.data_t.numel()
+            self.call("ndjir_amax", n, ps.data, P_(ps.wscale, 1))
+            self.call("ndjir_scale_update", 1, ps.wscale, P_(ps.wscale, 1), ps.wflags, self.scales.target_log2)
+            sc = ps.wscale.data_ptr()
+            self.call("ndjir_pack_h", 1, n, ps.data, n, 1, 1.0, HMat(ps.w16.data_ptr(), ps.w16.data_ptr() + 2 * n, n, sc, None))
+            self.call("ndjir_pack_h", 1, nt, ps.data_t, nt, 1, 1.0,
+                      HMat(ps.wt16.data_ptr(), ps.wt16.data_ptr() + 2 * nt, nt, sc, None))
+            return
         # pre-split lo parts of W and W^T: the weight operand of every tensor-core product arrives as two TMA tiles
         self.call("ndjir_split_lo", ps.data.numel(), ps.data_lo, ps.data)
         self.call("ndjir_split_lo", ps.data_t.numel(), ps.data_t_lo, ps.data_t)
@@ -411,7 +614,7 @@ class Engine:
     # geometric network (python/network.py:154-232)
     # ------------------------------------------------------------------------------------------------
     def geo_input(self, x, rows, A0, tag):
-        """A0 (rows, ld0) = [PE(x) | grid features]"""
+        """A0 (rows, ld0) fp32 = [PE(x) | grid features]"""
         g = self.conf.geometric_network
         self.call("ndjir_positional_encoding", rows, 3, g.pe_bands, P_(x), 3, 1, P_(A0), self.ld0)
         for part, width, off in self._grid_parts():
@@ -422,65 +625,57 @@ class Engine:
             self.call("ndjir_copy2d", rows, self.ld0 - self.din, P_(A0, self.din), self.ld0, P_(self.one), 0, 1, 0.0, 0)
 
     def geo_forward(self, x, rows, tag, store, want_feat=True, sdf_out=None, O=None):
-        """Forward pass.  store=True keeps every layer input in buffers `{tag}_A{l}` for the backward passes.
-        Returns (A list, sdf tensor)."""
-        ps, net = self.params, self.params.nets["geo"]
+        """Forward pass.  store=True keeps every layer input in matrices `{tag}_A{l}` for the backward passes.
+        O: 'fa' matrix whose fp32 columns [0, Df) receive the feature.  Returns (A list, sdf tensor)."""
+        net = self.params.nets["geo"]
         nl = len(net) - 2          # hidden layers (reference layers 0..L-2)
-        A = [self.buf(f"{tag}_A0", rows, self.ld0)]
-        self.geo_input(x, rows, A[0], tag)
+        A0 = self.mat(f"{tag}_A0", rows, self.din, "fa")
+        self.geo_input(x, rows, A0.f, tag)
+        self.sync_h(A0, self.din, rows)
+        A = [A0]
         for l in range(nl):
             L = net[l]
-            name = f"{tag}_A{l + 1}" if store else f"geo_pp{l % 2}"
-            ldn = r4(net[l + 1].K)
-            nxt = self.buf(name, rows, ldn)
-            osc = self.cskip if (l + 1) == self.skip else 1.0
-            self.gemm(rows, L.N, L.K, P_(A[l]), A[l].shape[1], 1, ps.W(L), L.ldw, 1, P_(nxt), ldn, EPI_SOFTPLUS,
-                      bias=ps.b(L), out_scale=osc)
+            nxt = self.mat(f"{tag}_A{l + 1}" if store else f"geo_pp{l % 2}", rows, net[l + 1].K, "a")
+            self.fwd(rows, L, A[l], nxt, 0, EPI_SOFTPLUS, out_scale=self.cskip if (l + 1) == self.skip else 1.0)
             if (l + 1) == self.skip:
-                self.copy2d(rows, self.din, P_(nxt, L.N), ldn, P_(A[0]), self.ld0, alpha=self.cskip)
+                self.fill_cols(nxt, L.N, A0.fptr(), A0.ldf, self.din, rows, alpha=self.cskip)
             A.append(nxt)
         Ls, Lf = net[-2], net[-1]
         sdf = sdf_out if sdf_out is not None else self.buf(f"{tag}_sdf", rows, 1)
-        last = A[-1]
-        self.gemm(rows, 1, Ls.K, P_(last), last.shape[1], 1, ps.W(Ls), Ls.ldw, 1, P_(sdf), 1, EPI_BIAS, bias=ps.b(Ls))
+        self.fwd(rows, Ls, A[-1], Mat(f=sdf), 0, EPI_BIAS)
         if want_feat:
-            self.gemm(rows, Lf.N, Lf.K, P_(last), last.shape[1], 1, ps.W(Lf), Lf.ldw, 1, P_(O), self.LDO, EPI_BIAS,
-                      bias=ps.b(Lf))
+            self.fwd(rows, Lf, A[-1], O, 0, EPI_BIAS)
         return A, sdf
 
     def geo_normal(self, x, rows, tag, A, nrm):
         """n = d sdf / d x by a reverse sweep (the nn.grad graph of renderer.py:52).  Keeps GZ[l] = dsdf/dz_l."""
-        ps, net = self.params, self.params.nets["geo"]
+        net = self.params.nets["geo"]
         nl = len(net) - 2
         Ls = net[-2]
-        GZ = [self.buf(f"{tag}_GZ{l}", rows, r4(net[l].N)) for l in range(nl)]
-        Gin = self.buf(f"{tag}_Gin", rows, self.ld0, zero=True)
+        GZ = [self.mat(f"{tag}_GZ{l}", rows, net[l].N, "a") for l in range(nl)]
+        Gin = self.mat(f"{tag}_Gin", rows, self.din, "f", zero=True)
         c = self.cskip
         # top: gA_{L-1}[p,:] = w_sdf ; GZ[nl-1] = gA * s
-        top = A[nl]
-        self.gemm(rows, Ls.K, 1, P_(self.one), 0, 1, *ps.Bt(Ls), P_(GZ[nl - 1]), GZ[nl - 1].shape[1],
-                  EPI_MUL_S, H=P_(top), ldh=top.shape[1])
+        self.dgrad(rows, Ls, self.ones_col, 0, GZ[nl - 1], 0, EPI_MUL_S, H=A[nl])
         skip_wrote = False
         for l in range(nl - 1, 0, -1):
             L = net[l]
             is_skip = (l == self.skip)
             n_prev = net[l - 1].N
-            self.gemm(rows, n_prev, L.N, P_(GZ[l]), GZ[l].shape[1], 1, *ps.Bt(L), P_(GZ[l - 1]),
-                      GZ[l - 1].shape[1], EPI_MUL_S, alpha=(c if is_skip else 1.0), H=P_(A[l]), ldh=A[l].shape[1],
-                      hscale=(1.0 / c if is_skip else 1.0))
+            self.dgrad(rows, L, GZ[l], 0, GZ[l - 1], 0, EPI_MUL_S, ncols=n_prev, alpha=(c if is_skip else 1.0),
+                       H=A[l], hscale=(1.0 / c if is_skip else 1.0), precise=self.precise_fwd)
             if is_skip:
-                self.gemm(rows, self.din, L.N, P_(GZ[l]), GZ[l].shape[1], 1, *ps.Bt(L, n_prev), P_(Gin),
-                          self.ld0, EPI_BIAS, alpha=c)
+                self.dgrad(rows, L, GZ[l], 0, Gin, 0, EPI_BIAS, row0=n_prev, ncols=self.din, alpha=c,
+                           precise=self.precise_fwd)
                 skip_wrote = True
-        L0 = net[0]
-        self.gemm(rows, self.din, L0.N, P_(GZ[0]), GZ[0].shape[1], 1, *ps.Bt(L0), P_(Gin), self.ld0,
-                  EPI_ACCUM if skip_wrote else EPI_BIAS)
+        self.dgrad(rows, net[0], GZ[0], 0, Gin, 0, EPI_ACCUM if skip_wrote else EPI_BIAS, ncols=self.din,
+                   precise=self.precise_fwd)
         g = self.conf.geometric_network
-        self.call("ndjir_positional_encoding_grad_input", rows, 3, g.pe_bands, P_(A[0]), self.ld0, P_(Gin), self.ld0,
-                  P_(nrm), 3, 0)
+        self.call("ndjir_positional_encoding_grad_input", rows, 3, g.pe_bands, A[0].fptr(), self.ld0, Gin.fptr(),
+                  self.ld0, P_(nrm), 3, 0)
         for part, width, off in self._grid_parts():
             tmp = self.buf(f"gg_{part}", rows, width)
-            self.copy2d(rows, width, P_(tmp), width, P_(Gin, self.npe + off), self.ld0)
+            self.copy2d(rows, width, P_(tmp), width, Gin.fptr(self.npe + off), self.ld0)
             self._grid_call("grad_query", part, rows, P_(nrm), P_(tmp), P_(x), P_(self.params.grid[part]))
         return GZ, Gin
 
@@ -491,138 +686,130 @@ class Engine:
         nl = len(net) - 2
         g = self.conf.geometric_network
         c = self.cskip
-        Ghat = [self.buf(f"{tag}_Gh0", rows, self.ld0, zero=True)]
-        self.call("ndjir_positional_encoding_grad_input_adjoint", rows, 3, g.pe_bands, P_(A[0]), self.ld0, P_(nbar), 3,
-                  P_(Ghat[0]), self.ld0)
+        Gh0 = self.mat(f"{tag}_Gh0", rows, self.din, "fa", zero=True, grad=True)
+        self.call("ndjir_positional_encoding_grad_input_adjoint", rows, 3, g.pe_bands, A[0].fptr(), self.ld0, P_(nbar), 3,
+                  Gh0.fptr(), self.ld0)
         for part, width, off in self._grid_parts():
             tmp = self.buf(f"gg_{part}", rows, width)       # g_in grid columns (dense)
-            self.copy2d(rows, width, P_(tmp), width, P_(Gin, self.npe + off), self.ld0)
+            self.copy2d(rows, width, P_(tmp), width, Gin.fptr(self.npe + off), self.ld0)
             tmp2 = self.buf(f"ggo_{part}", rows, width)
             self._grid_call("ggo", part, rows, P_(tmp2), P_(nbar), P_(x), P_(self.params.grid[part]))
-            self.copy2d(rows, width, P_(Ghat[0], self.npe + off), self.ld0, P_(tmp2), width)
+            self.copy2d(rows, width, Gh0.fptr(self.npe + off), self.ld0, P_(tmp2), width)
             self._grid_scatter("gqgf", part, rows, x, [nbar, tmp])
-        Z2 = []
+        self.sync_h(Gh0, self.din, rows)
+        Ghat, Z2 = [Gh0], []
         for l in range(nl):
             L = net[l]
-            ldn = r4(net[l + 1].K)
-            nxt = self.buf(f"{tag}_Gh{l + 1}", rows, ldn)
-            z2 = self.buf(f"{tag}_Z2{l}", rows, r4(L.N))
+            nxt = self.mat(f"{tag}_Gh{l + 1}", rows, net[l + 1].K, "a", grad=True)
+            z2 = self.mat(f"{tag}_Z2{l}", rows, L.N, "a", grad=True)
             is_skip = (l + 1) == self.skip
             Gh = Ghat[l]
-            self.gemm(rows, L.N, L.K, P_(Gh), Gh.shape[1], 1, ps.W(L), L.ldw, 1, P_(z2), z2.shape[1], EPI_ADJ,
-                      out_scale=(c if is_skip else 1.0), H=P_(A[l + 1]), ldh=A[l + 1].shape[1],
-                      hscale=(1.0 / c if is_skip else 1.0), U=P_(GZ[l]), ldu=GZ[l].shape[1], C2=P_(nxt), ldc2=ldn)
+            osc, hsc = (c if is_skip else 1.0), (1.0 / c if is_skip else 1.0)
+            if self.h16:
+                self.gemm_h(rows, L.N, L.K, EPI_ADJ, A=Gh.hmat(0, track=False), B=ps.WT16(L), out_scale=osc, hscale=hsc,
+                            Hh=A[l + 1].hmat(0, track=False), Uh=GZ[l].hmat(0, track=False), Ch=z2.hmat(),
+                            C2h=nxt.hmat())
+            else:
+                self.gemm(rows, L.N, L.K, Gh.fptr(), Gh.ldf, 1, ps.W(L), L.ldw, 1, z2.fptr(), z2.ldf, EPI_ADJ,
+                          out_scale=osc, H=A[l + 1].fptr(), ldh=A[l + 1].ldf, hscale=hsc, U=GZ[l].fptr(),
+                          ldu=GZ[l].ldf, C2=nxt.fptr(), ldc2=nxt.ldf)
             if is_skip:
-                self.copy2d(rows, self.din, P_(nxt, L.N), ldn, P_(Ghat[0]), self.ld0, alpha=c)
-            self.wgrad(rows, L.K, L.N, P_(Gh), Gh.shape[1], P_(GZ[l]), GZ[l].shape[1], ps.gW(L), L.ldw)
+                self.fill_cols(nxt, L.N, Gh0.fptr(), Gh0.ldf, self.din, rows, alpha=c)
+            self.wgrad_(rows, L, Gh, GZ[l], 0, bias=False)
             Ghat.append(nxt)
             Z2.append(z2)
         Ls = net[-2]
-        top = Ghat[nl]
         # g w_sdf[k] += sum_p Ghat_top[p,k]
-        self.gemm(Ls.K, 1, rows, P_(top), 1, top.shape[1], P_(self.one), 0, 1, ps.gW(Ls), Ls.ldw, EPI_ATOMIC,
-                  split_k=max(1, min(rows // 512, 148)))
+        self.wgrad_(rows, Ls, Ghat[nl], self.ones_col, 0, bias=False)
         return Z2
 
     def geo_backward(self, x, rows, tag, A, dsdf, dO, Z2):
-        """Standard reverse sweep.  dsdf (rows,1) or None, dO (rows, LDO) holds dL/dfeature in columns 0:Df,
-        Z2 = second-order terms from geo_normal_adjoint or None.  Scatters the grid gradient."""
-        ps, net = self.params, self.params.nets["geo"]
+        """Standard reverse sweep.  dsdf (rows,1) tensor or None, dO: 'fa' matrix holding dL/dfeature in its fp32
+        columns 0:Df, Z2 = second-order terms from geo_normal_adjoint or None.  Scatters the grid gradient."""
+        net = self.params.nets["geo"]
         nl = len(net) - 2
         Ls, Lf = net[-2], net[-1]
         c = self.cskip
         last = A[nl]
-        pp = [self.buf("geo_dz0", rows, r4(self.Df)), self.buf("geo_dz1", rows, r4(self.Df))]
+        self.sync_h(dO, self.Df, rows)
+        pp = [self.mat("geo_dz0", rows, self.Df, "a", grad=True), self.mat("geo_dz1", rows, self.Df, "a", grad=True)]
         # last layer
-        self.wgrad(rows, Lf.K, Lf.N, P_(last), last.shape[1], P_(dO), self.LDO, ps.gW(Lf), Lf.ldw, gb=ps.gb(Lf))
+        self.wgrad_(rows, Lf, last, dO, 0)
         cur = pp[0]
-        ldc = cur.shape[1]
-        self.gemm(rows, Lf.K, Lf.N, P_(dO), self.LDO, 1, *ps.Bt(Lf), P_(cur), ldc, EPI_MUL_S, H=P_(last),
-                  ldh=last.shape[1], U=(P_(Z2[nl - 1]) if Z2 else 0), ldu=(Z2[nl - 1].shape[1] if Z2 else 0))
+        self.dgrad(rows, Lf, dO, 0, cur, 0, EPI_MUL_S, H=last, U=(Z2[nl - 1] if Z2 else None))
         if dsdf is not None:
-            self.wgrad(rows, Ls.K, 1, P_(last), last.shape[1], P_(dsdf), 1, ps.gW(Ls), Ls.ldw)
-            self.call("ndjir_colsum", rows, 1, ps.gb(Ls), P_(dsdf), 1, 1.0)
-            self.gemm(rows, Ls.K, 1, P_(dsdf), 1, 1, *ps.Bt(Ls), P_(cur), ldc, EPI_MUL_S, H=P_(last),
-                      ldh=last.shape[1], U=P_(cur), ldu=ldc)
-        dgrid = self.buf("geo_dgrid", rows, max(self.Dg, 1)) if self.Dg else None
+            dsdf_m = Mat(f=dsdf)
+            self.wgrad_(rows, Ls, last, dsdf_m, 0)
+            self.dgrad(rows, Ls, dsdf_m, 0, cur, 0, EPI_MUL_S, H=last, U=cur)
+        dgrid = self.mat("geo_dgrid", rows, max(self.Dg, 1), "f") if self.Dg else None
         skip_wrote = False
         for l in range(nl - 1, -1, -1):
             L = net[l]
             Al = A[l]
-            self.wgrad(rows, L.K, L.N, P_(Al), Al.shape[1], P_(cur), ldc, ps.gW(L), L.ldw, gb=ps.gb(L))
+            self.wgrad_(rows, L, Al, cur, 0)
             if l > 0:
                 is_skip = (l == self.skip)
                 n_prev = net[l - 1].N
                 nxt = pp[1] if cur is pp[0] else pp[0]
-                self.gemm(rows, n_prev, L.N, P_(cur), ldc, 1, *ps.Bt(L), P_(nxt), nxt.shape[1], EPI_MUL_S,
-                          alpha=(c if is_skip else 1.0), H=P_(Al), ldh=Al.shape[1],
-                          hscale=(1.0 / c if is_skip else 1.0), U=(P_(Z2[l - 1]) if Z2 else 0),
-                          ldu=(Z2[l - 1].shape[1] if Z2 else 0))
+                self.dgrad(rows, L, cur, 0, nxt, 0, EPI_MUL_S, ncols=n_prev, alpha=(c if is_skip else 1.0), H=Al,
+                           hscale=(1.0 / c if is_skip else 1.0), U=(Z2[l - 1] if Z2 else None))
                 if is_skip and self.Dg:
-                    self.gemm(rows, self.Dg, L.N, P_(cur), ldc, 1, *ps.Bt(L, n_prev + self.npe), P_(dgrid),
-                              self.Dg, EPI_BIAS, alpha=c)
+                    self.dgrad(rows, L, cur, 0, dgrid, 0, EPI_BIAS, row0=n_prev + self.npe, ncols=self.Dg, alpha=c)
                     skip_wrote = True
-                cur, ldc = nxt, nxt.shape[1]
+                cur = nxt
             elif self.Dg:
-                self.gemm(rows, self.Dg, L.N, P_(cur), ldc, 1, *ps.Bt(L, self.npe), P_(dgrid), self.Dg,
-                          EPI_ACCUM if skip_wrote else EPI_BIAS)
+                self.dgrad(rows, L, cur, 0, dgrid, 0, EPI_ACCUM if skip_wrote else EPI_BIAS, row0=self.npe,
+                           ncols=self.Dg)
         for part, width, off in self._grid_parts():
             tmp = self.buf(f"gg_{part}", rows, width)
-            self.copy2d(rows, width, P_(tmp), width, P_(dgrid, off), self.Dg)
+            self.copy2d(rows, width, P_(tmp), width, dgrid.fptr(off), dgrid.ldf)
             self._grid_scatter("grad_feature", part, rows, x, [tmp])
 
     # ------------------------------------------------------------------------------------------------
     # generic softplus MLP (heads): forward keeps layer inputs, backward accumulates weight gradients
     # ------------------------------------------------------------------------------------------------
-    def mlp_forward(self, name, tag, X, ldx, rows, outs):
-        """outs: list of (ptr, ldc) for the (possibly split) last reference layer."""
-        ps, net = self.params, self.params.nets[name]
-        n_last = len(outs)
-        nh = len(net) - n_last
-        acts = []
-        Aptr, lda = X, ldx
+    def mlp_forward(self, name, tag, X, rows, outs):
+        """X: input matrix; outs: list of (matrix, column) for the (possibly split) last reference layer."""
+        net = self.params.nets[name]
+        nh = len(net) - len(outs)
+        acts, cur = [], X
         for l in range(nh):
             L = net[l]
-            nxt = self.buf(f"{tag}_h{l}", rows, r4(L.N))
-            self.gemm(rows, L.N, L.K, Aptr, lda, 1, ps.W(L), L.ldw, 1, P_(nxt), nxt.shape[1], EPI_SOFTPLUS,
-                      bias=ps.b(L))
+            nxt = self.mat(f"{tag}_h{l}", rows, L.N, "a")
+            self.fwd(rows, L, cur, nxt, 0, EPI_SOFTPLUS)
             acts.append(nxt)
-            Aptr, lda = P_(nxt), nxt.shape[1]
-        for (optr, ldo), L in zip(outs, net[nh:]):
-            self.gemm(rows, L.N, L.K, Aptr, lda, 1, ps.W(L), L.ldw, 1, optr, ldo, EPI_BIAS, bias=ps.b(L))
+            cur = nxt
+        for (Y, ycol), L in zip(outs, net[nh:]):
+            self.fwd(rows, L, cur, Y, ycol, EPI_BIAS)
         return acts
 
-    def mlp_backward(self, name, tag, X, ldx, rows, acts, douts, dX=0, lddx=0, accum_dx=False, dx_cols=None):
-        """douts: list of (ptr, ld) matching the last (split) layers.  dX (rows, dx_cols) (+)= input gradient."""
-        ps, net = self.params, self.params.nets[name]
-        n_last = len(douts)
-        nh = len(net) - n_last
-        wmax = max(r4(L.N) for L in net[:nh]) if nh else 4
-        pp = [self.buf("mlp_dz0", rows, wmax), self.buf("mlp_dz1", rows, wmax)]   # keyed by (name, width)
-        lastA, lda = (P_(acts[-1]), acts[-1].shape[1]) if nh else (X, ldx)
+    def mlp_backward(self, name, tag, X, rows, acts, douts, dX=None, accum_dx=False, dx_cols=None):
+        """douts: list of (matrix, column) matching the last (split) layers.  dX[:, :dx_cols] (+)= input gradient."""
+        net = self.params.nets[name]
+        nh = len(net) - len(douts)
+        wmax = max(L.N for L in net[:nh]) if nh else 8
+        pp = [self.mat("mlp_dz0", rows, wmax, "a", grad=True), self.mat("mlp_dz1", rows, wmax, "a", grad=True)]
+        lastA = acts[-1] if nh else X
         cur = pp[0]
         first = True
-        for (dptr, ldd), L in zip(douts, net[nh:]):
-            self.wgrad(rows, L.K, L.N, lastA, lda, dptr, ldd, ps.gW(L), L.ldw, gb=ps.gb(L))
+        for (dY, dcol), L in zip(douts, net[nh:]):
+            self.wgrad_(rows, L, lastA, dY, dcol)
             if nh:
-                self.gemm(rows, L.K, L.N, dptr, ldd, 1, *ps.Bt(L), P_(cur), wmax, EPI_MUL_S, H=lastA, ldh=lda,
-                          U=(0 if first else P_(cur)), ldu=(0 if first else wmax))
-            elif dX:
-                self.gemm(rows, dx_cols or L.K, L.N, dptr, ldd, 1, *ps.Bt(L), dX, lddx,
-                          EPI_ACCUM if (accum_dx or not first) else EPI_BIAS)
+                self.dgrad(rows, L, dY, dcol, cur, 0, EPI_MUL_S, H=lastA, U=(None if first else cur))
+            elif dX is not None:
+                self.dgrad(rows, L, dY, dcol, dX, 0, EPI_ACCUM if (accum_dx or not first) else EPI_BIAS,
+                           ncols=dx_cols or L.K)
             first = False
         for l in range(nh - 1, -1, -1):
             L = net[l]
-            Aptr, lda = (P_(acts[l - 1]), acts[l - 1].shape[1]) if l > 0 else (X, ldx)
-            self.wgrad(rows, L.K, L.N, Aptr, lda, P_(cur), wmax, ps.gW(L), L.ldw, gb=ps.gb(L))
+            Ain = acts[l - 1] if l > 0 else X
+            self.wgrad_(rows, L, Ain, cur, 0)
             if l > 0:
                 nxt = pp[1] if cur is pp[0] else pp[0]
-                self.gemm(rows, L.K, L.N, P_(cur), wmax, 1, *ps.Bt(L), P_(nxt), wmax, EPI_MUL_S, H=Aptr,
-                          ldh=lda)
+                self.dgrad(rows, L, cur, 0, nxt, 0, EPI_MUL_S, H=Ain)
                 cur = nxt
-            elif dX:
-                self.gemm(rows, dx_cols or L.K, L.N, P_(cur), wmax, 1, *ps.Bt(L), dX, lddx,
-                          EPI_ACCUM if accum_dx else EPI_BIAS)
+            elif dX is not None:
+                self.dgrad(rows, L, cur, 0, dX, 0, EPI_ACCUM if accum_dx else EPI_BIAS, ncols=dx_cols or L.K)
 
     # ------------------------------------------------------------------------------------------------
     # sample_points (python/sampler.py:256-299)
@@ -753,9 +940,19 @@ class Engine:
         P = NR * N
         Df, LDO = self.Df, self.LDO
         S = N + Nb
+        if self.h16 and not self._calibrated:
+            # First use of the split-fp16 engine: the per-tensor scales are derived from the running maxima of the
+            # tensors' PREVIOUS use, so the step is run twice beforehand (results discarded) to seed them.
+            self._calibrated = True
+            for _ in range(2):
+                self.train_step(camloc, raydir, color_gt, rnd, cos_anneal_ratio=cos_anneal_ratio, samples=samples,
+                                zero_grad=zero_grad, backward=(backward and zero_grad), inference=inference)
         if zero_grad:
             ps.zero_grad()
         self.refresh_transposes()       # the normal pass (forward half) already needs W^T
+        if self.h16:
+            self.n_launches += 1
+            self.scales.update(self.stream())    # last step's maxima -> this step's power-of-two scales
         self._weights_synced = True
         self._gather_cache = {}
         losses = self.buf("losses", 1, 16, zero=True)
@@ -774,12 +971,13 @@ class Engine:
         x_fg = x_fg.reshape(P, 3)
         maskv = mask.reshape(NR)
         # ---------------- geometric network + normal ----------------
-        O = self.buf("O", P, LDO)
+        O = self.mat("O", P, Df + 6, "fa")       # [feature | x | normal]: network output, head input, render operand
         A, sdf = self.geo_forward(x_fg, P, "main", store=True, O=O)
         nrm = self.buf("nrm", P, 3)
         GZ, Gin = self.geo_normal(x_fg, P, "main", A, nrm)
-        self.copy2d(P, 3, P_(O, Df), LDO, P_(x_fg), 3)
-        self.copy2d(P, 3, P_(O, Df + 3), LDO, P_(nrm), 3)
+        self.copy2d(P, 3, O.fptr(Df), LDO, P_(x_fg), 3)
+        self.copy2d(P, 3, O.fptr(Df + 3), LDO, P_(nrm), 3)
+        self.sync_h(O, Df + 6, P)
         # ---------------- NeuS alpha, background, compositing ----------------
         alpha_fg = self.buf("alpha_fg", P, 1)
         gain_p = ps.data.data_ptr() + 4 * ps.gain_off
@@ -787,23 +985,24 @@ class Engine:
                   float(cos_anneal_ratio))
         bgc = conf.background_network
         rows_bg = NR * Nb
-        Xbg0 = self.buf("Xbg0", rows_bg, r4(pe_dim(4, bgc.pe_bands0)))
-        self.call("ndjir_positional_encoding", rows_bg, 4, bgc.pe_bands0, P_(x_bg), 4, 1, P_(Xbg0), Xbg0.shape[1])
+        nbg0 = pe_dim(4, bgc.pe_bands0)
+        Xbg0 = self.mat("Xbg0", rows_bg, nbg0, "fa")
+        self.call("ndjir_positional_encoding", rows_bg, 4, bgc.pe_bands0, P_(x_bg), 4, 1, Xbg0.fptr(), Xbg0.ldf)
+        self.sync_h(Xbg0, nbg0, rows_bg)
         Dfb = bgc.feature_size0
         nvpe = pe_dim(3, bgc.pe_bands1)
-        ldb1 = r4(Dfb + 4 + 3 + nvpe)
-        Xbg1 = self.buf("Xbg1", rows_bg, ldb1)
+        Xbg1 = self.mat("Xbg1", rows_bg, Dfb + 4 + 3 + nvpe, "a")
         dens = self.buf("bg_dens", rows_bg, 1)
-        acts_bg0 = self.mlp_forward("bg0", "bg0", P_(Xbg0), Xbg0.shape[1], rows_bg, [(P_(dens), 1), (P_(Xbg1), ldb1)])
-        self.copy2d(rows_bg, 4, P_(Xbg1, Dfb), ldb1, P_(x_bg), 4)
+        acts_bg0 = self.mlp_forward("bg0", "bg0", Xbg0, rows_bg, [(Mat(f=dens), 0), (Xbg1, 0)])
+        self.fill_cols(Xbg1, Dfb, P_(x_bg), 4, 4, rows_bg)
         view = self.buf("view", NR, 3)
         self.copy2d(NR, 3, P_(view), 3, P_(raydir), 3, alpha=-1.0)
-        self.copy2d(rows_bg, 3, P_(Xbg1, Dfb + 4), ldb1, P_(view), 3, rep=Nb)
+        self.fill_cols(Xbg1, Dfb + 4, P_(view), 3, 3, rows_bg, rep=Nb)
         vpe_bg = self.buf("vpe_bg", NR, r4(nvpe))
         self.call("ndjir_positional_encoding", NR, 3, bgc.pe_bands1, P_(view), 3, 1, P_(vpe_bg), vpe_bg.shape[1])
-        self.copy2d(rows_bg, nvpe, P_(Xbg1, Dfb + 7), ldb1, P_(vpe_bg), vpe_bg.shape[1], rep=Nb)
+        self.fill_cols(Xbg1, Dfb + 7, P_(vpe_bg), vpe_bg.shape[1], nvpe, rows_bg, rep=Nb)
         bgraw = self.buf("bg_raw", rows_bg, 4)
-        acts_bg1 = self.mlp_forward("bg1", "bg1", P_(Xbg1), ldb1, rows_bg, [(P_(bgraw), 4)])
+        acts_bg1 = self.mlp_forward("bg1", "bg1", Xbg1, rows_bg, [(Mat(f=bgraw), 0)])
         alpha_bg = self.buf("alpha_bg", rows_bg, 1)
         self.call("ndjir_bg_alpha_forward", rows_bg, Nb, P_(alpha_bg), P_(dens), 1, P_(t_bg))
         w = self.buf("w", NR, S)
@@ -813,26 +1012,28 @@ class Engine:
         self.call("ndjir_bg_color_forward", NR, Nb, P_(w, N), S, P_(bgraw), 4, P_(colbg))
         # ---------------- pixel quantities ----------------
         pix = self.buf("pix", NR, LDO)
-        self.call("ndjir_volume_render_forward", NR, N, Df + 6, P_(w), S, P_(O), LDO, P_(pix), LDO)
+        self.call("ndjir_volume_render_forward", NR, N, Df + 6, P_(w), S, O.fptr(), LDO, P_(pix), LDO)
         nhat = self.buf("nhat", NR, 3)
         self.call("ndjir_pixel_normal_forward", NR, P_(pix, Df + 3), LDO, float(r.eps_normal), P_(nhat))
         # ---------------- per-sample heads ----------------
         RAW = self.buf("RAW", P, 16, zero=inference)     # inference leaves column 13 (perturbed base colour) unset
+        RAWm = Mat(f=RAW)
         acts = {}
-        acts["bc"] = self.mlp_forward("bc", "bc", P_(O), LDO, P, [(P_(RAW, 0), 16)])
-        acts["ii"] = self.mlp_forward("ii", "ii", P_(O), LDO, P, [(P_(RAW, 3), 16)])
-        acts["ro"] = self.mlp_forward("ro", "ro", P_(O), LDO, P, [(P_(RAW, 4), 16)])
-        acts["sp"] = self.mlp_forward("sp", "sp", P_(O), LDO, P, [(P_(RAW, 6), 16)])
+        acts["bc"] = self.mlp_forward("bc", "bc", O, P, [(RAWm, 0)])
+        acts["ii"] = self.mlp_forward("ii", "ii", O, P, [(RAWm, 3)])
+        acts["ro"] = self.mlp_forward("ro", "ro", O, P, [(RAWm, 4)])
+        acts["sp"] = self.mlp_forward("sp", "sp", O, P, [(RAWm, 6)])
         plc = conf.photogrammetric_light_network
         npl = pe_dim(3, plc.pe_bands)
-        ldpl = r4(Df + 6 + npl + 1)
-        Xpl = self.buf("Xpl", P, ldpl)
-        self.copy2d(P, Df + 6, P_(Xpl), ldpl, P_(O), LDO)
+        Xpl = self.mat("Xpl", P, Df + 6 + npl + 1, "a", slot="O")      # [O | PE(view) | 1/d^2], same scale as O
+        self.copy_cols(Xpl, O, Df + 6, P)
         vpe_pl = self.buf("vpe_pl", NR, r4(npl))
         self.call("ndjir_positional_encoding", NR, 3, plc.pe_bands, P_(view), 3, 1, P_(vpe_pl), vpe_pl.shape[1])
-        self.copy2d(P, npl, P_(Xpl, Df + 6), ldpl, P_(vpe_pl), vpe_pl.shape[1], rep=N)
-        self.call("ndjir_inv_sq_dist", P, R * N, P_(x_fg), P_(camloc), P_(Xpl, Df + 6 + npl), ldpl)
-        acts["pl"] = self.mlp_forward("pl", "pl", P_(Xpl), ldpl, P, [(P_(RAW, 12), 16)])
+        self.fill_cols(Xpl, Df + 6, P_(vpe_pl), vpe_pl.shape[1], npl, P, rep=N)
+        invd = self.buf("inv_sq_dist", P, 1)
+        self.call("ndjir_inv_sq_dist", P, R * N, P_(x_fg), P_(camloc), P_(invd), 1)
+        self.fill_cols(Xpl, Df + 6 + npl, P_(invd), 1, 1, P)
+        acts["pl"] = self.mlp_forward("pl", "pl", Xpl, P, [(RAWm, 12)])
         # ---------------- perturbed colour branch (renderer.py:187-193) ----------------
         # It only feeds the base-colour prior of the loss: image rendering (inference=True, forward only) skips the
         # second geometric-network evaluation and reads a zero base colour there.
@@ -842,10 +1043,11 @@ class Engine:
             x_ptb = self.buf("x_ptb", P, 3)
             self.copy2d(P, 3, P_(x_ptb), 3, P_(x_fg), 3)
             self.copy2d(P, 3, P_(x_ptb), 3, P_(rnd["perturb"]), 3, alpha=math.sqrt(3) * 2 * self.rad / G, accum=1)
-            Op = self.buf("O_ptb", P, LDO)
+            Op = self.mat("O_ptb", P, Df + 6, "fa")
             Ap, _ = self.geo_forward(x_ptb, P, "ptb", store=True, O=Op)
-            self.copy2d(P, 3, P_(Op, Df), LDO, P_(x_ptb), 3)
-            acts["bcp"] = self.mlp_forward("bc", "bcp", P_(Op), LDO, P, [(P_(RAW, 13), 16)])
+            self.copy2d(P, 3, Op.fptr(Df), LDO, P_(x_ptb), 3)
+            self.sync_h(Op, Df + 3, P)
+            acts["bcp"] = self.mlp_forward("bc", "bcp", Op, P, [(RAWm, 13)])
         # ---------------- material attributes + per-sample losses ----------------
         ro_c, sp_c = conf.roughness_network, conf.specular_reflectance_network
         cfg10 = [ro_c.lower_bound, ro_c.prior_value, sp_c.prior_value, sp_c.upper_bound_scale, ps.pl_gain,
@@ -867,25 +1069,23 @@ class Engine:
         elc, svc = conf.environment_light_network, conf.soft_visibility_light_network
         rows_d = NR * 2 * M
         nel = pe_dim(3, elc.pe_bands)
-        Xel = self.buf("Xel", rows_d, r4(nel))
-        ldel = Xel.shape[1]
+        Xel = self.mat("Xel", rows_d, nel, "fa")
+        ldel = Xel.ldf
         # rows (set, r, j): the diffuse set first, then the specular set
         for s_, dirs in enumerate((dirs_u, dirs_s)):
-            self.call("ndjir_positional_encoding", NR * M, 3, elc.pe_bands, P_(dirs), 3, 1, P_(Xel, s_ * NR * M * ldel),
-                      ldel)
+            self.call("ndjir_positional_encoding", NR * M, 3, elc.pe_bands, P_(dirs), 3, 1, Xel.fptr(0, s_ * NR * M), ldel)
+        self.sync_h(Xel, nel, rows_d)
         elraw = self.buf("el_raw", rows_d, 4)
-        acts["el"] = self.mlp_forward("el", "el", P_(Xel), ldel, rows_d, [(P_(elraw), 4)])
+        acts["el"] = self.mlp_forward("el", "el", Xel, rows_d, [(Mat(f=elraw), 0)])
         nsv = pe_dim(3, svc.pe_bands)
         assert nsv == nel
-        ldsv = r4(Df + 6 + nsv)
-        Xsv = self.buf("Xsv", rows_d, ldsv)
+        Xsv = self.mat("Xsv", rows_d, Df + 6 + nsv, "a")
         for s_ in range(2):
-            o_ = s_ * NR * M * ldsv
-            self.copy2d(NR * M, Df + 3, P_(Xsv, o_), ldsv, P_(pix), LDO, rep=M)            # f_pix | x_pix
-            self.copy2d(NR * M, 3, P_(Xsv, o_ + Df + 3), ldsv, P_(nhat), 3, rep=M)         # nhat
-        self.copy2d(rows_d, nsv, P_(Xsv, Df + 6), ldsv, P_(Xel), ldel)                     # PE(omega)
+            self.fill_cols(Xsv, 0, P_(pix), LDO, Df + 3, NR * M, rep=M, drow=s_ * NR * M)            # f_pix | x_pix
+            self.fill_cols(Xsv, Df + 3, P_(nhat), 3, 3, NR * M, rep=M, drow=s_ * NR * M)           # nhat
+        self.fill_cols(Xsv, Df + 6, Xel.fptr(), ldel, nsv, rows_d)                                 # PE(omega)
         svraw = self.buf("sv_raw", rows_d, 4)
-        acts["sv"] = self.mlp_forward("sv", "sv", P_(Xsv), ldsv, rows_d, [(P_(svraw), 4)])
+        acts["sv"] = self.mlp_forward("sv", "sv", Xsv, rows_d, [(Mat(f=svraw), 0)])
         # ---------------- shading + colour loss ----------------
         cfg5 = [r.eps_dot, conf.specular_brdf.weight, inv_rays, 1.0, 0.0 if tr.rgb_loss == "l1" else 1.0]
         color = self.buf("color", NR, 3)
@@ -904,7 +1104,7 @@ class Engine:
         if self.world_size > 1:
             allreduce_mask_sum(losses[0, :N_LOSSES], self.pg)     # report the loss of the union of all ranks' rays
         if keep:
-            self.debug.update(dict(O=O, sdf=sdf, nrm=nrm, alpha_fg=alpha_fg, alpha_bg=alpha_bg, w=w, T=T, pix=pix,
+            self.debug.update(dict(O=O.f, sdf=sdf, nrm=nrm, alpha_fg=alpha_fg, alpha_bg=alpha_bg, w=w, T=T, pix=pix,
                                    nhat=nhat, RAW=RAW, ATT=ATT, attpix=attpix, dirs_u=dirs_u, dirs_s=dirs_s,
                                    elraw=elraw, svraw=svraw, color=color, colbg=colbg, bgraw=bgraw, x_fg=x_fg,
                                    t_fg=t_fg, x_bg=x_bg, t_bg=t_bg, mask=mask, dims=(B, R, N, Nb, M)))
@@ -922,14 +1122,13 @@ class Engine:
                   P_(svraw), 4, P_(colbg), P_(color_gt), cfg5, P_(d_el), P_(d_sv), P_(d_attpix), P_(d_nhat),
                   P_(d_colbg))
         # environment light: parameters only (directions carry no gradient, sampler.py:391)
-        self.mlp_backward("el", "el", P_(Xel), ldel, rows_d, acts["el"], [(P_(d_el), 4)])
+        self.mlp_backward("el", "el", Xel, rows_d, acts["el"], [(Mat(f=d_el), 0)])
         # soft visibility: input gradient -> per-ray sums
-        dXsv = self.buf("dXsv", rows_d, r4(Df + 6))
-        self.mlp_backward("sv", "sv", P_(Xsv), ldsv, rows_d, acts["sv"], [(P_(d_sv), 4)], dX=P_(dXsv),
-                          lddx=dXsv.shape[1], dx_cols=Df + 6)
+        dXsv = self.mat("dXsv", rows_d, Df + 6, "f")
+        self.mlp_backward("sv", "sv", Xsv, rows_d, acts["sv"], [(Mat(f=d_sv), 0)], dX=dXsv, dx_cols=Df + 6)
         dpix = self.buf("dpix", NR, LDO, zero=True)
-        self.call("ndjir_group_sum", NR, M, Df + 6, P_(dpix), LDO, P_(dXsv), dXsv.shape[1], 0)
-        self.call("ndjir_group_sum", NR, M, Df + 6, P_(dpix), LDO, P_(dXsv, NR * M * dXsv.shape[1]), dXsv.shape[1], 1)
+        self.call("ndjir_group_sum", NR, M, Df + 6, P_(dpix), LDO, dXsv.fptr(), dXsv.ldf, 0)
+        self.call("ndjir_group_sum", NR, M, Df + 6, P_(dpix), LDO, dXsv.fptr(0, NR * M), dXsv.ldf, 1)
         # dpix columns Df+3:Df+6 currently hold d nhat from the visibility input; add the shading part, then
         # turn d nhat into d n_pix
         self.copy2d(NR, 3, P_(d_nhat), 3, P_(dpix, Df + 3), LDO, accum=1)
@@ -937,8 +1136,8 @@ class Engine:
                   P_(dpix, Df + 3), LDO, 0)
         # weights gradient
         dw = self.buf("dw", NR, S, zero=True)
-        dO = self.buf("dO", P, LDO)
-        self.call("ndjir_volume_render_backward", NR, N, Df + 6, P_(w), S, P_(O), LDO, P_(dpix), LDO, P_(dO), LDO, 0,
+        dO = self.mat("dO", P, Df + 6, "fa", grad=True)
+        self.call("ndjir_volume_render_backward", NR, N, Df + 6, P_(w), S, O.fptr(), LDO, P_(dpix), LDO, dO.fptr(), LDO, 0,
                   P_(dw), S)
         dATT = self.buf("dATT", P, 12)
         self.call("ndjir_volume_render_backward", NR, N, 12, P_(w), S, P_(ATT), 12, P_(d_attpix), 12, P_(dATT), 12, 0,
@@ -948,17 +1147,13 @@ class Engine:
                   P_(d_bgraw), 4)
         # material heads
         dRAW = self.buf("dRAW", P, 16)
+        dRAWm = Mat(f=dRAW)
         self.call("ndjir_sample_attributes_backward", P, N, P_(RAW), P_(dATT), P_(nrm), 3, P_(maskv), cfg10, inv_denorm,
-                  P_(dRAW), P_(dO, Df + 3), LDO)
-        self.mlp_backward("bc", "bc", P_(O), LDO, P, acts["bc"], [(P_(dRAW, 0), 16)], dX=P_(dO), lddx=LDO,
-                          accum_dx=True, dx_cols=Df + 3)
+                  P_(dRAW), dO.fptr(Df + 3), LDO)
+        self.mlp_backward("bc", "bc", O, P, acts["bc"], [(dRAWm, 0)], dX=dO, accum_dx=True, dx_cols=Df + 3)
         for name, col in (("ii", 3), ("ro", 4), ("sp", 6)):
-            self.mlp_backward(name, name, P_(O), LDO, P, acts[name], [(P_(dRAW, col), 16)], dX=P_(dO), lddx=LDO,
-                              accum_dx=True, dx_cols=Df + 6)
-        dXpl = self.buf("dXpl", P, r4(Df + 6))
-        self.mlp_backward("pl", "pl", P_(Xpl), ldpl, P, acts["pl"], [(P_(dRAW, 12), 16)], dX=P_(dXpl),
-                          lddx=dXpl.shape[1], dx_cols=Df + 6)
-        self.copy2d(P, Df + 6, P_(dO), LDO, P_(dXpl), dXpl.shape[1], accum=1)
+            self.mlp_backward(name, name, O, P, acts[name], [(dRAWm, col)], dX=dO, accum_dx=True, dx_cols=Df + 6)
+        self.mlp_backward("pl", "pl", Xpl, P, acts["pl"], [(dRAWm, 12)], dX=dO, accum_dx=True, dx_cols=Df + 6)
         # compositing + alpha
         dalpha_fg = self.buf("dalpha_fg", P, 1)
         dalpha_bg = self.buf("dalpha_bg", rows_bg, 1)
@@ -967,24 +1162,21 @@ class Engine:
         dsdf = self.buf("dsdf", P, 1, zero=True)
         g_gain = ps.grad.data_ptr() + 4 * ps.gain_off
         self.call("ndjir_neus_alpha_backward", P, N, P_(dalpha_fg), P_(sdf), P_(nrm), 3, P_(raydir), P_(t_fg), gain_p,
-                  float(cos_anneal_ratio), P_(dsdf), P_(dO, Df + 3), LDO, g_gain)
+                  float(cos_anneal_ratio), P_(dsdf), dO.fptr(Df + 3), LDO, g_gain)
         # background networks
-        dXbg1 = self.buf("dXbg1", rows_bg, r4(Dfb))
-        self.mlp_backward("bg1", "bg1", P_(Xbg1), ldb1, rows_bg, acts_bg1, [(P_(d_bgraw), 4)], dX=P_(dXbg1),
-                          lddx=dXbg1.shape[1], dx_cols=Dfb)
+        dXbg1 = self.mat("dXbg1", rows_bg, Dfb, "a", grad=True)
+        self.mlp_backward("bg1", "bg1", Xbg1, rows_bg, acts_bg1, [(Mat(f=d_bgraw), 0)], dX=dXbg1, dx_cols=Dfb)
         d_dens = self.buf("d_dens", rows_bg, 1)
         self.call("ndjir_bg_alpha_backward", rows_bg, Nb, P_(dalpha_bg), P_(dens), 1, P_(t_bg), P_(d_dens), 1)
-        self.mlp_backward("bg0", "bg0", P_(Xbg0), Xbg0.shape[1], rows_bg, acts_bg0,
-                          [(P_(d_dens), 1), (P_(dXbg1), dXbg1.shape[1])])
+        self.mlp_backward("bg0", "bg0", Xbg0, rows_bg, acts_bg0, [(Mat(f=d_dens), 0), (dXbg1, 0)])
         # geometric network: second-order terms from d L / d normal, then the standard sweep
         nbar = self.buf("nbar", P, 3)
-        self.copy2d(P, 3, P_(nbar), 3, P_(dO, Df + 3), LDO)
+        self.copy2d(P, 3, P_(nbar), 3, dO.fptr(Df + 3), LDO)
         Z2 = self.geo_normal_adjoint(x_fg, P, "main", A, GZ, Gin, nbar)
         self.geo_backward(x_fg, P, "main", A, dsdf, dO, Z2)
         # perturbed branch
-        dOp = self.buf("dO_ptb", P, LDO)
-        self.mlp_backward("bc", "bcp", P_(Op), LDO, P, acts["bcp"], [(P_(dRAW, 13), 16)], dX=P_(dOp), lddx=LDO,
-                          dx_cols=Df + 3)
+        dOp = self.mat("dO_ptb", P, Df + 6, "fa", grad=True)
+        self.mlp_backward("bc", "bcp", Op, P, acts["bcp"], [(dRAWm, 13)], dX=dOp, dx_cols=Df + 3)
         self.geo_backward(x_ptb, P, "ptb", Ap, None, dOp, None)
         # TV
         if tv_on:
@@ -995,7 +1187,7 @@ class Engine:
         if self.world_size > 1:
             allreduce_gradients(ps, self.pg, include_grid=not self._sparse_grid())
         if keep:
-            self.debug.update(dict(dO=dO, dsdf=dsdf, dw=dw, dRAW=dRAW, d_attpix=d_attpix, dpix=dpix, nbar=nbar,
+            self.debug.update(dict(dO=dO.f, dsdf=dsdf, dw=dw, dRAW=dRAW, d_attpix=d_attpix, dpix=dpix, nbar=nbar,
                                    dalpha_fg=dalpha_fg, dalpha_bg=dalpha_bg, d_el=d_el, d_sv=d_sv))
         self._weights_synced = False
         return losses[0, :N_LOSSES]

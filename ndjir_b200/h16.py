@@ -40,12 +40,13 @@ class Scales:
         self.names = {}
         self.target_log2 = target_log2
 
-    def slot(self, name):
+    def slot(self, name, init=1.0):
         i = self.names.get(name)
         if i is None:
             i = self.names[name] = len(self.names)
             if i >= self.scale.numel():
                 raise _lib.NdjirError("out of scale slots")
+            self.scale[i] = init
         return i
 
     def update(self, stream):
@@ -56,12 +57,12 @@ class HBuf:
     """(rows, ld) split-fp16 matrix: two fp16 planes in one allocation [2, rows, ld]; ld is a multiple of 64 halfs so
     that every row chunk is a whole TMA box row and the weight-gradient products can fetch 3-D boxes."""
 
-    def __init__(self, rows, cols, device, scales=None, name=None, ld=None):
+    def __init__(self, rows, cols, device, scales=None, name=None, ld=None, init=1.0):
         self.rows, self.cols = rows, cols
         self.ld = ld if ld is not None else (cols + 63) // 64 * 64
         self.t = torch.zeros((2, rows, self.ld), dtype=torch.float16, device=device)
         self.scales = scales
-        self.slot = scales.slot(name) if (scales is not None and name is not None) else None
+        self.slot = scales.slot(name, init) if (scales is not None and name is not None) else None
 
     def hmat(self, col=0, row=0, track=True):
         """ndjir_hmat view starting at (row, col)."""
