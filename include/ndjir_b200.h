@@ -401,6 +401,9 @@ int ndjir_adam_step(long long n, float* w, float* g, float* m, float* v, float a
                     cudaStream_t stream);
 /* flag[0] |= any(!isfinite(g)); the scan is skipped when only_if != NULL and *only_if == 0 (device) */
 int ndjir_nonfinite_flag(long long n, const float* g, int* flag, const int* only_if, cudaStream_t stream);
+/* the loop's second guard, `if np.any(np.isnan(loss.d)): continue` (python/train.py:144-146): a NaN among the n loss
+ * values raises both skip flags (DEVICE int[2]) so that ndjir_adam_tick / ndjir_adam_step skip the iteration */
+int ndjir_nan_loss_flag(int n, const float* loss, int* skip_flags, cudaStream_t stream);
 /* g += rate * w: S.Adam.weight_decay as its own pass (solver.py:48-50) */
 int ndjir_weight_decay(long long n, float* g, const float* w, float rate, cudaStream_t stream);
 
@@ -541,6 +544,8 @@ typedef struct ndjir_gemm_h_desc {
   const float* bias;
   const float* H; long long ldh; ndjir_hmat Hh;     /* activation the sigmoid factor is derived from (either form) */
   const float* U; long long ldu; ndjir_hmat Uh;     /* EPI_MUL_S addend / EPI_ADJ factor (either form) */
+  float* colsum;       /* mn_major only: colsum[n] += sum over the K rows of B(k, n): the bias gradient that goes with a
+                          weight gradient, carried by spare warps that read the B tiles the product stages anyway */
 } ndjir_gemm_h_desc;
 
 int ndjir_gemm_h(const ndjir_gemm_h_desc* d, cudaStream_t stream);

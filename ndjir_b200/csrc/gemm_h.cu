@@ -39,7 +39,9 @@ constexpr int NSLOT = 4;
 constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + 1024;
 constexpr int EPI_WARP0 = 2;
 constexpr int EPI_THREADS = 256;
-constexpr int THREADS = 64 + EPI_THREADS;
+constexpr int CS_WARP0 = EPI_WARP0 + EPI_THREADS / 32;   // column-sum warps (weight-gradient products with a bias gradient)
+constexpr int CS_WARPS = 4;
+constexpr int THREADS = 64 + EPI_THREADS + CS_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int CHUNK_BYTES = BK * 128;           // MN-major tiles: [chunk of 64 mn][k row][128 B]
 
@@ -69,7 +71,8 @@ struct HParams {
   int m_tiles, n_tiles, splits, kb_per_split, nkb_total;
   int a3d, b3d;          // MN-major operand fetched as one 3-D box per slot
   int b_box_rows;        // rows (K-major) / columns (MN-major) of B staged per slot: 64, 128 or 256
-  int vec_epi;           // every epilogue operand allows 16-byte accesses at 16-column granularity
+  int vec_epi;           // every epilogue operand allows 32-byte accesses at 16-column granularity
+  int do_colsum;         // MN-major mode: a.colsum[n] += column sums of B (the bias gradient of the layer)
   int dbg;
 };
 
@@ -80,6 +83,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * NSLOT + 4];
   __shared__ uint32_t tmem_base_sh;
+  __shared__ float colsum_sh[BN];
 
   const HArgs& a = p.a;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -96,7 +100,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), 1 + (p.do_colsum ? CS_WARPS : 0));   // tcgen05.commit (+ one arrival per column-sum warp)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);
@@ -235,6 +239,71 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
         }
         umma_commit(bar_acc_full(buf));
         ++tile_it;
+      }
+    }
+  } else if (warp >= CS_WARP0) {
+    // ===================== column sums of B (MN-major mode): the bias gradient rides on the weight gradient ==========
+    // B slots hold [chunk of 64 n][k row][128 B], 16-byte pieces XOR-swizzled with (row & 7).  A thread reads the same
+    // PHYSICAL piece of every row of two row classes (row & 7 == cl), so the logical columns it meets never change and
+    // its 2 x 8 sums stay in registers for a whole work item; items of m tile 0 carry the sums.
+    if (p.do_colsum) {
+      const int t = threadIdx.x - CS_WARP0 * 32;         // 0 .. 127
+      const int q = t & 31, chunk = q >> 3, pp = q & 7, rg = t >> 5;
+      const int b_chunks = p.b_box_rows / 64;
+      const float inv_b = 1.f / dev_scalar(a.b_scale);
+      for (int c = t; c < BN; c += CS_WARPS * 32) colsum_sh[c] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(CS_WARPS * 32) : "memory");
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        item_info(item, m0, n0, kb0, nkb);
+        const bool mine = (m0 == 0) && chunk < b_chunks;
+        float cs[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cs[j][e] = 0.f;
+        for (int i = 0; i < 2 * nkb; ++i, ++it) {          // both slots of every K block (hi and lo planes)
+          const int s = it % NSLOT;
+          mbar_wait(bar_full(s), (it / NSLOT) & 1);
+          if (mine) {
+            const uint8_t* bt = smem + s * SLOT_BYTES + A_BYTES + chunk * CHUNK_BYTES + pp * 16;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int cl = rg + 4 * j;
+#pragma unroll
+              for (int r8 = 0; r8 < BK / 8; ++r8) {
+                const uint4 x = *reinterpret_cast<const uint4*>(bt + (r8 * 8 + cl) * 128);
+                const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                  cs[j][2 * e] += f.x;
+                  cs[j][2 * e + 1] += f.y;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty(s));
+        }
+        if (m0 == 0) {
+          if (mine) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int col = chunk * 64 + ((pp ^ (rg + 4 * j)) << 3);     // logical piece = physical ^ (row & 7)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) atomicAdd(&colsum_sh[col + e], cs[j][e]);
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(CS_WARPS * 32) : "memory");
+          for (int c = t; c < BN; c += CS_WARPS * 32) {
+            const float v = colsum_sh[c];
+            colsum_sh[c] = 0.f;
+            if (v != 0.f && n0 + c < a.N) atomicAdd(a.colsum + n0 + c, v * inv_b);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(CS_WARPS * 32) : "memory");
+        }
       }
     }
   } else {
@@ -515,6 +584,7 @@ static int launch_epi(const HArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
+  p.do_colsum = (a.mn && a.colsum != nullptr) ? 1 : 0;
   p.m_tiles = (a.M + BM - 1) / BM;
   p.n_tiles = (a.N + BN - 1) / BN;
   p.nkb_total = (a.K + BK - 1) / BK;
@@ -590,6 +660,7 @@ extern "C" int ndjir_gemm_h(const ndjir_gemm_h_desc* d, cudaStream_t stream) {
   a.H = make_op(const_cast<float*>(d->H), d->ldh, d->Hh);
   a.U = make_op(const_cast<float*>(d->U), d->ldu, d->Uh);
   a.bias = d->bias;
+  a.colsum = d->colsum;
   if (!a.C.f && !a.C.hi) return NDJIR_ERR_ARG;
   if (corner_shape(a)) return launch_corner(a, stream);
   return launch_tc(a, stream);

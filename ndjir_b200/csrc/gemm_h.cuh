@@ -43,6 +43,7 @@ struct HArgs {
   const float* B32; long long b_rs, b_cs;
   Op C, C2, H, U;
   const float* bias;
+  float* colsum;       // MN-major mode: [N] += column sums of B (bias gradient), or nullptr
 };
 
 __device__ __forceinline__ float dev_scalar(const float* p) { return p ? __ldg(p) : 1.f; }

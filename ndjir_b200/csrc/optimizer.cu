@@ -83,6 +83,14 @@ nonfinite_kernel(long long n, const float* __restrict__ g, int* __restrict__ fla
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+// The reference's second guard (python/train.py:144-146): `if np.any(np.isnan(loss.d)): continue`.  A NaN in `loss`
+// raises BOTH skip flags, so the fused update is skipped whatever the gradient scans found.
+__global__ void nan_loss_kernel(int n, const float* __restrict__ loss, int* __restrict__ skip_flags) {
+  bool bad = false;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) bad |= isnan(loss[i]);
+  if (__any_sync(0xffffffffu, bad) && threadIdx.x == 0) { skip_flags[0] = 1; skip_flags[1] = 1; }
+}
+
 // t += 1 unless the step is skipped (nnabla's Adam counts update() calls; a skipped iteration does not call it)
 __global__ void tick_kernel(int* __restrict__ t_dev, const int* __restrict__ skip_flags) {
   bool skip = skip_flags && skip_flags[0] != 0 && skip_flags[1] != 0;
@@ -134,6 +142,13 @@ int ndjir_nonfinite_flag(long long n, const float* g, int* flag, const int* only
   if (n < 0 || !g || !flag) return NDJIR_ERR_ARG;
   bool vec = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
   nonfinite_kernel<<<grid_for((n + 3) / 4, NDJIR_BLOCK, 32), NDJIR_BLOCK, 0, stream>>>(n, g, flag, only_if, vec);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_nan_loss_flag(int n, const float* loss, int* skip_flags, cudaStream_t stream) {
+  if (n == 0) return NDJIR_OK;
+  if (n < 0 || !loss || !skip_flags) return NDJIR_ERR_ARG;
+  nan_loss_kernel<<<1, 32, 0, stream>>>(n, loss, skip_flags);
   NDJIR_RETURN_LAST_ERROR();
 }
 

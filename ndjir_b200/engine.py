@@ -204,10 +204,12 @@ class ParamStore:
             out[f"grid.{k}"] = v.detach().cpu().numpy()
         return out
 
-    def zero_grad(self):
-        self.grad.zero_()
+    def zero_grad(self, stream=None):
+        """zero every gradient buffer with the library's own fill kernel (ndjir_fill) on `stream`"""
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.call("ndjir_fill", self.grad.numel(), self.grad, 0.0, st)
         for v in self.grid_grad.values():
-            v.zero_()
+            _lib.call("ndjir_fill", v.numel(), v, 0.0, st)
 
     def lo_of(self, ptr):
         """Address of the pre-split lo part (x - tf32(x)) of a weight operand inside `data` / `data_t`, else 0."""
@@ -514,9 +516,7 @@ class Engine:
         tiles = ((kin + 127) // 128) * ((L.N + 255) // 256)
         split = max(1, min(rows // 256, (148 * 2) // tiles))
         self.gemm_h(kin, L.N, rows, EPI_ATOMIC, A=X.hmat(0, track=False), B=dY.hmat(dycol, track=False), mn_major=True,
-                    split_k=split, C=ps.gW(L), ldc=L.ldw)
-        if bias:
-            self.call("ndjir_colsum_h", rows, L.N, ps.gb(L), dY.hmat(dycol, track=False), 1.0)
+                    split_k=split, C=ps.gW(L), ldc=L.ldw, colsum=(ps.gb(L) if bias else None))
 
     def _sparse_grid(self):
         if self.world_size <= 1:
@@ -948,7 +948,8 @@ class Engine:
                 self.train_step(camloc, raydir, color_gt, rnd, cos_anneal_ratio=cos_anneal_ratio, samples=samples,
                                 zero_grad=zero_grad, backward=(backward and zero_grad), inference=inference)
         if zero_grad:
-            ps.zero_grad()
+            self.n_launches += 1 + len(ps.grid_grad)
+            ps.zero_grad(self.stream())
         self.refresh_transposes()       # the normal pass (forward half) already needs W^T
         if self.h16:
             self.n_launches += 1

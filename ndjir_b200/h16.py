@@ -26,7 +26,8 @@ class GemmHDesc(ctypes.Structure):
                 ("C2", ctypes.c_void_p), ("ldc2", ctypes.c_longlong), ("C2h", HMat),
                 ("bias", ctypes.c_void_p),
                 ("H", ctypes.c_void_p), ("ldh", ctypes.c_longlong), ("Hh", HMat),
-                ("U", ctypes.c_void_p), ("ldu", ctypes.c_longlong), ("Uh", HMat)]
+                ("U", ctypes.c_void_p), ("ldu", ctypes.c_longlong), ("Uh", HMat),
+                ("colsum", ctypes.c_void_p)]
 
 
 class Scales:
@@ -94,7 +95,7 @@ NULL_H = HMat(None, None, 0, None, None)
 
 def gemm_h(stream, M, N, K, epi, A=None, B=None, mn_major=False, precise=False, split_k=1, alpha=1.0, out_scale=1.0,
            beta=100.0, hscale=1.0, A32=None, a_rs=0, a_cs=1, B32=None, b_rs=0, b_cs=1, C=None, ldc=0, Ch=None,
-           C2=None, ldc2=0, C2h=None, bias=None, H=None, ldh=0, Hh=None, U=None, ldu=0, Uh=None):
+           C2=None, ldc2=0, C2h=None, bias=None, H=None, ldh=0, Hh=None, U=None, ldu=0, Uh=None, colsum=None):
     """One product of the split-fp16 engine.  A, B, Ch, C2h, Hh, Uh are HMat views; C, C2, H, U, bias, A32, B32 device
     addresses (int) of fp32 data."""
     d = GemmHDesc()
@@ -114,4 +115,5 @@ def gemm_h(stream, M, N, K, epi, A=None, B=None, mn_major=False, precise=False, 
     d.Hh = Hh if Hh is not None else NULL_H
     d.U, d.ldu = U, ldu
     d.Uh = Uh if Uh is not None else NULL_H
+    d.colsum = colsum
     _lib.call("ndjir_gemm_h", d, stream)

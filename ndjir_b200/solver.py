@@ -84,9 +84,15 @@ class Solvers:
         # the W^T copies of the input-gradient products are refreshed at the start of Engine.train_step
 
     # -- fused iteration ----------------------------------------------------------------------------------
-    def step(self):
-        """After train_step(zero_grad=False) accumulated dL/dw into zeroed buffers: decay + check + Adam + zero, fused."""
+    def step(self, loss=None):
+        """After train_step(zero_grad=False) accumulated dL/dw into zeroed buffers: decay + check + Adam + zero, fused.
+        The iteration is skipped on the device - gradients zeroed, Adam's count not advanced - when both solvers see a
+        non-finite gradient (solver.py:67-69) OR the loss is NaN (the loop's second guard, train.py:144-146; pass the
+        device tensor train_step returned).  With `voxel.type: none` the feat group is empty and only the loss guard
+        can trip, exactly as in the reference."""
         self._scan()
+        if loss is not None:
+            self._call("ndjir_nan_loss_flag", 1, loss, self._flags)
         self.update(fused_decay=self.conf.train.weight_decay, zero_grad=True, skip_flags=self._flags)
 
     # -- schedules (solver.py:71-119) -------------------------------------------------------------------

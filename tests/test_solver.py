@@ -167,3 +167,35 @@ def test_reference_call_order_equals_fused_step():
     assert (a - b).abs().max().item() <= 1e-6 * a.abs().max().item()
     for k in ga:
         assert (ga[k] - gb[k]).abs().max().item() <= 1e-6 * ga[k].abs().max().item()
+
+
+@pytest.mark.gpu
+def test_nan_loss_skips_the_fused_step_without_a_feature_grid():
+    """voxel.type = none: the feat solver is empty, so the gradient `and` can never trip (solver.py:67-69); the loop's
+    second guard - `if np.any(np.isnan(loss.d)): continue`, train.py:144-146 - must skip the iteration instead of letting
+    Adam write NaN into every MLP weight.  A finite loss with the same gradients is NOT skipped."""
+    import torch
+    from ndjir_b200.engine import Engine
+    from ndjir_b200.solver import Solvers
+    from ndjir_b200 import scene
+    from test_engine_gpu import small_conf
+    conf = small_conf("no_voxel")
+    eng = Engine(conf)
+    eng.params.load_reference(scene.init_params(conf, seed=313))
+    ps = eng.params
+    sv = Solvers(conf, eng)
+    sv.set_parameters()
+    sv.update_learning_rate(30)
+    before = ps.data.clone()
+    ps.zero_grad()
+    ps.grad += float("nan")
+    sv.step(loss=torch.tensor([float("nan")], device="cuda"))
+    torch.cuda.synchronize()
+    assert int(sv._t.item()) == 0, "skipped iterations do not advance Adam's count"
+    assert torch.equal(ps.data, before), "a NaN loss skips the update"
+    assert float(ps.grad.abs().max()) == 0.0, "the gradient is still zeroed for the next iteration"
+    ps.grad += 1e-3
+    sv.step(loss=torch.tensor([0.5], device="cuda"))
+    torch.cuda.synchronize()
+    assert int(sv._t.item()) == 1 and not torch.equal(ps.data, before)
+    assert bool(torch.isfinite(ps.data).all())

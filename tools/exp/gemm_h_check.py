@@ -95,14 +95,17 @@ def check_mn(rows, Kin, N, split, seed=0):
     A_, Z_ = bA.unpack(st()), bZ.unpack(st())
     want = A_.double().T @ Z_.double()
     gW = torch.zeros((Kin, N), device=dev)
+    cf = torch.zeros(N, device=dev)
     h16.gemm_h(st(), Kin, N, rows, h16.EPI_ATOMIC, A=bA.hmat(), B=bZ.hmat(), mn_major=True, split_k=split,
-               C=gW.data_ptr(), ldc=N)
+               C=gW.data_ptr(), ldc=N, colsum=cf.data_ptr())
     cs = torch.zeros(N, device=dev)
     _lib.call("ndjir_colsum_h", rows, N, cs, bZ.hmat(track=False), 1.0, st())
     torch.cuda.synchronize()
     e = rel(gW, want)
     ec = rel(cs, Z_.double().sum(0))
-    print(f"MN rows={rows} Kin={Kin} N={N} split={split}: err {e:.2e} colsum {ec:.2e} (repr {rel(Z_, dZ):.1e})")
+    ef = rel(cf, Z_.double().sum(0))
+    print(f"MN rows={rows} Kin={Kin} N={N} split={split}: err {e:.2e} colsum {ec:.2e} fused colsum {ef:.2e} (repr {rel(Z_, dZ):.1e})")
+    e = max(e, ef)
     return e
 
 
@@ -184,10 +187,14 @@ def bench(M=262144, N=256, K=256, iters=20):
         run(f"adjoint precise={precise}", lambda: h16.gemm_h(
             st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), precise=precise, Ch=bC.hmat(), C2h=bC2.hmat(),
             Hh=bH.hmat(), Uh=bU.hmat()), fl)
+    cs0 = torch.zeros(N, device=dev)
     for split in (148, 296, 592):
         run(f"wgrad split={split}", lambda: h16.gemm_h(
             st(), K, N, M, h16.EPI_ATOMIC, A=bA.hmat(), B=bC.hmat(), mn_major=True, split_k=split, C=gW.data_ptr(),
             ldc=N), fl)
+        run(f"wgrad + fused colsum split={split}", lambda: h16.gemm_h(
+            st(), K, N, M, h16.EPI_ATOMIC, A=bA.hmat(), B=bC.hmat(), mn_major=True, split_k=split, C=gW.data_ptr(),
+            ldc=N, colsum=cs0.data_ptr()), fl)
     cs = torch.zeros(N, device=dev)
     run("colsum_h", lambda: _lib.call("ndjir_colsum_h", M, N, cs, bC.hmat(track=False), 1.0, st()), fl)
     src = torch.randn((M, N), device=dev)
