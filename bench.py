@@ -40,7 +40,7 @@ def emit(line):
 
 def profiled_traffic():
     """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r1_traffic.json), or {}."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         return json.load(open(p))
     except Exception:
@@ -99,33 +99,40 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(conf):
+def grid_label(conf):
+    v = conf.geometric_network.voxel
+    if v.type == "voxel":
+        return f"voxel {v.grid_size}^3 x {v.feature_size}"
+    if v.type == "triplaneline":
+        return f"triplane 3 x {v.grid_size}^2 x {v.feature_size} + triline 3 x {v.grid_size} x {v.feature_size}"
+    return "none (MLP-only SDF)"
+
+
+def workload(conf, name="default"):
     r, tr = conf.renderer, conf.train
-    return dict(workload="default.yaml train step (fwd+bwd), synthetic DTU-shaped rays",
+    return dict(workload=f"{name}.yaml train step (fwd+bwd), synthetic DTU-shaped rays",
                 views=tr.batch_size, rays_per_view=tr.n_rays,
                 fg_samples=r.n_samples0 + r.n_upsamples * r.n_samples1, bg_samples=r.n_bg_samples,
-                light_dirs=2 * r.n_thetas * 2 * r.n_thetas,
-                grid=f"voxel {conf.geometric_network.voxel.grid_size}^3 x {conf.geometric_network.voxel.feature_size}",
-                l2="working set per step (~15 GB of activations + 4 GiB grid/grid-gradient) exceeds the 126 MB L2")
+                light_dirs=2 * r.n_thetas * 2 * r.n_thetas, grid=grid_label(conf),
+                l2="working set per step (~15 GB of activations + grid and grid-gradient tables) exceeds the 126 MB L2")
 
 
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle (CPU restatement of the reference path; nnabla is not installable
 # here) on the host cores
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(conf, steps, warmup, rays_per_step):
+def cpu_reference_run(conf, steps, warmup, rays_per_step, views=1):
     import torch
     from ndjir_b200 import scene
     from oracle import cpu_render as CR
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     P = scene.init_params(conf, seed=313)
-    v = conf.geometric_network.voxel
-    G, D = v.grid_size, v.feature_size
     gen = torch.Generator().manual_seed(313)
-    grids = {"voxel": (torch.randn((G, G, G, D), generator=gen) * 1e-3).numpy()} if v.type == "voxel" else None
-    model = CR.Model(conf, P, dtype=torch.float32, grids=grids)
-    B, R = 1, rays_per_step
+    grids = {k: (P["grid"].get(k) if P["grid"].get(k) is not None else (torch.randn(shp, generator=gen) * 1e-3).numpy())
+             for k, shp in scene.grid_shapes(conf).items()}
+    model = CR.Model(conf, P, dtype=torch.float32, grids=grids or None)
+    B, R = views, rays_per_step
     times = []
     for s in range(warmup + steps):
         camloc, raydir, color_gt = scene.make_batch(conf, step=s, B=B, R=R)
@@ -137,10 +144,12 @@ def cpu_reference_run(conf, steps, warmup, rays_per_step):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     return dict(value=B * R / (ms / 1e3), unit="rays/s", cores=cores, kind="port",
-                sample=f"{steps} steps of 1 view x {R} rays (default.yaml networks, 512^3x4 voxel grid, fwd+bwd incl. "
-                       f"the dense 2 GiB grid gradient, whose fixed per-step cost is amortised over {R} rays here and "
-                       f"over 2048 in the full batch) with torch CPU fp32 on {cores} threads; oracle/cpu_render.py",
-                ms_per_step=ms)
+                sample=f"{steps} timed step(s) after {warmup} warm-up of {B} view(s) x {R} rays (full per-ray config and "
+                       f"network widths, grid: {grid_label(conf)}, fwd+bwd incl. the dense grid gradient, whose fixed "
+                       f"per-step cost is amortised over {B * R} rays here and over "
+                       f"{conf.train.batch_size * conf.train.n_rays} in the full batch) with torch CPU fp32 on {cores} "
+                       f"threads; oracle/cpu_render.py",
+                ms_per_step=ms, warmup=warmup, steps=steps)
 
 
 def run_reference(args, conf):
@@ -148,11 +157,19 @@ def run_reference(args, conf):
     if rank != 0:
         return
     rays = args.ref_rays
-    cb = cpu_reference_run(conf, max(1, args.steps), min(args.warmup, 1), rays)
-    cfg = workload(conf)
+    ref_warmup = min(args.warmup, 1)          # one warm-up step is enough on the CPU; the line reports what was run
+    cb = cpu_reference_run(conf, max(1, args.steps), ref_warmup, rays)
+    cfg = workload(conf, args.config)
     cfg["sample"] = cb["sample"]
+    if not args.no_ref_full:
+        # the SAME batch as the GPU arm (all views x all rays), once: the bounded sample above amortises the dense grid
+        # gradient over fewer rays, this step does not
+        tr = conf.train
+        full = cpu_reference_run(conf, 1, 0, tr.n_rays, views=tr.batch_size)
+        cfg["full_batch_step"] = {"value": full["value"], "unit": "rays/s", "ms_per_step": full["ms_per_step"],
+                                  "views": tr.batch_size, "rays_per_view": tr.n_rays, "steps": 1, "warmup": 0}
     line = {"impl": "reference", "metric": "train_rays_per_sec_fwd_bwd", "value": cb["value"], "unit": "rays/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": ref_warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg, "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -264,18 +281,27 @@ def run_ours(args, conf):
     B, R = tr.batch_size, tr.n_rays
     nsteps = args.warmup + args.steps
 
-    # synthetic batches: every rank renders its own rays (weak scaling); host copies are pinned for the e2e arm
+    # synthetic batches; host copies are pinned for the e2e arm.  weak scaling: every rank renders its own full batch;
+    # strong scaling: ONE batch per step, sharded along the ray axis (parallel.shard_rays: rank k gets rays
+    # [k R / world, (k + 1) R / world) of every view)
+    strong = args.scaling == "strong" and world > 1
     host = []
     for s in range(nsteps):
-        camloc, raydir, color_gt = scene.make_batch(conf, step=s * world + rank)
-        rnd = scene.make_randoms(conf, B, R, step=s * world + rank)
+        seed = s if strong else s * world + rank
+        camloc, raydir, color_gt = scene.make_batch(conf, step=seed)
+        rnd = scene.make_randoms(conf, B, R, step=seed)
+        if strong:
+            n = R // world
+            assert n * world == R, "rays per view must divide by the number of GPUs"
+            raydir, color_gt = raydir[:, rank * n:(rank + 1) * n], color_gt[:, rank * n:(rank + 1) * n]
+            rnd = {k: v[:, rank * n:(rank + 1) * n] for k, v in rnd.items()}
         item = {"camloc": camloc, "raydir": raydir, "color_gt": color_gt, **rnd}
         host.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in item.items()})
     h2d_bytes = sum(v.numel() * 4 for v in host[0].values())
     resident = [{k: v.cuda(non_blocking=True) for k, v in item.items()} for item in host]
     torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph      # CUDA-graph replay of the step (Engine.train_step_graphed)
+    use_graph = not args.no_graph      # CUDA-graph replay of the step (Engine.train_step_graphed), NCCL exchanges included
     rnd_keys = [k for k in host[0] if k not in ("camloc", "raydir", "color_gt")]
 
     def run_step(item):
@@ -315,7 +341,7 @@ def run_ours(args, conf):
     ms_total = maxreduce(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
-    rays_per_step = B * R * world
+    rays_per_step = B * R if strong else B * R * world
     value = rays_per_step / (ms_step * 1e-3)
     loss_host = losses.detach().cpu().numpy()
 
@@ -364,12 +390,15 @@ def run_ours(args, conf):
     roof = None
     if gemm_ms > 0:
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        roof = {"kernel": "ndjir::gemm::gemm_tc_kernel (tcgen05 3xTF32 MLP products, fused epilogues; small shapes on the FFMA kernel)",
+        roof = {"kernel": "ndjir::gemmh::gemm_h_kernel (tcgen05 kind::f16 products on TMA-fed split-fp16 operands, three "
+                          "tensor-core products per algorithmic product, fused epilogues; <= 8-wide shapes on the "
+                          "memory-bound corner kernels)",
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sustained"],
-                "traffic": profiled_traffic().get("gemm_tc_kernel_fwd_hidden_layer_dram_bytes_per_launch"),
-                "traffic_note": "DRAM bytes of one 262144x256x256 forward product (algorithmic 537 MB)",
-                "ceiling_3xtf32": pk["tf_sustained"] / 6.0, "frac_of_3xtf32_ceiling": ach / (pk["tf_sustained"] / 6.0),
+                "traffic": profiled_traffic().get("gemm_h_kernel_fwd_hidden_layer_dram_bytes_per_launch"),
+                "traffic_note": "DRAM bytes of one 262144x256x256 forward product (algorithmic 537 MB: 4 B per "
+                                "element in, 4 B out)",
+                "ceiling_3_products": pk["tf_sustained"] / 3.0, "frac_of_3_product_ceiling": ach / (pk["tf_sustained"] / 3.0),
                 "peak_source": pk["source"] + " (bf16 sustained)",
                 "launches_per_step": len(eng.prof_events), "ms_per_step_in_kernel": gemm_ms,
                 "share_of_step": gemm_ms / ms_step, "breakdown": breakdown,
@@ -381,18 +410,21 @@ def run_ours(args, conf):
     if rank == 0:
         cb = None
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference_run(conf, 1, 1, args.ref_rays)
-        cfg = workload(conf)
+            cb = cpu_reference_run(conf, 2, 1, args.ref_rays)
+        cfg = workload(conf, args.config)
         cfg["launch"] = ("one CUDA-graph replay per step (Engine.train_step_graphed)" if use_graph
                          else "eager: every kernel enqueued from the host")
         if world > 1:
             cfg["grid_gradient_exchange"] = ("sparse: all-gather of the per-sample scatter inputs, replicated scatter"
                                              if eng._sparse_grid() else "dense all-reduce of the table gradient")
-        cfg["parallelism"] = f"ray-sharded x{world}, replicated parameters, NCCL gradient all-reduce" if world > 1 else "1 GPU"
+        cfg["parallelism"] = (f"ray-sharded x{world} ({'one batch split along the rays' if strong else 'one full batch per rank'}), "
+                              f"replicated parameters, NCCL gradient all-reduce") if world > 1 else "1 GPU"
+        if strong:
+            cfg["rays_per_view_per_rank"] = R // world
         line = {"metric": "train_rays_per_sec_fwd_bwd", "value": value, "unit": "rays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-                "clocks": clk,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg, "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": len(LOSS_NAMES) * 4, "ms_per_step": ms_e2e},
                 "gpu_launches": launches * args.steps,
@@ -401,7 +433,15 @@ def run_ours(args, conf):
                 "loss": {k: float(v) for k, v in zip(LOSS_NAMES, loss_host)}}
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graphs hold NCCL work: tearing the communicator down underneath them can block at interpreter
+        # exit.  Everything has been printed; leave without the collective teardown once every rank is done.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if _REAL_STDOUT is not None:
+            _REAL_STDOUT.flush()
+        os._exit(0)
 
 
 def main():
@@ -419,6 +459,9 @@ def main():
     ap.add_argument("--config", default="default")
     ap.add_argument("--ref-rays", type=int, default=256, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-full", action="store_true", help="reference arm: skip the one full-batch step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank renders its own full batch; strong = one batch sharded along the rays")
     ap.add_argument("--rays", type=int, default=0, help="override rays per view (debugging)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying "
                     "the captured CUDA graph of the step")

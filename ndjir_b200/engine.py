@@ -889,9 +889,8 @@ class Engine:
         ~1 ms per step - tools/exp/graph_step.py).  Inputs (device or pinned-host tensors) are copied into static
         device buffers, the returned loss tensor is the graph's static output.  The host scalars baked into the kernel
         arguments (cos_anneal_ratio, the light-visibility gain) and the input shapes key the cache: a change captures
-        a new graph.  Single-process only (the NCCL exchanges of the ray-sharded mode stay on the eager path)."""
-        if self.world_size > 1:
-            return self.train_step(camloc, raydir, color_gt, rnd, cos_anneal_ratio=cos_anneal_ratio)
+        a new graph.  With world_size > 1 the NCCL exchanges (mask sum, sparse grid-gradient all-gather, gradient
+        all-reduce) are captured inside the graph: every rank captures and replays the same sequence."""
         inputs = {"camloc": camloc, "raydir": raydir, "color_gt": color_gt, **rnd}
         key = (float(cos_anneal_ratio), float(self.params.pl_gain),
                tuple((k, tuple(v.shape)) for k, v in sorted(inputs.items())))

@@ -38,6 +38,12 @@ def main():
         losses = eng.train_step(dev(camloc), dev(raydir), dev(gt), {k: dev(v) for k, v in rnds[rank].items()})
         torch.cuda.synchronize()
         out[mode] = (eng.params.export_reference("grad"), losses.cpu().numpy())
+        # the same step replayed from ONE CUDA graph per rank, NCCL exchanges captured inside it
+        lg = eng.train_step_graphed(dev(camloc), dev(raydir), dev(gt), {k: dev(v) for k, v in rnds[rank].items()})
+        lg = eng.train_step_graphed(dev(camloc), dev(raydir), dev(gt), {k: dev(v) for k, v in rnds[rank].items()})
+        torch.cuda.synchronize()
+        gg = eng.params.export_reference("grad")
+        out[mode + "_graph"] = max(relerr(gg[k], out[mode][0][k]) for k in gg if np.abs(out[mode][0][k]).max() > 0)
     if rank == 0:
         # single process over the union: views of all ranks stacked along B
         conf1 = small_conf("default")
@@ -55,10 +61,13 @@ def main():
             g, l = out[mode]
             worst[mode] = max(relerr(g[k], g1[k]) for k in g1 if np.abs(g1[k]).max() > 0)
             worst[mode + "_loss"] = abs(float(l[0]) - float(l1[0])) / abs(float(l1[0]))
+            worst[mode + "_graph_vs_eager"] = out[mode + "_graph"]
         ok = all(v < 2e-4 for v in worst.values())
         print(("MULTI_GPU_OK " if ok else "MULTI_GPU_MISMATCH ") + str(worst), flush=True)
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)        # graphs hold NCCL work: skip the communicator teardown (it can block at exit)
 
 
 if __name__ == "__main__":
