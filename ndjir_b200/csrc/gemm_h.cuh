@@ -111,6 +111,9 @@ __device__ __forceinline__ void amax_commit(float* amax, float mx) {
 
 extern int g_h_dbg;                                   // gemm_h.cu: profiling switches
 int launch_tc(const HArgs& a, cudaStream_t st);       // gemm_h.cu
+extern int g_h_pair;                                  // gemm_h2.cu: 1 = CTA-pair kernel for the activation-row products
+bool pair_eligible(const HArgs& a);                   // gemm_h2.cu
+int launch_pair(const HArgs& a, cudaStream_t st);     // gemm_h2.cu
 bool corner_shape(const HArgs& a);                    // h16_ops.cu
 int launch_corner(const HArgs& a, cudaStream_t st);   // h16_ops.cu
 

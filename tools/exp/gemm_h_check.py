@@ -173,6 +173,22 @@ def bench(M=262144, N=256, K=256, iters=20):
         print(f"{name:<40s} {t:.4f} ms  {flops / t / 1e9:.1f} TFLOP/s")
 
     fl = 2.0 * M * N * K
+    for pair in (0, 1):     # 1: CTA-pair kernel (cta_group::2)
+        _lib.call("ndjir_set_option", "mlp_h_pair", pair)
+        for precise in (0, 1):
+            run(f"fwd softplus precise={precise} pair={pair}", lambda: h16.gemm_h(
+                st(), M, N, K, h16.EPI_SOFTPLUS, A=bA.hmat(), B=bB.hmat(), precise=precise, Ch=bC.hmat(),
+                bias=bias.data_ptr()), fl)
+        run(f"dgrad mul_s pair={pair}", lambda: h16.gemm_h(
+            st(), M, N, K, h16.EPI_MUL_S, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), Hh=bH.hmat()), fl)
+        run(f"dgrad mul_s+U pair={pair}", lambda: h16.gemm_h(
+            st(), M, N, K, h16.EPI_MUL_S, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), Hh=bH.hmat(), Uh=bU.hmat()), fl)
+        run(f"adjoint pair={pair}", lambda: h16.gemm_h(
+            st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), C2h=bC2.hmat(), Hh=bH.hmat(),
+            Uh=bU.hmat()), fl)
+    _lib.call("ndjir_set_option", "mlp_h_pair", 0)
+    if "--short" in sys.argv:
+        return
     for dbg in (0, 1, 2, 3):
         _lib.call("ndjir_set_option", "mlp_h_dbg", dbg)
         for precise in (0, 1):
@@ -201,7 +217,30 @@ def bench(M=262144, N=256, K=256, iters=20):
     run("pack_h", lambda: bC.pack(src, st()), fl)
 
 
+def ncu_once(M=262144, N=256, K=256):
+    """one launch of every hidden-layer product type (for `ncu --set full -k regex:gemm_h_kernel`)"""
+    sc = h16.Scales(dev)
+    bA = h16.HBuf(M, K, dev, sc, "A"); bB = h16.HBuf(N, K, dev, sc, "B"); bH = h16.HBuf(M, N, dev, sc, "H")
+    bU = h16.HBuf(M, N, dev, sc, "U"); bC = h16.HBuf(M, N, dev, sc, "C"); bC2 = h16.HBuf(M, N, dev, sc, "C2")
+    for b in (bA, bB, bH, bU):
+        b.t.normal_(0, 0.1)
+    bias = torch.zeros(N, device=dev)
+    gW = torch.zeros((K, N), device=dev)
+    cs0 = torch.zeros(N, device=dev)
+    h16.gemm_h(st(), M, N, K, h16.EPI_SOFTPLUS, A=bA.hmat(), B=bB.hmat(), precise=1, Ch=bC.hmat(), bias=bias.data_ptr())
+    h16.gemm_h(st(), M, N, K, h16.EPI_MUL_S, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), Hh=bH.hmat())
+    h16.gemm_h(st(), M, N, K, h16.EPI_MUL_S, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), Hh=bH.hmat(), Uh=bU.hmat())
+    h16.gemm_h(st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), C2h=bC2.hmat(), Hh=bH.hmat(),
+               Uh=bU.hmat())
+    h16.gemm_h(st(), K, N, M, h16.EPI_ATOMIC, A=bA.hmat(), B=bC.hmat(), mn_major=True, split_k=148, C=gW.data_ptr(),
+               ldc=N, colsum=cs0.data_ptr())
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
+    if "--ncu" in sys.argv:
+        ncu_once()
+        sys.exit(0)
     if "--bench" in sys.argv:
         bench()
         sys.exit(0)
