@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(NDJIR_BLOCK) skinny_w_h_kernel(HArgs a) {
   for (int n = 0; n < NT; ++n) acc0[n] = acc1[n] = 0.f;
   if (rl < lanes) {
     const bool pair = (m + 1 < a.M) && (a.lda % 2 == 0);
+    const bool bvec = (NT == 4 || NT == 8) && a.b_cs == 1 && a.b_rs % 4 == 0 && a.N == NT &&
+                      (reinterpret_cast<uintptr_t>(a.B32) & 15) == 0;       // the narrow gradient row as 16-byte loads
 #pragma unroll 4
     for (long long k = k0 + rl; k < k1; k += lanes) {
       float x0, x1 = 0.f;
@@ -220,13 +222,21 @@ __global__ void __launch_bounds__(NDJIR_BLOCK) skinny_w_h_kernel(HArgs a) {
         x0 = __half2float(a.Ahi[k * a.lda + m]) + __half2float(a.Alo[k * a.lda + m]);
         if (m + 1 < a.M) x1 = __half2float(a.Ahi[k * a.lda + m + 1]) + __half2float(a.Alo[k * a.lda + m + 1]);
       }
+      float b[NT];
+      if (bvec) {
+#pragma unroll
+        for (int j = 0; j < NT / 4; ++j) {
+          float4 t = __ldg(reinterpret_cast<const float4*>(a.B32 + k * a.b_rs) + j);
+          b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < NT; ++n) b[n] = n < a.N ? __ldg(a.B32 + k * a.b_rs + (long long)n * a.b_cs) : 0.f;
+      }
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
-        if (n < a.N) {
-          float b = __ldg(a.B32 + k * a.b_rs + (long long)n * a.b_cs);
-          acc0[n] += x0 * b;
-          acc1[n] += x1 * b;
-        }
+        acc0[n] += x0 * b[n];
+        acc1[n] += x1 * b[n];
       }
     }
   }

@@ -375,6 +375,10 @@ int ndjir_set_option(const char* key, int value) {
       {"voxel_binned", &ndjir::g_voxel_binned},             // -1 auto, 0 never, 1 whenever possible (brick-ordered sweeps)
       {"voxel_bin_mb", &ndjir::g_voxel_bin_mb},             // brick size in MiB
       {"hash_coarse_private", &ndjir::g_hash_coarse_private},  // 0 off, 1 batches >= 2^20 points, 2 always
+      {"voxel_tma_bx", &ndjir::g_voxel_tma_bx},             // brick extent along x of the TMA sweep (8 or 16)
+      {"voxel_tma_l2", &ndjir::g_voxel_tma_l2},             // L2 promotion of its requests (0 none, 1 128 B, 2 256 B)
+      {"voxel_tma_dbg", &ndjir::g_voxel_tma_dbg},           // experiment switch of the TMA sweep
+      {"voxel_tma", &ndjir::g_voxel_tma},                   // 1: fine-brick TMA sweep for the D = 4 forward gather
       {"voxel_pair256", &ndjir::g_voxel_pair256},           // 256-bit z-pair loads in the binned gather (measured slower)
   };
   for (const Opt& o : opts) {

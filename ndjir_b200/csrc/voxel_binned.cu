@@ -29,15 +29,7 @@ int g_voxel_pair256 = 0;    // 256-bit loads for z-neighbour pairs that share a 
 
 namespace voxel_binned {
 
-constexpr int kMaxBins = 512;
 constexpr int kPlaceBlock = 256;
-constexpr long long kHeaderBytes = 8192;  // kMaxBins cursors + padding; records start 16-byte aligned
-
-struct Bins {
-  unsigned px, py;   // planes / rows per brick
-  unsigned nby;      // bricks along y
-  unsigned n;        // total
-};
 
 static Bins make_bins(const int* G, int D, int target_mb) {
   Bins b;
@@ -310,7 +302,7 @@ scatter_kernel(long long B, float* __restrict__ gf, const float* __restrict__ go
 
 long long workspace_bytes(long long n_points) {
   if (n_points < 0) return -1;
-  return kHeaderBytes + 32 * n_points;
+  return kHeaderBytes + 32 * n_points + kTailBytes;     // cursors | two record buffers | fine-brick offsets
 }
 
 bool shape_ok(long long B, const int* G, int D) {
@@ -329,8 +321,13 @@ bool worthwhile(long long B, const int* G, int D) {
 // when `payload` is given.  Also used by the Lanczos voxel family (lanczos_voxel.cu).
 int build_records(long long B, const float* query, const float* payload, const GridFrame& g, const int* G, int D,
                   void* ws, long long ws_bytes, cudaStream_t st, const float4** rec_out) {
+  return build_records_bins(B, query, payload, g, make_bins(G, D, g_voxel_bin_mb), ws, ws_bytes, st, rec_out);
+}
+
+int build_records_bins(long long B, const float* query, const float* payload, const GridFrame& g, const Bins& b,
+                       void* ws, long long ws_bytes, cudaStream_t st, const float4** rec_out) {
   if (!ws || ws_bytes < workspace_bytes(B) || (reinterpret_cast<uintptr_t>(ws) & 15)) return NDJIR_ERR_ARG;
-  Bins b = make_bins(G, D, g_voxel_bin_mb);
+  if (b.n > (unsigned)kMaxBins) return NDJIR_ERR_ARG;
   unsigned* cursors = reinterpret_cast<unsigned*>(ws);
   float4* rec = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + kHeaderBytes);
   cudaError_t e = cudaMemsetAsync(cursors, 0, kMaxBins * sizeof(unsigned), st);
@@ -367,6 +364,7 @@ int query(long long B, float* out, const float* query_, const float* feat, const
   if (B == 0) return NDJIR_OK;
   if (!shape_ok(B, G, D) || !out || !query_ || !feat) return NDJIR_ERR_ARG;
   GridFrame g = make_frame(G[0], G[1], G[2], mn, mx);
+  if (voxel_tma::eligible(B, G, D, feat, out)) return voxel_tma::query(B, out, query_, feat, g, G, accum, ws, ws_bytes, st);
   const float4* rec = nullptr;
   int rc = build_records(B, query_, nullptr, g, G, D, ws, ws_bytes, st, &rec);
   if (rc != NDJIR_OK) return rc;

@@ -495,6 +495,11 @@ class Engine:
                         **kw)
         elif ncols <= 8:       # narrow fp32 result (grid-feature gradient)
             self.gemm_h(rows, ncols, L.N, epi, A=dY.hmat(dycol, track=False), B32=b32, b_rs=b_rs, b_cs=b_cs, **kw)
+        elif 256 < ncols <= 264 and dX.f is not None and epi in (EPI_BIAS, EPI_ACCUM) and H is None and U is None:
+            # [feature(256) | x | normal] input gradients: one 256-wide tensor-core tile + a memory-bound pass for the few
+            # remaining columns (a second 256-wide tile would stream dY again for 3-6 outputs)
+            self.dgrad(rows, L, dY, dycol, dX, dxcol, epi, row0=row0, ncols=256, alpha=alpha, precise=precise)
+            self.dgrad(rows, L, dY, dycol, dX, dxcol + 256, epi, row0=row0 + 256, ncols=ncols - 256, alpha=alpha)
         else:
             self.gemm_h(rows, ncols, L.N, epi, A=dY.hmat(dycol, track=False), B=ps.W16(L, row0), precise=precise,
                         **kw)

@@ -111,7 +111,7 @@ def test_set_option_keys():
     """Every documented option key is accepted (host-only call), unknown keys are an argument error."""
     from ndjir_b200 import _lib
     defaults = {"scatter_aggregate": 0, "mlp_tensor_cores": 1, "mlp_cta_pair": 0, "mlp_presplit": 1, "mlp_fused_colsum": 1, "mlp_dbg": 0,
-                "mlp_mask_hi": 0, "mlp_h_dbg": 0, "mlp_h_pair": 0, "voxel_binned": -1, "voxel_bin_mb": 16, "voxel_pair256": 0, "hash_coarse_private": 1}
+                "mlp_mask_hi": 0, "mlp_h_dbg": 0, "mlp_h_pair": 0, "voxel_binned": -1, "voxel_bin_mb": 16, "voxel_pair256": 0, "voxel_tma": 0, "voxel_tma_bx": 16, "voxel_tma_l2": 1, "voxel_tma_dbg": 0, "hash_coarse_private": 1}
     for k, v in defaults.items():
         _lib.call("ndjir_set_option", k, v)
     import pytest

@@ -581,6 +581,7 @@ def test_empty_and_bad_arguments():
 # ---- brick-ordered (binned) voxel gather / scatter ----------------------------------------------------------------
 BINNED_CASES = [  # B, G, D, spread, brick MiB  (x-slab bricks; y-strip bricks when one x-plane exceeds the brick size)
     (1, (8, 8, 8), 4, 1.0, 1), (4097, (64, 64, 64), 4, 1.05, 1), (100_003, (64, 64, 64), 4, 1.3, 1),
+    (70_001, (50, 33, 72), 4, 1.2, 1), (1 << 18, (300, 20, 40), 4, 1.0, 1),
     (50_000, (4, 512, 512), 4, 1.0, 1), (30_000, (33, 17, 65), 2, 1.1, 1), (30_000, (40, 40, 40), 3, 1.0, 1),
     (1 << 20, (128, 128, 128), 4, 1.0, 2)]
 
@@ -598,7 +599,7 @@ def test_voxel_binned_matches_direct_and_reference(B, G, D, spread, mb):
     q, f, go, gg = dev(q_np), dev(f_np), dev(go_np), dev(gg_np)
     N = B * D
     wsb = call("ndjir_voxel_binned_workspace_bytes", B)
-    assert wsb == 8192 + 32 * B
+    assert wsb == 8192 + 32 * B + (1 << 21) + 64      # cursors | two record buffers | fine-brick offsets
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     call("ndjir_set_option", "voxel_bin_mb", mb)
     try:
@@ -623,6 +624,16 @@ def test_voxel_binned_matches_direct_and_reference(B, G, D, spread, mb):
         call("ndjir_voxel_grad_query_grad_feature_binned", B, b1, gg, go, q, list(G), D, MN, MX, ws, wsb, 0)
         ref.grad_query_grad_feature(N, b2.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, False)
         close(b1, b2, 1e-4, "binned gq_gf")
+        # the fine-brick TMA sweep (option voxel_tma; D = 4, >= 2^16 points, G >= 16) and the L2-window sweep agree
+        for bx in (16, 8):
+            call("ndjir_set_option", "voxel_tma", 1)
+            call("ndjir_set_option", "voxel_tma_bx", bx)
+            for accum in (0, 1):
+                o5 = torch.full((B, D), 7.0).cuda()
+                call("ndjir_voxel_query_on_voxel_binned", B, o5, q, f, list(G), D, MN, MX, accum, ws, wsb, 0)
+                close(o5, o2 + 7.0 if accum else o2, 1e-5, f"binned fwd (TMA brick sweep, bx={bx}) accum={accum}")
+        call("ndjir_set_option", "voxel_tma", 0)
+        call("ndjir_set_option", "voxel_tma_bx", 16)
         # the experiment switch of the gather sweep (256-bit z-pair loads) does not change results
         for key, val in (("voxel_pair256", 1),):
             call("ndjir_set_option", key, val)

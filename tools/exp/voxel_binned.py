@@ -73,6 +73,11 @@ for mb in [int(x) for x in args.mbs.split(",")]:
          t(lambda: call("ndjir_voxel_grad_feature_binned", B, gf, go, q, [G] * 3, D, MN, MX, 1, ws, wsb, 0)), 284)
     print(f"    max-norm rel. diff vs direct: fwd {err:.2e}, grad_feature {err2:.2e}", flush=True)
 call("ndjir_set_option", "voxel_bin_mb", 16)
+call("ndjir_set_option", "voxel_tma", 0)
+show("gather binned, 16 MiB bricks, L2-window sweep (voxel_tma=0)",
+     t(lambda: call("ndjir_voxel_query_on_voxel_binned", B, out, q, feat, [G] * 3, D, MN, MX, 0, ws, wsb, 0)), 156)
+print(f"    max-norm rel. diff vs direct: {(out - ref_out).abs().max().item() / ref_out.abs().max().item():.2e}")
+call("ndjir_set_option", "voxel_tma", 1)
 call("ndjir_set_option", "voxel_pair256", 1)
 show("gather binned, 16 MiB, 256-bit z-pair loads",
      t(lambda: call("ndjir_voxel_query_on_voxel_binned", B, out, q, feat, [G] * 3, D, MN, MX, 0, ws, wsb, 0)), 156)
