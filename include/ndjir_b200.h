@@ -510,6 +510,26 @@ int ndjir_loss_inv_denorm(const float* mask_sum, int N, float* inv_denorm, cudaS
 int ndjir_finalize_losses(float* losses, const float* mask_sum, int N, float inv_rays, float w_eik, float w_tv,
                           float w_bc, float w_ro, float w_sp, cudaStream_t stream);
 
+/* ==== full-frame inference driver, device side (python/renderer.py:212-272, python/helper.py:44-81) ==
+ * The chunk loop of render_image as device work driven by a DEVICE chunk counter (chunk_dev may be NULL = chunk 0), so
+ * that one captured CUDA graph is replayed per chunk without host round trips.  Pixel p = pixel0 + chunk * n_rays + i,
+ * x = p % W, y = p / W. */
+/* raydir[i] = normalize(R_c2w (K^-1 [x, y, 1])) in float64 like helper.generate_raydir_camloc; kinv9 / rot9: DEVICE
+ * row-major 3x3 doubles (inverse intrinsic, camera-to-world rotation) */
+int ndjir_generate_rays(int n_rays, int W, long long n_pixels, long long pixel0, const int* chunk_dev,
+                        const double* kinv9_dev, const double* rot9_dev, float* raydir, cudaStream_t stream);
+/* out[i] = lo + (hi - lo) * u_i, u_i in [0, 1) from a counter-based generator keyed by (seed, *counter_dev, i): the
+ * explicit random inputs of sample_points / pb_render (F.rand in the reference) without a host generator */
+int ndjir_uniform(long long n, float lo, float hi, long long seed, const int* counter_dev, float* out,
+                  cudaStream_t stream);
+/* image[p] = clip(color[i], 0, 1) for p < n_pixels (renderer.py:266-268) */
+int ndjir_store_chunk(int n_rays, long long n_pixels, long long pixel0, const int* chunk_dev, const float* color,
+                      float* image, cudaStream_t stream);
+int ndjir_counter_add(int* counter_dev, int step, cudaStream_t stream);
+/* points of the marching-cubes lattice (python/extract_by_mc.py:47-73: np.linspace(-radius, radius, G) per axis, x the
+ * slowest): point i lies on x-plane ix0 + (i / G^2) * ix_stride (the rank stride of a sharded extraction) */
+int ndjir_lattice_points(long long n, int G, int ix0, int ix_stride, float radius, float* pts, cudaStream_t stream);
+
 /* ==== split-fp16 MLP engine (csrc/gemm_h.cu, csrc/h16_ops.cu) ==============================================
  * The hidden activations and gradients of the MLPs (nnabla PF.affine + F.softplus chains, python/network.py:84-93,
  * 154-232) are STORED as two fp16 planes, value = (hi + lo) / scale with hi = fp16(x*scale), lo = fp16(x*scale - hi):

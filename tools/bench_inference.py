@@ -48,13 +48,18 @@ def timed(fn):
     return r, dt
 
 
-renderer.render_image(poses[0], intr[0], (160, 120), conf, n_rays=4000)       # warm-up: buffers, kernel attributes
-img, t_img = timed(lambda: renderer.render_image(poses[0], intr[0], (W, H), conf, n_rays=4000, rank=rank, world_size=world))
+pg = dist.group.WORLD if world > 1 else None
+# warm-up: buffers, kernel attributes, the captured per-chunk graph (same chunk size and frame as the timed call)
+renderer.render_image(poses[1], intr[1], (W, H), conf, n_rays=4000, rank=rank, world_size=world, process_group=pg)
+img, t_img = timed(lambda: renderer.render_image(poses[0], intr[0], (W, H), conf, n_rays=4000, rank=rank,
+                                                 world_size=world, process_group=pg))
 renderer.sdf_volume(conf, 16)
-vol, t_vol = timed(lambda: renderer.sdf_volume(conf, args.lattice, batch_size=1 << 22, rank=rank, world_size=world))
+vol, t_vol = timed(lambda: renderer.sdf_volume(conf, args.lattice, batch_size=1 << 22, rank=rank, world_size=world,
+                                               process_group=pg, gather=True))
 if rank == 0:
     G = args.lattice
-    out = {"config": "default.yaml, 512^3 x 4 voxel grid, synthetic DTU-shaped camera", "n_gpus": world,
+    out = {"config": "default.yaml, 512^3 x 4 voxel grid, synthetic DTU-shaped camera; chunks / x-planes dealt to the "
+                     "ranks, results summed onto rank 0 inside the timed region", "n_gpus": world,
            "render_image": {"resolution": [W, H], "rays": W * H, "chunk_rays": 4000, "seconds": t_img,
                             "rays_per_s": W * H / t_img, "finite": bool(torch.isfinite(img).all())},
            "sdf_lattice": {"grid": G, "points": G ** 3, "seconds": t_vol, "points_per_s": G ** 3 / t_vol,
@@ -63,4 +68,7 @@ if rank == 0:
     json.dump(out, open(args.out, "w"), indent=1)
     print(json.dumps(out))
 if world > 1:
-    dist.destroy_process_group()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)      # captured graphs: skip the communicator teardown
