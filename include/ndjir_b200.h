@@ -464,6 +464,30 @@ int ndjir_volume_render_backward(int n_rays, int N, int C, const float* w, long 
                                  long long ld_v, const float* dpix, long long ld_dpix, float* dV, long long ld_dv,
                                  int accum_dv, float* dw, long long ld_dw, cudaStream_t stream);
 
+/* ---- ONE fused kernel per ray segment for the compositing stage (python/renderer.py:54-91, 179-185; network.py:544-545;
+ *      csrc/render_segment.cu): forward = NeuS alpha of the N foreground samples + background alpha of the Nb background
+ *      samples + exclusive-cumprod transmittance (chunked warp scan over N + Nb samples) + weights + the volume-rendering
+ *      reduction of the C per-sample columns of V + the background colour; backward = weight gradients from both
+ *      reductions (V, and the C2 material attributes V2) and the background colour + the division-free suffix warp scan +
+ *      alpha backward (dsdf, dnormal += into the normal columns the same call wrote as part of dV, dgain += ) + background
+ *      density backward.  dweights / dalpha_fg / dalpha_bg are optional copies of the intermediates (NULL = not stored). */
+int ndjir_render_segment_forward(int n_rays, int N, int Nb, int C, const float* sdf, const float* normal, long long ld_n,
+                                 const float* raydir, const float* t_fg, const float* gain_param,
+                                 float cos_anneal_ratio, const float* mask, const float* bg_h0, long long ld_h,
+                                 const float* t_bg, const float* bg_raw, long long ld_raw, const float* V,
+                                 long long ld_v, float* alpha_fg, float* alpha_bg, float* weights, float* trans,
+                                 float* pix, long long ld_pix, float* colbg, cudaStream_t stream);
+int ndjir_render_segment_backward(int n_rays, int N, int Nb, int C, int C2, const float* sdf, const float* normal,
+                                  long long ld_n, const float* raydir, const float* t_fg, const float* gain_param,
+                                  float cos_anneal_ratio, const float* mask, const float* bg_h0, long long ld_h,
+                                  const float* t_bg, const float* bg_raw, long long ld_raw, const float* V,
+                                  long long ld_v, const float* V2, long long ld_v2, const float* weights,
+                                  const float* trans, const float* dpix, long long ld_dpix, const float* dpix2,
+                                  long long ld_dpix2, const float* dcolbg, float* dV, long long ld_dv, float* dV2,
+                                  long long ld_dv2, float* d_bg_raw, long long ld_draw, float* d_bg_h0, long long ld_dh,
+                                  float* dsdf, float* dnormal, long long ld_dn, float* dgain_param, float* dweights,
+                                  float* dalpha_fg, float* dalpha_bg, cudaStream_t stream);
+
 /* ---- per-sample material activations + priors (python/network.py:235-509, python/loss.py:70-176).
  *      raw (P,16): bc 0:3 | ii 3 | ro 4:6 | sp 6:12 | pl 12 | bc_ptb 13:16;  att (P,12): ii | rough | spec(3) |
  *      pl | bc*pl(3) | pad.  cfg10 (HOST): rough_lb, rough_prior, spec_prior, spec_scale, pl_gain, w_eik, w_bc,

@@ -986,8 +986,6 @@ class Engine:
         # ---------------- NeuS alpha, background, compositing ----------------
         alpha_fg = self.buf("alpha_fg", P, 1)
         gain_p = ps.data.data_ptr() + 4 * ps.gain_off
-        self.call("ndjir_neus_alpha_forward", P, N, P_(alpha_fg), P_(sdf), P_(nrm), 3, P_(raydir), P_(t_fg), gain_p,
-                  float(cos_anneal_ratio))
         bgc = conf.background_network
         rows_bg = NR * Nb
         nbg0 = pe_dim(4, bgc.pe_bands0)
@@ -1008,16 +1006,16 @@ class Engine:
         self.fill_cols(Xbg1, Dfb + 7, P_(vpe_bg), vpe_bg.shape[1], nvpe, rows_bg, rep=Nb)
         bgraw = self.buf("bg_raw", rows_bg, 4)
         acts_bg1 = self.mlp_forward("bg1", "bg1", Xbg1, rows_bg, [(Mat(f=bgraw), 0)])
+        # one fused kernel per ray: NeuS alpha, background alpha, transmittance scan, weights, VR([feature | x | normal]),
+        # background colour (renderer.py:54-91; csrc/render_segment.cu)
         alpha_bg = self.buf("alpha_bg", rows_bg, 1)
-        self.call("ndjir_bg_alpha_forward", rows_bg, Nb, P_(alpha_bg), P_(dens), 1, P_(t_bg))
         w = self.buf("w", NR, S)
         T = self.buf("T", NR, S)
-        self.call("ndjir_composite_forward", NR, N, Nb, P_(alpha_fg), P_(maskv), P_(alpha_bg), P_(w), P_(T))
         colbg = self.buf("colbg", NR, 3)
-        self.call("ndjir_bg_color_forward", NR, Nb, P_(w, N), S, P_(bgraw), 4, P_(colbg))
-        # ---------------- pixel quantities ----------------
         pix = self.buf("pix", NR, LDO)
-        self.call("ndjir_volume_render_forward", NR, N, Df + 6, P_(w), S, O.fptr(), LDO, P_(pix), LDO)
+        self.call("ndjir_render_segment_forward", NR, N, Nb, Df + 6, P_(sdf), P_(nrm), 3, P_(raydir), P_(t_fg), gain_p,
+                  float(cos_anneal_ratio), P_(maskv), P_(dens), 1, P_(t_bg), P_(bgraw), 4, O.fptr(), LDO, P_(alpha_fg),
+                  P_(alpha_bg), P_(w), P_(T), P_(pix), LDO, P_(colbg))
         nhat = self.buf("nhat", NR, 3)
         self.call("ndjir_pixel_normal_forward", NR, P_(pix, Df + 3), LDO, float(r.eps_normal), P_(nhat))
         # ---------------- per-sample heads ----------------
@@ -1139,17 +1137,22 @@ class Engine:
         self.copy2d(NR, 3, P_(d_nhat), 3, P_(dpix, Df + 3), LDO, accum=1)
         self.call("ndjir_pixel_normal_backward", NR, P_(pix, Df + 3), LDO, float(r.eps_normal), P_(d_nhat),
                   P_(dpix, Df + 3), LDO, 0)
-        # weights gradient
-        dw = self.buf("dw", NR, S, zero=True)
+        # one fused kernel per ray: weight gradients of both reductions and the background colour, the suffix scan of the
+        # compositing backward, NeuS alpha backward (dsdf, dnormal, dgain) and background density backward
         dO = self.mat("dO", P, Df + 6, "fa", grad=True)
-        self.call("ndjir_volume_render_backward", NR, N, Df + 6, P_(w), S, O.fptr(), LDO, P_(dpix), LDO, dO.fptr(), LDO, 0,
-                  P_(dw), S)
         dATT = self.buf("dATT", P, 12)
-        self.call("ndjir_volume_render_backward", NR, N, 12, P_(w), S, P_(ATT), 12, P_(d_attpix), 12, P_(dATT), 12, 0,
-                  P_(dw), S)
         d_bgraw = self.buf("d_bgraw", rows_bg, 4)
-        self.call("ndjir_bg_color_backward", NR, Nb, P_(w, N), S, P_(bgraw), 4, P_(d_colbg), P_(dw, N), S,
-                  P_(d_bgraw), 4)
+        d_dens = self.buf("d_dens", rows_bg, 1)
+        dsdf = self.buf("dsdf", P, 1)
+        g_gain = ps.grad.data_ptr() + 4 * ps.gain_off
+        dw = self.buf("dw", NR, S) if keep else None
+        dalpha_fg = self.buf("dalpha_fg", P, 1) if keep else None
+        dalpha_bg = self.buf("dalpha_bg", rows_bg, 1) if keep else None
+        self.call("ndjir_render_segment_backward", NR, N, Nb, Df + 6, 12, P_(sdf), P_(nrm), 3, P_(raydir), P_(t_fg),
+                  gain_p, float(cos_anneal_ratio), P_(maskv), P_(dens), 1, P_(t_bg), P_(bgraw), 4, O.fptr(), LDO,
+                  P_(ATT), 12, P_(w), P_(T), P_(dpix), LDO, P_(d_attpix), 12, P_(d_colbg), dO.fptr(), LDO, P_(dATT), 12,
+                  P_(d_bgraw), 4, P_(d_dens), 1, P_(dsdf), dO.fptr(Df + 3), LDO, g_gain,
+                  P_(dw) if keep else None, P_(dalpha_fg) if keep else None, P_(dalpha_bg) if keep else None)
         # material heads
         dRAW = self.buf("dRAW", P, 16)
         dRAWm = Mat(f=dRAW)
@@ -1159,20 +1162,9 @@ class Engine:
         for name, col in (("ii", 3), ("ro", 4), ("sp", 6)):
             self.mlp_backward(name, name, O, P, acts[name], [(dRAWm, col)], dX=dO, accum_dx=True, dx_cols=Df + 6)
         self.mlp_backward("pl", "pl", Xpl, P, acts["pl"], [(dRAWm, 12)], dX=dO, accum_dx=True, dx_cols=Df + 6)
-        # compositing + alpha
-        dalpha_fg = self.buf("dalpha_fg", P, 1)
-        dalpha_bg = self.buf("dalpha_bg", rows_bg, 1)
-        self.call("ndjir_composite_backward", NR, N, Nb, P_(alpha_fg), P_(maskv), P_(alpha_bg), P_(T), P_(dw),
-                  P_(dalpha_fg), P_(dalpha_bg))
-        dsdf = self.buf("dsdf", P, 1, zero=True)
-        g_gain = ps.grad.data_ptr() + 4 * ps.gain_off
-        self.call("ndjir_neus_alpha_backward", P, N, P_(dalpha_fg), P_(sdf), P_(nrm), 3, P_(raydir), P_(t_fg), gain_p,
-                  float(cos_anneal_ratio), P_(dsdf), dO.fptr(Df + 3), LDO, g_gain)
         # background networks
         dXbg1 = self.mat("dXbg1", rows_bg, Dfb, "a", grad=True)
         self.mlp_backward("bg1", "bg1", Xbg1, rows_bg, acts_bg1, [(Mat(f=d_bgraw), 0)], dX=dXbg1, dx_cols=Dfb)
-        d_dens = self.buf("d_dens", rows_bg, 1)
-        self.call("ndjir_bg_alpha_backward", rows_bg, Nb, P_(dalpha_bg), P_(dens), 1, P_(t_bg), P_(d_dens), 1)
         self.mlp_backward("bg0", "bg0", Xbg0, rows_bg, acts_bg0, [(Mat(f=d_dens), 0), (dXbg1, 0)])
         # geometric network: second-order terms from d L / d normal, then the standard sweep
         nbar = self.buf("nbar", P, 3)

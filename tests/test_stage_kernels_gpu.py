@@ -337,3 +337,77 @@ def test_shade_forward_backward_128_directions():
     close(d_att[:, :9], A.grad.numpy()[:, :9], "d attpix")
     close(d_nh, n.grad.numpy(), "d nhat")
     close(d_cb, cb.grad.numpy(), "d colbg")
+
+
+@pytest.mark.parametrize("N,Nb,C,cos_anneal", [(128, 32, 262, 0.0), (128, 32, 262, 0.7), (16, 4, 70, 1.0), (40, 0, 9, 0.3)])
+def test_render_segment_fused_equals_stage_kernels(N, Nb, C, cos_anneal):
+    """ndjir_render_segment_{forward,backward} (ONE kernel per ray: alpha, background alpha, scan, weights, reductions,
+    background colour, and the whole backward of that stage) against the separate stage kernels it fuses
+    (ndjir_neus_alpha_*, ndjir_bg_alpha_*, ndjir_composite_*, ndjir_volume_render_*, ndjir_bg_color_*), which the tests
+    above and the engine parity tests check against the reference's arithmetic: forward bit-identical, backward 1e-6."""
+    rng = np.random.RandomState(11)
+    NR, C2 = 37, 12
+    P, S, rb = NR * N, N + Nb, NR * max(Nb, 1)
+    ld_v = C + 2
+    sdf = dev(rng.randn(P, 1) * 0.05)
+    nrm = dev(rng.randn(P, 3))
+    rd = rng.randn(NR, 3); rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    raydir = dev(rd)
+    t_fg = dev(np.sort(rng.rand(NR, N + 1) * 2 + 1, axis=1))
+    t_bg = dev(np.sort(rng.rand(NR, Nb + 1) * 20 + 3, axis=1))
+    gain = dev(np.array([0.3, 0, 0, 0]))
+    mask = dev((rng.rand(NR) > 0.2).astype(f32))
+    h0 = dev(rng.randn(rb, 1) * 0.02)
+    raw = dev(rng.randn(rb, 4))
+    V = dev(rng.randn(P, ld_v))
+    V2 = dev(rng.randn(P, C2))
+    z = lambda *s: torch.zeros(s, device="cuda")
+    # ---- separate kernels ----
+    a_fg, a_bg, w, T, pix, colbg = z(P, 1), z(rb, 1), z(NR, S), z(NR, S), z(NR, ld_v), z(NR, 3)
+    call("ndjir_neus_alpha_forward", P, N, a_fg, sdf, nrm, 3, raydir, t_fg, gain, cos_anneal)
+    if Nb:
+        call("ndjir_bg_alpha_forward", rb, Nb, a_bg, h0, 1, t_bg)
+    call("ndjir_composite_forward", NR, N, Nb, a_fg, mask, a_bg if Nb else None, w, T)
+    if Nb:
+        call("ndjir_bg_color_forward", NR, Nb, w.data_ptr() + 4 * N, S, raw, 4, colbg)
+    call("ndjir_volume_render_forward", NR, N, C, w, S, V, ld_v, pix, ld_v)
+    # ---- fused ----
+    a_fg2, a_bg2, w2, T2, pix2, colbg2 = z(P, 1), z(rb, 1), z(NR, S), z(NR, S), z(NR, ld_v), z(NR, 3)
+    call("ndjir_render_segment_forward", NR, N, Nb, C, sdf, nrm, 3, raydir, t_fg, gain, cos_anneal, mask,
+         h0 if Nb else None, 1, t_bg if Nb else None, raw if Nb else None, 4, V, ld_v, a_fg2, a_bg2 if Nb else None, w2, T2,
+         pix2, ld_v, colbg2 if Nb else None)
+    torch.cuda.synchronize()
+    for name, x, y in (("alpha_fg", a_fg, a_fg2), ("alpha_bg", a_bg, a_bg2), ("w", w, w2), ("T", T, T2),
+                       ("pix", pix[:, :C], pix2[:, :C]), ("colbg", colbg, colbg2)):
+        assert torch.equal(x, y), name
+    assert float(w.sum()) > 0
+    # ---- backward ----
+    dpix, dpix2, dcol = dev(rng.randn(NR, ld_v)), dev(rng.randn(NR, C2)), dev(rng.randn(NR, 3))
+    dV, dV2, dw = z(P, ld_v), z(P, C2), z(NR, S)
+    call("ndjir_volume_render_backward", NR, N, C, w, S, V, ld_v, dpix, ld_v, dV, ld_v, 0, dw, S)
+    call("ndjir_volume_render_backward", NR, N, C2, w, S, V2, C2, dpix2, C2, dV2, C2, 0, dw, S)
+    draw = z(rb, 4)
+    if Nb:
+        call("ndjir_bg_color_backward", NR, Nb, w.data_ptr() + 4 * N, S, raw, 4, dcol, dw.data_ptr() + 4 * N, S, draw, 4)
+    da_fg, da_bg = z(P, 1), z(rb, 1)
+    call("ndjir_composite_backward", NR, N, Nb, a_fg, mask, a_bg if Nb else None, T, dw, da_fg, da_bg if Nb else None)
+    dsdf, dg, dh0 = z(P, 1), z(4), z(rb, 1)
+    dn = dV[:, 3:6]                 # the normal columns live inside dV, as in the engine
+    call("ndjir_neus_alpha_backward", P, N, da_fg, sdf, nrm, 3, raydir, t_fg, gain, cos_anneal, dsdf, dn.data_ptr(), ld_v, dg)
+    if Nb:
+        call("ndjir_bg_alpha_backward", rb, Nb, da_bg, h0, 1, t_bg, dh0, 1)
+    dVf, dV2f, drawf, dh0f, dsdff, dgf = z(P, ld_v), z(P, C2), z(rb, 4), z(rb, 1), z(P, 1), z(4)
+    dwf, daf, dabf = z(NR, S), z(P, 1), z(rb, 1)
+    call("ndjir_render_segment_backward", NR, N, Nb, C, C2, sdf, nrm, 3, raydir, t_fg, gain, cos_anneal, mask,
+         h0 if Nb else None, 1, t_bg if Nb else None, raw if Nb else None, 4, V, ld_v, V2, C2, w, T, dpix, ld_v, dpix2, C2,
+         dcol if Nb else None, dVf, ld_v, dV2f, C2, drawf if Nb else None, 4, dh0f if Nb else None, 1, dsdff,
+         dVf.data_ptr() + 12, ld_v, dgf, dwf, daf, dabf if Nb else None)
+    torch.cuda.synchronize()
+
+    def close(name, x, y, tol=1e-6):
+        sc = max(float(y.abs().max()), 1e-30)
+        assert float((x - y).abs().max()) <= tol * sc, (name, float((x - y).abs().max()), sc)
+    close("dV", dVf[:, :C], dV[:, :C]); close("dV2", dV2f, dV2); close("dw", dwf, dw, 2e-6)
+    close("dalpha_fg", daf, da_fg, 1e-5); close("dsdf", dsdff, dsdf, 1e-5); close("dgain", dgf[:1], dg[:1], 1e-4)
+    if Nb:
+        close("draw", drawf[:, :3], draw[:, :3]); close("dalpha_bg", dabf, da_bg, 1e-5); close("dh0", dh0f, dh0, 1e-5)
