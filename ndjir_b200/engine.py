@@ -352,7 +352,10 @@ class Engine:
             t = torch.empty((max(rows, self._reserve), cols), dtype=dtype, device=self.device)
             self._bufs[key] = t
         if zero:
-            t[:rows].zero_()
+            if dtype == torch.float32:
+                self.call("ndjir_fill", rows * cols, t, 0.0)
+            else:
+                t[:rows].zero_()
         return t
 
     # ------------------------------------------------------------------------------------------------
@@ -373,11 +376,8 @@ class Engine:
                 h = h16.HBuf(need, cols, self.device, self.scales, slot or name, init=2.0 ** 24 if grad else 16.0)
             m = Mat(f, h, cols, need)
             self._bufs[key] = m
-        if zero:
-            if m.f is not None:
-                m.f[:rows].zero_()
-            if m.h is not None:
-                m.h.t[:, :rows].zero_()
+        if zero and m.f is not None:      # (planes are always rewritten by sync_h / an epilogue before they are read)
+            self.call("ndjir_fill", rows * m.f.shape[1], m.f, 0.0)
         return m
 
     def sync_h(self, m, cols, rows, col=0):
