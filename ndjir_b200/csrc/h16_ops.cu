@@ -39,17 +39,32 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_n_h_kernel(HArgs a, int 
     float acc[NT];
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[n] = 0.f;
-#pragma unroll 2
-    for (int k = sub * 8; k < K8; k += 64) {
-      uint4 xh = __ldg(reinterpret_cast<const uint4*>(rh + k));
-      uint4 xl = __ldg(reinterpret_cast<const uint4*>(rl + k));
-      float2 x0 = join2(xh.x, xl.x), x1 = join2(xh.y, xl.y), x2 = join2(xh.z, xl.z), x3 = join2(xh.w, xl.w);
+    // every 16-byte piece this lane owns of the row is requested before any is used (the kernel is bound by bytes in
+    // flight: 8 lanes x 64-column steps, up to 4 steps = 128 B per lane outstanding)
+    for (int kb = 0; kb < K8; kb += 256) {
+      uint4 xh[4], xl[4];
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        float4 b0 = *reinterpret_cast<const float4*>(Bs + n * Kp + k);
-        float4 b1 = *reinterpret_cast<const float4*>(Bs + n * Kp + k + 4);
-        acc[n] += x0.x * b0.x + x0.y * b0.y + x1.x * b0.z + x1.y * b0.w + x2.x * b1.x + x2.y * b1.y + x3.x * b1.z +
-                  x3.y * b1.w;
+      for (int j = 0; j < 4; ++j) {
+        const int k = kb + j * 64 + sub * 8;
+        if (k < K8) {
+          xh[j] = __ldg(reinterpret_cast<const uint4*>(rh + k));
+          xl[j] = __ldg(reinterpret_cast<const uint4*>(rl + k));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kb + j * 64 + sub * 8;
+        if (k < K8) {
+          float2 x0 = join2(xh[j].x, xl[j].x), x1 = join2(xh[j].y, xl[j].y), x2 = join2(xh[j].z, xl[j].z),
+                 x3 = join2(xh[j].w, xl[j].w);
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            float4 b0 = *reinterpret_cast<const float4*>(Bs + n * Kp + k);
+            float4 b1 = *reinterpret_cast<const float4*>(Bs + n * Kp + k + 4);
+            acc[n] += x0.x * b0.x + x0.y * b0.y + x1.x * b0.z + x1.y * b0.w + x2.x * b1.x + x2.y * b1.y + x3.x * b1.z +
+                      x3.y * b1.w;
+          }
+        }
       }
     }
     for (int k = K8 + sub; k < a.K; k += 8) {
@@ -190,56 +205,76 @@ __global__ void __launch_bounds__(NDJIR_BLOCK) skinny_k_h_kernel(HArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// C[m, n] += alpha * sum_k A(k, m) * B32(k, n), N <= 8.  A block walks a slab of the k rows; its 256 threads are
-// (row lane, pair of adjacent m): a warp reads 128 contiguous bytes of each plane per row.  Row lanes are folded through
-// shared memory, then one atomic per (m, n) and block.
+// C[m, n] += alpha * sum_k A(k, m) * B32(k, n), N <= 8.  A block walks a slab of the k rows in steps of RB rows; its
+// 256 threads are (row lane, pair of adjacent m): a warp reads 128 contiguous bytes of each plane per row.  The narrow
+// B rows of a step are staged in shared memory once (instead of NT broadcast loads per thread and row) and all A loads
+// of a step are issued before any is used.  Row lanes are folded through shared memory, one atomic per (m, n) and block.
 template <int NT>
 __global__ void __launch_bounds__(NDJIR_BLOCK) skinny_w_h_kernel(HArgs a) {
+  constexpr int RB = 64;                               // rows per step
   __shared__ float red[NDJIR_BLOCK * 2 * NT];
+  __shared__ float sb[RB * NT];
   const int pairs = (a.M + 1) / 2;                     // <= blockDim.x (checked by the launcher)
   const int lanes = blockDim.x / pairs;
   const int pr = threadIdx.x % pairs, rl = threadIdx.x / pairs;
   const int m = pr * 2;
-  const long long per = (a.K + gridDim.x - 1) / gridDim.x;
+  const long long per = ((a.K + gridDim.x - 1) / gridDim.x + RB - 1) / RB * RB;
   const long long k0 = (long long)blockIdx.x * per, k1 = k0 + per < a.K ? k0 + per : a.K;
   const float inv_a = 1.f / dev_scalar(a.a_scale);
   float acc0[NT], acc1[NT];
 #pragma unroll
   for (int n = 0; n < NT; ++n) acc0[n] = acc1[n] = 0.f;
-  if (rl < lanes) {
-    const bool pair = (m + 1 < a.M) && (a.lda % 2 == 0);
-    const bool bvec = (NT == 4 || NT == 8) && a.b_cs == 1 && a.b_rs % 4 == 0 && a.N == NT &&
-                      (reinterpret_cast<uintptr_t>(a.B32) & 15) == 0;       // the narrow gradient row as 16-byte loads
-#pragma unroll 4
-    for (long long k = k0 + rl; k < k1; k += lanes) {
-      float x0, x1 = 0.f;
-      if (pair) {
-        uint32_t xh = __ldg(reinterpret_cast<const uint32_t*>(a.Ahi + k * a.lda + m));
-        uint32_t xl = __ldg(reinterpret_cast<const uint32_t*>(a.Alo + k * a.lda + m));
-        float2 t = join2(xh, xl);
-        x0 = t.x; x1 = t.y;
-      } else {
-        x0 = __half2float(a.Ahi[k * a.lda + m]) + __half2float(a.Alo[k * a.lda + m]);
-        if (m + 1 < a.M) x1 = __half2float(a.Ahi[k * a.lda + m + 1]) + __half2float(a.Alo[k * a.lda + m + 1]);
-      }
-      float b[NT];
-      if (bvec) {
+  const bool pair = (m + 1 < a.M) && (a.lda % 2 == 0);
+  constexpr int UNR = 8;
+  for (long long kb = k0; kb < k1; kb += RB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < RB * NT; i += blockDim.x) {
+      const long long k = kb + i / NT;
+      const int n = i % NT;
+      sb[i] = (k < k1 && n < a.N) ? __ldg(a.B32 + k * a.b_rs + (long long)n * a.b_cs) : 0.f;
+    }
+    __syncthreads();
+    if (rl < lanes) {
+      for (int r0 = rl; r0 < RB; r0 += lanes * UNR) {
+        uint32_t xh[UNR], xl[UNR];
 #pragma unroll
-        for (int j = 0; j < NT / 4; ++j) {
-          float4 t = __ldg(reinterpret_cast<const float4*>(a.B32 + k * a.b_rs) + j);
-          b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
+        for (int u = 0; u < UNR; ++u) {
+          const int rr = r0 + u * lanes;
+          const long long k = kb + rr;
+          xh[u] = xl[u] = 0u;
+          if (rr < RB && k < k1) {
+            if (pair) {
+              xh[u] = __ldg(reinterpret_cast<const uint32_t*>(a.Ahi + k * a.lda + m));
+              xl[u] = __ldg(reinterpret_cast<const uint32_t*>(a.Alo + k * a.lda + m));
+            } else {
+              const unsigned short h0 = __half_as_ushort(a.Ahi[k * a.lda + m]), l0 = __half_as_ushort(a.Alo[k * a.lda + m]);
+              unsigned short h1 = 0, l1 = 0;
+              if (m + 1 < a.M) {
+                h1 = __half_as_ushort(a.Ahi[k * a.lda + m + 1]);
+                l1 = __half_as_ushort(a.Alo[k * a.lda + m + 1]);
+              }
+              xh[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              xl[u] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+          }
         }
-      } else {
 #pragma unroll
-        for (int n = 0; n < NT; ++n) b[n] = n < a.N ? __ldg(a.B32 + k * a.b_rs + (long long)n * a.b_cs) : 0.f;
-      }
+        for (int u = 0; u < UNR; ++u) {
+          const int rr = r0 + u * lanes;
+          if (rr < RB) {
+            const float2 t = join2(xh[u], xl[u]);
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        acc0[n] += x0 * b[n];
-        acc1[n] += x1 * b[n];
+            for (int n = 0; n < NT; ++n) {
+              const float bv = sb[rr * NT + n];
+              acc0[n] += t.x * bv;
+              acc1[n] += t.y * bv;
+            }
+          }
+        }
       }
     }
   }
+  __syncthreads();
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
     red[(threadIdx.x * 2) * NT + n] = acc0[n];
