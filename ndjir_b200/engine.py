@@ -204,6 +204,30 @@ class ParamStore:
             out[f"grid.{k}"] = v.detach().cpu().numpy()
         return out
 
+    def reference_dict(self):
+        """Current parameters in the layout scene.init_params / load_reference use."""
+        ex = self.export_reference("data")
+        P = {net: [(ex[f"{net}.W{i}"], ex[f"{net}.b{i}"]) for i, _ in self._ref_layers(net)] for net in NET_ORDER}
+        P["geo_gain"] = ex["geo_gain"]
+        P["pl_gain"] = np.asarray([self.pl_gain], np.float32)
+        P["grid"] = {k: ex[f"grid.{k}"] for k in self.grid}
+        return P
+
+    def save_parameters(self, path):
+        """`nn.save_parameters(path)` of the reference (python/train.py:101): an nnabla `.h5` parameter file with the
+        reference's scope names, (in, out) weight layout, `need_grad` / `index` attributes (ndjir_b200/h5lite.py)."""
+        from . import h5lite, nnabla_names
+        params = nnabla_names.to_nnabla(self.conf, self.reference_dict())
+        # the photogrammetric-light gain is scheduled, not trained (network.py:418-420)
+        ng = {n: not n.endswith("photogrammetric-light-network/gain") for n in params}
+        h5lite.save_parameters(path, params, need_grad=ng)
+
+    def load_parameters(self, path):
+        """`nn.load_parameters(path)` of the reference (python/render_image.py:43, extract_by_mc.py:300)."""
+        from . import h5lite, nnabla_names
+        params, _ = h5lite.load_parameters(path)
+        self.load_reference(nnabla_names.from_nnabla(self.conf, params))
+
     def zero_grad(self, stream=None):
         """zero every gradient buffer with the library's own fill kernel (ndjir_fill) on `stream`"""
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
