@@ -36,8 +36,21 @@ constexpr int BK = 64;                          // halfs per K block: 128-byte r
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES = BN * BK * 2;            // 32 KB
 constexpr int SLOT_BYTES = A_BYTES + B_BYTES;   // 48 KB
-constexpr int NSLOT = 4;
-constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + 1024;
+constexpr int MAX_NSLOT = 4;
+constexpr int EPI_WARPS = 8;
+// Per-epilogue configuration.  The products with operand-reading epilogues (sigmoid factor, adjoint) are bound by their
+// epilogue, not by the main loop (a 3-slot ring changes their time by < 2 %), so they trade one ring slot for 64 KB of
+// TMA staging (4 plane slots of 2 KB per epilogue warp: WIDE, whenever a second operand U or a second result C2 is
+// staged); the others keep 4 slots and stage 2 planes (result C, in place over the operand H if there is one).
+template <int EPI, bool WIDE>
+struct Cfg {
+  static constexpr bool HEAVY = (EPI == EPI_MUL_S || EPI == EPI_ADJ);
+  static constexpr bool STAGED = (EPI == EPI_BIAS || EPI == EPI_SOFTPLUS || HEAVY);
+  static constexpr int NSLOT = WIDE ? 3 : 4;
+  static constexpr int STG_WARP = STAGED ? (WIDE ? 4 : 2) * STG_PLANE : 0;
+  static constexpr int STG_OFF = NSLOT * SLOT_BYTES;
+  static constexpr int SMEM = STG_OFF + EPI_WARPS * STG_WARP + 1024;
+};
 constexpr int EPI_WARP0 = 2;
 constexpr int EPI_THREADS = 256;
 constexpr int CS_WARP0 = EPI_WARP0 + EPI_THREADS / 32;   // column-sum warps (weight-gradient products with a bias gradient)
@@ -55,17 +68,20 @@ struct HParams {
   int b_box_rows;        // rows (K-major) / columns (MN-major) of B staged per slot: 64, 128 or 256
   int vec_epi;           // every epilogue operand allows 32-byte accesses at 16-column granularity
   int do_colsum;         // MN-major mode: a.colsum[n] += column sums of B (the bias gradient of the layer)
+  int tma_epi;           // operands and results of the epilogue move by TMA through shared memory (gemm_h_epi.cuh)
   int dbg;
 };
 
-template <int EPI>
+template <int EPI, bool WIDE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
-              const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, HParams p) {
+              const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+              const __grid_constant__ EpiMaps em, HParams p) {
+  constexpr int NSLOT = Cfg<EPI, WIDE>::NSLOT;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * NSLOT + 4];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_NSLOT + 4 + EPI_WARPS];
   __shared__ uint32_t tmem_base_sh;
-  __shared__ float colsum_sh[BN];
+  __shared__ float colsum_sh[EPI == EPI_ATOMIC ? BN : 4];   // only the weight-gradient products carry column sums
 
   const HArgs& a = p.a;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -73,9 +89,9 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   auto bar_full = [&](int s) { return smem_u32(&bars[s]); };
-  auto bar_empty = [&](int s) { return smem_u32(&bars[NSLOT + s]); };
-  auto bar_acc_full = [&](int b) { return smem_u32(&bars[2 * NSLOT + b]); };
-  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[2 * NSLOT + 2 + b]); };
+  auto bar_empty = [&](int s) { return smem_u32(&bars[MAX_NSLOT + s]); };
+  auto bar_acc_full = [&](int b) { return smem_u32(&bars[2 * MAX_NSLOT + b]); };
+  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[2 * MAX_NSLOT + 2 + b]); };
   auto a_dst = [&](int s) { return smem_base + s * SLOT_BYTES; };
   auto b_dst = [&](int s) { return smem_base + s * SLOT_BYTES + A_BYTES; };
 
@@ -88,10 +104,13 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
       mbar_init(bar_acc_full(b), 1);
       mbar_init(bar_acc_empty(b), EPI_THREADS);
     }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(smem_u32(&bars[2 * MAX_NSLOT + 4 + w]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapAhi); prefetch_tmap(&mapAlo); prefetch_tmap(&mapBhi); prefetch_tmap(&mapBlo);
+    if (p.tma_epi)
+      for (int i = 0; i < 8; ++i) prefetch_tmap(&em.m[i]);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
@@ -299,6 +318,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
     const float inv_h = 1.f / dev_scalar(a.H.scale), inv_u = 1.f / dev_scalar(a.U.scale);
     float mx = 0.f, mx2 = 0.f;
     uint32_t tile_it = 0;
+    const int ew = warp - EPI_WARP0;
+    const uint32_t stg = smem_base + Cfg<EPI, WIDE>::STG_OFF + ew * Cfg<EPI, WIDE>::STG_WARP;
+    const uint32_t ld_bar = smem_u32(&bars[2 * MAX_NSLOT + 4 + ew]);
+    uint32_t ld_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int m0, n0, kb0, nkb;
       item_info(item, m0, n0, kb0, nkb);
@@ -307,15 +330,21 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
       const int buf = tile_it & 1;
       const long long m = m0 + q * 32 + lane;
       const bool row_ok = m < a.M;
-      mbar_wait(bar_acc_full(buf), (tile_it >> 1) & 1);
-      tc_fence_after();
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<EPI>(a, p.vec_epi, p.dbg, m, row_ok, n0, n_valid, tacc, chalf, need_u, need_b, inv_ab, sc, sc2, inv_h,
-                         inv_u, mx, mx2);
+      if (Cfg<EPI, WIDE>::STAGED && p.tma_epi) {
+        epilogue_tile_tma<EPI>(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), (tile_it >> 1) & 1, m0 + q * 32,
+                               row_ok, n0, n_valid, tacc, chalf, need_u, need_b, inv_ab, sc, sc2, inv_h, inv_u, mx, mx2);
+      } else {
+        mbar_wait(bar_acc_full(buf), (tile_it >> 1) & 1);
+        tc_fence_after();
+        epilogue_tile<EPI>(a, p.vec_epi, p.dbg, m, row_ok, n0, n_valid, tacc, chalf * 16, 32, need_u, need_b, inv_ab, sc,
+                           sc2, inv_h, inv_u, mx, mx2);
+      }
       tc_fence_before();
       mbar_arrive(bar_acc_empty(buf));
       ++tile_it;
     }
+    if (Cfg<EPI, WIDE>::STAGED && p.tma_epi && lane == 0) bulk_wait0();     // shared memory stays valid until TMA has read it
     if (EPI != EPI_ATOMIC) {
       amax_commit(a.C.amax, mx);
       if (EPI == EPI_ADJ) amax_commit(a.C2.amax, mx2);
@@ -333,7 +362,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled get_encode() {
+PFN_cuTensorMapEncodeTiled get_encode() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -350,7 +379,7 @@ static PFN_cuTensorMapEncodeTiled get_encode() {
 static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // K-major plane: `rows` rows of `k` halfs (row stride ld); box = 64 halfs x box_rows rows
-static bool map_kmajor(CUtensorMap* map, const __half* base, long long k, long long rows, long long ld, int box_rows) {
+bool map_kmajor(CUtensorMap* map, const __half* base, long long k, long long rows, long long ld, int box_rows) {
   PFN_cuTensorMapEncodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
@@ -387,8 +416,24 @@ static bool map_mnmajor2(CUtensorMap* map, const __half* base, long long mn, lon
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPI>
-static int launch_epi(const HArgs& a, cudaStream_t st) {
+// plane of an epilogue operand / result: N columns x M rows of halfs, boxes of 32 columns x 32 rows, 64-byte swizzle
+static bool map_epi(CUtensorMap* map, const __half* base, long long cols, long long rows, long long ld) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)STG_COLS, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int g_h_tma_epi = 1;   // 0: every epilogue on the direct (row-per-lane global access) path
+
+template <int EPI, bool WIDE>
+static int launch_epi_w(const HArgs& a, cudaStream_t st) {
+  constexpr int SMEM_BYTES = Cfg<EPI, WIDE>::SMEM;
   HParams p;
   p.a = a;
   p.dbg = g_h_dbg;
@@ -416,9 +461,28 @@ static int launch_epi(const HArgs& a, cudaStream_t st) {
     else ok = ok && map_mnmajor2(&mBh, a.Bhi, a.N, a.K, a.ldb) && map_mnmajor2(&mBl, a.Blo, a.N, a.K, a.ldb);
   }
   if (!ok) return NDJIR_ERR_ARG;
+  // TMA epilogue: K-major products whose epilogue operands and results are all split-fp16 planes
+  EpiMaps em;
+  for (int i = 0; i < 8; ++i) em.m[i] = mAh;
+  p.tma_epi = 0;
+  if (Cfg<EPI, WIDE>::STAGED && g_h_tma_epi && !a.mn && a.N % 16 == 0) {
+    auto plane_ok = [&](const Op& o) { return o.hi && o.lo && al16p(o.hi) && al16p(o.lo) && o.ldh % 8 == 0; };
+    auto absent = [&](const Op& o) { return !o.hi && !o.f; };
+    bool eligible = plane_ok(a.C) && (a.bias == nullptr || al16p(a.bias));
+    if (Cfg<EPI, WIDE>::HEAVY) eligible = eligible && plane_ok(a.H) && (absent(a.U) || plane_ok(a.U));
+    if (EPI == EPI_ADJ) eligible = eligible && plane_ok(a.U) && plane_ok(a.C2);
+    if (eligible) {
+      bool mok = map_epi(&em.m[4], a.C.hi, a.N, a.M, a.C.ldh) && map_epi(&em.m[5], a.C.lo, a.N, a.M, a.C.ldh);
+      if (Cfg<EPI, WIDE>::HEAVY) mok = mok && map_epi(&em.m[0], a.H.hi, a.N, a.M, a.H.ldh) && map_epi(&em.m[1], a.H.lo, a.N, a.M, a.H.ldh);
+      if (Cfg<EPI, WIDE>::HEAVY && a.U.hi)
+        mok = mok && map_epi(&em.m[2], a.U.hi, a.N, a.M, a.U.ldh) && map_epi(&em.m[3], a.U.lo, a.N, a.M, a.U.ldh);
+      if (EPI == EPI_ADJ) mok = mok && map_epi(&em.m[6], a.C2.hi, a.N, a.M, a.C2.ldh) && map_epi(&em.m[7], a.C2.lo, a.N, a.M, a.C2.ldh);
+      p.tma_epi = mok ? 1 : 0;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_h_kernel<EPI, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -431,8 +495,14 @@ static int launch_epi(const HArgs& a, cudaStream_t st) {
   p.splits = (p.nkb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   int n_items = p.m_tiles * p.n_tiles * p.splits;
   int grid = n_items < NDJIR_NUM_SMS ? n_items : NDJIR_NUM_SMS;
-  gemm_h_kernel<EPI><<<grid, THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  gemm_h_kernel<EPI, WIDE><<<grid, THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, em, p);
   NDJIR_RETURN_LAST_ERROR();
+}
+
+template <int EPI>
+static int launch_epi(const HArgs& a, cudaStream_t st) {
+  const bool wide = (EPI == EPI_ADJ) || (EPI == EPI_MUL_S && (a.U.hi || a.U.f));
+  return wide ? launch_epi_w<EPI, true>(a, st) : launch_epi_w<EPI, false>(a, st);
 }
 
 int launch_tc(const HArgs& a, cudaStream_t st) {
@@ -446,6 +516,7 @@ int launch_tc(const HArgs& a, cudaStream_t st) {
   if (a.epi == EPI_MUL_S && !a.H.f && !a.H.hi) return NDJIR_ERR_ARG;
   if (a.epi == EPI_ADJ && ((!a.H.f && !a.H.hi) || (!a.U.f && !a.U.hi) || (!a.C2.f && !a.C2.hi))) return NDJIR_ERR_ARG;
   if (pair_eligible(a)) return launch_pair(a, st);
+  if (resident_eligible(a)) return launch_resident(a, st);
   switch (a.epi) {
     case EPI_BIAS: return launch_epi<EPI_BIAS>(a, st);
     case EPI_SOFTPLUS: return launch_epi<EPI_SOFTPLUS>(a, st);

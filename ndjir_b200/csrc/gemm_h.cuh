@@ -110,10 +110,14 @@ __device__ __forceinline__ void amax_commit(float* amax, float mx) {
 }
 
 extern int g_h_dbg;                                   // gemm_h.cu: profiling switches
+extern int g_h_tma_epi;                               // gemm_h.cu: 1 = TMA-staged epilogue where the operands allow it
 int launch_tc(const HArgs& a, cudaStream_t st);       // gemm_h.cu
 extern int g_h_pair;                                  // gemm_h2.cu: 1 = CTA-pair kernel for the activation-row products
 bool pair_eligible(const HArgs& a);                   // gemm_h2.cu
 int launch_pair(const HArgs& a, cudaStream_t st);     // gemm_h2.cu
+extern int g_h_resident;                              // gemm_h3.cu: 1 = resident-weight kernel for K-major products, K <= 256
+bool resident_eligible(const HArgs& a);               // gemm_h3.cu
+int launch_resident(const HArgs& a, cudaStream_t st); // gemm_h3.cu
 bool corner_shape(const HArgs& a);                    // h16_ops.cu
 int launch_corner(const HArgs& a, cudaStream_t st);   // h16_ops.cu
 

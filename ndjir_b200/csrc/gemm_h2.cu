@@ -269,7 +269,7 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       mbar_wait(bar_acc_full(buf), (tile_it >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<EPI>(a, p.vec_epi, p.dbg, m, row_ok, n0, n_valid, tacc, chalf, need_u, need_b, inv_ab, sc, sc2, inv_h,
+      epilogue_tile<EPI>(a, p.vec_epi, p.dbg, m, row_ok, n0, n_valid, tacc, chalf * 16, 32, need_u, need_b, inv_ab, sc, sc2, inv_h,
                          inv_u, mx, mx2);
       tc_fence_before();
       if (leader) mbar_arrive(bar_acc_empty(buf));

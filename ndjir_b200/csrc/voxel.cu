@@ -371,6 +371,8 @@ int ndjir_set_option(const char* key, int value) {
       {"mlp_dbg", &ndjir::gemm::g_mlp_dbg},                 // profiling switches of the tcgen05 kernel
       {"mlp_mask_hi", &ndjir::gemm::g_mlp_mask_hi},
       {"mlp_h_dbg", &ndjir::gemmh::g_h_dbg},                // profiling switches of the split-fp16 tcgen05 kernel
+      {"mlp_h_tma_epi", &ndjir::gemmh::g_h_tma_epi},        // 0: row-per-lane global accesses in every epilogue
+      {"mlp_h_resident", &ndjir::gemmh::g_h_resident},      // 1 (default): resident-weight kernel (csrc/gemm_h3.cu)
       {"mlp_h_pair", &ndjir::gemmh::g_h_pair},              // 1: CTA-pair (cta_group::2) kernel for activation-row products
       {"voxel_binned", &ndjir::g_voxel_binned},             // -1 auto, 0 never, 1 whenever possible (brick-ordered sweeps)
       {"voxel_bin_mb", &ndjir::g_voxel_bin_mb},             // brick size in MiB

@@ -173,29 +173,59 @@ def bench(M=262144, N=256, K=256, iters=20):
         print(f"{name:<40s} {t:.4f} ms  {flops / t / 1e9:.1f} TFLOP/s")
 
     fl = 2.0 * M * N * K
-    for pair in (0, 1):     # 1: CTA-pair kernel (cta_group::2)
-        _lib.call("ndjir_set_option", "mlp_h_pair", pair)
+    _lib.call("ndjir_set_option", "mlp_h_resident", 0)
+    for pair in (0, 1):     # 1: TMA-staged epilogue, 0: direct row-per-lane epilogue (reported as "resident=" for history)
+        _lib.call("ndjir_set_option", "mlp_h_tma_epi", pair)
         for precise in (0, 1):
-            run(f"fwd softplus precise={precise} pair={pair}", lambda: h16.gemm_h(
+            run(f"fwd softplus precise={precise} tma_epi={pair}", lambda: h16.gemm_h(
                 st(), M, N, K, h16.EPI_SOFTPLUS, A=bA.hmat(), B=bB.hmat(), precise=precise, Ch=bC.hmat(),
                 bias=bias.data_ptr()), fl)
-        run(f"dgrad mul_s pair={pair}", lambda: h16.gemm_h(
+        run(f"dgrad mul_s tma_epi={pair}", lambda: h16.gemm_h(
             st(), M, N, K, h16.EPI_MUL_S, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), Hh=bH.hmat()), fl)
-        run(f"dgrad mul_s+U pair={pair}", lambda: h16.gemm_h(
+        run(f"dgrad mul_s+U tma_epi={pair}", lambda: h16.gemm_h(
             st(), M, N, K, h16.EPI_MUL_S, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), Hh=bH.hmat(), Uh=bU.hmat()), fl)
-        run(f"adjoint pair={pair}", lambda: h16.gemm_h(
+        run(f"adjoint tma_epi={pair}", lambda: h16.gemm_h(
+            st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), C2h=bC2.hmat(), Hh=bH.hmat(),
+            Uh=bU.hmat()), fl)
+    _lib.call("ndjir_set_option", "mlp_h_resident", 0)
+    _lib.call("ndjir_set_option", "mlp_h_pair", 1)
+    for dbg in ():
+        _lib.call("ndjir_set_option", "mlp_h_dbg", dbg)
+        for precise in (0, 1):
+            run(f"fwd softplus precise={precise} dbg={dbg} PAIR", lambda: h16.gemm_h(
+                st(), M, N, K, h16.EPI_SOFTPLUS, A=bA.hmat(), B=bB.hmat(), precise=precise, Ch=bC.hmat(),
+                bias=bias.data_ptr()), fl)
+        run(f"adjoint dbg={dbg} PAIR", lambda: h16.gemm_h(
             st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), C2h=bC2.hmat(), Hh=bH.hmat(),
             Uh=bU.hmat()), fl)
     _lib.call("ndjir_set_option", "mlp_h_pair", 0)
+    _lib.call("ndjir_set_option", "mlp_h_dbg", 0)
+    for pf in ():
+        for dbg in (0, 1, 3):
+            _lib.call("ndjir_set_option", "mlp_h_dbg", dbg | (pf << 4))
+            run(f"fwd softplus dbg={dbg} resident=1 prefetch={pf}", lambda: h16.gemm_h(
+                st(), M, N, K, h16.EPI_SOFTPLUS, A=bA.hmat(), B=bB.hmat(), precise=1, Ch=bC.hmat(),
+                bias=bias.data_ptr()), fl)
+        _lib.call("ndjir_set_option", "mlp_h_dbg", pf << 4)
+        run(f"adjoint resident=1 prefetch={pf}", lambda: h16.gemm_h(
+            st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), C2h=bC2.hmat(), Hh=bH.hmat(),
+            Uh=bU.hmat()), fl)
+    for res in (1, 0):
+        _lib.call("ndjir_set_option", "mlp_h_resident", res)
+        for dbg in (1, 2, 3):
+            _lib.call("ndjir_set_option", "mlp_h_dbg", dbg)
+            for precise in ((0, 1) if not res else (1,)):
+                run(f"fwd softplus precise={precise} dbg={dbg} resident={res}", lambda: h16.gemm_h(
+                    st(), M, N, K, h16.EPI_SOFTPLUS, A=bA.hmat(), B=bB.hmat(), precise=precise, Ch=bC.hmat(),
+                    bias=bias.data_ptr()), fl)
+            if dbg == 1:
+                run(f"adjoint dbg={dbg} resident={res}", lambda: h16.gemm_h(
+                    st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), C2h=bC2.hmat(), Hh=bH.hmat(),
+                    Uh=bU.hmat()), fl)
+    _lib.call("ndjir_set_option", "mlp_h_dbg", 0)
+    _lib.call("ndjir_set_option", "mlp_h_resident", 0)
     if "--short" in sys.argv:
         return
-    for dbg in (0, 1, 2, 3):
-        _lib.call("ndjir_set_option", "mlp_h_dbg", dbg)
-        for precise in (0, 1):
-            run(f"fwd softplus precise={precise} dbg={dbg}", lambda: h16.gemm_h(
-                st(), M, N, K, h16.EPI_SOFTPLUS, A=bA.hmat(), B=bB.hmat(), precise=precise, Ch=bC.hmat(),
-                bias=bias.data_ptr()), fl)
-    _lib.call("ndjir_set_option", "mlp_h_dbg", 0)
     for precise in (0, 1):
         run(f"dgrad mul_s+U precise={precise}", lambda: h16.gemm_h(
             st(), M, N, K, h16.EPI_MUL_S, A=bA.hmat(), B=bB.hmat(), precise=precise, Ch=bC.hmat(), Hh=bH.hmat(),
@@ -237,7 +267,30 @@ def ncu_once(M=262144, N=256, K=256):
     torch.cuda.synchronize()
 
 
+def ncu_resident(M=262144, N=256, K=256):
+    """resident-weight kernel: forward, forward without epilogue traffic and with one product per K step, adjoint"""
+    sc = h16.Scales(dev)
+    bA = h16.HBuf(M, K, dev, sc, "A"); bB = h16.HBuf(N, K, dev, sc, "B"); bH = h16.HBuf(M, N, dev, sc, "H")
+    bU = h16.HBuf(M, N, dev, sc, "U"); bC = h16.HBuf(M, N, dev, sc, "C"); bC2 = h16.HBuf(M, N, dev, sc, "C2")
+    for b in (bA, bB, bH, bU):
+        b.t.normal_(0, 0.1)
+    bias = torch.zeros(N, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for dbg in (0, 3, 1):
+        _lib.call("ndjir_set_option", "mlp_h_dbg", dbg)
+        flush.zero_()
+        h16.gemm_h(st(), M, N, K, h16.EPI_SOFTPLUS, A=bA.hmat(), B=bB.hmat(), precise=1, Ch=bC.hmat(), bias=bias.data_ptr())
+    _lib.call("ndjir_set_option", "mlp_h_dbg", 0)
+    flush.zero_()
+    h16.gemm_h(st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), Ch=bC.hmat(), C2h=bC2.hmat(), Hh=bH.hmat(),
+               Uh=bU.hmat())
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
+    if "--ncu-res" in sys.argv:
+        ncu_resident()
+        sys.exit(0)
     if "--ncu" in sys.argv:
         ncu_once()
         sys.exit(0)
