@@ -13,79 +13,121 @@ namespace gemmh {
 constexpr int SK_WARPS = 8;
 
 // ---------------------------------------------------------------------------------------------------------------
+// C (M x N <= 8) = A(split) B32.  Eight lanes share a row (each owns 8 of every 64 columns); a lane works on SK_R rows
+// at once so that one read of the staged B serves SK_R x 4 rows of the warp: ncu showed the first version (one row per
+// lane group) bound by its shared-memory wavefronts (L1 data pipe 77-87 %, DRAM 18-40 %), not by the operand stream.
+// B is staged as [n][64-column step][half][lane][4 floats]: the eight lanes of a row read 128 contiguous bytes per
+// instruction, the four row groups of a warp the same bytes (broadcast).  The row sums are folded across the eight
+// lanes by recursive halving (7 shuffles for 8 outputs instead of 24), which leaves output n in lane n.
+template <int NT>
+struct SkR {
+  static constexpr int R = NT >= 8 ? 2 : 4;     // rows per lane: bounded by the NT x R accumulators a lane can hold
+};
+
+template <int NT>
+__device__ __forceinline__ float fold8(float (&acc)[NT], int sub) {
+  int cnt = NT;
+#pragma unroll
+  for (int d = 4; d >= 1; d >>= 1) {
+    if (cnt > d) {                 // halving stage: the lanes with bit d set keep the upper half of the outputs
+      const int half = cnt / 2;
+      const bool up = (sub & d) != 0;
+#pragma unroll
+      for (int t = 0; t < half; ++t) {
+        const float send = up ? acc[t] : acc[t + half];
+        const float keep = up ? acc[t + half] : acc[t];
+        acc[t] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+      }
+      cnt = half;
+    } else {
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        if (t < cnt) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], d);
+    }
+  }
+  return acc[0];
+}
+
 template <int NT, int EPI>
-__global__ void __launch_bounds__(SK_WARPS * 32) skinny_n_h_kernel(HArgs a, int vec) {
-  // B staged as [NT][Kp] (k contiguous): the eight lanes of a row read consecutive 32-byte pieces, the four row groups
-  // of a warp the same addresses (broadcast): conflict-free
+__global__ void __launch_bounds__(SK_WARPS * 32, 2) skinny_n_h_kernel(HArgs a, int vec) {
+  constexpr int SK_R = SkR<NT>::R;
   extern __shared__ __align__(16) float Bs[];
-  const int Kp = (a.K + 7) & ~7;
-  for (int i = threadIdx.x; i < Kp * NT; i += blockDim.x) {
-    int n = i / Kp, k = i - n * Kp;
+  const int steps = (a.K + 63) / 64;
+  for (int i = threadIdx.x; i < steps * 64 * NT; i += blockDim.x) {
+    // i = ((n * steps + j) * 2 + half) * 32 + lane8 * 4 + e   <->   k = j * 64 + lane8 * 8 + half * 4 + e
+    const int e = i & 3, l8 = (i >> 2) & 7, hf = (i >> 5) & 1, nj = i >> 6;
+    const int j = nj % steps, n = nj / steps;
+    const int k = j * 64 + l8 * 8 + hf * 4 + e;
     Bs[i] = (n < a.N && k < a.K) ? __ldg(a.B32 + (long long)k * a.b_rs + (long long)n * a.b_cs) : 0.f;
   }
   __syncthreads();
   const float inv_a = 1.f / dev_scalar(a.a_scale);
   const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-  const long long row0 = ((long long)blockIdx.x * SK_WARPS + (threadIdx.x >> 5)) * 4 + grp;
-  const long long row_stride = (long long)gridDim.x * SK_WARPS * 4;
+  const long long rows_per_block = (long long)SK_WARPS * 4 * SK_R;
   const int K8 = vec ? (a.K & ~7) : 0;
-  const long long rounds = (a.M + row_stride - 1) / row_stride;
-  for (long long r = 0; r < rounds; ++r) {
-    const long long m = row0 + r * row_stride;
-    const bool active = m < a.M;
-    const long long mm = active ? m : a.M - 1;
-    const __half* rh = a.Ahi + mm * a.lda;
-    const __half* rl = a.Alo + mm * a.lda;
-    float acc[NT];
+  for (long long blk = blockIdx.x; blk * rows_per_block < a.M; blk += gridDim.x) {
+    const long long m0 = blk * rows_per_block + ((threadIdx.x >> 5) * 4 + grp) * SK_R;
+    const __half* rh[SK_R];
+    const __half* rl[SK_R];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
-    // every 16-byte piece this lane owns of the row is requested before any is used (the kernel is bound by bytes in
-    // flight: 8 lanes x 64-column steps, up to 4 steps = 128 B per lane outstanding)
-    for (int kb = 0; kb < K8; kb += 256) {
-      uint4 xh[4], xl[4];
+    for (int r = 0; r < SK_R; ++r) {
+      const long long mm = m0 + r < a.M ? m0 + r : a.M - 1;
+      rh[r] = a.Ahi + mm * a.lda;
+      rl[r] = a.Alo + mm * a.lda;
+    }
+    float acc[SK_R][NT];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kb + j * 64 + sub * 8;
-        if (k < K8) {
-          xh[j] = __ldg(reinterpret_cast<const uint4*>(rh + k));
-          xl[j] = __ldg(reinterpret_cast<const uint4*>(rl + k));
+    for (int r = 0; r < SK_R; ++r)
+#pragma unroll
+      for (int n = 0; n < NT; ++n) acc[r][n] = 0.f;
+    for (int j = 0; j < steps; ++j) {
+      const int k = j * 64 + sub * 8;
+      if (k < K8) {
+        uint4 xh[SK_R], xl[SK_R];
+#pragma unroll
+        for (int r = 0; r < SK_R; ++r) {
+          xh[r] = __ldg(reinterpret_cast<const uint4*>(rh[r] + k));
+          xl[r] = __ldg(reinterpret_cast<const uint4*>(rl[r] + k));
         }
-      }
+        float x[SK_R][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kb + j * 64 + sub * 8;
-        if (k < K8) {
-          float2 x0 = join2(xh[j].x, xl[j].x), x1 = join2(xh[j].y, xl[j].y), x2 = join2(xh[j].z, xl[j].z),
-                 x3 = join2(xh[j].w, xl[j].w);
+        for (int r = 0; r < SK_R; ++r) {
+          const float2 x0 = join2(xh[r].x, xl[r].x), x1 = join2(xh[r].y, xl[r].y), x2 = join2(xh[r].z, xl[r].z),
+                       x3 = join2(xh[r].w, xl[r].w);
+          x[r][0] = x0.x; x[r][1] = x0.y; x[r][2] = x1.x; x[r][3] = x1.y;
+          x[r][4] = x2.x; x[r][5] = x2.y; x[r][6] = x3.x; x[r][7] = x3.y;
+        }
 #pragma unroll
-          for (int n = 0; n < NT; ++n) {
-            float4 b0 = *reinterpret_cast<const float4*>(Bs + n * Kp + k);
-            float4 b1 = *reinterpret_cast<const float4*>(Bs + n * Kp + k + 4);
-            acc[n] += x0.x * b0.x + x0.y * b0.y + x1.x * b0.z + x1.y * b0.w + x2.x * b1.x + x2.y * b1.y + x3.x * b1.z +
-                      x3.y * b1.w;
-          }
+        for (int n = 0; n < NT; ++n) {
+          const float* bp = Bs + ((n * steps + j) * 2) * 32 + sub * 4;
+          const float4 b0 = *reinterpret_cast<const float4*>(bp);
+          const float4 b1 = *reinterpret_cast<const float4*>(bp + 32);
+#pragma unroll
+          for (int r = 0; r < SK_R; ++r)
+            acc[r][n] += x[r][0] * b0.x + x[r][1] * b0.y + x[r][2] * b0.z + x[r][3] * b0.w + x[r][4] * b1.x +
+                         x[r][5] * b1.y + x[r][6] * b1.z + x[r][7] * b1.w;
         }
       }
     }
+    // columns the 16-byte path does not cover (K % 8 != 0 or unaligned planes)
     for (int k = K8 + sub; k < a.K; k += 8) {
-      float x = __half2float(rh[k]) + __half2float(rl[k]);
+      const int j = k >> 6, l8 = (k >> 3) & 7, hf = (k >> 2) & 1, e = k & 3;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) acc[n] += x * Bs[n * Kp + k];
+      for (int r = 0; r < SK_R; ++r) {
+        const float xv = __half2float(rh[r][k]) + __half2float(rl[r][k]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[r][n] += xv * Bs[((n * steps + j) * 2 + hf) * 32 + l8 * 4 + e];
+      }
     }
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 1);
-      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 2);
-      acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], 4);
-    }
-    if (active && sub < a.N) {
-      float v = 0.f;
-#pragma unroll
-      for (int n = 0; n < NT; ++n) if (sub == n) v = acc[n];
-      v *= inv_a;
-      float* cp = a.C.f + m * a.C.ldf + sub;
-      if (EPI == EPI_BIAS) *cp = a.alpha * v + (a.bias ? __ldg(a.bias + sub) : 0.f);
-      else *cp += a.alpha * v;
+    for (int r = 0; r < SK_R; ++r) {
+      const float v = fold8<NT>(acc[r], sub) * inv_a;
+      const long long m = m0 + r;
+      if (m < a.M && sub < a.N && sub < NT) {
+        float* cp = a.C.f + m * a.C.ldf + sub;
+        if (EPI == EPI_BIAS) *cp = a.alpha * v + (a.bias ? __ldg(a.bias + sub) : 0.f);
+        else *cp += a.alpha * v;
+      }
     }
   }
 }
@@ -312,10 +354,11 @@ bool corner_shape(const HArgs& a) { return which_corner(a) != 0; }
 template <int NT>
 static void launch_skinny_n(const HArgs& a, cudaStream_t st) {
   int vec = al16s(a.Ahi) && al16s(a.Alo) && a.lda % 8 == 0;
-  long long blocks = (a.M + SK_WARPS * 4 - 1) / (SK_WARPS * 4);
-  long long cap = (long long)NDJIR_NUM_SMS * 16;
+  const long long rows_per_block = (long long)SK_WARPS * 4 * SkR<NT>::R;
+  long long blocks = (a.M + rows_per_block - 1) / rows_per_block;
+  long long cap = (long long)NDJIR_NUM_SMS * 8;
   int grid = (int)(blocks < cap ? blocks : cap);
-  size_t smem = (size_t)((a.K + 7) & ~7) * NT * sizeof(float);
+  size_t smem = (size_t)((a.K + 63) / 64) * 64 * NT * sizeof(float);
   if (a.epi == EPI_BIAS) skinny_n_h_kernel<NT, EPI_BIAS><<<grid, SK_WARPS * 32, smem, st>>>(a, vec);
   else skinny_n_h_kernel<NT, EPI_ACCUM><<<grid, SK_WARPS * 32, smem, st>>>(a, vec);
 }
