@@ -46,9 +46,17 @@ template <int EPI, bool WIDE>
 struct Cfg {
   static constexpr bool HEAVY = (EPI == EPI_MUL_S || EPI == EPI_ADJ);
   static constexpr bool STAGED = (EPI == EPI_BIAS || EPI == EPI_SOFTPLUS || HEAVY);
+  // weight-gradient products (MN-major, atomic epilogue), WIDE: one work item covers 256 rows of A^T (two 128-row
+  // halves, one 256-column accumulator each - all of TMEM), so the dZ tile it stages serves both halves: L2 -> SM
+  // traffic per product 805 -> 537 MB.  The accumulators are single-buffered then; with one or two long K ranges per
+  // CTA nothing is lost.
+  static constexpr bool TALL = (EPI == EPI_ATOMIC) && WIDE;
+  static constexpr int TM = TALL ? 2 * BM : BM;
+  static constexpr int A_PIECE = TM * BK * 2;
+  static constexpr int SLOT = A_PIECE + B_BYTES;
   static constexpr int NSLOT = WIDE ? 3 : 4;
   static constexpr int STG_WARP = STAGED ? (WIDE ? 4 : 2) * STG_PLANE : 0;
-  static constexpr int STG_OFF = NSLOT * SLOT_BYTES;
+  static constexpr int STG_OFF = NSLOT * SLOT;
   static constexpr int SMEM = STG_OFF + EPI_WARPS * STG_WARP + 1024;
 };
 constexpr int EPI_WARP0 = 2;
@@ -78,6 +86,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
               const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
               const __grid_constant__ EpiMaps em, HParams p) {
   constexpr int NSLOT = Cfg<EPI, WIDE>::NSLOT;
+  constexpr bool TALL = Cfg<EPI, WIDE>::TALL;
+  constexpr int TM = Cfg<EPI, WIDE>::TM;               // rows of the A side per work item
+  constexpr int A_PIECE = Cfg<EPI, WIDE>::A_PIECE;
+  constexpr int SLOT = Cfg<EPI, WIDE>::SLOT;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_NSLOT + 4 + EPI_WARPS];
   __shared__ uint32_t tmem_base_sh;
@@ -92,8 +104,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
   auto bar_empty = [&](int s) { return smem_u32(&bars[MAX_NSLOT + s]); };
   auto bar_acc_full = [&](int b) { return smem_u32(&bars[2 * MAX_NSLOT + b]); };
   auto bar_acc_empty = [&](int b) { return smem_u32(&bars[2 * MAX_NSLOT + 2 + b]); };
-  auto a_dst = [&](int s) { return smem_base + s * SLOT_BYTES; };
-  auto b_dst = [&](int s) { return smem_base + s * SLOT_BYTES + A_BYTES; };
+  auto a_dst = [&](int s) { return smem_base + s * SLOT; };
+  auto b_dst = [&](int s) { return smem_base + s * SLOT + A_PIECE; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) {
@@ -130,7 +142,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
     int rest = item / p.m_tiles;
     int ntile = rest % p.n_tiles;
     int sp = rest / p.n_tiles;
-    m0 = mt * BM;
+    // weight gradients: only the m-tile-0 items carry the bias-gradient column sums; rotating the row tile by the round
+    // gives every CTA its share of them (co-running neighbours still share one K range, i.e. the same dZ tiles in L2)
+    if (a.mn && gridDim.x % p.m_tiles == 0) mt = (mt + item / (int)gridDim.x) % p.m_tiles;
+    m0 = mt * TM;
     n0 = ntile * BN;
     kb0 = sp * p.kb_per_split;
     int kb1 = min(p.nkb_total, kb0 + p.kb_per_split);
@@ -141,7 +156,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       const int b_chunks = p.b_box_rows / 64;
-      const uint32_t tx_bytes = A_BYTES + (uint32_t)p.b_box_rows * 128u;
+      const uint32_t tx_bytes = A_PIECE + (uint32_t)p.b_box_rows * 128u;
       uint32_t it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int m0, n0, kb0, nkb;
@@ -162,7 +177,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
               tma_load_3d(a_dst(s), ma, 0, k0, m0 / 64, bar_full(s));
             } else {
 #pragma unroll
-              for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst(s) + c * CHUNK_BYTES, ma, m0 + c * 64, k0, bar_full(s));
+              for (int c = 0; c < TM / 64; ++c) tma_load_2d(a_dst(s) + c * CHUNK_BYTES, ma, m0 + c * 64, k0, bar_full(s));
             }
             if (p.b3d) {
               tma_load_3d(b_dst(s), mb, 0, k0, n0 / 64, bar_full(s));
@@ -197,10 +212,12 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
         const int umma_n = (min(BN, a.N - n0) + 15) & ~15;
         const uint32_t idesc = (1u << 4) | ((uint32_t)a.mn << 15) | ((uint32_t)a.mn << 16) |
                                ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const int buf = tile_it & 1;
-        mbar_wait(bar_acc_empty(buf), ((tile_it >> 1) & 1) ^ 1);
+        const int buf = TALL ? 0 : (tile_it & 1);
+        mbar_wait(bar_acc_empty(buf), (TALL ? (tile_it & 1) : ((tile_it >> 1) & 1)) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * BN;
+        const bool second = TALL && (m0 + BM < a.M);      // the lower 128 rows of a tall item hold valid outputs
+        const uint64_t oh2 = (uint64_t)((2 * CHUNK_BYTES) >> 4);   // descriptor offset of the second 128-row half of A
         uint32_t first = 0;   // accumulate flag of the next instruction
         for (int i = 0; i < nkb; ++i) {
           const int sx = it % NSLOT, sy = (it + 1) % NSLOT;
@@ -209,16 +226,21 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
           tc_fence_after();
           const int ksteps = min(BK / 16, (k_total - (kb0 + i) * BK + 15) / 16);
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ox = (uint64_t)((sx * SLOT_BYTES + ks * kstep) >> 4);
-            const uint64_t oy = (uint64_t)((sy * SLOT_BYTES + ks * kstep) >> 4);
+            const uint64_t ox = (uint64_t)((sx * SLOT + ks * kstep) >> 4);
+            const uint64_t oy = (uint64_t)((sy * SLOT + ks * kstep) >> 4);
             if (p.dbg & 2) {
               umma_f16(tacc, da0 + ox, db0 + ox, idesc, first);
               first = 1;
             } else {
               umma_f16(tacc, da0 + oy, db0 + ox, idesc, first);   // lo * hi   (small terms first)
-              first = 1;
               umma_f16(tacc, da0 + ox, db0 + oy, idesc, 1u);      // hi * lo
               if (!a.precise) umma_f16(tacc, da0 + ox, db0 + ox, idesc, 1u);   // hi * hi
+              if (second) {
+                umma_f16(tacc + BN, da0 + oy + oh2, db0 + ox, idesc, first);
+                umma_f16(tacc + BN, da0 + ox + oh2, db0 + oy, idesc, 1u);
+                if (!a.precise) umma_f16(tacc + BN, da0 + ox + oh2, db0 + ox, idesc, 1u);
+              }
+              first = 1;
             }
           }
           umma_commit(bar_empty(sx));
@@ -232,8 +254,9 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
             tc_fence_after();
             const int ksteps = min(BK / 16, (k_total - (kb0 + i) * BK + 15) / 16);
             for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t o = (uint64_t)((s * SLOT_BYTES + ks * kstep) >> 4);
+              const uint64_t o = (uint64_t)((s * SLOT + ks * kstep) >> 4);
               umma_f16(tacc, da0 + o, db0 + o, idesc, 1u);         // hi * hi at full magnitude, last
+              if (second) umma_f16(tacc + BN, da0 + o + oh2, db0 + o, idesc, 1u);
             }
             umma_commit(bar_empty(s));
           }
@@ -268,7 +291,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
           const int s = it % NSLOT;
           mbar_wait(bar_full(s), (it / NSLOT) & 1);
           if (mine) {
-            const uint8_t* bt = smem + s * SLOT_BYTES + A_BYTES + chunk * CHUNK_BYTES + pp * 16;
+            const uint8_t* bt = smem + s * SLOT + A_PIECE + chunk * CHUNK_BYTES + pp * 16;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const int cl = rg + 4 * j;
@@ -327,18 +350,22 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
       item_info(item, m0, n0, kb0, nkb);
       if (nkb == 0) continue;
       const int n_valid = min(BN, a.N - n0);
-      const int buf = tile_it & 1;
+      const int buf = TALL ? 0 : (tile_it & 1);
+      const uint32_t acc_parity = TALL ? (tile_it & 1) : ((tile_it >> 1) & 1);
       const long long m = m0 + q * 32 + lane;
       const bool row_ok = m < a.M;
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       if (Cfg<EPI, WIDE>::STAGED && p.tma_epi) {
-        epilogue_tile_tma<EPI>(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), (tile_it >> 1) & 1, m0 + q * 32,
+        epilogue_tile_tma<EPI>(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), acc_parity, m0 + q * 32,
                                row_ok, n0, n_valid, tacc, chalf, need_u, need_b, inv_ab, sc, sc2, inv_h, inv_u, mx, mx2);
       } else {
-        mbar_wait(bar_acc_full(buf), (tile_it >> 1) & 1);
+        mbar_wait(bar_acc_full(buf), acc_parity);
         tc_fence_after();
         epilogue_tile<EPI>(a, p.vec_epi, p.dbg, m, row_ok, n0, n_valid, tacc, chalf * 16, 32, need_u, need_b, inv_ab, sc,
                            sc2, inv_h, inv_u, mx, mx2);
+        if (TALL && m0 + BM < a.M)
+          epilogue_tile<EPI>(a, p.vec_epi, p.dbg, m + BM, m + BM < a.M, n0, n_valid, tacc + BN, chalf * 16, 32, need_u,
+                             need_b, inv_ab, sc, sc2, inv_h, inv_u, mx, mx2);
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty(buf));
@@ -429,11 +456,13 @@ static bool map_epi(CUtensorMap* map, const __half* base, long long cols, long l
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int g_h_tall = 0;      // 1: weight-gradient work items of 256 rows (measured slower: 3 slots of 64 KB starve the ring)
 int g_h_tma_epi = 1;   // 0: every epilogue on the direct (row-per-lane global access) path
 
 template <int EPI, bool WIDE>
 static int launch_epi_w(const HArgs& a, cudaStream_t st) {
   constexpr int SMEM_BYTES = Cfg<EPI, WIDE>::SMEM;
+  constexpr int TM = Cfg<EPI, WIDE>::TM;
   HParams p;
   p.a = a;
   p.dbg = g_h_dbg;
@@ -455,7 +484,7 @@ static int launch_epi_w(const HArgs& a, cudaStream_t st) {
   } else {
     p.a3d = a.lda % 64 == 0;
     p.b3d = a.ldb % 64 == 0;
-    if (p.a3d) ok = ok && map_mnmajor3(&mAh, a.Ahi, a.K, a.lda, BM / 64) && map_mnmajor3(&mAl, a.Alo, a.K, a.lda, BM / 64);
+    if (p.a3d) ok = ok && map_mnmajor3(&mAh, a.Ahi, a.K, a.lda, TM / 64) && map_mnmajor3(&mAl, a.Alo, a.K, a.lda, TM / 64);
     else ok = ok && map_mnmajor2(&mAh, a.Ahi, a.M, a.K, a.lda) && map_mnmajor2(&mAl, a.Alo, a.M, a.K, a.lda);
     if (p.b3d) ok = ok && map_mnmajor3(&mBh, a.Bhi, a.K, a.ldb, p.b_box_rows / 64) && map_mnmajor3(&mBl, a.Blo, a.K, a.ldb, p.b_box_rows / 64);
     else ok = ok && map_mnmajor2(&mBh, a.Bhi, a.N, a.K, a.ldb) && map_mnmajor2(&mBl, a.Blo, a.N, a.K, a.ldb);
@@ -487,7 +516,7 @@ static int launch_epi_w(const HArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   p.do_colsum = (a.mn && a.colsum != nullptr) ? 1 : 0;
-  p.m_tiles = (a.M + BM - 1) / BM;
+  p.m_tiles = (a.M + TM - 1) / TM;
   p.n_tiles = (a.N + BN - 1) / BN;
   p.nkb_total = (a.K + BK - 1) / BK;
   int splits = (a.mn && a.split_k > 1) ? a.split_k : 1;
@@ -501,7 +530,8 @@ static int launch_epi_w(const HArgs& a, cudaStream_t st) {
 
 template <int EPI>
 static int launch_epi(const HArgs& a, cudaStream_t st) {
-  const bool wide = (EPI == EPI_ADJ) || (EPI == EPI_MUL_S && (a.U.hi || a.U.f));
+  const bool wide = (EPI == EPI_ADJ) || (EPI == EPI_MUL_S && (a.U.hi || a.U.f)) ||
+                    (EPI == EPI_ATOMIC && a.mn && a.M > BM && g_h_tall);
   return wide ? launch_epi_w<EPI, true>(a, st) : launch_epi_w<EPI, false>(a, st);
 }
 

@@ -110,6 +110,7 @@ __device__ __forceinline__ void amax_commit(float* amax, float mx) {
 }
 
 extern int g_h_dbg;                                   // gemm_h.cu: profiling switches
+extern int g_h_tall;                                  // gemm_h.cu: 1 = 256-row work items for the weight-gradient products
 extern int g_h_tma_epi;                               // gemm_h.cu: 1 = TMA-staged epilogue where the operands allow it
 int launch_tc(const HArgs& a, cudaStream_t st);       // gemm_h.cu
 extern int g_h_pair;                                  // gemm_h2.cu: 1 = CTA-pair kernel for the activation-row products

@@ -105,9 +105,20 @@ def test_products_match_float64(epi, precise, resident, kernel_choice):
                 assert abs(float(sc.amax[b["C"].slot]) - float(want.abs().max())) <= 1e-5 * float(want.abs().max())
 
 
+@pytest.mark.parametrize("tall", [0, 1])
 @pytest.mark.parametrize("rows,Kin,N,split", [(4096, 256, 256, 4), (10000, 256, 213, 8), (5000, 44, 256, 3),
-                                              (8192, 262, 128, 16), (65536, 256, 256, 148)])
-def test_weight_gradient_with_fused_bias_gradient(rows, Kin, N, split):
+                                              (8192, 262, 128, 16), (65536, 256, 256, 148), (7000, 200, 256, 5)])
+def test_weight_gradient_with_fused_bias_gradient(rows, Kin, N, split, tall):
+    """tall = 1: work items of 256 rows of A^T (two accumulators, the dZ tile staged once; measured slower, off by
+    default); 0: 128 rows"""
+    _lib.call("ndjir_set_option", "mlp_h_tall", tall)
+    try:
+        _weight_gradient_case(rows, Kin, N, split)
+    finally:
+        _lib.call("ndjir_set_option", "mlp_h_tall", 0)
+
+
+def _weight_gradient_case(rows, Kin, N, split):
     dev = torch.device("cuda")
     g = torch.Generator(device="cuda").manual_seed(1)
     A = torch.rand((rows, Kin), device=dev, generator=g) * 0.5

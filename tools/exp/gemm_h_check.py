@@ -224,7 +224,7 @@ def bench(M=262144, N=256, K=256, iters=20):
                     Uh=bU.hmat()), fl)
     _lib.call("ndjir_set_option", "mlp_h_dbg", 0)
     _lib.call("ndjir_set_option", "mlp_h_resident", 0)
-    if "--short" in sys.argv:
+    if "--short" in sys.argv and "--wgrad" not in sys.argv:
         return
     for precise in (0, 1):
         run(f"dgrad mul_s+U precise={precise}", lambda: h16.gemm_h(
@@ -234,6 +234,18 @@ def bench(M=262144, N=256, K=256, iters=20):
             st(), M, N, K, h16.EPI_ADJ, A=bA.hmat(), B=bB.hmat(), precise=precise, Ch=bC.hmat(), C2h=bC2.hmat(),
             Hh=bH.hmat(), Uh=bU.hmat()), fl)
     cs0 = torch.zeros(N, device=dev)
+    if "--wgrad" in sys.argv:
+        for tall in (0, 1):
+            _lib.call("ndjir_set_option", "mlp_h_tall", tall)
+            for split in (74, 148, 296):
+                run(f"wgrad tall={tall} split={split}", lambda: h16.gemm_h(
+                    st(), K, N, M, h16.EPI_ATOMIC, A=bA.hmat(), B=bC.hmat(), mn_major=True, split_k=split, C=gW.data_ptr(),
+                    ldc=N), fl)
+                run(f"wgrad + fused colsum tall={tall} split={split}", lambda: h16.gemm_h(
+                    st(), K, N, M, h16.EPI_ATOMIC, A=bA.hmat(), B=bC.hmat(), mn_major=True, split_k=split, C=gW.data_ptr(),
+                    ldc=N, colsum=cs0.data_ptr()), fl)
+        _lib.call("ndjir_set_option", "mlp_h_tall", 0)
+        return
     for split in (148, 296, 592):
         run(f"wgrad split={split}", lambda: h16.gemm_h(
             st(), K, N, M, h16.EPI_ATOMIC, A=bA.hmat(), B=bC.hmat(), mn_major=True, split_k=split, C=gW.data_ptr(),
