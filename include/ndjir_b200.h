@@ -610,6 +610,78 @@ int ndjir_amax(long long n, const float* x, float* amax, cudaStream_t stream);
  * amax * old scale exceeded the fp16 range (values were clamped), |= 2 if a scale changed. */
 int ndjir_scale_update(int n_slots, float* scales, float* amax, int* flags, int target_log2, cudaStream_t stream);
 
+/* ==== fused path behind the C ABI (last row): host-side sequencing in C++ ======================
+ * The reference composes these stages from ~40 nnabla calls per round in Python; here the whole stage is ONE entry
+ * point that enqueues the library's own kernels on `stream`, so a host that is not Python can run it.  Everything the
+ * call needs is a POD description plus caller-owned device buffers: nothing is allocated, nothing synchronises.
+ *
+ * ndjir_geo_sdf_forward   python/network.py:154-232 geometric_network (positional encoding + grid features ->
+ *                         hidden affine + softplus_100 layers with the skip connection -> sdf column)
+ * ndjir_sample_points_fwd python/sampler.py:140-314 SamplePoints._forward_impl / sample_points: ray bounds,
+ *                         stratified distances, n_upsamples SDF-guided rounds (incremental: only the new samples of
+ *                         a round are evaluated), background samples
+ * Split-fp16 engine only (the weights are given as the planes of W^T the tensor-core products read). */
+#define NDJIR_MAX_MLP_LAYERS 16
+typedef struct ndjir_mlp_layer {
+  int K, N;               /* inputs, outputs */
+  const float* W;         /* fp32 weights, K rows of N (row stride ldw): read by the <= 8-output products */
+  long long ldw;
+  const float* bias;      /* N */
+  ndjir_hmat Wt;          /* split-fp16 planes of W^T (N rows of K halfs, scale = the weight scale); unused when N <= 8 */
+} ndjir_mlp_layer;
+
+typedef struct ndjir_geo_net {
+  int n_hidden;                                   /* hidden layers (affine + softplus_100) */
+  ndjir_mlp_layer hidden[NDJIR_MAX_MLP_LAYERS];
+  ndjir_mlp_layer sdf;                            /* sdf column of the last layer (N = 1) */
+  int skip_layer;         /* hidden layer whose INPUT is [a | encoded input] * skip_scale (network.py:171-176); -1 none */
+  float skip_scale;       /* 1 / sqrt(2) */
+  int pe_bands;           /* encoded input = [x, cos, sin] (3 + 6 pe_bands columns) | grid features */
+  int grid_kind;          /* 0 none, 1 voxel (G^3 x D), 2 triplane + triline (3 G^2 D + 3 G D) */
+  int grid_size, grid_channels;
+  const float* grid0;     /* voxel / triplane table */
+  const float* grid1;     /* triline table */
+  int precise;            /* accumulation order of the forward products (ndjir_gemm_h_desc.precise) */
+} ndjir_geo_net;
+
+/* caller-owned scratch of one network evaluation over up to `rows` points */
+typedef struct ndjir_geo_scratch {
+  float* enc;             /* rows x ld_enc fp32: the encoded input */
+  long long ld_enc;       /* >= 3 + 6 pe_bands + grid width, multiple of 4 */
+  float* grid_tmp;        /* rows x grid width fp32 (unused without a grid) */
+  ndjir_hmat ench;        /* planes of the encoded input */
+  ndjir_hmat act[2];      /* two activation plane buffers, rows x (widest hidden input), used alternately */
+} ndjir_geo_scratch;
+
+int ndjir_geo_sdf_forward(const ndjir_geo_net* net, long long rows, const float* x, float* sdf,
+                          const ndjir_geo_scratch* ws, cudaStream_t stream);
+
+typedef struct ndjir_sampler_config {
+  int n_samples0, n_samples1, n_upsamples, n_bg_samples;    /* renderer.n_samples0 / n_samples1 / n_upsamples / n_bg_samples */
+  float sampling_sigmoid_gain;                               /* doubled every round (sampler.py:188) */
+  int bounds;                                                /* 0: intersect_with_aabb, 1: intersect_with_r_sphere */
+  float radius;                                              /* renderer.bounding_sphere_radius */
+} ndjir_sampler_config;
+
+/* caller-owned scratch; n = B R rays, N = n_samples0 + n_upsamples n_samples1, Mx = max(n_samples0, n_samples1) */
+typedef struct ndjir_sampler_workspace {
+  float *t_near, *t_far, *n_hits;   /* n each */
+  float* sdf_cur;                   /* n x N: SDF of the current sorted samples, carried from round to round */
+  float* t_pend;                    /* n x Mx: the stratified distances */
+  float* t_new[2];                  /* n x n_samples1 each: the new distances of a round, alternating */
+  float* x;                         /* n Mx x 3: points of the pending samples */
+  float* sdf_pend;                  /* n Mx */
+  ndjir_geo_scratch geo;            /* sized for n Mx rows */
+} ndjir_sampler_workspace;
+
+/* camloc (B,3), raydir (B,R,3), stratified (B,R,n_samples0), background (B,R,n_bg_samples+1): device fp32.
+ * Outputs: x_fg (n,N,3), t_fg (n,N+1) [= sorted distances | t_far], x_bg (n,Nb,4), t_bg (n,Nb+1), mask (n);
+ * mask_sum[0] += sum(mask) when mask_sum is given. */
+int ndjir_sample_points_fwd(const ndjir_sampler_config* cfg, const ndjir_geo_net* net, int B, int R, const float* camloc,
+                            const float* raydir, const float* stratified, const float* background,
+                            const ndjir_sampler_workspace* ws, float* x_fg, float* t_fg, float* x_bg, float* t_bg,
+                            float* mask, float* mask_sum, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,156 @@
+// Host-side sequencing of the fused per-ray path behind the C ABI: the stages the reference
+// composes from nnabla calls in Python (python/sampler.py:140-314, python/network.py:154-232) as single entry points
+// that enqueue this library's kernels.  No allocation, no synchronisation, no Python: a C / C++ host can run them.
+#include "common.cuh"
+#include "gemm.cuh"
+#include "../../include/ndjir_b200.h"
+
+namespace {
+
+#define NDJIR_TRY(call)                 \
+  do {                                  \
+    int rc_ = (call);                   \
+    if (rc_ != NDJIR_OK) return rc_;    \
+  } while (0)
+
+inline ndjir_hmat view(const ndjir_hmat& m, long long col, bool track) {
+  ndjir_hmat v = m;
+  v.hi = reinterpret_cast<char*>(m.hi) + 2 * col;
+  v.lo = reinterpret_cast<char*>(m.lo) + 2 * col;
+  if (!track) v.amax = nullptr;
+  return v;
+}
+
+// fp32 columns -> planes; the 16-byte vector path of ndjir_pack_h wants whole groups of 8 columns, so a ragged width
+// goes as bulk + tail
+int pack_cols(long long rows, int ncols, const float* src, long long ld_src, float alpha, const ndjir_hmat& dst,
+              long long dcol, cudaStream_t st) {
+  const int bulk = (dcol % 8 == 0 && ncols >= 16 && ncols % 8) ? (ncols / 8) * 8 : 0;
+  if (bulk) {
+    ndjir_hmat d0 = view(dst, dcol, true), d1 = view(dst, dcol + bulk, true);
+    NDJIR_TRY(ndjir_pack_h(rows, bulk, src, ld_src, 1, alpha, &d0, st));
+    return ndjir_pack_h(rows, ncols - bulk, src + bulk, ld_src, 1, alpha, &d1, st);
+  }
+  ndjir_hmat d = view(dst, dcol, true);
+  return ndjir_pack_h(rows, ncols, src, ld_src, 1, alpha, &d, st);
+}
+
+int grid_width(const ndjir_geo_net* net) {
+  if (net->grid_kind == 1) return net->grid_channels;
+  if (net->grid_kind == 2) return 6 * net->grid_channels;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int ndjir_geo_sdf_forward(const ndjir_geo_net* net, long long rows, const float* x, float* sdf,
+                                     const ndjir_geo_scratch* ws, cudaStream_t st) {
+  if (!net || !ws || !x || !sdf || rows < 0) return NDJIR_ERR_ARG;
+  if (rows == 0) return NDJIR_OK;
+  if (net->n_hidden < 1 || net->n_hidden > NDJIR_MAX_MLP_LAYERS || net->grid_kind < 0 || net->grid_kind > 2)
+    return NDJIR_ERR_ARG;
+  const int npe = 3 + 6 * net->pe_bands, gw = grid_width(net), din = npe + gw;
+  if (ws->ld_enc < din || !ws->enc || !ws->ench.hi || !ws->act[0].hi || !ws->act[1].hi || (gw && !ws->grid_tmp))
+    return NDJIR_ERR_ARG;
+  if (net->hidden[0].K != din) return NDJIR_ERR_ARG;
+  // encoded input [PE(x) | grid features | zero padding]   (network.py:96-151)
+  NDJIR_TRY(ndjir_positional_encoding(rows, 3, net->pe_bands, x, 3, 1, ws->enc, ws->ld_enc, st));
+  const float mn[3] = {-1.f, -1.f, -1.f}, mx[3] = {1.f, 1.f, 1.f};     // PF defaults (voxel_feature.py:147-148)
+  const int G = net->grid_size, D = net->grid_channels;
+  if (net->grid_kind == 1) {
+    const int gs[3] = {G, G, G};
+    NDJIR_TRY(ndjir_voxel_query_on_voxel(rows, ws->grid_tmp, x, net->grid0, gs, D, mn, mx, 0, st));
+    NDJIR_TRY(ndjir_copy2d(rows, D, ws->enc + npe, ws->ld_enc, ws->grid_tmp, D, 1, 1.f, 0, st));
+  } else if (net->grid_kind == 2) {
+    NDJIR_TRY(ndjir_triplane_query_on_triplane(rows, ws->grid_tmp, x, net->grid0, G, D, mn, mx, 0, st));
+    NDJIR_TRY(ndjir_copy2d(rows, 3 * D, ws->enc + npe, ws->ld_enc, ws->grid_tmp, 3 * D, 1, 1.f, 0, st));
+    NDJIR_TRY(ndjir_triline_query_on_triline(rows, ws->grid_tmp, x, net->grid1, G, D, mn, mx, 0, st));
+    NDJIR_TRY(ndjir_copy2d(rows, 3 * D, ws->enc + npe + 3 * D, ws->ld_enc, ws->grid_tmp, 3 * D, 1, 1.f, 0, st));
+  }
+  if (ws->ld_enc > din) {
+    cudaError_t e = cudaMemset2DAsync(ws->enc + din, ws->ld_enc * sizeof(float), 0, (ws->ld_enc - din) * sizeof(float),
+                                      rows, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  NDJIR_TRY(pack_cols(rows, din, ws->enc, ws->ld_enc, 1.f, ws->ench, 0, st));
+  // hidden layers: affine + softplus_100, the skip layer's input is [a | encoded input] / sqrt2   (network.py:160-188)
+  ndjir_hmat cur = ws->ench;
+  for (int l = 0; l < net->n_hidden; ++l) {
+    const ndjir_mlp_layer& L = net->hidden[l];
+    const ndjir_hmat& nxt = ws->act[l & 1];
+    const bool into_skip = (l + 1) == net->skip_layer;
+    ndjir_gemm_h_desc d = {};
+    d.M = (int)rows; d.N = L.N; d.K = L.K;
+    d.epilogue = ndjir::gemm::EPI_SOFTPLUS; d.precise = net->precise; d.split_k = 1;
+    d.alpha = 1.f; d.out_scale = into_skip ? net->skip_scale : 1.f; d.beta = 100.f; d.hscale = 1.f;
+    d.A = view(cur, 0, false);
+    d.B = L.Wt;
+    d.a_cs = 1; d.b_cs = 1;
+    d.Ch = view(nxt, 0, true);
+    d.bias = L.bias;
+    NDJIR_TRY(ndjir_gemm_h(&d, st));
+    if (into_skip) NDJIR_TRY(pack_cols(rows, din, ws->enc, ws->ld_enc, net->skip_scale, nxt, L.N, st));
+    cur = nxt;
+  }
+  // sdf column (network.py:190-214): one pass over the last activations, fp32 weights, fp32 output
+  ndjir_gemm_h_desc d = {};
+  d.M = (int)rows; d.N = 1; d.K = net->sdf.K;
+  d.epilogue = ndjir::gemm::EPI_BIAS; d.split_k = 1;
+  d.alpha = 1.f; d.out_scale = 1.f; d.beta = 100.f; d.hscale = 1.f;
+  d.A = view(cur, 0, false);
+  d.a_cs = 1;
+  d.B32 = net->sdf.W; d.b_rs = net->sdf.ldw; d.b_cs = 1;
+  d.bias = net->sdf.bias;
+  d.C = sdf; d.ldc = 1;
+  return ndjir_gemm_h(&d, st);
+}
+
+extern "C" int ndjir_sample_points_fwd(const ndjir_sampler_config* cfg, const ndjir_geo_net* net, int B, int R,
+                                       const float* camloc, const float* raydir, const float* stratified,
+                                       const float* background, const ndjir_sampler_workspace* ws, float* x_fg,
+                                       float* t_fg, float* x_bg, float* t_bg, float* mask, float* mask_sum,
+                                       cudaStream_t st) {
+  if (!cfg || !net || !ws || !camloc || !raydir || !stratified || !background || !x_fg || !t_fg || !x_bg || !t_bg || !mask)
+    return NDJIR_ERR_ARG;
+  if (B <= 0 || R <= 0 || cfg->n_samples0 < 1 || cfg->n_samples1 < 1 || cfg->n_upsamples < 0 || cfg->n_bg_samples < 1)
+    return NDJIR_ERR_ARG;
+  const int n = B * R, N0 = cfg->n_samples0, M = cfg->n_samples1, U = cfg->n_upsamples, Nb = cfg->n_bg_samples;
+  const int N = N0 + U * M;
+  const long long ld = N + 1;
+  // ray bounds and the hit mask (sampler.py:59-104)
+  if (cfg->bounds == 0) {
+    const float lo[3] = {-cfg->radius, -cfg->radius, -cfg->radius}, hi[3] = {cfg->radius, cfg->radius, cfg->radius};
+    NDJIR_TRY(ndjir_ray_aabb_intersection(n, ws->t_near, ws->t_far, ws->n_hits, camloc, raydir, B, R, lo, hi, st));
+  } else if (cfg->bounds == 1) {
+    NDJIR_TRY(ndjir_ray_sphere_intersection(n, ws->t_near, ws->t_far, ws->n_hits, camloc, raydir, B, R, cfg->radius, st));
+  } else {
+    return NDJIR_ERR_ARG;
+  }
+  NDJIR_TRY(ndjir_hit_mask(n, ws->n_hits, mask, mask_sum, st));
+  // stratified distances, then U SDF-guided rounds.  t_fg holds the sorted distances, merged in place round by round;
+  // only the pending samples (the stratified ones, then the M new ones of each round) are evaluated: a sample's SDF
+  // does not change between rounds (the reference re-evaluates all of them: sampler.py:190-192)
+  NDJIR_TRY(ndjir_stratified_dists(n, N0, ws->t_pend, ws->t_near, ws->t_far, stratified, st));
+  const float* pend = ws->t_pend;
+  int Nt = 0, Mp = N0;
+  for (int u = 0; u <= U; ++u) {
+    const bool last = u == U;
+    if (!last) {
+      NDJIR_TRY(ndjir_ray_points(n, Mp, R, ws->x, camloc, raydir, pend, Mp, st));
+      NDJIR_TRY(ndjir_geo_sdf_forward(net, (long long)n * Mp, ws->x, ws->sdf_pend, &ws->geo, st));
+    }
+    float gain = cfg->sampling_sigmoid_gain;
+    for (int i = 0; i < u; ++i) gain *= 2.f;
+    float* tnew = ws->t_new[u & 1];
+    // the last call only merges the final M samples (their SDF is not needed)
+    NDJIR_TRY(ndjir_importance_round_incremental(n, Nt, Mp, last ? 0 : M, t_fg, ld, ws->sdf_cur, N, pend, ws->sdf_pend,
+                                                 ws->t_near, ws->t_far, gain, tnew, nullptr, st));
+    Nt += Mp;
+    pend = tnew;
+    Mp = M;
+  }
+  // t_fg = concat(t, t_far); points of both segments (sampler.py:276-299)
+  NDJIR_TRY(ndjir_copy2d(n, 1, t_fg + N, ld, ws->t_far, 1, 1, 1.f, 0, st));
+  NDJIR_TRY(ndjir_ray_points(n, N, R, x_fg, camloc, raydir, t_fg, ld, st));
+  return ndjir_background_samples(n, Nb, R, camloc, raydir, ws->t_far, mask, background, cfg->radius, t_bg, x_bg, st);
+}

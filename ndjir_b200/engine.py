@@ -357,6 +357,7 @@ class Engine:
         self.scales = h16.Scales(self.device) if self.h16 else None
         self._calibrated = not self.h16
         self.precise_fwd = True
+        self.fused_sampler = True     # sample_points as one C-ABI call (ndjir_sample_points_fwd); False: sequenced here
         self.rad = float(conf.renderer.bounding_sphere_radius)
         self.debug = {}
         self.profile, self.prof_events, self.n_launches = False, [], 0
@@ -843,6 +844,74 @@ class Engine:
     # ------------------------------------------------------------------------------------------------
     # sample_points (python/sampler.py:256-299)
     # ------------------------------------------------------------------------------------------------
+    def geo_net_desc(self):
+        """POD description of the geometric network for the C-ABI fused path (ndjir_geo_net): hidden layers with the
+        planes of W^T, the sdf column, skip layer, encoding and grid tables."""
+        ps, g = self.params, self.conf.geometric_network
+        net = ps.nets["geo"]
+        d = h16.GeoNet()
+        d.n_hidden = len(net) - 2
+
+        def layer(L, planes):
+            m = h16.MlpLayer()
+            m.K, m.N, m.W, m.ldw, m.bias = L.K, L.N, ps.W(L), L.ldw, ps.b(L)
+            m.Wt = ps.WT16(L) if planes else h16.NULL_H
+            return m
+
+        for l in range(d.n_hidden):
+            d.hidden[l] = layer(net[l], True)
+        d.sdf = layer(net[-2], False)
+        d.skip_layer, d.skip_scale, d.pe_bands = self.skip, self.cskip, g.pe_bands
+        v = g.voxel
+        d.grid_kind = {"voxel": 1, "triplaneline": 2}.get(v.type, 0)
+        d.grid_size, d.grid_channels = (v.grid_size, v.feature_size) if d.grid_kind else (0, 0)
+        d.grid0 = ps.grid["voxel"].data_ptr() if d.grid_kind == 1 else (ps.grid["triplane"].data_ptr() if d.grid_kind == 2 else None)
+        d.grid1 = ps.grid["triline"].data_ptr() if d.grid_kind == 2 else None
+        d.precise = int(self.precise_fwd)
+        return d
+
+    def _sample_points_c(self, camloc, raydir, stratified_sample, background_sample, mask_sum):
+        """sample_points as ONE C-ABI call (ndjir_sample_points_fwd: the round loop runs in the library, csrc/fused_path.cu)
+        on the same buffers and scale slots the Python sequencing below uses."""
+        r = self.conf.renderer
+        B, R, _ = raydir.shape
+        NR = B * R
+        N0, M, U, Nb = r.n_samples0, r.n_samples1, r.n_upsamples, r.n_bg_samples
+        N, Mx = N0 + U * M, max(N0, M)
+        cfg = h16.SamplerConfig(N0, M, U, Nb, float(r.sampling_sigmoid_gain),
+                                {"intersect_with_aabb": 0, "intersect_with_r_sphere": 1}[r.t_near_far_method], self.rad)
+        ws = h16.SamplerWorkspace()
+        ws.t_near, ws.t_far, ws.n_hits = (self.buf(k, NR, 1).data_ptr() for k in ("t_near", "t_far", "n_hits"))
+        mask = self.buf("mask", NR, 1)
+        cur = self.buf("t_a", NR, N + 1)
+        ws.sdf_cur = self.buf("smp_sdf_m", NR, N).data_ptr()
+        ws.t_pend = self.buf("smp_t_pend", NR, Mx).data_ptr()
+        ws.t_new[0], ws.t_new[1] = (self.buf(f"smp_tnew{i}", NR, M).data_ptr() for i in (0, 1))
+        self._reserve = NR * Mx
+        ws.x = self.buf("smp_x", NR * Mx, 3).data_ptr()
+        ws.sdf_pend = self.buf("smp_sdf", NR * Mx, 1).data_ptr()
+        A0 = self.mat("smp_A0", NR * Mx, self.din, "fa")
+        widest = max(L.K for L in self.params.nets["geo"][1:])
+        act = [self.mat(f"geo_pp{i}", NR * Mx, widest, "a") for i in (0, 1)]
+        self._reserve = 0
+        ws.geo.enc, ws.geo.ld_enc = A0.f.data_ptr(), self.ld0
+        gw = sum(w for _, w, _ in self._grid_parts())
+        ws.geo.grid_tmp = self.buf("gq_fused", NR * Mx, max(gw, 1)).data_ptr() if gw else None
+        ws.geo.ench = A0.hmat(0)
+        ws.geo.act[0], ws.geo.act[1] = act[0].hmat(0), act[1].hmat(0)
+        x_fg = self.buf("x_fg", NR * N, 3)
+        t_bg = self.buf("t_bg", NR, Nb + 1)
+        x_bg = self.buf("x_bg", NR * Nb, 4)
+        # kernel launches inside the call: bounds, mask, stratified, per round (points, encoding, grid, padding, pack,
+        # layers, sdf, placement), final merge, t_far column, points, background
+        self.n_launches += 6 + U * (len(self.params.nets["geo"]) + 6 + 2 * len(self._grid_parts()))
+        self.call("ndjir_sample_points_fwd", cfg, self.geo_net_desc(), B, R, P_(camloc), P_(raydir), P_(stratified_sample),
+                  P_(background_sample), ws, P_(x_fg), P_(cur), P_(x_bg), P_(t_bg), P_(mask),
+                  P_(mask_sum) if mask_sum is not None else None)
+        self.debug["sampler"] = []
+        return (x_fg[:NR * N].view(B, R, N, 3), cur[:NR].reshape(B, R, N + 1, 1), x_bg[:NR * Nb].view(B, R, Nb, 4),
+                t_bg[:NR].view(B, R, Nb + 1, 1), mask[:NR].reshape(B, R, 1, 1))
+
     def sample_points(self, camloc, raydir, stratified_sample, background_sample, mask_sum=None, debug=False):
         """camloc (B,3), raydir (B,R,3), stratified_sample (B,R,N0,1), background_sample (B,R,Nb+1,1) device fp32.
         Returns x_fg (B,R,N,3), t_fg (B,R,N+1,1), x_bg (B,R,Nb,4), t_bg (B,R,Nb+1,1), mask (B,R,1,1)."""
@@ -851,6 +920,8 @@ class Engine:
         NR = B * R
         if not getattr(self, "_weights_synced", False):
             self.refresh_transposes()   # standalone call: the registered lo copies of the weights must be current
+        if self.h16 and self.fused_sampler and not debug:
+            return self._sample_points_c(camloc, raydir, stratified_sample, background_sample, mask_sum)
         N0, M, U, Nb = r.n_samples0, r.n_samples1, r.n_upsamples, r.n_bg_samples
         N = N0 + U * M
         tn, tf, nh = (self.buf(k, NR, 1) for k in ("t_near", "t_far", "n_hits"))

@@ -30,6 +30,39 @@ class GemmHDesc(ctypes.Structure):
                 ("colsum", ctypes.c_void_p)]
 
 
+# ---- PODs of the fused-path entry points (include/ndjir_b200.h, "fused path behind the C ABI") ----
+MAX_MLP_LAYERS = 16
+
+
+class MlpLayer(ctypes.Structure):
+    _fields_ = [("K", ctypes.c_int), ("N", ctypes.c_int), ("W", ctypes.c_void_p), ("ldw", ctypes.c_longlong),
+                ("bias", ctypes.c_void_p), ("Wt", HMat)]
+
+
+class GeoNet(ctypes.Structure):
+    _fields_ = [("n_hidden", ctypes.c_int), ("hidden", MlpLayer * MAX_MLP_LAYERS), ("sdf", MlpLayer),
+                ("skip_layer", ctypes.c_int), ("skip_scale", ctypes.c_float), ("pe_bands", ctypes.c_int),
+                ("grid_kind", ctypes.c_int), ("grid_size", ctypes.c_int), ("grid_channels", ctypes.c_int),
+                ("grid0", ctypes.c_void_p), ("grid1", ctypes.c_void_p), ("precise", ctypes.c_int)]
+
+
+class GeoScratch(ctypes.Structure):
+    _fields_ = [("enc", ctypes.c_void_p), ("ld_enc", ctypes.c_longlong), ("grid_tmp", ctypes.c_void_p),
+                ("ench", HMat), ("act", HMat * 2)]
+
+
+class SamplerConfig(ctypes.Structure):
+    _fields_ = [("n_samples0", ctypes.c_int), ("n_samples1", ctypes.c_int), ("n_upsamples", ctypes.c_int),
+                ("n_bg_samples", ctypes.c_int), ("sampling_sigmoid_gain", ctypes.c_float), ("bounds", ctypes.c_int),
+                ("radius", ctypes.c_float)]
+
+
+class SamplerWorkspace(ctypes.Structure):
+    _fields_ = [("t_near", ctypes.c_void_p), ("t_far", ctypes.c_void_p), ("n_hits", ctypes.c_void_p),
+                ("sdf_cur", ctypes.c_void_p), ("t_pend", ctypes.c_void_p), ("t_new", ctypes.c_void_p * 2),
+                ("x", ctypes.c_void_p), ("sdf_pend", ctypes.c_void_p), ("geo", GeoScratch)]
+
+
 class Scales:
     """Device arrays scale[n], amax[n] (+ a flag word): one slot per split tensor.  update() turns the running maxima
     of the tensors' last use into the power-of-two scales of their next use (delayed scaling)."""

@@ -151,6 +151,27 @@ def setup(kind, seed=0, miss=True, grid_std=0.05, shape="small", mlp="h16"):
 
 
 @pytest.mark.parametrize("kind,shape", [("default", "small"), ("triplaneline", "small"), ("no_voxel", "small"),
+                                        ("default", "full")])
+def test_sample_points_one_c_abi_call_equals_the_sequenced_path(kind, shape):
+    """ndjir_sample_points_fwd (csrc/fused_path.cu: the round loop of sampler.py:140-314 sequenced inside the library,
+    what a non-Python host calls) enqueues the same kernels on the same buffers as the stage-by-stage sequencing of
+    Engine.sample_points: every output must be bit-identical, and so must the hit count."""
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind, shape=shape)
+    args = [dev(camloc), dev(raydir), dev(rnd["stratified"]), dev(rnd["background"])]
+    outs = {}
+    for fused in (False, True, False, True):      # twice each: the delayed scales of the second pass are the settled ones
+        eng.fused_sampler = fused
+        ms = torch.zeros(1, device="cuda")
+        o = eng.sample_points(*args, mask_sum=ms)
+        torch.cuda.synchronize()
+        outs[fused] = [t.clone() for t in o] + [ms.clone()]
+    eng.fused_sampler = True
+    for name, a, b in zip(("x_fg", "t_fg", "x_bg", "t_bg", "mask", "mask_sum"), outs[False], outs[True]):
+        assert torch.equal(a, b), name
+    assert float(outs[True][5]) == float(outs[True][4].sum())
+
+
+@pytest.mark.parametrize("kind,shape", [("default", "small"), ("triplaneline", "small"), ("no_voxel", "small"),
                                         ("default", "full"), ("triplaneline", "full")])
 def test_sample_points_stage_by_stage(kind, shape):
     """sample_points (sampler.py:256-299) checked stage by stage, each stage on the inputs the ENGINE gave it:
