@@ -337,6 +337,14 @@ int ndjir_squareplus_forward(long long size, float* output, const float* input, 
 int ndjir_squareplus_backward(long long size, float* dinput, const float* doutput, const float* input, float b,
                               int accum, cudaStream_t stream);
 
+/* ---- measurement helper: random-gather throughput of the memory hierarchy (the yardstick of the L2-resident grid
+ *      families: voxel hash, triline, Lanczos voxel; tools/bench_gather.py, profiles/r2_gather_roofline.md).
+ *      Every thread sums `per_thread` independent gathers of `elem_bytes` (4, 8 or 16) at counter-hashed element
+ *      indices of `table` (table_bytes, a multiple of elem_bytes); sink[0] receives a value that depends on all of
+ *      them.  coherent = 1: the 32 lanes of a warp read 32 consecutive elements at a hashed position instead. */
+int ndjir_bench_gather(long long n_threads, int per_thread, int elem_bytes, const void* table, long long table_bytes,
+                       int coherent, int seed, float* sink, cudaStream_t stream);
+
 /* ==== fused per-ray path ==================================================================================
  * No native counterpart in the reference: there these stages are ~400 stock nnabla ops composed in
  * python/sampler.py, network.py, renderer.py, specular_brdf.py and loss.py, differentiated by nnabla's autodiff.

@@ -116,6 +116,43 @@ squareplus_fwd_kernel(long long n, float* __restrict__ y, const float* __restric
 using namespace ndjir;
 using namespace ndjir::misc;
 
+// ---- random-gather throughput probe (include/ndjir_b200.h: ndjir_bench_gather) ----
+namespace ndjir {
+namespace probe {
+__device__ __forceinline__ unsigned mix(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+template <typename T>
+__device__ __forceinline__ float fold(const T& v);
+template <> __device__ __forceinline__ float fold<float>(const float& v) { return v; }
+template <> __device__ __forceinline__ float fold<float2>(const float2& v) { return v.x + v.y; }
+template <> __device__ __forceinline__ float fold<float4>(const float4& v) { return v.x + v.y + v.z + v.w; }
+
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(NDJIR_BLOCK) gather_kernel(long long n_threads, int per_thread, const T* table,
+                                                             unsigned n_elems, int coherent, unsigned seed, float* sink) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_threads) return;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned key = coherent ? (unsigned)(tid >> 5) : (unsigned)tid;
+  float acc = 0.f;
+  for (int g = 0; g < per_thread; g += UNROLL) {
+    T v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      unsigned h = mix(key * 0x9e3779b9u + (unsigned)(g + u) * 0x85ebca6bu + seed);
+      unsigned idx = coherent ? ((h % (n_elems / 32u)) * 32u + lane) : (h % n_elems);
+      v[u] = __ldg(table + idx);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) acc += fold<T>(v[u]);
+  }
+  if (acc == 1.2345e-30f) sink[0] = acc;     // keeps the loads alive without a store per thread
+}
+}  // namespace probe
+}  // namespace ndjir
+
 extern "C" {
 
 int ndjir_ray_aabb_intersection(int n_rays, float* t_near, float* t_far, float* n_hits, const float* camloc,
@@ -177,6 +214,28 @@ int ndjir_squareplus_backward(long long size, float* dinput, const float* doutpu
   if (size < 0 || !dinput || !doutput || !input) return NDJIR_ERR_ARG;
   if (accum) squareplus_bwd_kernel<true><<<grid_for(size), NDJIR_BLOCK, 0, stream>>>(size, dinput, doutput, input, b);
   else squareplus_bwd_kernel<false><<<grid_for(size), NDJIR_BLOCK, 0, stream>>>(size, dinput, doutput, input, b);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_bench_gather(long long n_threads, int per_thread, int elem_bytes, const void* table, long long table_bytes,
+                       int coherent, int seed, float* sink, cudaStream_t stream) {
+  using namespace ndjir::probe;
+  if (n_threads <= 0 || per_thread <= 0) return NDJIR_OK;
+  if (!table || !sink || table_bytes < 32LL * elem_bytes || table_bytes % elem_bytes) return NDJIR_ERR_ARG;
+  const long long n_elems = table_bytes / elem_bytes;
+  if (n_elems > 0xffffffffLL) return NDJIR_ERR_ARG;
+  const int grid = (int)((n_threads + NDJIR_BLOCK - 1) / NDJIR_BLOCK);
+  if (elem_bytes == 4)
+    gather_kernel<float, 8><<<grid, NDJIR_BLOCK, 0, stream>>>(n_threads, per_thread, (const float*)table, (unsigned)n_elems,
+                                                             coherent, (unsigned)seed, sink);
+  else if (elem_bytes == 8)
+    gather_kernel<float2, 8><<<grid, NDJIR_BLOCK, 0, stream>>>(n_threads, per_thread, (const float2*)table,
+                                                              (unsigned)n_elems, coherent, (unsigned)seed, sink);
+  else if (elem_bytes == 16)
+    gather_kernel<float4, 8><<<grid, NDJIR_BLOCK, 0, stream>>>(n_threads, per_thread, (const float4*)table,
+                                                              (unsigned)n_elems, coherent, (unsigned)seed, sink);
+  else
+    return NDJIR_ERR_ARG;
   NDJIR_RETURN_LAST_ERROR();
 }
 
