@@ -17,6 +17,7 @@
 //
 // Workspace: 16 B per point + 8 KB (ndjir_voxel_binned_workspace_bytes).  The order inside a brick is not
 // deterministic (atomics), which does not matter: gathers are per-point independent and scatters are atomic sums.
+#include <mutex>
 #include "grid_common.cuh"
 #include "voxel_binned.cuh"
 #include "../../include/ndjir_b200.h"
@@ -407,22 +408,36 @@ int scatter(bool second, long long B, float* gf, const float* go, const float* g
   NDJIR_RETURN_LAST_ERROR();
 }
 
-// Stream-ordered scratch for the reference-signature entry points (no host synchronisation; the pool keeps the
-// block for the next call).  Returns nullptr when the allocation is refused - the caller then runs the direct kernel.
+// Stream-ordered scratch for the reference-signature entry points (no host synchronisation).  The blocks come from a
+// memory pool this library owns, one per device, created on first use: its release threshold keeps freed scratch for the
+// next call, and the host application's default pool (and PyTorch's allocator behind it) is left exactly as it was.
+// Returns nullptr when the allocation is refused - the caller then runs the direct kernel.
 void* scratch_alloc(long long bytes, cudaStream_t st) {
-  static bool pool_configured = false;
-  if (!pool_configured) {  // keep freed scratch in the pool across synchronisations instead of returning it to the OS
-    int devi = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&devi) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, devi) == cudaSuccess) {
+  constexpr int MAX_DEV = 64;
+  static cudaMemPool_t pools[MAX_DEV] = {};
+  static std::mutex mu;
+  int devi = 0;
+  if (cudaGetDevice(&devi) != cudaSuccess || devi < 0 || devi >= MAX_DEV) { (void)cudaGetLastError(); return nullptr; }
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[devi]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = devi;
+      cudaMemPool_t created;
+      if (cudaMemPoolCreate(&created, &props) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
       unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      cudaMemPoolSetAttribute(created, cudaMemPoolAttrReleaseThreshold, &keep);
+      (void)cudaGetLastError();
+      pools[devi] = created;
     }
-    (void)cudaGetLastError();
-    pool_configured = true;
+    pool = pools[devi];
   }
   void* p = nullptr;
-  cudaError_t e = cudaMallocAsync(&p, (size_t)bytes, st);
+  cudaError_t e = cudaMallocFromPoolAsync(&p, (size_t)bytes, pool, st);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
   return p;
 }

@@ -556,7 +556,9 @@ int ndjir_voxel_hash_voxel_hash_feature(long long n_points, float* output, const
   if (g_hash_coarse_private && n_points >= (g_hash_coarse_private == 2 ? 1 : (1ll << 20))) {
     long long max_fl = 0;
     while (l_begin < L) {       // the dense prefix of levels whose table fits 160 KB of shared memory
-      long long fl = (long long)level_table_size(level_grid_size(G0, growth_factor, l_begin), T0) * D;
+      // sized for a grid one cell larger than the host evaluates: the kernels index shared memory with the table the
+      // DEVICE builds, and host pow / device powf may floor G0 * gf^l differently (q2)
+      long long fl = (long long)level_table_size(level_grid_size(G0, growth_factor, l_begin) + 1, T0) * D;
       if (fl * 4 > 160 * 1024) break;
       if (fl > max_fl) max_fl = fl;
       ++l_begin;
@@ -630,7 +632,9 @@ int ndjir_voxel_hash_grad_feature(long long n_points, float* grad_feature, const
     // shared-memory privatised kernel
     long long max_fl = 0;
     while (l_begin < L) {
-      long long fl = (long long)level_table_size(level_grid_size(G0, growth_factor, l_begin), T0) * D;
+      // sized for a grid one cell larger than the host evaluates: the kernels index shared memory with the table the
+      // DEVICE builds, and host pow / device powf may floor G0 * gf^l differently (q2)
+      long long fl = (long long)level_table_size(level_grid_size(G0, growth_factor, l_begin) + 1, T0) * D;
       if (fl * 4 > 160 * 1024 || fl / D >= n_points) break;              // too large, or too few points to contend
       if (fl > max_fl) max_fl = fl;
       ++l_begin;

@@ -341,9 +341,29 @@ class Engine:
         self.ld0 = r4(self.din)
         self.LDO = r4(self.Df + 6)
         self.skip = g.skip_layers[0] if len(g.skip_layers) else -1
-        assert len(g.skip_layers) <= 1 and g.geometric_init and not g.voxel.use_ste
-        assert conf.diffuse_brdf.entangle and conf.specular_brdf.sampling == "importance"
-        assert conf.background_modeling
+        # every configuration key the kernels hard-code: a config outside BASELINE's three (e.g. the reference's ue4.yaml)
+        # must fail here instead of silently rendering default.yaml's branches
+        def need(ok, what):
+            if not ok:
+                raise NotImplementedError(f"ndjir_b200 implements the default.yaml branch only: {what}")
+        need(len(g.skip_layers) <= 1 and g.geometric_init and not g.voxel.use_ste and g.act == "softplus",
+             "geometric_network (one skip layer, geometric_init, no STE, softplus)")
+        need(conf.diffuse_brdf.entangle, "diffuse_brdf.entangle")
+        sb = conf.specular_brdf
+        need(sb.model == "filament" and sb.remap and sb.sampling == "importance" and not sb.use_split_sum,
+             "specular_brdf (filament, remap, importance sampling, no split sum)")
+        need(conf.background_modeling, "background_modeling")
+        need(not conf.use_wn, "use_wn")
+        el, sv, ii = conf.environment_light_network, conf.soft_visibility_light_network, conf.implicit_illumination_network
+        need(el.act_last == "softplus" and el.upper_bound <= 0 and el.channels == 1, "environment_light_network head")
+        need(sv.act_last == "sigmoid" and sv.channels == 1 and sv.use_geometric_feature and sv.use_normal,
+             "soft_visibility_light_network head")
+        need(ii.act_last == "sigmoid" and ii.use_me and not ii.use_me_on_specular and ii.channels == 1,
+             "implicit_illumination_network head")
+        need(conf.photogrammetric_light_network.use_me and conf.photogrammetric_light_network.use_inverse_distance,
+             "photogrammetric_light_network")
+        need(not conf.specular_reflectance_network.fixme, "specular_reflectance_network.fixme")
+        need(conf.train.rgb_loss == "l1" and conf.train.mask_weight == 0.0, "train.rgb_loss l1, mask_weight 0")
         self.cskip = 1.0 / math.sqrt(2.0) if g.use_inv_square else 1.0
         self._bufs = {}
         self._graphs = {}
@@ -1148,7 +1168,9 @@ class Engine:
             acts["bcp"] = self.mlp_forward("bc", "bcp", Op, P, [(RAWm, 13)])
         # ---------------- material attributes + per-sample losses ----------------
         ro_c, sp_c = conf.roughness_network, conf.specular_reflectance_network
-        cfg10 = [ro_c.lower_bound, ro_c.prior_value, sp_c.prior_value, sp_c.upper_bound_scale, ps.pl_gain,
+        # filament + remap: specular reflectance = 0.16 sigmoid(h)^2 with the literal 0.16 of network.py:503-504
+        # (upper_bound_scale only enters the other branch, :506, which __init__ rejects)
+        cfg10 = [ro_c.lower_bound, ro_c.prior_value, sp_c.prior_value, 0.16, ps.pl_gain,
                  tr.eikonal_weight, tr.base_color_prior_weight, tr.roughness_prior_weight,
                  tr.specular_reflectance_prior_weight, float(tr.base_color_prior_sym_backward)]
         ATT = self.buf("ATT", P, 12)
