@@ -94,7 +94,12 @@ class HBuf:
     def __init__(self, rows, cols, device, scales=None, name=None, ld=None, init=1.0):
         self.rows, self.cols = rows, cols
         self.ld = ld if ld is not None else (cols + 63) // 64 * 64
-        self.t = torch.zeros((2, rows, self.ld), dtype=torch.float16, device=device)
+        # zeroed once with the library's own fill (the planes viewed as rows * ld floats): padding columns stay zero
+        self.t = torch.empty((2, rows, self.ld), dtype=torch.float16, device=device)
+        if self.t.is_cuda:
+            _lib.call("ndjir_fill", rows * self.ld, self.t.data_ptr(), 0.0, torch.cuda.current_stream().cuda_stream)
+        else:
+            self.t.zero_()
         self.scales = scales
         self.slot = scales.slot(name, init) if (scales is not None and name is not None) else None
 
