@@ -45,7 +45,7 @@ constexpr int EPI_WARPS = 8;
 template <int EPI, bool WIDE>
 struct Cfg {
   static constexpr bool HEAVY = (EPI == EPI_MUL_S || EPI == EPI_ADJ);
-  static constexpr bool STAGED = (EPI == EPI_BIAS || EPI == EPI_SOFTPLUS || HEAVY);
+  static constexpr bool STAGED = (EPI == EPI_BIAS || EPI == EPI_SOFTPLUS || EPI == EPI_ACCUM || HEAVY);
   // weight-gradient products (MN-major, atomic epilogue), WIDE: one work item covers 256 rows of A^T (two 128-row
   // halves, one 256-column accumulator each - all of TMEM), so the dZ tile it stages serves both halves: L2 -> SM
   // traffic per product 805 -> 537 MB.  The accumulators are single-buffered then; with one or two long K ranges per
@@ -355,7 +355,10 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
       const long long m = m0 + q * 32 + lane;
       const bool row_ok = m < a.M;
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-      if (Cfg<EPI, WIDE>::STAGED && p.tma_epi) {
+      if (EPI == EPI_ACCUM && p.tma_epi) {
+        epilogue_tile_tma_accum(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), acc_parity, m0 + q * 32, n0, n_valid,
+                                tacc, chalf, inv_ab);
+      } else if (Cfg<EPI, WIDE>::STAGED && p.tma_epi) {
         epilogue_tile_tma<EPI>(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), acc_parity, m0 + q * 32,
                                row_ok, n0, n_valid, tacc, chalf, need_u, need_b, inv_ab, sc, sc2, inv_h, inv_u, mx, mx2);
       } else {
@@ -443,6 +446,18 @@ static bool map_mnmajor2(CUtensorMap* map, const __half* base, long long mn, lon
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 rows of an accumulated result: boxes of 32 columns (128 bytes) x 32 rows, 128-byte swizzle
+static bool map_epi_f32(CUtensorMap* map, const float* base, long long cols, long long rows, long long ld) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)STG_COLS, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // plane of an epilogue operand / result: N columns x M rows of halfs, boxes of 32 columns x 32 rows, 64-byte swizzle
 static bool map_epi(CUtensorMap* map, const __half* base, long long cols, long long rows, long long ld) {
   PFN_cuTensorMapEncodeTiled enc = get_encode();
@@ -494,7 +509,10 @@ static int launch_epi_w(const HArgs& a, cudaStream_t st) {
   EpiMaps em;
   for (int i = 0; i < 8; ++i) em.m[i] = mAh;
   p.tma_epi = 0;
-  if (Cfg<EPI, WIDE>::STAGED && g_h_tma_epi && !a.mn && a.N % 16 == 0) {
+  if (EPI == EPI_ACCUM) {
+    if (g_h_tma_epi && !a.mn && a.N % 16 == 0 && a.C.f && al16p(a.C.f) && a.C.ldf % 4 == 0)
+      p.tma_epi = map_epi_f32(&em.m[4], a.C.f, a.N, a.M, a.C.ldf) ? 1 : 0;
+  } else if (Cfg<EPI, WIDE>::STAGED && g_h_tma_epi && !a.mn && a.N % 16 == 0) {
     auto plane_ok = [&](const Op& o) { return o.hi && o.lo && al16p(o.hi) && al16p(o.lo) && o.ldh % 8 == 0; };
     auto absent = [&](const Op& o) { return !o.hi && !o.f; };
     bool eligible = plane_ok(a.C) && (a.bias == nullptr || al16p(a.bias));
