@@ -523,6 +523,22 @@ int ndjir_shade_backward(int n_rays, int M, const float* nhat, const float* attp
                          const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
                          const float* cfg5, float* d_el_raw, float* d_sv_raw, float* d_attpix, float* d_nhat,
                          float* d_colbg, cudaStream_t stream);
+/* the same with a per-ray weight on the colour loss (python/loss.py:63-65: with train.mask_weight > 0 the colour loss
+ * covers the object's rays only); ray_weight NULL = the calls above */
+int ndjir_shade_forward_weighted(int n_rays, int M, const float* nhat, const float* attpix, const float* raydir,
+                                 const float* dirs_u, const float* dirs_s, const float* el_raw, long long ld_el,
+                                 const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
+                                 const float* cfg5, const float* ray_weight, float* color, float* losses,
+                                 cudaStream_t stream);
+int ndjir_shade_backward_weighted(int n_rays, int M, const float* nhat, const float* attpix, const float* raydir,
+                                  const float* dirs_u, const float* dirs_s, const float* el_raw, long long ld_el,
+                                  const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
+                                  const float* cfg5, const float* ray_weight, float* d_el_raw, float* d_sv_raw,
+                                  float* d_attpix, float* d_nhat, float* d_colbg, cudaStream_t stream);
+/* out[r] = obj_mask[r] * n_rays_total / (obj_sum[0] + 1e-5): the weights that turn the 1 / n_rays_total normalisation of
+ * the colour loss into loss.py:64's 1 / (sum(obj_mask) + 1e-5) */
+int ndjir_ray_loss_weights(int n_rays, const float* obj_mask, const float* obj_sum, float n_rays_total, float* out,
+                           cudaStream_t stream);
 int ndjir_bg_color_forward(int n_rays, int Nb, const float* w_bg, long long ld_w, const float* raw, long long ld_raw,
                            float* colbg, cudaStream_t stream);
 int ndjir_bg_color_backward(int n_rays, int Nb, const float* w_bg, long long ld_w, const float* raw, long long ld_raw,
@@ -532,6 +548,20 @@ int ndjir_bg_color_backward(int n_rays, int Nb, const float* w_bg, long long ld_
 /* inverse squared camera distance fed to the photogrammetric-light network (python/network.py:396-400) */
 int ndjir_inv_sq_dist(long long n_points, long long points_per_view, const float* x, const float* camloc, float* out,
                       long long ld_out, cudaStream_t stream);
+
+/* ---- mask loss (python/loss.py:108-116) on obj_mask_pred = sum_i alpha_fg_i T_i (python/renderer.py:183-185; alpha_fg
+ *      there is the UNMASKED foreground alpha while T comes from alpha_fg * mask, so a ray that misses the bounds has
+ *      obj_mask_pred = sum_i alpha_fg_i, a ray that hits has the sum of its foreground weights).
+ *      p = clip(obj_mask_pred, 1e-3, 1 - 1e-3), term = sum_r BCE(p, obj_mask[r]) / (mask_sum + 1e-5).
+ *      acc (n_rays, ld): column `col` holds sum_i w_i (the volume-rendering reduction of a constant-1 attribute column);
+ *      alpha_fg (n_rays, N) the stored foreground alphas; mask (n_rays) the hit mask.
+ *      losses (may be NULL): [NDJIR_LOSS_MASK] += term, [NDJIR_LOSS_TOTAL] += weight * term.
+ *      d_acc / dalpha_missed (both or neither): d_acc[r, col] = weight * d term / d obj_mask_pred for rays that hit (else 0);
+ *      dalpha_missed (n_rays, N) = the same factor for every sample of a ray that misses (else 0), to be fed to
+ *      ndjir_neus_alpha_backward, which accumulates.  The gradient is 0 where the clip is active. */
+int ndjir_mask_loss(int n_rays, int N, const float* acc, long long ld, int col, const float* alpha_fg, const float* mask,
+                    const float* obj_mask, const float* mask_sum, float weight, float* losses, float* d_acc,
+                    long long ld_d, float* dalpha_missed, cudaStream_t stream);
 
 /* ---- loss plumbing (python/loss.py:59-192) ---- */
 int ndjir_ray_mask_fill(long long n_points, int N, int C, float* out, const float* mask, const float* dev_scalar,

@@ -567,6 +567,7 @@ pixel_normal_bwd_kernel(int NR, const float* __restrict__ npix, long long ld, fl
 // ---------------------------------------------------------------------------------------------------------------
 struct ShadeCfg {
   float eps_dot, spec_weight, inv_rays;   // inv_rays = 1 / (B*R over all ranks)
+  const float* ray_weight;                // per-ray weight of the colour loss (loss.py:63-65), or nullptr = 1
   int entangle, l2;
 };
 
@@ -656,12 +657,13 @@ shade_kernel(int NR, int M, const float* __restrict__ nhat, const float* __restr
     col[k] = cfg.entangle ? BCPL[k] * DL + PL * S[k] : PL * (BCPL[k] * DL + S[k]);
     col[k] += __ldg(colbg + r * 3 + k);
     float diff = col[k] - __ldg(color_gt + r * 3 + k);
-    if (cfg.l2) dc[k] = 2.f * diff * cfg.inv_rays;
-    else dc[k] = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * cfg.inv_rays;
+    const float wr = cfg.ray_weight ? __ldg(cfg.ray_weight + r) : 1.f;
+    if (cfg.l2) dc[k] = 2.f * diff * cfg.inv_rays * wr;
+    else dc[k] = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * cfg.inv_rays * wr;
     if (!BWD) {
       if (lane == 0) {
         color[r * 3 + k] = col[k];
-        atomicAdd(losses + NDJIR_LOSS_RGB, (cfg.l2 ? diff * diff : fabsf(diff)));
+        atomicAdd(losses + NDJIR_LOSS_RGB, wr * (cfg.l2 ? diff * diff : fabsf(diff)));
       }
     }
   }
@@ -823,6 +825,52 @@ hit_mask_kernel(int NR, const float* __restrict__ n_hits, float* __restrict__ ma
   if ((threadIdx.x & 31) == 0 && acc != 0.f && mask_sum) atomicAdd(mask_sum, acc);
 }
 
+// mask loss (loss.py:108-116): binary cross entropy between the clipped obj_mask_pred of a ray (renderer.py:183-185:
+// the sum of its foreground weights, or of its unmasked alphas when the ray misses the bounds) and the object mask,
+// over all rays, normalised by the hit count
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+mask_loss_kernel(int NR, int N, const float* __restrict__ acc, long long ld, int col, const float* __restrict__ alpha_fg,
+                 const float* __restrict__ mask, const float* __restrict__ obj_mask, const float* __restrict__ mask_sum,
+                 float weight, float* __restrict__ losses, float* __restrict__ d_acc, long long ld_d,
+                 float* __restrict__ dalpha_missed) {
+  const float inv = 1.f / (__ldg(mask_sum) + 1e-5f);
+  float sum = 0.f;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < NR; r += gridDim.x * blockDim.x) {
+    const bool hit = __ldg(mask + r) != 0.f;
+    float p0;
+    if (hit) {
+      p0 = acc[r * ld + col];
+    } else {
+      p0 = 0.f;
+      for (int i = 0; i < N; ++i) p0 += __ldg(alpha_fg + (long long)r * N + i);
+    }
+    const float y = __ldg(obj_mask + r);
+    const float p = fminf(fmaxf(p0, 1e-3f), 1.f - 1e-3f);
+    sum += -(y * logf(p) + (1.f - y) * logf(1.f - p));
+    if (d_acc) {
+      const bool inside = p0 > 1e-3f && p0 < 1.f - 1e-3f;
+      const float g = inside ? weight * inv * ((1.f - y) / (1.f - p) - y / p) : 0.f;
+      d_acc[r * ld_d + col] = hit ? g : 0.f;
+      const float gm = hit ? 0.f : g;
+      for (int i = 0; i < N; ++i) dalpha_missed[(long long)r * N + i] = gm;
+    }
+  }
+  sum = warp_sum(sum);
+  if (losses && (threadIdx.x & 31) == 0 && sum != 0.f) {
+    atomicAdd(losses + NDJIR_LOSS_MASK, sum * inv);
+    atomicAdd(losses + NDJIR_LOSS_TOTAL, weight * sum * inv);
+  }
+}
+
+// per-ray weights of the colour loss when a mask term is on (loss.py:63-65): sum_r |c - gt| obj_mask_r / (sum obj_mask + 1e-5)
+// = (1 / n_total) sum_r w_r |c - gt| with w_r = obj_mask_r n_total / (sum obj_mask + 1e-5)
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+ray_loss_weights_kernel(int NR, const float* __restrict__ obj_mask, const float* __restrict__ obj_sum, float n_total,
+                        float* __restrict__ out) {
+  const float k = n_total / (__ldg(obj_sum) + 1e-5f);
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < NR; r += gridDim.x * blockDim.x) out[r] = __ldg(obj_mask + r) * k;
+}
+
 // final loss assembly on the device (loss.py:180-192): losses[] holds raw sums, scal = [mask_sum_global]
 __global__ void finalize_losses_kernel(float* __restrict__ losses, const float* __restrict__ mask_sum, int N,
                                        float inv_rays, float w_eik, float w_tv, float w_bc, float w_ro, float w_sp,
@@ -851,6 +899,26 @@ using namespace ndjir;
 using namespace ndjir::render;
 
 extern "C" {
+
+int ndjir_ray_loss_weights(int n_rays, const float* obj_mask, const float* obj_sum, float n_rays_total, float* out,
+                           cudaStream_t stream) {
+  if (n_rays == 0) return NDJIR_OK;
+  if (n_rays < 0 || !obj_mask || !obj_sum || !out) return NDJIR_ERR_ARG;
+  ray_loss_weights_kernel<<<grid_for(n_rays), NDJIR_BLOCK, 0, stream>>>(n_rays, obj_mask, obj_sum, n_rays_total, out);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_mask_loss(int n_rays, int N, const float* acc, long long ld, int col, const float* alpha_fg, const float* mask,
+                    const float* obj_mask, const float* mask_sum, float weight, float* losses, float* d_acc,
+                    long long ld_d, float* dalpha_missed, cudaStream_t stream) {
+  if (n_rays == 0) return NDJIR_OK;
+  if (n_rays < 0 || N <= 0 || !acc || !alpha_fg || !mask || !obj_mask || !mask_sum || col < 0 || col >= ld ||
+      (d_acc != nullptr) != (dalpha_missed != nullptr) || (d_acc && col >= ld_d))
+    return NDJIR_ERR_ARG;
+  mask_loss_kernel<<<grid_for(n_rays), NDJIR_BLOCK, 0, stream>>>(n_rays, N, acc, ld, col, alpha_fg, mask, obj_mask,
+                                                                 mask_sum, weight, losses, d_acc, ld_d, dalpha_missed);
+  NDJIR_RETURN_LAST_ERROR();
+}
 
 int ndjir_copy2d(long long rows, int cols, float* dst, long long ld_dst, const float* src, long long ld_src, int rep,
                  float alpha, int accum, cudaStream_t stream) {
@@ -1052,9 +1120,10 @@ int ndjir_pixel_normal_backward(int n_rays, const float* npix, long long ld, flo
   NDJIR_RETURN_LAST_ERROR();
 }
 
-static ShadeCfg make_shade_cfg(const float* c) {
+static ShadeCfg make_shade_cfg(const float* c, const float* ray_weight = nullptr) {
   ShadeCfg s;
   s.eps_dot = c[0]; s.spec_weight = c[1]; s.inv_rays = c[2]; s.entangle = c[3] != 0.f; s.l2 = c[4] != 0.f;
+  s.ray_weight = ray_weight;
   return s;
 }
 
@@ -1062,13 +1131,22 @@ int ndjir_shade_forward(int n_rays, int M, const float* nhat, const float* attpi
                         const float* dirs_u, const float* dirs_s, const float* el_raw, long long ld_el,
                         const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
                         const float* cfg5, float* color, float* losses, cudaStream_t stream) {
+  return ndjir_shade_forward_weighted(n_rays, M, nhat, attpix, raydir, dirs_u, dirs_s, el_raw, ld_el, sv_raw, ld_sv, colbg,
+                                      color_gt, cfg5, nullptr, color, losses, stream);
+}
+
+int ndjir_shade_forward_weighted(int n_rays, int M, const float* nhat, const float* attpix, const float* raydir,
+                                 const float* dirs_u, const float* dirs_s, const float* el_raw, long long ld_el,
+                                 const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
+                                 const float* cfg5, const float* ray_weight, float* color, float* losses,
+                                 cudaStream_t stream) {
   if (n_rays == 0) return NDJIR_OK;
   if (n_rays < 0 || M <= 0 || !nhat || !attpix || !raydir || !dirs_u || !dirs_s || !el_raw || !sv_raw || !colbg ||
       !color_gt || !cfg5 || !color || !losses)
     return NDJIR_ERR_ARG;
   shade_kernel<false><<<(n_rays + SWARPS - 1) / SWARPS, SWARPS * 32, 0, stream>>>(
       n_rays, M, nhat, attpix, raydir, dirs_u, dirs_s, el_raw, ld_el, sv_raw, ld_sv, colbg, color_gt,
-      make_shade_cfg(cfg5), color, losses, nullptr, nullptr, nullptr, nullptr, nullptr);
+      make_shade_cfg(cfg5, ray_weight), color, losses, nullptr, nullptr, nullptr, nullptr, nullptr);
   NDJIR_RETURN_LAST_ERROR();
 }
 
@@ -1077,13 +1155,22 @@ int ndjir_shade_backward(int n_rays, int M, const float* nhat, const float* attp
                          const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
                          const float* cfg5, float* d_el_raw, float* d_sv_raw, float* d_attpix, float* d_nhat,
                          float* d_colbg, cudaStream_t stream) {
+  return ndjir_shade_backward_weighted(n_rays, M, nhat, attpix, raydir, dirs_u, dirs_s, el_raw, ld_el, sv_raw, ld_sv, colbg,
+                                       color_gt, cfg5, nullptr, d_el_raw, d_sv_raw, d_attpix, d_nhat, d_colbg, stream);
+}
+
+int ndjir_shade_backward_weighted(int n_rays, int M, const float* nhat, const float* attpix, const float* raydir,
+                                  const float* dirs_u, const float* dirs_s, const float* el_raw, long long ld_el,
+                                  const float* sv_raw, long long ld_sv, const float* colbg, const float* color_gt,
+                                  const float* cfg5, const float* ray_weight, float* d_el_raw, float* d_sv_raw,
+                                  float* d_attpix, float* d_nhat, float* d_colbg, cudaStream_t stream) {
   if (n_rays == 0) return NDJIR_OK;
   if (n_rays < 0 || M <= 0 || !nhat || !attpix || !raydir || !dirs_u || !dirs_s || !el_raw || !sv_raw || !colbg ||
       !color_gt || !cfg5 || !d_el_raw || !d_sv_raw || !d_attpix || !d_nhat || !d_colbg)
     return NDJIR_ERR_ARG;
   shade_kernel<true><<<(n_rays + SWARPS - 1) / SWARPS, SWARPS * 32, 0, stream>>>(
       n_rays, M, nhat, attpix, raydir, dirs_u, dirs_s, el_raw, ld_el, sv_raw, ld_sv, colbg, color_gt,
-      make_shade_cfg(cfg5), nullptr, nullptr, d_el_raw, d_sv_raw, d_attpix, d_nhat, d_colbg);
+      make_shade_cfg(cfg5, ray_weight), nullptr, nullptr, d_el_raw, d_sv_raw, d_attpix, d_nhat, d_colbg);
   NDJIR_RETURN_LAST_ERROR();
 }
 

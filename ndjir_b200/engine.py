@@ -363,7 +363,7 @@ class Engine:
         need(conf.photogrammetric_light_network.use_me and conf.photogrammetric_light_network.use_inverse_distance,
              "photogrammetric_light_network")
         need(not conf.specular_reflectance_network.fixme, "specular_reflectance_network.fixme")
-        need(conf.train.rgb_loss == "l1" and conf.train.mask_weight == 0.0, "train.rgb_loss l1, mask_weight 0")
+        need(conf.train.rgb_loss in ("l1", "l2"), "train.rgb_loss l1 / l2")
         self.cskip = 1.0 / math.sqrt(2.0) if g.use_inv_square else 1.0
         self._bufs = {}
         self._graphs = {}
@@ -1045,7 +1045,7 @@ class Engine:
     # total_loss forward + backward (python/loss.py:27-192 over python/renderer.py:32-209)
     # ------------------------------------------------------------------------------------------------
     def train_step(self, camloc, raydir, color_gt, rnd, cos_anneal_ratio=0.0, samples=None, zero_grad=True,
-                   backward=True, keep=False, inference=False):
+                   backward=True, keep=False, inference=False, obj_mask=None):
         """One loss.forward() + loss.backward().  `rnd` holds the explicit random tensors (scene.make_randoms) on
         the device.  Returns the (N_LOSSES,) device tensor of loss terms; gradients accumulate in self.params.grad /
         grid_grad (all-reduced over the process group when world_size > 1)."""
@@ -1065,7 +1065,8 @@ class Engine:
             self._calibrated = True
             for _ in range(2):
                 self.train_step(camloc, raydir, color_gt, rnd, cos_anneal_ratio=cos_anneal_ratio, samples=samples,
-                                zero_grad=zero_grad, backward=(backward and zero_grad), inference=inference)
+                                zero_grad=zero_grad, backward=(backward and zero_grad), inference=inference,
+                                obj_mask=obj_mask)
         if zero_grad:
             self.n_launches += 1 + len(ps.grid_grad)
             ps.zero_grad(self.stream())
@@ -1175,6 +1176,15 @@ class Engine:
                  tr.specular_reflectance_prior_weight, float(tr.base_color_prior_sym_backward)]
         ATT = self.buf("ATT", P, 12)
         self.call("ndjir_sample_attributes_forward", P, N, P_(RAW), P_(ATT), P_(nrm), 3, P_(maskv), cfg10, P_(losses))
+        # mask loss (loss.py:108-116): obj_mask_pred = sum_i alpha_i T_i (renderer.py:183-185) is the volume-rendering
+        # reduction of a constant-1 attribute: spare column 9 of ATT carries it through the forward reduction and, with
+        # d_attpix[:, 9] = d loss / d obj_mask_pred, through the weight gradients of the compositing backward
+        mask_term = tr.mask_weight > 0.0
+        if mask_term:
+            obj_mask = rnd.get("obj_mask") if obj_mask is None else obj_mask
+            if obj_mask is None:
+                raise ValueError("train.mask_weight > 0 needs obj_mask (B, R, 1)")
+            self.call("ndjir_copy2d", P, 1, P_(ATT, 9), 12, P_(self.one), 0, 1, 1.0, 0)
         attpix = self.buf("attpix", NR, 12)
         self.call("ndjir_volume_render_forward", NR, N, 12, P_(w), S, P_(ATT), 12, P_(attpix), 12)
         # ---------------- light directions, environment light, soft visibility ----------------
@@ -1209,8 +1219,16 @@ class Engine:
         # ---------------- shading + colour loss ----------------
         cfg5 = [r.eps_dot, conf.specular_brdf.weight, inv_rays, 1.0, 0.0 if tr.rgb_loss == "l1" else 1.0]
         color = self.buf("color", NR, 3)
-        self.call("ndjir_shade_forward", NR, M, P_(nhat), P_(attpix), P_(raydir), P_(dirs_u), P_(dirs_s), P_(elraw), 4,
-                  P_(svraw), 4, P_(colbg), P_(color_gt), cfg5, P_(color), P_(losses))
+        ray_w = None
+        if mask_term:     # loss.py:63-65: the colour loss over the object's rays only, / (sum(obj_mask) + 1e-5)
+            self.call("ndjir_colsum", NR, 1, P_(scal, 2), P_(obj_mask), 1, 1.0)
+            if self.world_size > 1:
+                allreduce_mask_sum(scal[0, 2:3], self.pg)
+            ray_w = self.buf("ray_loss_w", NR, 1)
+            self.call("ndjir_ray_loss_weights", NR, P_(obj_mask), P_(scal, 2), float(NR * self.world_size), P_(ray_w))
+        self.call("ndjir_shade_forward_weighted", NR, M, P_(nhat), P_(attpix), P_(raydir), P_(dirs_u), P_(dirs_s),
+                  P_(elraw), 4, P_(svraw), 4, P_(colbg), P_(color_gt), cfg5, P_(ray_w) if ray_w is not None else None,
+                  P_(color), P_(losses))
         # ---------------- TV loss ----------------
         tv_on = conf.geometric_network.voxel.type != "none" and tr.tv_weight > 0
         if tv_on:
@@ -1221,6 +1239,9 @@ class Engine:
         self.call("ndjir_finalize_losses", P_(losses), mask_sum, N, inv_rays, tr.eikonal_weight,
                   tr.tv_weight if tv_on else 0.0, tr.base_color_prior_weight, tr.roughness_prior_weight,
                   tr.specular_reflectance_prior_weight)
+        if mask_term:
+            self.call("ndjir_mask_loss", NR, N, P_(attpix), 12, 9, P_(alpha_fg), P_(maskv), P_(obj_mask), mask_sum,
+                      float(tr.mask_weight), P_(losses), None, 0, None)
         if self.world_size > 1:
             allreduce_mask_sum(losses[0, :N_LOSSES], self.pg)     # report the loss of the union of all ranks' rays
         if keep:
@@ -1238,9 +1259,13 @@ class Engine:
         d_attpix = self.buf("d_attpix", NR, 12)
         d_nhat = self.buf("d_nhat", NR, 3)
         d_colbg = self.buf("d_colbg", NR, 3)
-        self.call("ndjir_shade_backward", NR, M, P_(nhat), P_(attpix), P_(raydir), P_(dirs_u), P_(dirs_s), P_(elraw), 4,
-                  P_(svraw), 4, P_(colbg), P_(color_gt), cfg5, P_(d_el), P_(d_sv), P_(d_attpix), P_(d_nhat),
-                  P_(d_colbg))
+        self.call("ndjir_shade_backward_weighted", NR, M, P_(nhat), P_(attpix), P_(raydir), P_(dirs_u), P_(dirs_s),
+                  P_(elraw), 4, P_(svraw), 4, P_(colbg), P_(color_gt), cfg5, P_(ray_w) if ray_w is not None else None,
+                  P_(d_el), P_(d_sv), P_(d_attpix), P_(d_nhat), P_(d_colbg))
+        if mask_term:
+            dalpha_missed = self.buf("dalpha_missed", P, 1)
+            self.call("ndjir_mask_loss", NR, N, P_(attpix), 12, 9, P_(alpha_fg), P_(maskv), P_(obj_mask), mask_sum,
+                      float(tr.mask_weight), None, P_(d_attpix), 12, P_(dalpha_missed))
         # environment light: parameters only (directions carry no gradient, sampler.py:391)
         self.mlp_backward("el", "el", Xel, rows_d, acts["el"], [(Mat(f=d_el), 0)])
         # soft visibility: input gradient -> per-ray sums
@@ -1270,6 +1295,9 @@ class Engine:
                   P_(ATT), 12, P_(w), P_(T), P_(dpix), LDO, P_(d_attpix), 12, P_(d_colbg), dO.fptr(), LDO, P_(dATT), 12,
                   P_(d_bgraw), 4, P_(d_dens), 1, P_(dsdf), dO.fptr(Df + 3), LDO, g_gain,
                   P_(dw) if keep else None, P_(dalpha_fg) if keep else None, P_(dalpha_bg) if keep else None)
+        if mask_term:   # rays that miss the bounds: obj_mask_pred = sum_i alpha_fg_i reaches the SDF network through alpha alone
+            self.call("ndjir_neus_alpha_backward", P, N, P_(dalpha_missed), P_(sdf), P_(nrm), 3, P_(raydir), P_(t_fg),
+                      gain_p, float(cos_anneal_ratio), P_(dsdf), dO.fptr(Df + 3), LDO, g_gain)
         # material heads
         dRAW = self.buf("dRAW", P, 16)
         dRAWm = Mat(f=dRAW)

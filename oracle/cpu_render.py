@@ -495,9 +495,9 @@ def pb_render(model, x_fg, t_fg, x_bg, t_bg, camloc, raydir, mask, cos_anneal_ra
 
 
 def total_loss(model, camloc, raydir, color_gt, cos_anneal_ratio, rnd, return_all=False, samples=None,
-               fixed_dirs=None):
-    """loss.py:27-192 with mask_weight = 0 (obj_mask = 1, denorm = B*R).  `samples` = (x_fg,t_fg,x_bg,t_bg,mask)
-    overrides sample_points (tests freeze the non-differentiable placement)."""
+               fixed_dirs=None, obj_mask=None):
+    """loss.py:27-192.  `samples` = (x_fg,t_fg,x_bg,t_bg,mask) overrides sample_points (tests freeze the
+    non-differentiable placement).  obj_mask (B,R,1) is read when train.mask_weight > 0 (loss.py:108-116)."""
     conf, dt = model.conf, model.dtype
     tr = conf.train
     if samples is None:
@@ -507,10 +507,12 @@ def total_loss(model, camloc, raydir, color_gt, cos_anneal_ratio, rnd, return_al
     res = pb_render(model, x_fg, t_fg, x_bg, t_bg, camloc, raydir, mask, cos_anneal_ratio, rnd, fixed_dirs)
     B, Rr, N, _ = x_fg.shape
     gt = T(color_gt, dt)
-    if tr.rgb_loss == "l1":
-        loss_rgb = (res["color_pixel"] - gt).abs().sum() / (B * Rr)
+    per_ray = (res["color_pixel"] - gt).abs() if tr.rgb_loss == "l1" else (res["color_pixel"] - gt) ** 2
+    if tr.mask_weight > 0.0:      # loss.py:63-65: with a mask term the colour loss covers the object's rays only
+        om = T(obj_mask, dt).reshape(B, Rr, 1)
+        loss_rgb = (per_ray * om).sum() / (om.sum() + 1e-5)
     else:
-        loss_rgb = ((res["color_pixel"] - gt) ** 2).sum() / (B * Rr)
+        loss_rgb = per_ray.sum() / (B * Rr)
     denorm = mask.sum() * N + 1e-5
     losses = {"loss_rgb": loss_rgb}
     gn = torch.sqrt((res["grad_x_fg"] ** 2).sum(-1, keepdim=True))
@@ -532,7 +534,15 @@ def total_loss(model, camloc, raydir, color_gt, cos_anneal_ratio, rnd, return_al
     losses["prior_specular_reflectance"] = (((sp - conf.specular_reflectance_network.prior_value).abs() / ss)
                                             * mask).sum() / denorm
     losses["reg_std_specular_reflectance"] = (torch.clamp(torch.log(ss), 1e-5, 1e5) * mask).sum() / denorm
+    # mask loss (loss.py:108-116): BCE of the clipped opacity sum_i alpha_i T_i (renderer.py:183-185) against the mask
+    losses["loss_mask"] = zero
+    if tr.mask_weight > 0.0:
+        # renderer.py:183-185: the UNMASKED alpha_fg times the transmittance of the masked alphas
+        pred = torch.clamp((res["alpha_fg"] * res["trans_fg"]).sum(dim=2), 1e-3, 1.0 - 1e-3)
+        y = T(obj_mask, dt).reshape(pred.shape)
+        losses["loss_mask"] = (-(y * torch.log(pred) + (1 - y) * torch.log(1 - pred))).sum() / (mask.sum() + 1e-5)
     loss = (losses["loss_rgb"] + tr.eikonal_weight * losses["loss_eikonal"] + tr.tv_weight * losses["loss_tv"]
+            + tr.mask_weight * losses["loss_mask"]
             + tr.base_color_prior_weight * losses["prior_base_color"]
             + tr.roughness_prior_weight * (losses["prior_roughness"] + losses["reg_std_roughness"])
             + tr.specular_reflectance_prior_weight * (losses["prior_specular_reflectance"]
@@ -569,12 +579,13 @@ class _TVNoSym(torch.autograd.Function):
         return None, torch.as_tensor(gf, dtype=F.dtype), None
 
 
-def train_step(model, camloc, raydir, color_gt, cos_anneal_ratio, rnd, samples=None, fixed_dirs=None):
+def train_step(model, camloc, raydir, color_gt, cos_anneal_ratio, rnd, samples=None, fixed_dirs=None, obj_mask=None):
     """loss.forward() + loss.backward() (python/train.py:135-140): returns ({loss terms}, {param: grad})."""
     params = model.parameters()
     for p in params.values():
         p.grad = None
-    losses = total_loss(model, camloc, raydir, color_gt, cos_anneal_ratio, rnd, samples=samples, fixed_dirs=fixed_dirs)
+    losses = total_loss(model, camloc, raydir, color_gt, cos_anneal_ratio, rnd, samples=samples, fixed_dirs=fixed_dirs,
+                        obj_mask=obj_mask)
     losses["loss"].backward()
     grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
     return {k: float(v.detach()) for k, v in losses.items()}, grads

@@ -7,6 +7,7 @@ path on the same inputs).  Parameters and inputs are rebuilt from seeds, so only
                  gradient is stored
   full_default   default.yaml widths (256 / 128, skip 213 + 43), voxel 32^3 x 4, 1 view x 8 rays; large gradient
                  tensors are stored as norms + sampled entries (sampled_view)
+  small_default_mask   small_default with train.mask_weight = 0.5 and a seeded object mask (obj_mask_of)
 """
 import numpy as np
 
@@ -18,12 +19,14 @@ CASES = {
     "small_triplaneline": dict(kind="triplaneline", small=True, B=2, R=4, cos_anneal=0.0, G=32),
     "small_no_voxel": dict(kind="no_voxel", small=True, B=2, R=4, cos_anneal=1.0, G=None),
     "full_default": dict(kind="default", small=False, B=1, R=8, cos_anneal=0.5, G=32),
+    # the mask term of loss.py:108-116 (weight 0 in every BASELINE config): mask_weight 0.5, a seeded 0 / 1 object mask
+    "small_default_mask": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.6, G=16, mask_weight=0.5),
 }
 
 
 def case_conf(name):
     c = CASES[name]
-    over = dict(train={"batch_size": c["B"], "n_rays": c["R"]})
+    over = dict(train={"batch_size": c["B"], "n_rays": c["R"], "mask_weight": c.get("mask_weight", 0.0)})
     if c["small"]:
         over.update(
             geometric_network={"feature_size": 64},
@@ -55,6 +58,14 @@ def build_case(name):
     raydir[0, 0] = -raydir[0, 0]          # one ray that misses the box (mask 0)
     rnd = scene.make_randoms(conf, c["B"], c["R"], step=3)
     return conf, P, camloc, raydir, color_gt, rnd, c["cos_anneal"]
+
+
+def obj_mask_of(name):
+    """(B, R, 1) object mask of a case with a mask term (seeded), else None"""
+    c = CASES[name]
+    if not c.get("mask_weight"):
+        return None
+    return (np.random.RandomState(11).rand(c["B"], c["R"], 1) > 0.4).astype(np.float32)
 
 
 BIG = 16384

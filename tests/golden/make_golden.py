@@ -251,15 +251,6 @@ def golden_grids():
     return out
 
 
-if __name__ == "__main__":
-    if not os.path.isdir(REF):
-        sys.exit(f"{REF} not found: golden vectors can only be regenerated where the reference is mounted")
-    a = golden_intersection(); print("intersection.npz", len(a))
-    b = golden_directions(); print("directions.npz", len(b))
-    c = golden_grids(); print("grids.npz", len(c))
-    print("render_*.npz / solver.npz", golden_render())
-
-
 # ----------------------------------------------------------------------------------------------------
 # the nnabla-composed part of the path: the reference's sampler.py / network.py / renderer.py / specular_brdf.py /
 # loss.py / solver.py EXECUTED through tests/golden/nnabla_standin.py on the seeded cases of tests/golden/cases.py
@@ -271,7 +262,10 @@ def golden_render():
     from ndjir_b200 import nnabla_names
     mods = S.load_reference_modules()
     done = {}
+    only = os.environ.get("NDJIR_GOLDEN_ONLY")        # regenerate one case without touching the other fixtures
     for name in cases.CASES:
+        if only and name != only:
+            continue
         conf, P, camloc, raydir, color_gt, rnd, cos_anneal = cases.build_case(name)
         S.set_parameters(nnabla_names.to_nnabla(conf, P))
         r, tr = conf.renderer, conf.train
@@ -295,7 +289,8 @@ def golden_render():
         # total_loss (loss.py:27) forward + backward (train.py:135-140): runs sample_points + pb_render again inside
         for p in S.get_parameters().values():
             p.grad = None
-        losses = mods["loss"].total_loss(cam, ray, gt, None, car, conf)
+        om = cases.obj_mask_of(name)
+        losses = mods["loss"].total_loss(cam, ray, gt, S.V(om) if om is not None else None, car, conf)
         for k, v in losses.items():
             out[f"loss.{k}"] = np.float64(v.detach().numpy())
         losses["loss"].backward()
@@ -317,6 +312,8 @@ def golden_render():
                 out[f"grad.{okey}"] = g
         np.savez_compressed(os.path.join(OUT, f"render_{name}.npz"), **out)
         done[name] = len(out)
+    if only:
+        return done
     # solver.py: schedules + one Solvers iteration in the order of train.py:135-148 over a tiny parameter set
     out = {}
     conf = cases.case_conf("small_default")
@@ -360,3 +357,13 @@ def golden_render():
     np.savez_compressed(os.path.join(OUT, "solver.npz"), **out)
     done["solver"] = len(out)
     return done
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        sys.exit(f"{REF} not found: golden vectors can only be regenerated where the reference is mounted")
+    if not os.environ.get("NDJIR_GOLDEN_ONLY"):      # NDJIR_GOLDEN_ONLY=<render case>: write that fixture alone
+        a = golden_intersection(); print("intersection.npz", len(a))
+        b = golden_directions(); print("directions.npz", len(b))
+        c = golden_grids(); print("grids.npz", len(c))
+    print("render_*.npz / solver.npz", golden_render())

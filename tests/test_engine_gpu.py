@@ -114,9 +114,10 @@ class Report:
         assert not self.bad, "\n".join(self.bad)
 
 
-def setup(kind, seed=0, miss=True, grid_std=0.05, shape="small", mlp="h16"):
+def setup(kind, seed=0, miss=True, grid_std=0.05, shape="small", mlp="h16", mask_weight=0.0):
     from ndjir_b200.engine import Engine
     conf = small_conf(kind) if shape == "small" else full_conf(kind)
+    conf.train.mask_weight = mask_weight
     # A scene WITH a surface: the geometric initialisation's sphere (radius 0.6 here) stays intact under a small
     # perturbation of the SDF network, and every second ray is aimed at it.  (Perturbing the SDF network as much as the
     # heads pushes the SDF above 0.6 everywhere: no ray meets a surface, every alpha sits at its 1e-5 floor where
@@ -336,6 +337,61 @@ def test_train_step_matches_oracle(kind, cos_anneal, shape, mlp_path):
             continue
         w32 = params32[k].grad.detach().numpy() if params32[k].grad is not None else np.zeros(tuple(p.shape))
         rep.check(f"grad.{k}", ours[k], want, g_tol, w32, l2_tol=1e-4)
+    rep.finish()
+
+
+@pytest.mark.parametrize("mlp_path", ["h16", "ffma"])
+def test_mask_loss_term_matches_oracle(mlp_path):
+    """train.mask_weight > 0 (loss.py:108-116; weight 0 in every BASELINE config): BCE between the clipped opacity
+    sum_i alpha_i T_i of a ray and the object mask.  The scene has rays with a surface (opacity ~1, clip active, zero
+    gradient) and rays without (opacity inside the clip range): loss value, total loss and every parameter gradient
+    against the oracle's autograd, which tests/test_render_golden.py pins on the reference's own loss.py for this term."""
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup("default", shape="small",
+                                                               mlp="h16" if mlp_path == "h16" else "fp32",
+                                                               mask_weight=0.5)
+    rep = Report(f"train_mask_{mlp_path}")
+    B, R = conf.train.batch_size, conf.train.n_rays
+    obj_mask = (np.random.RandomState(11).rand(B, R, 1) > 0.4).astype(np.float32)
+    samples = CR.sample_points(model, camloc, raydir, rnd["stratified"], rnd["background"])
+    samples32 = [dev(s.numpy()) for s in samples]
+    drnd = {k: dev(v) for k, v in rnd.items()}
+    losses = eng.train_step(dev(camloc), dev(raydir), dev(color_gt), drnd, cos_anneal_ratio=0.4, samples=samples32,
+                            keep=True, obj_mask=dev(obj_mask))
+    torch.cuda.synchronize()
+    d = eng.debug
+    B, R, N, Nb, M = d["dims"]
+    NR = B * R
+    fixed = (d["dirs_u"][:NR * M].reshape(B, R, M, 3).cpu().numpy(), d["dirs_s"][:NR * M].reshape(B, R, M, 3).cpu().numpy())
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        m = model if dt == torch.float64 else CR.Model(conf, P, dtype=torch.float32)
+        smp = [torch.as_tensor(s.cpu().numpy(), dtype=dt) for s in samples32]
+        ol, res, _ = CR.total_loss(m, camloc, raydir, color_gt, 0.4, rnd, return_all=True, samples=smp, fixed_dirs=fixed,
+                                   obj_mask=obj_mask)
+        params = m.parameters()
+        for p in params.values():
+            p.grad = None
+        ol["loss"].backward()
+        out[dt] = (ol, res, params)
+    ol, res, params = out[torch.float64]
+    pred = res["weights_fg"].sum(dim=2).detach().reshape(NR)
+    inside = ((pred > 1e-3) & (pred < 1 - 1e-3)).numpy()
+    assert inside.any() and float(ol["loss_mask"]) > 0
+    rep.check("obj_mask_pred", d["attpix"][:NR, 9], pred, 5e-5)
+    for i, k in ((0, "loss"), (4, "loss_mask")):
+        want, got = float(ol[k].detach()), float(losses[i])
+        e = abs(got - want) / abs(want)
+        rep.rows.append(dict(what=f"loss.{k}", err=e, tol=5e-5, ok=bool(e <= 5e-5)))
+        if e > 5e-5:
+            rep.bad.append(f"loss.{k}: got {got} want {want}")
+    ours = eng.params.export_reference("grad")
+    for k, p in params.items():
+        want = p.grad.detach().numpy() if p.grad is not None else np.zeros(tuple(p.shape))
+        if np.abs(want).max() == 0 and np.abs(ours[k]).max() == 0:
+            continue
+        p32 = out[torch.float32][2][k]
+        w32 = p32.grad.detach().numpy() if p32.grad is not None else np.zeros(tuple(p.shape))
+        rep.check(f"grad.{k}", ours[k], want, 1e-4, w32, l2_tol=1e-4)
     rep.finish()
 
 

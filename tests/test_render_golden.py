@@ -36,7 +36,7 @@ def case(request):
     conf, P, camloc, raydir, color_gt, rnd, cos_anneal = cases.build_case(name)
     model = CR.Model(conf, P, dtype=torch.float64)
     return dict(name=name, g=g, conf=conf, P=P, camloc=camloc, raydir=raydir, color_gt=color_gt, rnd=rnd,
-                cos_anneal=cos_anneal, model=model)
+                cos_anneal=cos_anneal, model=model, obj_mask=cases.obj_mask_of(name))
 
 
 def test_sample_points_equals_reference(case):
@@ -57,22 +57,27 @@ def test_pb_render_and_losses_equal_reference(case):
     g, m = case["g"], case["model"]
     samples = [torch.as_tensor(g[f"samples.{k}"]) for k in ("x_fg", "t_fg", "x_bg", "t_bg", "mask")]
     losses, res, _ = CR.total_loss(m, case["camloc"], case["raydir"], case["color_gt"], case["cos_anneal"], case["rnd"],
-                                   return_all=True, samples=samples)
+                                   return_all=True, samples=samples, obj_mask=case["obj_mask"])
     for k in ("color_pixel", "sdf_x_fg", "grad_x_fg", "alpha_fg", "trans_fg", "base_color", "base_color_ptb",
               "roughness", "specular_reflectance", "std_roughness", "std_specular_reflectance"):
         assert rel(res[k], g[f"render.{k}"]) < TOL, (k, rel(res[k], g[f"render.{k}"]))
-    for k in ("loss", "loss_rgb", "loss_eikonal", "loss_tv", "prior_base_color", "prior_roughness",
+    for k in ("loss", "loss_rgb", "loss_eikonal", "loss_tv", "loss_mask", "prior_base_color", "prior_roughness",
               "prior_specular_reflectance", "reg_std_roughness", "reg_std_specular_reflectance"):
         want = float(g[f"loss.{k}"])
         got = float(losses[k].detach())
         assert abs(got - want) <= TOL * max(abs(want), 1e-12), (k, got, want)
-    assert float(g["loss.loss_mask"]) == 0.0
+    if case["obj_mask"] is None:
+        assert float(g["loss.loss_mask"]) == 0.0
+    else:       # the mask term of loss.py:108-116 on the reference's own obj_mask_pred (renderer.py:183-185)
+        assert float(g["loss.loss_mask"]) > 0.0
+        assert rel((res["alpha_fg"] * res["trans_fg"]).sum(dim=2), g["render.obj_mask_pred"]) < TOL
 
 
 def test_gradients_equal_reference(case):
     """loss.backward() of the reference (every MLP, the gain, the grid tables) against the oracle's autograd."""
     g, m = case["g"], case["model"]
-    _, grads = CR.train_step(m, case["camloc"], case["raydir"], case["color_gt"], case["cos_anneal"], case["rnd"])
+    _, grads = CR.train_step(m, case["camloc"], case["raydir"], case["color_gt"], case["cos_anneal"], case["rnd"],
+                             obj_mask=case["obj_mask"])
     seen = 0
     for k, gr in grads.items():
         gr = gr.numpy()
