@@ -694,6 +694,14 @@ typedef struct ndjir_geo_scratch {
 int ndjir_geo_sdf_forward(const ndjir_geo_net* net, long long rows, const float* x, float* sdf,
                           const ndjir_geo_scratch* ws, cudaStream_t stream);
 
+/* SDF on the marching-cubes lattice (python/extract_by_mc.py:47-73 compute_pts_vol: linspace(-radius, radius, G)^3, x the
+ * slowest axis): `n_planes` x-planes ix0, ix0 + ix_stride, ... (the rank stride of a sharded extraction), evaluated in
+ * batches of whole planes of at most batch_points points.  pts: scratch for batch_points x 3 floats; ws: sized for
+ * batch_points rows; sdf_out (n_planes, G, G). */
+int ndjir_sdf_lattice(const ndjir_geo_net* net, int G, int ix0, int ix_stride, int n_planes, float radius,
+                      long long batch_points, float* pts, const ndjir_geo_scratch* ws, float* sdf_out,
+                      cudaStream_t stream);
+
 typedef struct ndjir_sampler_config {
   int n_samples0, n_samples1, n_upsamples, n_bg_samples;    /* renderer.n_samples0 / n_samples1 / n_upsamples / n_bg_samples */
   float sampling_sigmoid_gain;                               /* doubled every round (sampler.py:188) */

@@ -105,6 +105,22 @@ extern "C" int ndjir_geo_sdf_forward(const ndjir_geo_net* net, long long rows, c
   return ndjir_gemm_h(&d, st);
 }
 
+extern "C" int ndjir_sdf_lattice(const ndjir_geo_net* net, int G, int ix0, int ix_stride, int n_planes, float radius,
+                                 long long batch_points, float* pts, const ndjir_geo_scratch* ws, float* sdf_out,
+                                 cudaStream_t st) {
+  if (!net || !ws || !pts || !sdf_out || G < 2 || ix0 < 0 || ix_stride < 1 || n_planes < 0) return NDJIR_ERR_ARG;
+  const long long plane = (long long)G * G;
+  const long long per = batch_points / plane;
+  if (per < 1) return NDJIR_ERR_ARG;
+  for (long long p0 = 0; p0 < n_planes; p0 += per) {
+    const long long cnt = (n_planes - p0) < per ? (n_planes - p0) : per;
+    const long long n = cnt * plane;
+    NDJIR_TRY(ndjir_lattice_points(n, G, ix0 + (int)p0 * ix_stride, ix_stride, radius, pts, st));
+    NDJIR_TRY(ndjir_geo_sdf_forward(net, n, pts, sdf_out + p0 * plane, ws, st));
+  }
+  return NDJIR_OK;
+}
+
 extern "C" int ndjir_sample_points_fwd(const ndjir_sampler_config* cfg, const ndjir_geo_net* net, int B, int R,
                                        const float* camloc, const float* raydir, const float* stratified,
                                        const float* background, const ndjir_sampler_workspace* ws, float* x_fg,

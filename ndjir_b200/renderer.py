@@ -108,6 +108,26 @@ def sdf_volume(conf, grid_size, batch_size=1 << 20, rank=0, world_size=1, proces
     per = max(1, batch_size // (G * G))
     pts = torch.empty((per * G * G, 3), dtype=torch.float32, device="cuda")
     eng.refresh_transposes()      # W^T and the split copies of the weights must match the current parameters
+    if eng.h16 and eng.fused_sampler and len(xs):
+        # the whole extraction is ONE C-ABI call (ndjir_sdf_lattice, csrc/fused_path.cu): lattice points and network
+        # evaluation are sequenced inside the library, on the engine's own scratch buffers and scale slots
+        from . import h16
+        rows = per * G * G
+        eng._reserve = rows
+        A0 = eng.mat("smp_A0", rows, eng.din, "fa")
+        widest = max(L.K for L in eng.params.nets["geo"][1:])
+        act = [eng.mat(f"geo_pp{i}", rows, widest, "a") for i in (0, 1)]
+        gw = sum(w for _, w, _ in eng._grid_parts())
+        gtmp = eng.buf("gq_fused", rows, max(gw, 1)) if gw else None
+        eng._reserve = 0
+        ws = h16.GeoScratch()
+        ws.enc, ws.ld_enc = A0.f.data_ptr(), eng.ld0
+        ws.grid_tmp = gtmp.data_ptr() if gtmp is not None else None
+        ws.ench = A0.hmat(0)
+        ws.act[0], ws.act[1] = act[0].hmat(0), act[1].hmat(0)
+        _lib.call("ndjir_sdf_lattice", eng.geo_net_desc(), G, xs[0], world_size, len(xs), rad, rows, pts, ws, out,
+                  torch.cuda.current_stream().cuda_stream)
+        xs = []
     for s0 in range(0, len(xs), per):
         cnt = min(per, len(xs) - s0)
         npts = cnt * G * G

@@ -200,6 +200,17 @@ def test_render_image_is_chunk_invariant_and_sdf_volume_matches_oracle():
     pts = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), dim=-1).reshape(-1, 3)
     want = model.geometric_network(pts)[0].detach().reshape(9, 9, 9).numpy()
     np.testing.assert_allclose(vol.cpu().numpy(), want, atol=2e-5 * np.abs(want).max())
+    # the extraction as ONE C-ABI call (ndjir_sdf_lattice) against the chunk loop sequenced in Python: same kernels on the
+    # same buffers, bit-identical; and a sharded extraction (rank 1 of 2) returns that rank's x-planes
+    eng = get_engine(conf)
+    eng.fused_sampler = False
+    vol_py = renderer.sdf_volume(conf, 9, batch_size=200)
+    part_py = renderer.sdf_volume(conf, 9, batch_size=200, rank=1, world_size=2)
+    eng.fused_sampler = True
+    vol_c = renderer.sdf_volume(conf, 9, batch_size=200)
+    part_c = renderer.sdf_volume(conf, 9, batch_size=200, rank=1, world_size=2)
+    assert torch.equal(vol_c, vol_py) and torch.equal(part_c, part_py)
+    assert part_c.shape == (4, 9, 9) and torch.equal(part_c, vol_c[1::2])
 
 
 def test_device_ray_generation_and_uniform_numbers():
