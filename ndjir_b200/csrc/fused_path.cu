@@ -3,6 +3,7 @@
 // that enqueue this library's kernels.  No allocation, no synchronisation, no Python: a C / C++ host can run them.
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm_h.cuh"
 #include "../../include/ndjir_b200.h"
 
 namespace {
@@ -73,6 +74,12 @@ extern "C" int ndjir_geo_sdf_forward(const ndjir_geo_net* net, long long rows, c
     if (e != cudaSuccess) return (int)e;
   }
   NDJIR_TRY(pack_cols(rows, din, ws->enc, ws->ld_enc, 1.f, ws->ench, 0, st));
+  // all layers in ONE kernel with the activations on chip (csrc/gemm_h_chain.cu) when the shapes fit it
+  {
+    const int rc = ndjir::gemmh::launch_geo_chain(net, rows, din, &ws->ench, ws->enc, ws->ld_enc, ws->act, sdf, st);
+    if (rc == NDJIR_OK) return NDJIR_OK;
+    if (rc != NDJIR_ERR_ARG) return rc;
+  }
   // hidden layers: affine + softplus_100, the skip layer's input is [a | encoded input] / sqrt2   (network.py:160-188)
   ndjir_hmat cur = ws->ench;
   for (int l = 0; l < net->n_hidden; ++l) {

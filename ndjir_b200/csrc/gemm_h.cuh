@@ -119,6 +119,9 @@ int launch_pair(const HArgs& a, cudaStream_t st);     // gemm_h2.cu
 extern int g_h_resident;                              // gemm_h3.cu: 1 = resident-weight kernel for K-major products, K <= 256
 bool resident_eligible(const HArgs& a);               // gemm_h3.cu
 int launch_resident(const HArgs& a, cudaStream_t st); // gemm_h3.cu
+extern int g_h_chain;                                 // gemm_h_chain.cu: 1 = the SDF network as one kernel, activations on chip
+int launch_geo_chain(const ndjir_geo_net* net, long long rows, int din, const ndjir_hmat* ench, const float* enc32,
+                     long long ld_enc32, const ndjir_hmat* act, float* sdf, cudaStream_t st);   // gemm_h_chain.cu
 bool corner_shape(const HArgs& a);                    // h16_ops.cu
 int launch_corner(const HArgs& a, cudaStream_t st);   // h16_ops.cu
 

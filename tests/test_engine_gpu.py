@@ -157,19 +157,36 @@ def test_sample_points_one_c_abi_call_equals_the_sequenced_path(kind, shape):
     """ndjir_sample_points_fwd (csrc/fused_path.cu: the round loop of sampler.py:140-314 sequenced inside the library,
     what a non-Python host calls) enqueues the same kernels on the same buffers as the stage-by-stage sequencing of
     Engine.sample_points: every output must be bit-identical, and so must the hit count."""
+    from ndjir_b200 import _lib
     conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind, shape=shape)
     args = [dev(camloc), dev(raydir), dev(rnd["stratified"]), dev(rnd["background"])]
     outs = {}
-    for fused in (False, True, False, True):      # twice each: the delayed scales of the second pass are the settled ones
-        eng.fused_sampler = fused
-        ms = torch.zeros(1, device="cuda")
-        o = eng.sample_points(*args, mask_sum=ms)
-        torch.cuda.synchronize()
-        outs[fused] = [t.clone() for t in o] + [ms.clone()]
+    _lib.call("ndjir_set_option", "mlp_h_chain", 0)      # layer-by-layer network evaluation on both sides
+    try:
+        for fused in (False, True, False, True):  # twice each: the delayed scales of the second pass are the settled ones
+            eng.fused_sampler = fused
+            ms = torch.zeros(1, device="cuda")
+            o = eng.sample_points(*args, mask_sum=ms)
+            torch.cuda.synchronize()
+            outs[fused] = [t.clone() for t in o] + [ms.clone()]
+    finally:
+        _lib.call("ndjir_set_option", "mlp_h_chain", 1)
     eng.fused_sampler = True
     for name, a, b in zip(("x_fg", "t_fg", "x_bg", "t_bg", "mask", "mask_sum"), outs[False], outs[True]):
         assert torch.equal(a, b), name
     assert float(outs[True][5]) == float(outs[True][4].sum())
+    # the default: the SDF network of every round as ONE kernel with the activations on chip (csrc/gemm_h_chain.cu).  Its
+    # SDF differs from the layer-wise one by float32 rounding (the last activation is not rounded to the split format
+    # before the sdf column), which moves samples continuously except where a CDF decision flips.
+    for _ in range(2):
+        ms = torch.zeros(1, device="cuda")
+        o = eng.sample_points(*args, mask_sum=ms)
+    torch.cuda.synchronize()
+    assert torch.equal(o[4], outs[True][4]) and float(ms) == float(outs[True][5])
+    t_c, t_l = o[1].reshape(-1), outs[True][1].reshape(-1)
+    close = ((t_c - t_l).abs() <= 1e-4 * t_l.abs().max()).float().mean()
+    assert float(close) >= 0.99, float(close)
+    assert torch.allclose(o[3], outs[True][3])
 
 
 @pytest.mark.parametrize("kind,shape", [("default", "small"), ("triplaneline", "small"), ("no_voxel", "small"),
