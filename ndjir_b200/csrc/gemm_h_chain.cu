@@ -300,7 +300,8 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 
 }  // namespace chain
 
-int g_h_chain = 1;    // 0: ndjir_geo_sdf_forward runs the layers as separate products
+int g_h_chain = 0;    // 1: ndjir_geo_sdf_forward runs the whole network in this kernel (measured slower than the layer-wise
+                      // products: the weights re-stream from L2 for every 128-row tile)
 
 // The SDF network of `net` over `rows` encoded inputs (planes `ench`, fp32 rows `enc`), layer scales / running maxima
 // in act[l & 1] like the layer-wise sequencing.  Returns NDJIR_ERR_ARG when the shapes do not fit the kernel (the caller

@@ -371,7 +371,7 @@ int ndjir_set_option(const char* key, int value) {
       {"mlp_dbg", &ndjir::gemm::g_mlp_dbg},                 // profiling switches of the tcgen05 kernel
       {"mlp_mask_hi", &ndjir::gemm::g_mlp_mask_hi},
       {"mlp_h_dbg", &ndjir::gemmh::g_h_dbg},                // profiling switches of the split-fp16 tcgen05 kernel
-      {"mlp_h_chain", &ndjir::gemmh::g_h_chain},            // 0: the SDF-only network evaluation layer by layer
+      {"mlp_h_chain", &ndjir::gemmh::g_h_chain},            // 1: the SDF-only network evaluation as one on-chip kernel
       {"mlp_h_tall", &ndjir::gemmh::g_h_tall},              // 0: 128-row work items in the weight-gradient products
       {"mlp_h_tma_epi", &ndjir::gemmh::g_h_tma_epi},        // 0: row-per-lane global accesses in every epilogue
       {"mlp_h_resident", &ndjir::gemmh::g_h_resident},      // 1 (default): resident-weight kernel (csrc/gemm_h3.cu)

@@ -204,21 +204,21 @@ def test_render_image_is_chunk_invariant_and_sdf_volume_matches_oracle():
     # same buffers, bit-identical; and a sharded extraction (rank 1 of 2) returns that rank's x-planes
     from ndjir_b200 import _lib
     eng = get_engine(conf)
-    _lib.call("ndjir_set_option", "mlp_h_chain", 0)       # layer-by-layer network evaluation on both sides
-    try:
-        eng.fused_sampler = False
-        vol_py = renderer.sdf_volume(conf, 9, batch_size=200)
-        part_py = renderer.sdf_volume(conf, 9, batch_size=200, rank=1, world_size=2)
-        eng.fused_sampler = True
-        vol_c = renderer.sdf_volume(conf, 9, batch_size=200)
-        part_c = renderer.sdf_volume(conf, 9, batch_size=200, rank=1, world_size=2)
-    finally:
-        _lib.call("ndjir_set_option", "mlp_h_chain", 1)
-        eng.fused_sampler = True
+    eng.fused_sampler = False
+    vol_py = renderer.sdf_volume(conf, 9, batch_size=200)
+    part_py = renderer.sdf_volume(conf, 9, batch_size=200, rank=1, world_size=2)
+    eng.fused_sampler = True
+    vol_c = renderer.sdf_volume(conf, 9, batch_size=200)
+    part_c = renderer.sdf_volume(conf, 9, batch_size=200, rank=1, world_size=2)
     assert torch.equal(vol_c, vol_py) and torch.equal(part_c, part_py)
     assert part_c.shape == (4, 9, 9) and torch.equal(part_c, vol_c[1::2])
-    # (`vol` above came from the default path: the whole network as one kernel, csrc/gemm_h_chain.cu)
-    np.testing.assert_allclose(vol.cpu().numpy(), vol_c.cpu().numpy(), atol=1e-5 * np.abs(want).max())
+    # option mlp_h_chain: the whole network as one kernel with the activations on chip (csrc/gemm_h_chain.cu)
+    _lib.call("ndjir_set_option", "mlp_h_chain", 1)
+    try:
+        vol_chain = renderer.sdf_volume(conf, 9, batch_size=200)
+    finally:
+        _lib.call("ndjir_set_option", "mlp_h_chain", 0)
+    np.testing.assert_allclose(vol_chain.cpu().numpy(), want, atol=2e-5 * np.abs(want).max())
 
 
 def test_device_ray_generation_and_uniform_numbers():

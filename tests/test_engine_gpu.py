@@ -161,27 +161,27 @@ def test_sample_points_one_c_abi_call_equals_the_sequenced_path(kind, shape):
     conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind, shape=shape)
     args = [dev(camloc), dev(raydir), dev(rnd["stratified"]), dev(rnd["background"])]
     outs = {}
-    _lib.call("ndjir_set_option", "mlp_h_chain", 0)      # layer-by-layer network evaluation on both sides
-    try:
-        for fused in (False, True, False, True):  # twice each: the delayed scales of the second pass are the settled ones
-            eng.fused_sampler = fused
-            ms = torch.zeros(1, device="cuda")
-            o = eng.sample_points(*args, mask_sum=ms)
-            torch.cuda.synchronize()
-            outs[fused] = [t.clone() for t in o] + [ms.clone()]
-    finally:
-        _lib.call("ndjir_set_option", "mlp_h_chain", 1)
+    for fused in (False, True, False, True):      # twice each: the delayed scales of the second pass are the settled ones
+        eng.fused_sampler = fused
+        ms = torch.zeros(1, device="cuda")
+        o = eng.sample_points(*args, mask_sum=ms)
+        torch.cuda.synchronize()
+        outs[fused] = [t.clone() for t in o] + [ms.clone()]
     eng.fused_sampler = True
     for name, a, b in zip(("x_fg", "t_fg", "x_bg", "t_bg", "mask", "mask_sum"), outs[False], outs[True]):
         assert torch.equal(a, b), name
     assert float(outs[True][5]) == float(outs[True][4].sum())
-    # the default: the SDF network of every round as ONE kernel with the activations on chip (csrc/gemm_h_chain.cu).  Its
-    # SDF differs from the layer-wise one by float32 rounding (the last activation is not rounded to the split format
-    # before the sdf column), which moves samples continuously except where a CDF decision flips.
-    for _ in range(2):
-        ms = torch.zeros(1, device="cuda")
-        o = eng.sample_points(*args, mask_sum=ms)
-    torch.cuda.synchronize()
+    # option mlp_h_chain: the SDF network of every round as ONE kernel with the activations on chip
+    # (csrc/gemm_h_chain.cu).  Its SDF differs from the layer-wise one by float32 rounding (the last activation is not
+    # rounded to the split format before the sdf column), which moves samples continuously except where a CDF decision flips.
+    _lib.call("ndjir_set_option", "mlp_h_chain", 1)
+    try:
+        for _ in range(2):
+            ms = torch.zeros(1, device="cuda")
+            o = eng.sample_points(*args, mask_sum=ms)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("ndjir_set_option", "mlp_h_chain", 0)
     assert torch.equal(o[4], outs[True][4]) and float(ms) == float(outs[True][5])
     t_c, t_l = o[1].reshape(-1), outs[True][1].reshape(-1)
     close = ((t_c - t_l).abs() <= 1e-4 * t_l.abs().max()).float().mean()

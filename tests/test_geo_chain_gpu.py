@@ -45,12 +45,12 @@ def test_chained_sdf_network_matches_oracle_and_layerwise(kind, rows):
     pts = (torch.rand((rows, 3), device="cuda", generator=g) * 1.6 - 0.8).contiguous()
     with torch.no_grad():
         want = model.geometric_network(pts.cpu().double())[0].reshape(-1).numpy()
-    got_chain = sdf_through_c_abi(eng, pts).cpu().numpy()
-    _lib.call("ndjir_set_option", "mlp_h_chain", 0)
+    got_layers = sdf_through_c_abi(eng, pts).cpu().numpy()
+    _lib.call("ndjir_set_option", "mlp_h_chain", 1)       # off by default (measured slower)
     try:
-        got_layers = sdf_through_c_abi(eng, pts).cpu().numpy()
+        got_chain = sdf_through_c_abi(eng, pts).cpu().numpy()
     finally:
-        _lib.call("ndjir_set_option", "mlp_h_chain", 1)
+        _lib.call("ndjir_set_option", "mlp_h_chain", 0)
     scale = np.abs(want).max()
     e_chain, e_layers = np.abs(got_chain - want).max() / scale, np.abs(got_layers - want).max() / scale
     assert e_layers < 1e-5, e_layers
