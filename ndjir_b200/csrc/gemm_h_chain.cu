@@ -8,7 +8,9 @@
 //   * the tile's current activation lives in shared memory as the A operand of the next product: 4 K blocks x 2 planes
 //     (hi, lo) x 16 KB = 128 KB, K-major 128-byte-swizzled rows exactly as TMA would have written them;
 //   * the weights stream: a ring of 3 slots of 32 KB (one 256 x 64 piece of one plane of W^T), fetched by TMA while the
-//     previous layer's epilogue runs;
+//     previous layer's epilogue runs.  CTAs run as clusters of two that walk their tiles in lockstep: each fetches HALF
+//     of every weight piece and multicasts it into both CTAs' slots, so a tile-layer pulls 128-192 KB instead of
+//     256-384 KB through the L2 -> SM path (which bounded the first version: 27.7 k cycles per tile-layer);
 //   * the epilogue reads the 128 x 256 accumulator from TMEM (one row per thread), applies bias + softplus_100 (+ the
 //     skip layer's 1/sqrt2 and the concatenation with the encoded input, network.py:171-176), splits the result into
 //     hi / lo halves with the layer's power-of-two scale and writes them IN PLACE over the operand tile the finished
@@ -70,7 +72,7 @@ struct ChainParams {
 
 struct ChainMaps {
   CUtensorMap enc[2];                 // encoded input planes: box 64 x 128 rows
-  CUtensorMap w[MAX_LAYERS][2];       // W^T planes per layer: box 64 x 256 rows
+  CUtensorMap w[MAX_LAYERS][2];       // W^T planes per layer: box 64 x 128 rows (one CTA's half of a piece)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -95,7 +97,7 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), 2);          // both CTAs of the cluster have consumed the slot (multicast commits)
     }
     mbar_init(bar_a0, 1);
     mbar_init(bar_layer, EPI_THREADS);
@@ -115,16 +117,24 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  cluster_barrier();           // both CTAs' barriers exist before any multicast write / remote arrival
   tc_fence_after();
   const uint32_t tacc0 = tmem_base_sh;
   const int n_tiles = (int)((p.rows + BM - 1) / BM);
   const int nkb0 = (p.din + BK - 1) / BK;
+  // the two CTAs of a cluster take adjacent tiles and the same number of them (a tile index past the end is a dummy:
+  // zero-filled input, nothing stored), so their weight rings advance together
+  const uint32_t crank = cluster_rank();
+  const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int iters = (n_tiles + 2 * n_clusters - 1) / (2 * n_clusters);
+  auto tile_of = [&](int k) { return (k * n_clusters + cluster_id) * 2 + (int)crank; };
 
   if (warp == 0) {
     // ===================== TMA producer: the tile's encoded input, then every layer's weight pieces =====================
     if (lane == 0) {
-      uint32_t it = 0, tile_it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+      uint32_t it = 0;
+      for (int tile_it = 0; tile_it < iters; ++tile_it) {
+        const int tile = tile_of(tile_it);
         if (tile_it) mbar_wait(bar_tile, (tile_it - 1) & 1);      // the previous tile's last products have read the operand tile
         mbar_expect_tx(bar_a0, (uint32_t)(nkb0 * 2 * PIECE));
         for (int kb = 0; kb < nkb0; ++kb) {
@@ -136,8 +146,9 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           auto load = [&](int plane, int kb) {
             const int s = it % NSLOT;
             mbar_wait(bar_empty(s), ((it / NSLOT) & 1) ^ 1);
-            mbar_expect_tx(bar_full(s), (uint32_t)B_SLOT);
-            tma_load_2d(b_slot(s), &maps.w[l][plane], kb * BK, 0, bar_full(s));
+            mbar_expect_tx(bar_full(s), (uint32_t)B_SLOT);       // this CTA's half + the peer's half
+            tma_load_2d_mc(b_slot(s) + crank * (B_SLOT / 2), &maps.w[l][plane], kb * BK, (int)crank * (BN / 2), bar_full(s),
+                           (uint16_t)3);
             ++it;
           };
           for (int kb = 0; kb < nkb; ++kb) { load(0, kb); load(1, kb); }
@@ -150,8 +161,8 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint64_t d0 = make_desc(smem_base, 16, 1024, 2);      // K-major SWIZZLE_128B, a K step of 16 halfs = +32 B
-      uint32_t it = 0, tile_it = 0, layer_it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+      uint32_t it = 0, layer_it = 0;
+      for (int tile_it = 0; tile_it < iters; ++tile_it) {
         for (int l = 0; l < p.n_layers; ++l, ++layer_it) {
           const LayerP& L = p.L[l];
           const int nkb = (L.K + BK - 1) / BK;
@@ -179,8 +190,8 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               umma_f16(tacc0, ah, bl, idesc, 1u);        // hi * lo
               if (!p.precise) umma_f16(tacc0, ah, bh, idesc, 1u);
             }
-            umma_commit(bar_empty(sx));
-            umma_commit(bar_empty(sy));
+            umma_commit_mc(bar_empty(sx), (uint16_t)3);
+            umma_commit_mc(bar_empty(sy), (uint16_t)3);
             it += 2;
           }
           if (p.precise) {
@@ -194,7 +205,7 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                 const uint64_t bh = d0 + (uint64_t)((A_BYTES + s * B_SLOT + ks * 32) >> 4);
                 umma_f16(tacc0, ah, bh, idesc, 1u);      // hi * hi at full magnitude, last
               }
-              umma_commit(bar_empty(s));
+              umma_commit_mc(bar_empty(s), (uint16_t)3);
             }
           }
           umma_commit(bar_acc);
@@ -211,8 +222,8 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     const uint32_t tacc = tacc0 + ((uint32_t)(q * 32) << 16);
     const uint32_t sw = (uint32_t)(row & 7);
     uint32_t layer_it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long m = (long long)tile * BM + row;
+    for (int tile_it = 0; tile_it < iters; ++tile_it) {
+      const long long m = (long long)tile_of(tile_it) * BM + row;
       const bool row_ok = m < p.rows;
 #pragma unroll 1
       for (int l = 0; l < p.n_layers; ++l, ++layer_it) {
@@ -292,6 +303,7 @@ geo_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  cluster_barrier();           // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tacc0), "r"((uint32_t)BN) : "memory");
@@ -335,8 +347,8 @@ int launch_geo_chain(const ndjir_geo_net* net, long long rows, int din, const nd
     o.append_enc = into_skip ? 1 : 0;
     o.w_scale = L.Wt.scale;
     o.o_scale = act[l & 1].scale; o.o_amax = act[l & 1].amax;
-    if (!map_kmajor(&maps.w[l][0], (const __half*)L.Wt.hi, L.K, L.N, L.Wt.ld, BN) ||
-        !map_kmajor(&maps.w[l][1], (const __half*)L.Wt.lo, L.K, L.N, L.Wt.ld, BN))
+    if (!map_kmajor(&maps.w[l][0], (const __half*)L.Wt.hi, L.K, L.N, L.Wt.ld, BN / 2) ||
+        !map_kmajor(&maps.w[l][1], (const __half*)L.Wt.lo, L.K, L.N, L.Wt.ld, BN / 2))
       return NDJIR_ERR_ARG;
     k_expect = L.N + (into_skip ? din : 0);
     if (k_expect > 4 * BK) return NDJIR_ERR_ARG;
@@ -349,8 +361,20 @@ int launch_geo_chain(const ndjir_geo_net* net, long long rows, int din, const nd
     attr_set = true;
   }
   const int n_tiles = (int)((rows + BM - 1) / BM);
-  const int grid = n_tiles < NDJIR_NUM_SMS ? n_tiles : NDJIR_NUM_SMS;
-  geo_chain_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(maps, p);
+  int n_clusters = (n_tiles + 1) / 2;
+  if (n_clusters > NDJIR_NUM_SMS / 2) n_clusters = NDJIR_NUM_SMS / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * n_clusters);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, geo_chain_kernel, maps, p);
+  if (e != cudaSuccess) return (int)e;
   NDJIR_RETURN_LAST_ERROR();
 }
 
