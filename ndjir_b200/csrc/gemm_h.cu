@@ -355,12 +355,20 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
       const long long m = m0 + q * 32 + lane;
       const bool row_ok = m < a.M;
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-      if (EPI == EPI_ACCUM && p.tma_epi) {
-        epilogue_tile_tma_accum(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), acc_parity, m0 + q * 32, n0, n_valid,
-                                tacc, chalf, inv_ab);
-      } else if (Cfg<EPI, WIDE>::STAGED && p.tma_epi) {
-        epilogue_tile_tma<EPI>(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), acc_parity, m0 + q * 32,
-                               row_ok, n0, n_valid, tacc, chalf, need_u, need_b, inv_ab, sc, sc2, inv_h, inv_u, mx, mx2);
+      if (Cfg<EPI, WIDE>::STAGED && p.tma_epi) {
+        // whole 32-column groups move by TMA; a ragged remainder (the 213- / 43-wide matrices of the skip layer) takes
+        // the direct path: TMA clips a store at 16-byte granularity, so a partial last group would clobber up to 7
+        // halves of whatever follows the view in its rows
+        const int n_tma = n_valid & ~(STG_COLS - 1);
+        if (EPI == EPI_ACCUM)
+          epilogue_tile_tma_accum(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), acc_parity, m0 + q * 32, n0,
+                                  n_tma, tacc, chalf, inv_ab);
+        else
+          epilogue_tile_tma<EPI>(a, em, p.dbg, stg, ld_bar, ld_phase, bar_acc_full(buf), acc_parity, m0 + q * 32, row_ok,
+                                 n0, n_tma, tacc, chalf, need_u, need_b, inv_ab, sc, sc2, inv_h, inv_u, mx, mx2);
+        if (n_tma < n_valid)
+          epilogue_tile<EPI>(a, p.vec_epi, p.dbg, m, row_ok, n0, n_valid, tacc, n_tma + chalf * 16, 32, need_u, need_b,
+                             inv_ab, sc, sc2, inv_h, inv_u, mx, mx2);
       } else {
         mbar_wait(bar_acc_full(buf), acc_parity);
         tc_fence_after();
@@ -510,9 +518,9 @@ static int launch_epi_w(const HArgs& a, cudaStream_t st) {
   for (int i = 0; i < 8; ++i) em.m[i] = mAh;
   p.tma_epi = 0;
   if (EPI == EPI_ACCUM) {
-    if (g_h_tma_epi && !a.mn && a.N % 16 == 0 && a.C.f && al16p(a.C.f) && a.C.ldf % 4 == 0)
+    if (g_h_tma_epi && !a.mn && a.N >= STG_COLS && a.C.f && al16p(a.C.f) && a.C.ldf % 4 == 0)
       p.tma_epi = map_epi_f32(&em.m[4], a.C.f, a.N, a.M, a.C.ldf) ? 1 : 0;
-  } else if (Cfg<EPI, WIDE>::STAGED && g_h_tma_epi && !a.mn && a.N % 16 == 0) {
+  } else if (Cfg<EPI, WIDE>::STAGED && g_h_tma_epi && !a.mn && a.N >= STG_COLS) {
     auto plane_ok = [&](const Op& o) { return o.hi && o.lo && al16p(o.hi) && al16p(o.lo) && o.ldh % 8 == 0; };
     auto absent = [&](const Op& o) { return !o.hi && !o.f; };
     bool eligible = plane_ok(a.C) && (a.bias == nullptr || al16p(a.bias));

@@ -48,7 +48,7 @@ def make(M, N, K, seed=0):
 
 
 SHAPES = [(256, 256, 256), (1000, 256, 256), (4096, 128, 128), (777, 213, 256), (512, 256, 44), (300, 43, 256),
-          (640, 262, 128), (40000, 256, 256)]
+          (640, 262, 128), (40000, 256, 256), (1000, 21, 64), (900, 21, 43), (700, 17, 256)]
 
 
 @pytest.fixture
@@ -196,3 +196,17 @@ def test_pack_scale_update_round_trip():
     torch.cuda.synchronize()
     assert int(sc.flags[0]) & 1
     assert torch.isfinite(b.unpack(st())).all()
+
+
+@pytest.mark.parametrize("M,N,K,ldc", [(1000, 70, 32, 72), (600, 43, 256, 44), (900, 256, 128, 264), (5000, 21, 64, 24)])
+def test_accumulate_into_fp32_view_with_ragged_width(M, N, K, ldc):
+    """C (fp32 rows, row stride ldc > N: a view into a wider matrix) += alpha * A B^T through the TMA-staged epilogue:
+    the columns of the parent matrix beyond N must stay untouched, the last 16-column chunk is partial."""
+    b, v, bias, sc, g = make(M, N, K)
+    C = torch.randn((M, ldc), device="cuda", generator=g)
+    want = C.clone().double()
+    want[:, :N] += 0.7 * (v["A"].double() @ v["B"].double().T)
+    h16.gemm_h(st(), M, N, K, h16.EPI_ACCUM, A=b["A"].hmat(), B=b["B"].hmat(), alpha=0.7, C=C.data_ptr(), ldc=ldc)
+    torch.cuda.synchronize()
+    assert rel(C[:, :N], want[:, :N]) < 5e-6
+    assert torch.equal(C[:, N:].double(), want[:, N:])
