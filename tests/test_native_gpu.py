@@ -619,7 +619,13 @@ def test_voxel_binned_matches_direct_and_reference(B, G, D, spread, mb):
             ref.grad_feature(N, g2.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, bool(accum))
             close(g1, g2, 1e-4, f"binned grad_feature accum={accum}")
             if not accum:
-                assert torch.equal(g1 != 0, g2 != 0), "touched cells differ from the reference kernel"
+                # identical touched cells; a cell whose few contributions cancel to exactly 0.0 in one summation order and
+                # to a rounding residue in the other (seen once in ~20 runs at 2^20 points) is not a different cell
+                diff = (g1 != 0) ^ (g2 != 0)
+                if bool(diff.any()):
+                    resid = torch.maximum(g1[diff].abs().max(), g2[diff].abs().max())
+                    assert float(resid) <= 1e-6 * float(g2.abs().max()) and int(diff.sum()) <= 8, \
+                        "touched cells differ from the reference kernel"
         b1, b2 = torch.zeros(tuple(G) + (D,)).cuda(), torch.zeros(tuple(G) + (D,)).cuda()
         call("ndjir_voxel_grad_query_grad_feature_binned", B, b1, gg, go, q, list(G), D, MN, MX, ws, wsb, 0)
         ref.grad_query_grad_feature(N, b2.data_ptr(), gg.data_ptr(), go.data_ptr(), q.data_ptr(), G, D, MN, MX, False, False)
