@@ -668,6 +668,20 @@ typedef struct ndjir_mlp_layer {
   ndjir_hmat Wt;          /* split-fp16 planes of W^T (N rows of K halfs, scale = the weight scale); unused when N <= 8 */
 } ndjir_mlp_layer;
 
+/* One of the reference's head networks (python/network.py:235-561: base colour, implicit illumination, roughness,
+ * specular reflectance, photogrammetric / environment light, soft visibility, the two background networks) evaluated
+ * as ONE call: n_hidden affine + softplus_100 layers whose outputs are kept in acts[l] (the backward reads them),
+ * then n_out output layers (the reference's last layer, split by column group where the engine splits it) with plain
+ * affine epilogues, each into fp32 rows (out32[i], row stride ld_out[i]) or, when out32[i] is NULL, into planes outh[i]. */
+typedef struct ndjir_mlp_desc {
+  int n_hidden, n_out;
+  ndjir_mlp_layer hidden[NDJIR_MAX_MLP_LAYERS];
+  ndjir_mlp_layer out[4];
+  int precise;
+} ndjir_mlp_desc;
+int ndjir_mlp_forward(const ndjir_mlp_desc* net, long long rows, const ndjir_hmat* x, const ndjir_hmat* acts,
+                      float* const* out32, const long long* ld_out, const ndjir_hmat* outh, cudaStream_t stream);
+
 typedef struct ndjir_geo_net {
   int n_hidden;                                   /* hidden layers (affine + softplus_100) */
   ndjir_mlp_layer hidden[NDJIR_MAX_MLP_LAYERS];

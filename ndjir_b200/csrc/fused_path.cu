@@ -44,6 +44,47 @@ int grid_width(const ndjir_geo_net* net) {
 
 }  // namespace
 
+namespace {
+// one layer of a head: Y = epi(X W + b), Y as planes (tracked) or fp32 rows; <= 8 outputs take the memory-bound kernels
+int head_layer(const ndjir_mlp_layer& L, long long rows, const ndjir_hmat& X, int epi, int precise, float* y32,
+               long long ld_y, const ndjir_hmat* yh, cudaStream_t st) {
+  ndjir_gemm_h_desc d = {};
+  d.M = (int)rows; d.N = L.N; d.K = L.K;
+  d.epilogue = epi; d.split_k = 1;
+  d.alpha = 1.f; d.out_scale = 1.f; d.beta = 100.f; d.hscale = 1.f;
+  d.A = view(X, 0, false);
+  d.a_cs = 1; d.b_cs = 1;
+  d.bias = L.bias;
+  if (L.N <= 8) {
+    if (!y32) return NDJIR_ERR_ARG;
+    d.B32 = L.W; d.b_rs = L.ldw; d.b_cs = 1;
+    d.C = y32; d.ldc = ld_y;
+  } else {
+    d.B = L.Wt;
+    d.precise = precise;
+    if (y32) { d.C = y32; d.ldc = ld_y; } else if (yh) { d.Ch = view(*yh, 0, true); } else return NDJIR_ERR_ARG;
+  }
+  return ndjir_gemm_h(&d, st);
+}
+}  // namespace
+
+extern "C" int ndjir_mlp_forward(const ndjir_mlp_desc* net, long long rows, const ndjir_hmat* x, const ndjir_hmat* acts,
+                                 float* const* out32, const long long* ld_out, const ndjir_hmat* outh, cudaStream_t st) {
+  if (!net || !x || rows < 0 || net->n_hidden < 0 || net->n_hidden > NDJIR_MAX_MLP_LAYERS || net->n_out < 1 ||
+      net->n_out > 4 || (net->n_hidden && !acts) || !out32 || !ld_out)
+    return NDJIR_ERR_ARG;
+  if (rows == 0) return NDJIR_OK;
+  const ndjir_hmat* cur = x;
+  for (int l = 0; l < net->n_hidden; ++l) {
+    NDJIR_TRY(head_layer(net->hidden[l], rows, *cur, ndjir::gemm::EPI_SOFTPLUS, net->precise, nullptr, 0, &acts[l], st));
+    cur = &acts[l];
+  }
+  for (int i = 0; i < net->n_out; ++i)
+    NDJIR_TRY(head_layer(net->out[i], rows, *cur, ndjir::gemm::EPI_BIAS, net->precise, out32[i], ld_out[i],
+                         outh ? &outh[i] : nullptr, st));
+  return NDJIR_OK;
+}
+
 extern "C" int ndjir_geo_sdf_forward(const ndjir_geo_net* net, long long rows, const float* x, float* sdf,
                                      const ndjir_geo_scratch* ws, cudaStream_t st) {
   if (!net || !ws || !x || !sdf || rows < 0) return NDJIR_ERR_ARG;

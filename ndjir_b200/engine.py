@@ -12,6 +12,7 @@ renderer.py:52); here the backward is hand-derived and eve
 
 There is no CPU or PyTorch fallback: every stage raises NdjirError if the CUDA library is missing.
 """
+import ctypes
 import math
 
 import numpy as np
@@ -822,6 +823,34 @@ class Engine:
         """X: input matrix; outs: list of (matrix, column) for the (possibly split) last reference layer."""
         net = self.params.nets[name]
         nh = len(net) - len(outs)
+        if self.h16 and self.fused_sampler:
+            # the whole head as ONE C-ABI call (ndjir_mlp_forward, csrc/fused_path.cu): same products, same buffers
+            ps = self.params
+            acts = [self.mat(f"{tag}_h{l}", rows, net[l].N, "a") for l in range(nh)]
+            d = h16.MlpDesc()
+            d.n_hidden, d.n_out, d.precise = nh, len(outs), int(self.precise_fwd)
+
+            def layer(L):
+                m = h16.MlpLayer()
+                m.K, m.N, m.W, m.ldw, m.bias = L.K, L.N, ps.W(L), L.ldw, ps.b(L)
+                m.Wt = ps.WT16(L) if L.N > 8 else h16.NULL_H
+                return m
+
+            for l in range(nh):
+                d.hidden[l] = layer(net[l])
+            out32 = (ctypes.c_void_p * 4)()
+            ld_out = (ctypes.c_longlong * 4)()
+            outh = (h16.HMat * 4)()
+            for i, ((Y, ycol), L) in enumerate(zip(outs, net[nh:])):
+                d.out[i] = layer(L)
+                if Y.f is not None:
+                    out32[i], ld_out[i] = Y.fptr(ycol), Y.ldf
+                else:
+                    out32[i], ld_out[i], outh[i] = None, 0, Y.hmat(ycol)
+            acts_h = (h16.HMat * max(nh, 1))(*[a.hmat(0) for a in acts])
+            self.n_launches += nh + len(outs) - 1
+            self.call("ndjir_mlp_forward", d, rows, X.hmat(0, track=False), acts_h, out32, ld_out, outh)
+            return acts
         acts, cur = [], X
         for l in range(nh):
             L = net[l]

@@ -39,6 +39,11 @@ class MlpLayer(ctypes.Structure):
                 ("bias", ctypes.c_void_p), ("Wt", HMat)]
 
 
+class MlpDesc(ctypes.Structure):
+    _fields_ = [("n_hidden", ctypes.c_int), ("n_out", ctypes.c_int), ("hidden", MlpLayer * MAX_MLP_LAYERS),
+                ("out", MlpLayer * 4), ("precise", ctypes.c_int)]
+
+
 class GeoNet(ctypes.Structure):
     _fields_ = [("n_hidden", ctypes.c_int), ("hidden", MlpLayer * MAX_MLP_LAYERS), ("sdf", MlpLayer),
                 ("skip_layer", ctypes.c_int), ("skip_scale", ctypes.c_float), ("pe_bands", ctypes.c_int),
