@@ -666,6 +666,8 @@ typedef struct ndjir_mlp_layer {
   long long ldw;
   const float* bias;      /* N */
   ndjir_hmat Wt;          /* split-fp16 planes of W^T (N rows of K halfs, scale = the weight scale); unused when N <= 8 */
+  ndjir_hmat Wp;          /* split-fp16 planes of W itself (K rows of N halfs): the operand of the input-gradient products
+                             (ndjir_geo_normal); may be empty for forward-only use */
 } ndjir_mlp_layer;
 
 /* One of the reference's head networks (python/network.py:235-561: base colour, implicit illumination, roughness,
@@ -694,6 +696,7 @@ typedef struct ndjir_geo_net {
   const float* grid0;     /* voxel / triplane table */
   const float* grid1;     /* triline table */
   int precise;            /* accumulation order of the forward products (ndjir_gemm_h_desc.precise) */
+  ndjir_mlp_layer feat;   /* feature block of the output layer (N = feature_size); used by ndjir_geo_forward only */
 } ndjir_geo_net;
 
 /* caller-owned scratch of one network evaluation over up to `rows` points */
@@ -707,6 +710,30 @@ typedef struct ndjir_geo_scratch {
 
 int ndjir_geo_sdf_forward(const ndjir_geo_net* net, long long rows, const float* x, float* sdf,
                           const ndjir_geo_scratch* ws, cudaStream_t stream);
+
+/* The geometric network with every layer input kept (python/network.py:154-232 as python/renderer.py:46-52 uses it):
+ * acts[0] = planes of the encoded input, acts[l] = input of hidden layer l, acts[n_hidden] = the last activation; sdf
+ * (rows) and, when feat32 is given, the feature block (rows x feature_size fp32, row stride ld_feat). */
+typedef struct ndjir_geo_store {
+  float* enc;             /* rows x ld_enc fp32: the encoded input [PE(x) | grid features | 0] */
+  long long ld_enc;
+  float* grid_tmp;        /* rows x grid width fp32 scratch (unused without a grid) */
+  ndjir_hmat acts[NDJIR_MAX_MLP_LAYERS + 1];
+} ndjir_geo_store;
+int ndjir_geo_forward(const ndjir_geo_net* net, long long rows, const float* x, float* sdf, float* feat32,
+                      long long ld_feat, const ndjir_geo_store* ws, cudaStream_t stream);
+
+/* normal = d sdf / d x (nn.grad([sdf], [x]), python/renderer.py:52) by a reverse sweep over the stored activations:
+ * gz[l] = d sdf / d z_l (kept: the adjoint pass of the backward reads them), g_in (rows x ld_enc fp32) = d sdf / d
+ * (encoded input), then through the positional encoding and the grid's grad_query.  `ones`: device float(s) = 1.0. */
+typedef struct ndjir_geo_normal_ws {
+  ndjir_hmat gz[NDJIR_MAX_MLP_LAYERS];
+  float* g_in;
+  float* grid_tmp;        /* rows x grid width fp32 scratch */
+  const float* ones;
+} ndjir_geo_normal_ws;
+int ndjir_geo_normal(const ndjir_geo_net* net, long long rows, const float* x, const ndjir_geo_store* fwd,
+                     const ndjir_geo_normal_ws* ws, float* normal, long long ld_n, cudaStream_t stream);
 
 /* SDF on the marching-cubes lattice (python/extract_by_mc.py:47-73 compute_pts_vol: linspace(-radius, radius, G)^3, x the
  * slowest axis): `n_planes` x-planes ix0, ix0 + ix_stride, ... (the rank stride of a sharded extraction), evaluated in

@@ -85,6 +85,148 @@ extern "C" int ndjir_mlp_forward(const ndjir_mlp_desc* net, long long rows, cons
   return NDJIR_OK;
 }
 
+namespace {
+// encoded input [PE(x) | grid features | zero padding]   (network.py:96-151)
+int encode_input(const ndjir_geo_net* net, long long rows, const float* x, float* enc, long long ld_enc, float* grid_tmp,
+                 cudaStream_t st) {
+  const int npe = 3 + 6 * net->pe_bands, gw = grid_width(net), din = npe + gw;
+  NDJIR_TRY(ndjir_positional_encoding(rows, 3, net->pe_bands, x, 3, 1, enc, ld_enc, st));
+  const float mn[3] = {-1.f, -1.f, -1.f}, mx[3] = {1.f, 1.f, 1.f};     // PF defaults (voxel_feature.py:147-148)
+  const int G = net->grid_size, D = net->grid_channels;
+  if (net->grid_kind == 1) {
+    const int gs[3] = {G, G, G};
+    NDJIR_TRY(ndjir_voxel_query_on_voxel(rows, grid_tmp, x, net->grid0, gs, D, mn, mx, 0, st));
+    NDJIR_TRY(ndjir_copy2d(rows, D, enc + npe, ld_enc, grid_tmp, D, 1, 1.f, 0, st));
+  } else if (net->grid_kind == 2) {
+    NDJIR_TRY(ndjir_triplane_query_on_triplane(rows, grid_tmp, x, net->grid0, G, D, mn, mx, 0, st));
+    NDJIR_TRY(ndjir_copy2d(rows, 3 * D, enc + npe, ld_enc, grid_tmp, 3 * D, 1, 1.f, 0, st));
+    NDJIR_TRY(ndjir_triline_query_on_triline(rows, grid_tmp, x, net->grid1, G, D, mn, mx, 0, st));
+    NDJIR_TRY(ndjir_copy2d(rows, 3 * D, enc + npe + 3 * D, ld_enc, grid_tmp, 3 * D, 1, 1.f, 0, st));
+  }
+  if (ld_enc > din) {
+    cudaError_t e = cudaMemset2DAsync(enc + din, ld_enc * sizeof(float), 0, (ld_enc - din) * sizeof(float), rows, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return NDJIR_OK;
+}
+
+inline ndjir_hmat rows_from(const ndjir_hmat& m, long long row0) {      // rows [row0, ...) of a plane pair
+  ndjir_hmat v = m;
+  v.hi = reinterpret_cast<char*>(m.hi) + 2 * row0 * m.ld;
+  v.lo = reinterpret_cast<char*>(m.lo) + 2 * row0 * m.ld;
+  return v;
+}
+}  // namespace
+
+extern "C" int ndjir_geo_forward(const ndjir_geo_net* net, long long rows, const float* x, float* sdf, float* feat32,
+                                 long long ld_feat, const ndjir_geo_store* ws, cudaStream_t st) {
+  if (!net || !ws || !x || !sdf || rows < 0 || net->n_hidden < 1 || net->n_hidden > NDJIR_MAX_MLP_LAYERS ||
+      net->grid_kind < 0 || net->grid_kind > 2 || !ws->enc)
+    return NDJIR_ERR_ARG;
+  if (rows == 0) return NDJIR_OK;
+  const int din = 3 + 6 * net->pe_bands + grid_width(net);
+  if (ws->ld_enc < din || net->hidden[0].K != din || (grid_width(net) && !ws->grid_tmp)) return NDJIR_ERR_ARG;
+  for (int l = 0; l <= net->n_hidden; ++l)
+    if (!ws->acts[l].hi || !ws->acts[l].lo) return NDJIR_ERR_ARG;
+  NDJIR_TRY(encode_input(net, rows, x, ws->enc, ws->ld_enc, ws->grid_tmp, st));
+  NDJIR_TRY(pack_cols(rows, din, ws->enc, ws->ld_enc, 1.f, ws->acts[0], 0, st));
+  for (int l = 0; l < net->n_hidden; ++l) {
+    const ndjir_mlp_layer& L = net->hidden[l];
+    const bool into_skip = (l + 1) == net->skip_layer;
+    ndjir_gemm_h_desc d = {};
+    d.M = (int)rows; d.N = L.N; d.K = L.K;
+    d.epilogue = ndjir::gemm::EPI_SOFTPLUS; d.precise = net->precise; d.split_k = 1;
+    d.alpha = 1.f; d.out_scale = into_skip ? net->skip_scale : 1.f; d.beta = 100.f; d.hscale = 1.f;
+    d.A = view(ws->acts[l], 0, false);
+    d.B = L.Wt;
+    d.a_cs = 1; d.b_cs = 1;
+    d.Ch = view(ws->acts[l + 1], 0, true);
+    d.bias = L.bias;
+    NDJIR_TRY(ndjir_gemm_h(&d, st));
+    if (into_skip) NDJIR_TRY(pack_cols(rows, din, ws->enc, ws->ld_enc, net->skip_scale, ws->acts[l + 1], L.N, st));
+  }
+  const ndjir_hmat& last = ws->acts[net->n_hidden];
+  NDJIR_TRY(head_layer(net->sdf, rows, last, ndjir::gemm::EPI_BIAS, net->precise, sdf, 1, nullptr, st));
+  if (feat32) NDJIR_TRY(head_layer(net->feat, rows, last, ndjir::gemm::EPI_BIAS, net->precise, feat32, ld_feat, nullptr, st));
+  return NDJIR_OK;
+}
+
+extern "C" int ndjir_geo_normal(const ndjir_geo_net* net, long long rows, const float* x, const ndjir_geo_store* fwd,
+                                const ndjir_geo_normal_ws* ws, float* normal, long long ld_n, cudaStream_t st) {
+  if (!net || !fwd || !ws || !x || !normal || rows < 0 || net->n_hidden < 1 || net->n_hidden > NDJIR_MAX_MLP_LAYERS ||
+      !ws->g_in || !ws->ones || !fwd->enc || ld_n != 3)      // (the grid's grad_query writes packed (rows, 3) normals)
+    return NDJIR_ERR_ARG;
+  if (rows == 0) return NDJIR_OK;
+  const int nl = net->n_hidden, npe = 3 + 6 * net->pe_bands, gw = grid_width(net), din = npe + gw;
+  if (gw && !ws->grid_tmp) return NDJIR_ERR_ARG;
+  const float c = net->skip_scale;
+  cudaError_t e = cudaMemsetAsync(ws->g_in, 0, (size_t)rows * fwd->ld_enc * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  auto base = [&](int M, int N, int K, int epi) {
+    ndjir_gemm_h_desc d = {};
+    d.M = M; d.N = N; d.K = K; d.epilogue = epi; d.split_k = 1;
+    d.alpha = 1.f; d.out_scale = 1.f; d.beta = 100.f; d.hscale = 1.f;
+    d.a_cs = 1; d.b_cs = 1;
+    return d;
+  };
+  {
+    // top: gz[nl-1] = w_sdf (x) s(a_nl): a rank-1 update with the sigmoid factor (ones (rows x 1) times the sdf column)
+    ndjir_gemm_h_desc d = base((int)rows, net->sdf.K, 1, ndjir::gemm::EPI_MUL_S);
+    d.A32 = ws->ones; d.a_rs = 0; d.a_cs = 1;
+    d.B32 = net->sdf.W; d.b_rs = 1; d.b_cs = net->sdf.ldw;
+    d.Ch = view(ws->gz[nl - 1], 0, true);
+    d.Hh = view(fwd->acts[nl], 0, false);
+    NDJIR_TRY(ndjir_gemm_h(&d, st));
+  }
+  bool skip_wrote = false;
+  for (int l = nl - 1; l >= 1; --l) {
+    const ndjir_mlp_layer& L = net->hidden[l];
+    const bool is_skip = l == net->skip_layer;
+    const int n_prev = net->hidden[l - 1].N;
+    ndjir_gemm_h_desc d = base((int)rows, n_prev, L.N, ndjir::gemm::EPI_MUL_S);
+    d.precise = net->precise;
+    d.alpha = is_skip ? c : 1.f; d.hscale = is_skip ? 1.f / c : 1.f;
+    d.A = view(ws->gz[l], 0, false);
+    d.B = L.Wp;
+    d.Ch = view(ws->gz[l - 1], 0, true);
+    d.Hh = view(fwd->acts[l], 0, false);
+    NDJIR_TRY(ndjir_gemm_h(&d, st));
+    if (is_skip) {     // the encoded-input rows of the skip layer's weights
+      ndjir_gemm_h_desc s = base((int)rows, din, L.N, ndjir::gemm::EPI_BIAS);
+      s.precise = net->precise; s.alpha = c;
+      s.A = view(ws->gz[l], 0, false);
+      s.B = rows_from(L.Wp, n_prev);
+      s.C = ws->g_in; s.ldc = fwd->ld_enc;
+      NDJIR_TRY(ndjir_gemm_h(&s, st));
+      skip_wrote = true;
+    }
+  }
+  {
+    const ndjir_mlp_layer& L = net->hidden[0];
+    ndjir_gemm_h_desc d = base((int)rows, din, L.N, skip_wrote ? ndjir::gemm::EPI_ACCUM : ndjir::gemm::EPI_BIAS);
+    d.precise = net->precise;
+    d.A = view(ws->gz[0], 0, false);
+    d.B = L.Wp;
+    d.C = ws->g_in; d.ldc = fwd->ld_enc;
+    NDJIR_TRY(ndjir_gemm_h(&d, st));
+  }
+  NDJIR_TRY(ndjir_positional_encoding_grad_input(rows, 3, net->pe_bands, fwd->enc, fwd->ld_enc, ws->g_in, fwd->ld_enc, normal,
+                                                 ld_n, 0, st));
+  const float mn[3] = {-1.f, -1.f, -1.f}, mx[3] = {1.f, 1.f, 1.f};
+  const int G = net->grid_size, D = net->grid_channels;
+  if (net->grid_kind == 1) {
+    const int gs[3] = {G, G, G};
+    NDJIR_TRY(ndjir_copy2d(rows, D, ws->grid_tmp, D, ws->g_in + npe, fwd->ld_enc, 1, 1.f, 0, st));
+    NDJIR_TRY(ndjir_voxel_grad_query(rows, normal, ws->grid_tmp, x, net->grid0, gs, D, mn, mx, 1, st));
+  } else if (net->grid_kind == 2) {
+    NDJIR_TRY(ndjir_copy2d(rows, 3 * D, ws->grid_tmp, 3 * D, ws->g_in + npe, fwd->ld_enc, 1, 1.f, 0, st));
+    NDJIR_TRY(ndjir_triplane_grad_query(rows, normal, ws->grid_tmp, x, net->grid0, G, D, mn, mx, 1, st));
+    NDJIR_TRY(ndjir_copy2d(rows, 3 * D, ws->grid_tmp, 3 * D, ws->g_in + npe + 3 * D, fwd->ld_enc, 1, 1.f, 0, st));
+    NDJIR_TRY(ndjir_triline_grad_query(rows, normal, ws->grid_tmp, x, net->grid1, G, D, mn, mx, 1, st));
+  }
+  return NDJIR_OK;
+}
+
 extern "C" int ndjir_geo_sdf_forward(const ndjir_geo_net* net, long long rows, const float* x, float* sdf,
                                      const ndjir_geo_scratch* ws, cudaStream_t st) {
   if (!net || !ws || !x || !sdf || rows < 0) return NDJIR_ERR_ARG;

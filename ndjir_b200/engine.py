@@ -681,6 +681,21 @@ class Engine:
         net = self.params.nets["geo"]
         nl = len(net) - 2          # hidden layers (reference layers 0..L-2)
         A0 = self.mat(f"{tag}_A0", rows, self.din, "fa")
+        if self.h16 and self.fused_sampler and store:
+            # ONE C-ABI call (ndjir_geo_forward, csrc/fused_path.cu) on the same buffers: encoding, grid query, every layer
+            # with its input kept, sdf column, feature block
+            A = [A0] + [self.mat(f"{tag}_A{l + 1}", rows, net[l + 1].K, "a") for l in range(nl)]
+            sdf = sdf_out if sdf_out is not None else self.buf(f"{tag}_sdf", rows, 1)
+            gw = sum(w for _, w, _ in self._grid_parts())
+            ws = h16.GeoStore()
+            ws.enc, ws.ld_enc = A0.f.data_ptr(), self.ld0
+            ws.grid_tmp = self.buf("gq_fused", rows, max(gw, 1)).data_ptr() if gw else None
+            for l, a in enumerate(A):
+                ws.acts[l] = a.hmat(0)
+            feat = (O.fptr(0), O.ldf) if want_feat else (None, 0)
+            self.n_launches += nl + 6
+            self.call("ndjir_geo_forward", self.geo_net_desc(), rows, P_(x), P_(sdf), feat[0], feat[1], ws)
+            return A, sdf
         self.geo_input(x, rows, A0.f, tag)
         self.sync_h(A0, self.din, rows)
         A = [A0]
@@ -704,6 +719,23 @@ class Engine:
         nl = len(net) - 2
         Ls = net[-2]
         GZ = [self.mat(f"{tag}_GZ{l}", rows, net[l].N, "a") for l in range(nl)]
+        if self.h16 and self.fused_sampler:
+            # ONE C-ABI call (ndjir_geo_normal): the reverse sweep, the encoding's and the grid's input gradients
+            Gin = self.mat(f"{tag}_Gin", rows, self.din, "f")
+            gw = sum(w for _, w, _ in self._grid_parts())
+            fw = h16.GeoStore()
+            fw.enc, fw.ld_enc, fw.grid_tmp = A[0].f.data_ptr(), self.ld0, None
+            for l, a in enumerate(A):
+                fw.acts[l] = a.hmat(0)
+            ws = h16.GeoNormalWs()
+            for l, gz in enumerate(GZ):
+                ws.gz[l] = gz.hmat(0)
+            ws.g_in = Gin.f.data_ptr()
+            ws.grid_tmp = self.buf("gg_fused", rows, max(gw, 1)).data_ptr() if gw else None
+            ws.ones = self.one.data_ptr()
+            self.n_launches += nl + 5
+            self.call("ndjir_geo_normal", self.geo_net_desc(), rows, P_(x), fw, ws, P_(nrm), 3)
+            return GZ, Gin
         Gin = self.mat(f"{tag}_Gin", rows, self.din, "f", zero=True)
         c = self.cskip
         # top: gA_{L-1}[p,:] = w_sdf ; GZ[nl-1] = gA * s
@@ -905,11 +937,13 @@ class Engine:
             m = h16.MlpLayer()
             m.K, m.N, m.W, m.ldw, m.bias = L.K, L.N, ps.W(L), L.ldw, ps.b(L)
             m.Wt = ps.WT16(L) if planes else h16.NULL_H
+            m.Wp = ps.W16(L) if planes else h16.NULL_H
             return m
 
         for l in range(d.n_hidden):
             d.hidden[l] = layer(net[l], True)
         d.sdf = layer(net[-2], False)
+        d.feat = layer(net[-1], True)
         d.skip_layer, d.skip_scale, d.pe_bands = self.skip, self.cskip, g.pe_bands
         v = g.voxel
         d.grid_kind = {"voxel": 1, "triplaneline": 2}.get(v.type, 0)

@@ -36,7 +36,7 @@ MAX_MLP_LAYERS = 16
 
 class MlpLayer(ctypes.Structure):
     _fields_ = [("K", ctypes.c_int), ("N", ctypes.c_int), ("W", ctypes.c_void_p), ("ldw", ctypes.c_longlong),
-                ("bias", ctypes.c_void_p), ("Wt", HMat)]
+                ("bias", ctypes.c_void_p), ("Wt", HMat), ("Wp", HMat)]
 
 
 class MlpDesc(ctypes.Structure):
@@ -48,12 +48,22 @@ class GeoNet(ctypes.Structure):
     _fields_ = [("n_hidden", ctypes.c_int), ("hidden", MlpLayer * MAX_MLP_LAYERS), ("sdf", MlpLayer),
                 ("skip_layer", ctypes.c_int), ("skip_scale", ctypes.c_float), ("pe_bands", ctypes.c_int),
                 ("grid_kind", ctypes.c_int), ("grid_size", ctypes.c_int), ("grid_channels", ctypes.c_int),
-                ("grid0", ctypes.c_void_p), ("grid1", ctypes.c_void_p), ("precise", ctypes.c_int)]
+                ("grid0", ctypes.c_void_p), ("grid1", ctypes.c_void_p), ("precise", ctypes.c_int), ("feat", MlpLayer)]
 
 
 class GeoScratch(ctypes.Structure):
     _fields_ = [("enc", ctypes.c_void_p), ("ld_enc", ctypes.c_longlong), ("grid_tmp", ctypes.c_void_p),
                 ("ench", HMat), ("act", HMat * 2)]
+
+
+class GeoStore(ctypes.Structure):
+    _fields_ = [("enc", ctypes.c_void_p), ("ld_enc", ctypes.c_longlong), ("grid_tmp", ctypes.c_void_p),
+                ("acts", HMat * (MAX_MLP_LAYERS + 1))]
+
+
+class GeoNormalWs(ctypes.Structure):
+    _fields_ = [("gz", HMat * MAX_MLP_LAYERS), ("g_in", ctypes.c_void_p), ("grid_tmp", ctypes.c_void_p),
+                ("ones", ctypes.c_void_p)]
 
 
 class SamplerConfig(ctypes.Structure):

@@ -22,7 +22,8 @@ EXE = os.path.join(ROOT, "build_host", "sample_points_host")
 
 def build_host():
     src = os.path.join(ROOT, "tests", "host", "sample_points_host.cpp")
-    if os.path.exists(EXE) and os.path.getmtime(EXE) >= os.path.getmtime(src):
+    hdr = os.path.join(ROOT, "include", "ndjir_b200.h")      # the PODs live there: a changed header means a rebuild
+    if os.path.exists(EXE) and os.path.getmtime(EXE) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
         return
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     subprocess.run(["g++", "-O2", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", src, "-o", EXE,

@@ -190,6 +190,40 @@ def test_sample_points_one_c_abi_call_equals_the_sequenced_path(kind, shape):
 
 
 @pytest.mark.parametrize("kind,shape", [("default", "small"), ("triplaneline", "small"), ("no_voxel", "small"),
+                                        ("default", "full")])
+def test_geo_forward_and_normal_as_c_abi_calls_equal_the_sequenced_path(kind, shape):
+    """ndjir_geo_forward (encoding, grid query, every layer with its input kept, sdf, feature) and ndjir_geo_normal (the
+    nn.grad reverse sweep of renderer.py:52) sequence the same products on the same buffers as Engine.geo_forward /
+    geo_normal do call by call: sdf, feature, normal and every kept activation / gradient must be bit-identical."""
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind, shape=shape)
+    eng.refresh_transposes()
+    rows = 1000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.rand((rows, 3), device="cuda", generator=g) * 1.6 - 0.8).contiguous()
+    res = {}
+    for fused in (False, True, False, True):      # twice each: the second pass of each uses the settled scales
+        eng.fused_sampler = fused
+        O = eng.mat("t_O", rows, eng.Df + 6, "fa")
+        nrm = eng.buf("t_nrm", rows, 3)
+        A, sdf = eng.geo_forward(x, rows, "t", store=True, O=O)
+        GZ, Gin = eng.geo_normal(x, rows, "t", A, nrm)
+        torch.cuda.synchronize()
+        res[fused] = dict(sdf=sdf[:rows].clone(), feat=O.f[:rows, :eng.Df].clone(), nrm=nrm[:rows].clone(),
+                          gin=Gin.f[:rows].clone(), acts=[a.h.t[:, :rows].clone() for a in A],
+                          gz=[z.h.t[:, :rows].clone() for z in GZ])
+    eng.fused_sampler = True
+    a, b = res[False], res[True]
+    for k in ("sdf", "feat", "nrm", "gin"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("acts", "gz"):
+        for i, (u, v) in enumerate(zip(a[k], b[k])):
+            assert torch.equal(u, v), (k, i)
+    with torch.no_grad():
+        want = model.geometric_network(x.cpu().double())[0].reshape(-1).numpy()
+    assert np.abs(b["sdf"].cpu().numpy().reshape(-1) - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("kind,shape", [("default", "small"), ("triplaneline", "small"), ("no_voxel", "small"),
                                         ("default", "full"), ("triplaneline", "full")])
 def test_sample_points_stage_by_stage(kind, shape):
     """sample_points (sampler.py:256-299) checked stage by stage, each stage on the inputs the ENGINE gave it:
