@@ -22,16 +22,9 @@ inline ndjir_hmat view(const ndjir_hmat& m, long long col, bool track) {
   return v;
 }
 
-// fp32 columns -> planes; the 16-byte vector path of ndjir_pack_h wants whole groups of 8 columns, so a ragged width
-// goes as bulk + tail
+// fp32 columns -> planes at column dcol of dst
 int pack_cols(long long rows, int ncols, const float* src, long long ld_src, float alpha, const ndjir_hmat& dst,
               long long dcol, cudaStream_t st) {
-  const int bulk = (dcol % 8 == 0 && ncols >= 16 && ncols % 8) ? (ncols / 8) * 8 : 0;
-  if (bulk) {
-    ndjir_hmat d0 = view(dst, dcol, true), d1 = view(dst, dcol + bulk, true);
-    NDJIR_TRY(ndjir_pack_h(rows, bulk, src, ld_src, 1, alpha, &d0, st));
-    return ndjir_pack_h(rows, ncols - bulk, src + bulk, ld_src, 1, alpha, &d1, st);
-  }
   ndjir_hmat d = view(dst, dcol, true);
   return ndjir_pack_h(rows, ncols, src, ld_src, 1, alpha, &d, st);
 }

@@ -455,7 +455,17 @@ pack_h_kernel(long long rows, int cols, const float* __restrict__ src, long long
     const long long r = i / ncol;
     const int c = (int)(i - r * ncol) * CPT;
     const float* sp = src + (r / rep) * ld_src + c;
-    if (vec) {
+    if (vec && c + 8 > cols) {
+      // ragged last group of a row (cols % 8 != 0): element by element, nothing written beyond the view's width
+      for (int e = 0; c + e < cols; ++e) {
+        const float x = alpha * __ldg(sp + e);
+        mx = fmaxf(mx, fabsf(x));
+        __half h, l;
+        split1(x * sc, h, l);
+        d.hi[r * d.ld + c + e] = h;
+        d.lo[r * d.ld + c + e] = l;
+      }
+    } else if (vec) {
       float4 t0 = __ldg(reinterpret_cast<const float4*>(sp)), t1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
       float x[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
       uint32_t hi[4], lo[4];
@@ -569,9 +579,10 @@ int ndjir_pack_h(long long rows, int cols, const float* src, long long ld_src, i
   if (rows == 0 || cols == 0) return NDJIR_OK;
   if (rows < 0 || cols < 0 || !src || !dst || !dst->hi || !dst->lo || rep < 1) return NDJIR_ERR_ARG;
   HM d = to_hm(dst);
-  int vec = cols % 8 == 0 && al16s(src) && ld_src % 4 == 0 && al16s(d.hi) && al16s(d.lo) && d.ld % 8 == 0;
-  pack_h_kernel<<<ndjir::grid_for(rows * (vec ? cols / 8 : cols)), NDJIR_BLOCK, 0, stream>>>(rows, cols, src, ld_src, rep,
-                                                                                           alpha, d, vec);
+  // groups of 8 columns move as 16-byte accesses; a ragged last group (cols % 8 != 0) is handled inside the same launch
+  int vec = cols >= 8 && al16s(src) && ld_src % 4 == 0 && al16s(d.hi) && al16s(d.lo) && d.ld % 8 == 0;
+  pack_h_kernel<<<ndjir::grid_for(rows * (vec ? (cols + 7) / 8 : cols)), NDJIR_BLOCK, 0, stream>>>(rows, cols, src, ld_src,
+                                                                                                  rep, alpha, d, vec);
   NDJIR_RETURN_LAST_ERROR();
 }
 

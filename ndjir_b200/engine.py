@@ -432,14 +432,8 @@ class Engine:
             self._pack(rows, cols, m.fptr(col), m.ldf, 1, 1.0, m, col, 0)
 
     def _pack(self, rows, ncols, src, ld_src, rep, alpha, dst, dcol, drow):
-        """ndjir_pack_h with the 16-byte-aligned bulk of the columns on the vector path and the ragged tail separately"""
-        bulk = (ncols // 8) * 8 if (dcol % 8 == 0 and ncols >= 16 and ncols % 8) else 0
-        if bulk:
-            self.call("ndjir_pack_h", rows, bulk, src, ld_src, rep, alpha, dst.hmat(dcol, row=drow))
-            self.call("ndjir_pack_h", rows, ncols - bulk, src + 4 * bulk, ld_src, rep, alpha,
-                      dst.hmat(dcol + bulk, row=drow))
-        else:
-            self.call("ndjir_pack_h", rows, ncols, src, ld_src, rep, alpha, dst.hmat(dcol, row=drow))
+        """fp32 columns -> planes (ndjir_pack_h: 16-byte groups of 8 columns, a ragged last group inside the same launch)"""
+        self.call("ndjir_pack_h", rows, ncols, src, ld_src, rep, alpha, dst.hmat(dcol, row=drow))
 
     def fill_cols(self, dst, dcol, src, ld_src, ncols, rows, rep=1, alpha=1.0, drow=0):
         """dst[drow + r, dcol:dcol+ncols] = alpha * src[r // rep, :ncols]   (src: fp32 device address)"""

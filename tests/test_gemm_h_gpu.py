@@ -198,6 +198,28 @@ def test_pack_scale_update_round_trip():
     assert torch.isfinite(b.unpack(st())).all()
 
 
+@pytest.mark.parametrize("cols,col", [(262, 0), (43, 8), (9, 64), (6, 16), (301, 0), (13, 3)])
+def test_pack_ragged_width_into_a_view(cols, col):
+    """ndjir_pack_h of a width that is no multiple of 8 into columns [col, col + cols) of a wider split matrix: one
+    launch (16-byte groups + a ragged last group); bit-identical to packing column by column, and the columns either
+    side of the view keep their contents."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(cols)
+    rows, wide = 777, col + cols + 40
+    src = torch.randn((rows, cols + 2), device=dev, generator=g)[:, :cols]        # row stride cols + 2
+    full = torch.randn((rows, wide), device=dev, generator=g)
+    a, b, keep = h16.HBuf(rows, wide, dev), h16.HBuf(rows, wide, dev), h16.HBuf(rows, wide, dev)
+    for buf in (a, b, keep):
+        buf.pack(full, st())
+    a.pack(src, st(), cols=cols, col=col)
+    for c in range(cols):                                                          # 1-wide packs: the scalar path
+        _lib.call("ndjir_pack_h", rows, 1, src.data_ptr() + 4 * c, src.stride(0), 1, 1.0, b.hmat(col + c), st())
+    torch.cuda.synchronize()
+    assert torch.equal(a.t, b.t)
+    assert torch.equal(a.t[:, :, :col], keep.t[:, :, :col]) and torch.equal(a.t[:, :, col + cols:], keep.t[:, :, col + cols:])
+    assert rel(a.unpack(st())[:, col:col + cols], src) < 2.5e-7
+
+
 @pytest.mark.parametrize("M,N,K,ldc", [(1000, 70, 32, 72), (600, 43, 256, 44), (900, 256, 128, 264), (5000, 21, 64, 24)])
 def test_accumulate_into_fp32_view_with_ragged_width(M, N, K, ldc):
     """C (fp32 rows, row stride ldc > N: a view into a wider matrix) += alpha * A B^T through the TMA-staged epilogue:
