@@ -684,6 +684,27 @@ typedef struct ndjir_mlp_desc {
 int ndjir_mlp_forward(const ndjir_mlp_desc* net, long long rows, const ndjir_hmat* x, const ndjir_hmat* acts,
                       float* const* out32, const long long* ld_out, const ndjir_hmat* outh, cudaStream_t stream);
 
+/* Reverse of ndjir_mlp_forward (the backward nnabla derives for python/network.py:235-561 heads): weight and bias
+ * gradients ACCUMULATE into g_hidden[l] / g_out[i] (fp32, the layout of W / bias); the gradient with respect to the
+ * input, if wanted, goes to dx (columns [0, dx_cols)), overwritten or, with accum_dx, added to.
+ *   douts[i]   dL/d(output block i): fp32 rows (d32, row stride ld) or planes (dh) when d32 is NULL
+ *   dz[0..1]   two plane pairs of rows x max hidden width (ping-pong of the hidden-layer gradients; their scale
+ *              slots are tracked like any gradient tensor)
+ * Products issued: per output block one weight-gradient product (+ a column sum for fp32 blocks) and one
+ * input-gradient product with the sigmoid factor of the last hidden activation; per hidden layer the same pair. */
+typedef struct ndjir_mlp_grad {
+  float* gW;              /* K rows of N, row stride = the layer's ldw */
+  float* gb;              /* N; may be NULL (no bias gradient) */
+} ndjir_mlp_grad;
+typedef struct ndjir_mlp_dmat {
+  float* d32;             /* fp32 rows ... */
+  long long ld;
+  ndjir_hmat dh;          /* ... or planes when d32 is NULL */
+} ndjir_mlp_dmat;
+int ndjir_mlp_backward(const ndjir_mlp_desc* net, const ndjir_mlp_grad* g_hidden, const ndjir_mlp_grad* g_out,
+                       long long rows, const ndjir_hmat* x, const ndjir_hmat* acts, const ndjir_mlp_dmat* douts,
+                       const ndjir_hmat* dz, const ndjir_mlp_dmat* dx, int dx_cols, int accum_dx, cudaStream_t stream);
+
 typedef struct ndjir_geo_net {
   int n_hidden;                                   /* hidden layers (affine + softplus_100) */
   ndjir_mlp_layer hidden[NDJIR_MAX_MLP_LAYERS];
@@ -734,6 +755,20 @@ typedef struct ndjir_geo_normal_ws {
 } ndjir_geo_normal_ws;
 int ndjir_geo_normal(const ndjir_geo_net* net, long long rows, const float* x, const ndjir_geo_store* fwd,
                      const ndjir_geo_normal_ws* ws, float* normal, long long ld_n, cudaStream_t stream);
+
+/* Reverse sweep of the geometric network (the backward of python/network.py:154-232 incl. the second-order terms of the
+ * normal): weight / bias gradients accumulate into g_hidden[l], g_sdf, g_feat; the gradient with respect to the grid
+ * features of the encoded input is written to dgrid (rows x grid width, row stride ld_dgrid; the caller scatters it
+ * into the grid with ndjir_*_grad_feature).
+ *   fwd      activations kept by ndjir_geo_forward
+ *   dfeat    planes of dL/d(feature output) (rows x feat.N)
+ *   dsdf     dL/d(sdf) (rows x 1 fp32) or NULL
+ *   z2       NULL, or n_hidden plane pairs: addends to dL/dz_l from the adjoint of ndjir_geo_normal
+ *   dz[0..1] two plane pairs of rows x hidden width (ping-pong) */
+int ndjir_geo_backward(const ndjir_geo_net* net, const ndjir_mlp_grad* g_hidden, const ndjir_mlp_grad* g_sdf,
+                       const ndjir_mlp_grad* g_feat, long long rows, const ndjir_geo_store* fwd, const ndjir_hmat* dfeat,
+                       const float* dsdf, const ndjir_hmat* z2, const ndjir_hmat* dz, float* dgrid, long long ld_dgrid,
+                       cudaStream_t stream);
 
 /* SDF on the marching-cubes lattice (python/extract_by_mc.py:47-73 compute_pts_vol: linspace(-radius, radius, G)^3, x the
  * slowest axis): `n_planes` x-planes ix0, ix0 + ix_stride, ... (the rank stride of a sharded extraction), evaluated in

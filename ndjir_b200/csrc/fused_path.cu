@@ -353,3 +353,164 @@ extern "C" int ndjir_sample_points_fwd(const ndjir_sampler_config* cfg, const nd
   NDJIR_TRY(ndjir_ray_points(n, N, R, x_fg, camloc, raydir, t_fg, ld, st));
   return ndjir_background_samples(n, Nb, R, camloc, raydir, ws->t_far, mask, background, cfg->radius, t_bg, x_bg, st);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// reverse sweeps: weight gradients (split-K atomic products over the rows) and input gradients with the sigmoid factor
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+inline ndjir_gemm_h_desc product(long long M, int N, long long K, int epi) {
+  ndjir_gemm_h_desc d = {};
+  d.M = (int)M; d.N = N; d.K = (int)K; d.epilogue = epi; d.split_k = 1;
+  d.alpha = 1.f; d.out_scale = 1.f; d.beta = 100.f; d.hscale = 1.f;
+  d.a_cs = 1; d.b_cs = 1;
+  return d;
+}
+
+inline ndjir_mlp_dmat planes(const ndjir_hmat& h) {
+  ndjir_mlp_dmat m = {};
+  m.dh = h;
+  return m;
+}
+
+// gW[:kin, :] += X[:, :kin]^T dY;  gb += column sums of dY
+int weight_grad(const ndjir_mlp_layer& L, const ndjir_mlp_grad& g, long long rows, const ndjir_hmat& X,
+                const ndjir_mlp_dmat& dY, int kin, bool bias, cudaStream_t st) {
+  if (!g.gW) return NDJIR_ERR_ARG;
+  ndjir_gemm_h_desc d = product(kin, L.N, rows, ndjir::gemm::EPI_ATOMIC);
+  d.mn_major = 1;
+  d.A = view(X, 0, false);
+  d.C = g.gW; d.ldc = L.ldw;
+  if (dY.d32) {      // a few fp32 columns: the memory-bound product, the bias gradient as its own column sum
+    d.B32 = dY.d32; d.b_rs = dY.ld; d.b_cs = 1;
+    NDJIR_TRY(ndjir_gemm_h(&d, st));
+    if (bias && g.gb) NDJIR_TRY(ndjir_colsum(rows, L.N, g.gb, dY.d32, dY.ld, 1.f, st));
+    return NDJIR_OK;
+  }
+  const long long tiles = (long long)((kin + 127) / 128) * ((L.N + 255) / 256);
+  long long split = (148 * 2) / tiles;
+  if (split > rows / 256) split = rows / 256;
+  if (split < 1) split = 1;
+  d.split_k = (int)split;
+  d.B = view(dY.dh, 0, false);
+  d.colsum = bias ? g.gb : nullptr;
+  return ndjir_gemm_h(&d, st);
+}
+
+// dX[:, :ncols] = epi(alpha * dY W[row0 : row0 + ncols, :]^T)   (H: activation of the sigmoid factor, U: addend)
+int input_grad(const ndjir_mlp_layer& L, long long rows, const ndjir_mlp_dmat& dY, const ndjir_mlp_dmat& dX, long long dxcol,
+               int epi, int row0, int ncols, float alpha, const ndjir_hmat* H, float hscale, const ndjir_hmat* U,
+               cudaStream_t st) {
+  const bool plain = (epi == ndjir::gemm::EPI_BIAS || epi == ndjir::gemm::EPI_ACCUM) && !H && !U;
+  if (!dY.d32 && ncols > 256 && ncols <= 264 && dX.d32 && plain) {
+    // [feature (256) | x | normal]: one 256-wide tensor-core tile + a memory-bound pass for the few remaining columns
+    NDJIR_TRY(input_grad(L, rows, dY, dX, dxcol, epi, row0, 256, alpha, nullptr, 1.f, nullptr, st));
+    return input_grad(L, rows, dY, dX, dxcol + 256, epi, row0 + 256, ncols - 256, alpha, nullptr, 1.f, nullptr, st);
+  }
+  ndjir_gemm_h_desc d = product(rows, ncols, L.N, epi);
+  d.alpha = alpha; d.hscale = hscale;
+  if (dX.d32) { d.C = dX.d32 + dxcol; d.ldc = dX.ld; } else { d.Ch = view(dX.dh, dxcol, true); }
+  if (H) d.Hh = view(*H, 0, false);
+  if (U) d.Uh = view(*U, 0, false);
+  const float* w32 = L.W + (long long)row0 * L.ldw;      // B(k, j) = W[row0 + j, k]
+  if (dY.d32) {
+    d.A32 = dY.d32; d.a_rs = dY.ld; d.a_cs = 1;
+    d.B32 = w32; d.b_rs = 1; d.b_cs = L.ldw;
+  } else if (ncols <= 8) {
+    d.A = view(dY.dh, 0, false);
+    d.B32 = w32; d.b_rs = 1; d.b_cs = L.ldw;
+  } else {
+    if (!L.Wp.hi) return NDJIR_ERR_ARG;
+    d.A = view(dY.dh, 0, false);
+    d.B = rows_from(L.Wp, row0);
+  }
+  return ndjir_gemm_h(&d, st);
+}
+
+}  // namespace
+
+extern "C" int ndjir_mlp_backward(const ndjir_mlp_desc* net, const ndjir_mlp_grad* g_hidden, const ndjir_mlp_grad* g_out,
+                                  long long rows, const ndjir_hmat* x, const ndjir_hmat* acts, const ndjir_mlp_dmat* douts,
+                                  const ndjir_hmat* dz, const ndjir_mlp_dmat* dx, int dx_cols, int accum_dx,
+                                  cudaStream_t st) {
+  if (!net || !g_out || !x || !douts || rows < 0 || net->n_hidden < 0 || net->n_hidden > NDJIR_MAX_MLP_LAYERS ||
+      net->n_out < 1 || net->n_out > 4 || (net->n_hidden && (!acts || !dz || !g_hidden)))
+    return NDJIR_ERR_ARG;
+  if (rows == 0) return NDJIR_OK;
+  const int nh = net->n_hidden;
+  const ndjir_hmat& last = nh ? acts[nh - 1] : *x;
+  int cur = 0;
+  for (int i = 0; i < net->n_out; ++i) {
+    const ndjir_mlp_layer& L = net->out[i];
+    NDJIR_TRY(weight_grad(L, g_out[i], rows, last, douts[i], L.K, true, st));
+    if (nh)
+      NDJIR_TRY(input_grad(L, rows, douts[i], planes(dz[cur]), 0, ndjir::gemm::EPI_MUL_S, 0, L.K, 1.f, &last, 1.f,
+                           i ? &dz[cur] : nullptr, st));
+    else if (dx)
+      NDJIR_TRY(input_grad(L, rows, douts[i], *dx, 0, (accum_dx || i) ? ndjir::gemm::EPI_ACCUM : ndjir::gemm::EPI_BIAS, 0,
+                           dx_cols > 0 ? dx_cols : L.K, 1.f, nullptr, 1.f, nullptr, st));
+  }
+  for (int l = nh - 1; l >= 0; --l) {
+    const ndjir_mlp_layer& L = net->hidden[l];
+    const ndjir_hmat& in = l > 0 ? acts[l - 1] : *x;
+    NDJIR_TRY(weight_grad(L, g_hidden[l], rows, in, planes(dz[cur]), L.K, true, st));
+    if (l > 0) {
+      NDJIR_TRY(input_grad(L, rows, planes(dz[cur]), planes(dz[cur ^ 1]), 0, ndjir::gemm::EPI_MUL_S, 0, L.K, 1.f, &in, 1.f,
+                           nullptr, st));
+      cur ^= 1;
+    } else if (dx) {
+      NDJIR_TRY(input_grad(L, rows, planes(dz[cur]), *dx, 0, accum_dx ? ndjir::gemm::EPI_ACCUM : ndjir::gemm::EPI_BIAS, 0,
+                           dx_cols > 0 ? dx_cols : L.K, 1.f, nullptr, 1.f, nullptr, st));
+    }
+  }
+  return NDJIR_OK;
+}
+
+extern "C" int ndjir_geo_backward(const ndjir_geo_net* net, const ndjir_mlp_grad* g_hidden, const ndjir_mlp_grad* g_sdf,
+                                  const ndjir_mlp_grad* g_feat, long long rows, const ndjir_geo_store* fwd,
+                                  const ndjir_hmat* dfeat, const float* dsdf, const ndjir_hmat* z2, const ndjir_hmat* dz,
+                                  float* dgrid, long long ld_dgrid, cudaStream_t st) {
+  if (!net || !g_hidden || !g_feat || !fwd || !dfeat || !dz || rows < 0 || net->n_hidden < 1 ||
+      net->n_hidden > NDJIR_MAX_MLP_LAYERS || (dsdf && !g_sdf))
+    return NDJIR_ERR_ARG;
+  if (rows == 0) return NDJIR_OK;
+  const int nl = net->n_hidden, npe = 3 + 6 * net->pe_bands, gw = grid_width(net);
+  if (gw && (!dgrid || ld_dgrid < gw)) return NDJIR_ERR_ARG;
+  const float c = net->skip_scale;
+  const ndjir_hmat& last = fwd->acts[nl];
+  int cur = 0;
+  // output layer: the feature block, then the sdf column on top of it
+  NDJIR_TRY(weight_grad(net->feat, *g_feat, rows, last, planes(*dfeat), net->feat.K, true, st));
+  NDJIR_TRY(input_grad(net->feat, rows, planes(*dfeat), planes(dz[cur]), 0, ndjir::gemm::EPI_MUL_S, 0, net->feat.K, 1.f,
+                       &last, 1.f, z2 ? &z2[nl - 1] : nullptr, st));
+  if (dsdf) {
+    ndjir_mlp_dmat ds = {};
+    ds.d32 = const_cast<float*>(dsdf); ds.ld = 1;
+    NDJIR_TRY(weight_grad(net->sdf, *g_sdf, rows, last, ds, net->sdf.K, true, st));
+    NDJIR_TRY(input_grad(net->sdf, rows, ds, planes(dz[cur]), 0, ndjir::gemm::EPI_MUL_S, 0, net->sdf.K, 1.f, &last, 1.f,
+                         &dz[cur], st));
+  }
+  ndjir_mlp_dmat dg = {};
+  dg.d32 = dgrid; dg.ld = ld_dgrid;
+  bool skip_wrote = false;
+  for (int l = nl - 1; l >= 0; --l) {
+    const ndjir_mlp_layer& L = net->hidden[l];
+    NDJIR_TRY(weight_grad(L, g_hidden[l], rows, fwd->acts[l], planes(dz[cur]), L.K, true, st));
+    if (l > 0) {
+      const bool is_skip = l == net->skip_layer;
+      const int n_prev = net->hidden[l - 1].N;
+      NDJIR_TRY(input_grad(L, rows, planes(dz[cur]), planes(dz[cur ^ 1]), 0, ndjir::gemm::EPI_MUL_S, 0, n_prev,
+                           is_skip ? c : 1.f, &fwd->acts[l], is_skip ? 1.f / c : 1.f, z2 ? &z2[l - 1] : nullptr, st));
+      if (is_skip && gw) {      // the grid-feature rows of the skip layer's weights
+        NDJIR_TRY(input_grad(L, rows, planes(dz[cur]), dg, 0, ndjir::gemm::EPI_BIAS, n_prev + npe, gw, c, nullptr, 1.f,
+                             nullptr, st));
+        skip_wrote = true;
+      }
+      cur ^= 1;
+    } else if (gw) {
+      NDJIR_TRY(input_grad(L, rows, planes(dz[cur]), dg, 0, skip_wrote ? ndjir::gemm::EPI_ACCUM : ndjir::gemm::EPI_BIAS, npe,
+                           gw, 1.f, nullptr, 1.f, nullptr, st));
+    }
+  }
+  return NDJIR_OK;
+}

@@ -810,6 +810,24 @@ class Engine:
         last = A[nl]
         self.sync_h(dO, self.Df, rows)
         pp = [self.mat("geo_dz0", rows, self.Df, "a", grad=True), self.mat("geo_dz1", rows, self.Df, "a", grad=True)]
+        if self.h16 and self.fused_sampler:
+            # the MLP part of the sweep as ONE C-ABI call (ndjir_geo_backward, csrc/fused_path.cu); the scatter of the
+            # grid-feature gradient (with its multi-GPU exchange) stays below
+            dgrid = self.mat("geo_dgrid", rows, max(self.Dg, 1), "f") if self.Dg else None
+            st = h16.GeoStore()
+            for l in range(nl + 1):
+                st.acts[l] = A[l].hmat(0, track=False)
+            z2 = (h16.HMat * nl)(*[z.hmat(0, track=False) for z in Z2]) if Z2 else None
+            dz = (h16.HMat * 2)(pp[0].hmat(0), pp[1].hmat(0))
+            self.n_launches += 2 + (3 if dsdf is not None else 0) + 2 * nl - 1 + (2 if self.Dg else 0) - 1
+            self.call("ndjir_geo_backward", self.geo_net_desc(), self._grads(net[:nl]), self._grads([Ls]),
+                      self._grads([Lf]), rows, st, dO.hmat(0, track=False), (P_(dsdf) if dsdf is not None else None), z2,
+                      dz, (dgrid.fptr() if dgrid is not None else None), (dgrid.ldf if dgrid is not None else 0))
+            for part, width, off in self._grid_parts():
+                tmp = self.buf(f"gg_{part}", rows, width)
+                self.copy2d(rows, width, P_(tmp), width, dgrid.fptr(off), dgrid.ldf)
+                self._grid_scatter("grad_feature", part, rows, x, [tmp])
+            return
         # last layer
         self.wgrad_(rows, Lf, last, dO, 0)
         cur = pp[0]
@@ -845,30 +863,52 @@ class Engine:
     # ------------------------------------------------------------------------------------------------
     # generic softplus MLP (heads): forward keeps layer inputs, backward accumulates weight gradients
     # ------------------------------------------------------------------------------------------------
+    def mlp_desc(self, name, n_out):
+        """POD description of a head for the C-ABI fused path (ndjir_mlp_desc): hidden layers, then the reference's last
+        layer as n_out column blocks; planes of W^T (forward) and of W (input gradients) for the tensor-core products"""
+        ps, net = self.params, self.params.nets[name]
+        nh = len(net) - n_out
+        d = h16.MlpDesc()
+        d.n_hidden, d.n_out, d.precise = nh, n_out, int(self.precise_fwd)
+
+        def layer(L):
+            m = h16.MlpLayer()
+            m.K, m.N, m.W, m.ldw, m.bias = L.K, L.N, ps.W(L), L.ldw, ps.b(L)
+            m.Wt = ps.WT16(L) if L.N > 8 else h16.NULL_H
+            m.Wp = ps.W16(L)
+            return m
+
+        for l in range(nh):
+            d.hidden[l] = layer(net[l])
+        for i, L in enumerate(net[nh:]):
+            d.out[i] = layer(L)
+        return d
+
+    def _dmat(self, M, col=0, out=False):
+        """ndjir_mlp_dmat of a matrix: its fp32 rows when it has them (results) / no planes (operands), else its planes"""
+        m = h16.MlpDmat()
+        if M.f is not None and (out or M.h is None):
+            m.d32, m.ld = M.fptr(col), M.ldf
+        else:
+            m.dh = M.hmat(col, track=out)
+        return m
+
+    def _grads(self, layers):
+        ps = self.params
+        return (h16.MlpGrad * max(len(layers), 1))(*[h16.MlpGrad(ps.gW(L), ps.gb(L)) for L in layers])
+
     def mlp_forward(self, name, tag, X, rows, outs):
         """X: input matrix; outs: list of (matrix, column) for the (possibly split) last reference layer."""
         net = self.params.nets[name]
         nh = len(net) - len(outs)
         if self.h16 and self.fused_sampler:
             # the whole head as ONE C-ABI call (ndjir_mlp_forward, csrc/fused_path.cu): same products, same buffers
-            ps = self.params
             acts = [self.mat(f"{tag}_h{l}", rows, net[l].N, "a") for l in range(nh)]
-            d = h16.MlpDesc()
-            d.n_hidden, d.n_out, d.precise = nh, len(outs), int(self.precise_fwd)
-
-            def layer(L):
-                m = h16.MlpLayer()
-                m.K, m.N, m.W, m.ldw, m.bias = L.K, L.N, ps.W(L), L.ldw, ps.b(L)
-                m.Wt = ps.WT16(L) if L.N > 8 else h16.NULL_H
-                return m
-
-            for l in range(nh):
-                d.hidden[l] = layer(net[l])
+            d = self.mlp_desc(name, len(outs))
             out32 = (ctypes.c_void_p * 4)()
             ld_out = (ctypes.c_longlong * 4)()
             outh = (h16.HMat * 4)()
-            for i, ((Y, ycol), L) in enumerate(zip(outs, net[nh:])):
-                d.out[i] = layer(L)
+            for i, (Y, ycol) in enumerate(outs):
                 if Y.f is not None:
                     out32[i], ld_out[i] = Y.fptr(ycol), Y.ldf
                 else:
@@ -894,6 +934,23 @@ class Engine:
         nh = len(net) - len(douts)
         wmax = max(L.N for L in net[:nh]) if nh else 8
         pp = [self.mat("mlp_dz0", rows, wmax, "a", grad=True), self.mat("mlp_dz1", rows, wmax, "a", grad=True)]
+        if self.h16 and self.fused_sampler:
+            # the whole reverse sweep as ONE C-ABI call (ndjir_mlp_backward, csrc/fused_path.cu)
+            d = self.mlp_desc(name, len(douts))
+            dys = (h16.MlpDmat * 4)(*[self._dmat(dY, dcol) for dY, dcol in douts])
+            acts_h = (h16.HMat * max(nh, 1))(*[a.hmat(0, track=False) for a in acts[:nh]])
+            dz = (h16.HMat * 2)(pp[0].hmat(0), pp[1].hmat(0))
+            dxm = self._dmat(dX, 0, out=True) if dX is not None else None
+            n = 0                      # launches the call makes (products + column sums), for gpu_launches
+            for (dY, _), L in zip(douts, net[nh:]):
+                n += 1 + (dY.h is None) + (1 if (nh or dX is not None) else 0)
+            n += 2 * nh - (1 if (nh and dX is None) else 0)
+            if dX is not None and dX.f is not None and 256 < (dx_cols or net[0].K) <= 264:
+                n += 1
+            self.n_launches += n - 1
+            self.call("ndjir_mlp_backward", d, self._grads(net[:nh]), self._grads(net[nh:]), rows, X.hmat(0, track=False),
+                      acts_h, dys, dz, dxm, dx_cols or 0, int(accum_dx))
+            return
         lastA = acts[-1] if nh else X
         cur = pp[0]
         first = True

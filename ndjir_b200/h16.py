@@ -44,6 +44,14 @@ class MlpDesc(ctypes.Structure):
                 ("out", MlpLayer * 4), ("precise", ctypes.c_int)]
 
 
+class MlpGrad(ctypes.Structure):
+    _fields_ = [("gW", ctypes.c_void_p), ("gb", ctypes.c_void_p)]
+
+
+class MlpDmat(ctypes.Structure):
+    _fields_ = [("d32", ctypes.c_void_p), ("ld", ctypes.c_longlong), ("dh", HMat)]
+
+
 class GeoNet(ctypes.Structure):
     _fields_ = [("n_hidden", ctypes.c_int), ("hidden", MlpLayer * MAX_MLP_LAYERS), ("sdf", MlpLayer),
                 ("skip_layer", ctypes.c_int), ("skip_scale", ctypes.c_float), ("pe_bands", ctypes.c_int),

@@ -224,6 +224,31 @@ def test_geo_forward_and_normal_as_c_abi_calls_equal_the_sequenced_path(kind, sh
 
 
 @pytest.mark.parametrize("kind,shape", [("default", "small"), ("triplaneline", "small"), ("no_voxel", "small"),
+                                        ("default", "full")])
+def test_backward_sweeps_as_c_abi_calls_equal_the_sequenced_path(kind, shape):
+    """ndjir_mlp_backward / ndjir_geo_backward (csrc/fused_path.cu: the reverse sweeps of the heads and of the geometric
+    network, one call each) issue the same products on the same buffers as Engine.mlp_backward / geo_backward do call
+    by call.  Losses and accumulated gradients agree up to the order of the atomic adds of the loss sums / split-K products
+    (the same run-to-run spread either path has against itself)."""
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup(kind, shape=shape)
+    drnd = {k: dev(v) for k, v in rnd.items()}
+    runs = []
+    for fused in (False, True, False, True):      # the second pair runs on the settled delayed scales
+        eng.fused_sampler = fused
+        losses = eng.train_step(dev(camloc), dev(raydir), dev(color_gt), drnd, cos_anneal_ratio=0.3)
+        torch.cuda.synchronize()
+        runs.append((losses.clone(), eng.params.export_reference("grad")))
+    eng.fused_sampler = True
+    (l_seq, g_seq), (l_c, g_c) = runs[2], runs[3]
+    assert torch.allclose(l_seq, l_c, rtol=2e-6, atol=0)      # (the loss sums are atomic too)
+    for k in g_seq:
+        scale = max(np.abs(g_seq[k]).max(), 1e-30)
+        d_paths = np.abs(g_seq[k] - g_c[k]).max() / scale
+        assert d_paths <= 2e-6, (k, d_paths)
+    assert any(np.abs(v).max() > 0 for v in g_c.values())
+
+
+@pytest.mark.parametrize("kind,shape", [("default", "small"), ("triplaneline", "small"), ("no_voxel", "small"),
                                         ("default", "full"), ("triplaneline", "full")])
 def test_sample_points_stage_by_stage(kind, shape):
     """sample_points (sampler.py:256-299) checked stage by stage, each stage on the inputs the ENGINE gave it:
