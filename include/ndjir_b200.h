@@ -756,6 +756,20 @@ typedef struct ndjir_geo_normal_ws {
 int ndjir_geo_normal(const ndjir_geo_net* net, long long rows, const float* x, const ndjir_geo_store* fwd,
                      const ndjir_geo_normal_ws* ws, float* normal, long long ld_n, cudaStream_t stream);
 
+/* Adjoint of ndjir_geo_normal's sweep (double backward of nn.grad, renderer.py:52): given the seed gh0 = dL/d(g_in)
+ * (the adjoint of the encoding's input gradient, which the caller forms with
+ * ndjir_positional_encoding_grad_input_adjoint and the grids' *_grad_query_grad_grad_output calls; fp32 rows AND
+ * their planes), walks the layers upwards: per layer ONE product with two results (EPI_ADJ: the second-order addend
+ * z2[l] to dL/dz_l and the next Ghat), the weight gradient Ghat_l^T gz[l], and at the top the sdf column's gradient.
+ *   gz       plane pairs kept by ndjir_geo_normal (ws->gz)
+ *   ghat     n_hidden plane pairs (scratch): ghat[l] = input of layer l + 1 of the walk
+ *   z2       n_hidden plane pairs (result; ndjir_geo_backward adds them)
+ *   ones     one float 1.0f on the device */
+int ndjir_geo_normal_adjoint(const ndjir_geo_net* net, const ndjir_mlp_grad* g_hidden, const ndjir_mlp_grad* g_sdf,
+                             long long rows, const ndjir_geo_store* fwd, const ndjir_hmat* gz, const float* gh0,
+                             long long ld_gh0, const ndjir_hmat* gh0h, const ndjir_hmat* ghat, const ndjir_hmat* z2,
+                             const float* ones, cudaStream_t stream);
+
 /* Reverse sweep of the geometric network (the backward of python/network.py:154-232 incl. the second-order terms of the
  * normal): weight / bias gradients accumulate into g_hidden[l], g_sdf, g_feat; the gradient with respect to the grid
  * features of the encoded input is written to dgrid (rows x grid width, row stride ld_dgrid; the caller scatters it

@@ -514,3 +514,35 @@ extern "C" int ndjir_geo_backward(const ndjir_geo_net* net, const ndjir_mlp_grad
   }
   return NDJIR_OK;
 }
+
+extern "C" int ndjir_geo_normal_adjoint(const ndjir_geo_net* net, const ndjir_mlp_grad* g_hidden, const ndjir_mlp_grad* g_sdf,
+                                        long long rows, const ndjir_geo_store* fwd, const ndjir_hmat* gz, const float* gh0,
+                                        long long ld_gh0, const ndjir_hmat* gh0h, const ndjir_hmat* ghat,
+                                        const ndjir_hmat* z2, const float* ones, cudaStream_t st) {
+  if (!net || !g_hidden || !g_sdf || !fwd || !gz || !gh0 || !gh0h || !ghat || !z2 || !ones || rows < 0 ||
+      net->n_hidden < 1 || net->n_hidden > NDJIR_MAX_MLP_LAYERS)
+    return NDJIR_ERR_ARG;
+  if (rows == 0) return NDJIR_OK;
+  const int nl = net->n_hidden, din = 3 + 6 * net->pe_bands + grid_width(net);
+  const float c = net->skip_scale;
+  const ndjir_hmat* in = gh0h;
+  for (int l = 0; l < nl; ++l) {
+    const ndjir_mlp_layer& L = net->hidden[l];
+    const bool into_skip = (l + 1) == net->skip_layer;
+    ndjir_gemm_h_desc d = product(rows, L.N, L.K, ndjir::gemm::EPI_ADJ);
+    d.out_scale = into_skip ? c : 1.f; d.hscale = into_skip ? 1.f / c : 1.f;
+    d.A = view(*in, 0, false);
+    d.B = L.Wt;
+    d.Hh = view(fwd->acts[l + 1], 0, false);
+    d.Uh = view(gz[l], 0, false);
+    d.Ch = view(z2[l], 0, true);
+    d.C2h = view(ghat[l], 0, true);
+    NDJIR_TRY(ndjir_gemm_h(&d, st));
+    if (into_skip) NDJIR_TRY(pack_cols(rows, din, gh0, ld_gh0, c, ghat[l], L.N, st));
+    NDJIR_TRY(weight_grad(L, g_hidden[l], rows, *in, planes(gz[l]), L.K, false, st));
+    in = &ghat[l];
+  }
+  ndjir_mlp_dmat one = {};      // g w_sdf[k] += sum_p Ghat_top[p, k]: a column of ones (row stride 0)
+  one.d32 = const_cast<float*>(ones); one.ld = 0;
+  return weight_grad(net->sdf, *g_sdf, rows, *in, one, net->sdf.K, false, st);
+}

@@ -387,6 +387,12 @@ class Engine:
     def stream(self):
         return torch.cuda.current_stream().cuda_stream
 
+    @property
+    def fused_calls(self):
+        """stages as single C-ABI calls (csrc/fused_path.cu).  The instrumented step (profile: CUDA events around every
+        product) sequences the same products call by call instead, so that each one can be timed."""
+        return self.h16 and self.fused_sampler and not self.profile
+
     def call(self, name, *args):
         self.n_launches += 1
         _lib.call(name, *args, self.stream())
@@ -675,7 +681,7 @@ class Engine:
         net = self.params.nets["geo"]
         nl = len(net) - 2          # hidden layers (reference layers 0..L-2)
         A0 = self.mat(f"{tag}_A0", rows, self.din, "fa")
-        if self.h16 and self.fused_sampler and store:
+        if self.fused_calls and store:
             # ONE C-ABI call (ndjir_geo_forward, csrc/fused_path.cu) on the same buffers: encoding, grid query, every layer
             # with its input kept, sdf column, feature block
             A = [A0] + [self.mat(f"{tag}_A{l + 1}", rows, net[l + 1].K, "a") for l in range(nl)]
@@ -713,7 +719,7 @@ class Engine:
         nl = len(net) - 2
         Ls = net[-2]
         GZ = [self.mat(f"{tag}_GZ{l}", rows, net[l].N, "a") for l in range(nl)]
-        if self.h16 and self.fused_sampler:
+        if self.fused_calls:
             # ONE C-ABI call (ndjir_geo_normal): the reverse sweep, the encoding's and the grid's input gradients
             Gin = self.mat(f"{tag}_Gin", rows, self.din, "f")
             gw = sum(w for _, w, _ in self._grid_parts())
@@ -774,6 +780,19 @@ class Engine:
             self.copy2d(rows, width, Gh0.fptr(self.npe + off), self.ld0, P_(tmp2), width)
             self._grid_scatter("gqgf", part, rows, x, [nbar, tmp])
         self.sync_h(Gh0, self.din, rows)
+        if self.fused_calls:
+            # the upward walk as ONE C-ABI call (ndjir_geo_normal_adjoint, csrc/fused_path.cu)
+            Gh = [self.mat(f"{tag}_Gh{l + 1}", rows, net[l + 1].K, "a", grad=True) for l in range(nl)]
+            Z2 = [self.mat(f"{tag}_Z2{l}", rows, net[l].N, "a", grad=True) for l in range(nl)]
+            st = h16.GeoStore()
+            for l in range(nl + 1):
+                st.acts[l] = A[l].hmat(0, track=False)
+            arr = lambda ms, track: (h16.HMat * nl)(*[m.hmat(0, track=track) for m in ms])
+            self.n_launches += 2 * nl + (1 if 0 < self.skip <= nl else 0)
+            self.call("ndjir_geo_normal_adjoint", self.geo_net_desc(), self._grads(net[:nl]), self._grads([net[-2]]), rows,
+                      st, arr(GZ, False), Gh0.fptr(), Gh0.ldf, Gh0.hmat(0, track=False), arr(Gh, True), arr(Z2, True),
+                      self.ones_col.fptr())
+            return Z2
         Ghat, Z2 = [Gh0], []
         for l in range(nl):
             L = net[l]
@@ -810,7 +829,7 @@ class Engine:
         last = A[nl]
         self.sync_h(dO, self.Df, rows)
         pp = [self.mat("geo_dz0", rows, self.Df, "a", grad=True), self.mat("geo_dz1", rows, self.Df, "a", grad=True)]
-        if self.h16 and self.fused_sampler:
+        if self.fused_calls:
             # the MLP part of the sweep as ONE C-ABI call (ndjir_geo_backward, csrc/fused_path.cu); the scatter of the
             # grid-feature gradient (with its multi-GPU exchange) stays below
             dgrid = self.mat("geo_dgrid", rows, max(self.Dg, 1), "f") if self.Dg else None
@@ -901,7 +920,7 @@ class Engine:
         """X: input matrix; outs: list of (matrix, column) for the (possibly split) last reference layer."""
         net = self.params.nets[name]
         nh = len(net) - len(outs)
-        if self.h16 and self.fused_sampler:
+        if self.fused_calls:
             # the whole head as ONE C-ABI call (ndjir_mlp_forward, csrc/fused_path.cu): same products, same buffers
             acts = [self.mat(f"{tag}_h{l}", rows, net[l].N, "a") for l in range(nh)]
             d = self.mlp_desc(name, len(outs))
@@ -934,7 +953,7 @@ class Engine:
         nh = len(net) - len(douts)
         wmax = max(L.N for L in net[:nh]) if nh else 8
         pp = [self.mat("mlp_dz0", rows, wmax, "a", grad=True), self.mat("mlp_dz1", rows, wmax, "a", grad=True)]
-        if self.h16 and self.fused_sampler:
+        if self.fused_calls:
             # the whole reverse sweep as ONE C-ABI call (ndjir_mlp_backward, csrc/fused_path.cu)
             d = self.mlp_desc(name, len(douts))
             dys = (h16.MlpDmat * 4)(*[self._dmat(dY, dcol) for dY, dcol in douts])
@@ -1054,7 +1073,7 @@ class Engine:
         NR = B * R
         if not getattr(self, "_weights_synced", False):
             self.refresh_transposes()   # standalone call: the registered lo copies of the weights must be current
-        if self.h16 and self.fused_sampler and not debug:
+        if self.fused_calls and not debug:
             return self._sample_points_c(camloc, raydir, stratified_sample, background_sample, mask_sum)
         N0, M, U, Nb = r.n_samples0, r.n_samples1, r.n_upsamples, r.n_bg_samples
         N = N0 + U * M

@@ -108,7 +108,7 @@ def sdf_volume(conf, grid_size, batch_size=1 << 20, rank=0, world_size=1, proces
     per = max(1, batch_size // (G * G))
     pts = torch.empty((per * G * G, 3), dtype=torch.float32, device="cuda")
     eng.refresh_transposes()      # W^T and the split copies of the weights must match the current parameters
-    if eng.h16 and eng.fused_sampler and len(xs):
+    if eng.fused_calls and len(xs):
         # the whole extraction is ONE C-ABI call (ndjir_sdf_lattice, csrc/fused_path.cu): lattice points and network
         # evaluation are sequenced inside the library, on the engine's own scratch buffers and scale slots
         from . import h16

@@ -751,4 +751,9 @@ def test_voxel_hash_grad_feature_coarse_levels_private(B, G0, L, D, T0):
         close(res[2], g_ref, 1e-4, f"private coarse levels vs reference kernel, accum={accum}")
         close(res[2], res[0], 1e-4, f"private coarse levels vs global reductions, accum={accum}")
         if not accum:
-            assert torch.equal(res[2] != 0, g_ref != 0), "touched entries differ"
+            # identical touched entries (an entry whose contributions cancel to exactly 0.0 in one summation order and to
+            # a rounding residue in the other is not a different entry: same bar as the binned voxel test above)
+            diff = (res[2] != 0) ^ (g_ref != 0)
+            if bool(diff.any()):
+                resid = torch.maximum(res[2][diff].abs().max(), g_ref[diff].abs().max())
+                assert float(resid) <= 1e-6 * float(g_ref.abs().max()) and int(diff.sum()) <= 8, "touched entries differ"
