@@ -588,6 +588,19 @@ int ndjir_uniform(long long n, float lo, float hi, long long seed, const int* co
 int ndjir_store_chunk(int n_rays, long long n_pixels, long long pixel0, const int* chunk_dev, const float* color,
                       float* image, cudaStream_t stream);
 int ndjir_counter_add(int* counter_dev, int step, cudaStream_t stream);
+/* One TRAINING batch assembled on the device (python/dataset.py:33-55 IDRDataSource._get_data, default
+ * branch, + python/train.py:126-130 -> helper.generate_raydir_camloc): with the dataset resident in HBM (images
+ * (n_views, H*W, 3) fp32 in [0, 1], masks (n_views, H*W) fp32 or NULL, per view the float64 inverse intrinsic kinv9 and
+ * camera-to-world rotation rot9 and the fp32 camera position) a step's inputs are one launch and no host->device copy.
+ *   view_ids   B ints (device): the dataset rows of this step (the reference's rng.permutation order)
+ *   pixel_idx  B x R ints (device): flat pixel y*W+x per ray (the reference's rng.randint draw), or NULL: drawn here,
+ *              uniform over H*W, from the counter-based generator keyed by (seed, *counter_dev, ray)
+ *   outputs    raydir (B,R,3), camloc (B,3), color_gt (B,R,3), obj_mask (B,R,1; may be NULL; 1 without masks),
+ *              pixel_out (B x R ints, may be NULL): the pixels used */
+int ndjir_train_batch(int B, int R, int W, long long n_pixels, const int* view_ids, const int* pixel_idx, long long seed,
+                      const int* counter_dev, const float* images, const float* masks, const double* kinv9,
+                      const double* rot9, const float* camloc_all, float* raydir, float* camloc, float* color_gt,
+                      float* obj_mask, int* pixel_out, cudaStream_t stream);
 /* points of the marching-cubes lattice (python/extract_by_mc.py:47-73: np.linspace(-radius, radius, G) per axis, x the
  * slowest): point i lies on x-plane ix0 + (i / G^2) * ix_stride (the rank stride of a sharded extraction) */
 int ndjir_lattice_points(long long n, int G, int ix0, int ix_stride, float radius, float* pts, cudaStream_t stream);

@@ -71,6 +71,48 @@ store_chunk_kernel(int n, long long n_pixels, long long pixel0, const int* __res
 
 __global__ void counter_add_kernel(int* counter, int step) { *counter += step; }
 
+// One training batch assembled on the device (python/dataset.py:33-55 IDRDataSource._get_data, default branch:
+// colour = image[pixel_idx], mask = mask[pixel_idx], xy = xy[pixel_idx]; python/train.py:126-130 turns xy into rays with
+// helper.generate_raydir_camloc).  One thread per ray; the pixel is given (the reference's host-drawn indices) or drawn
+// here from the counter-based generator.
+__global__ void __launch_bounds__(NDJIR_BLOCK)
+train_batch_kernel(int B, int R, int W, long long n_pixels, const int* __restrict__ view_ids,
+                   const int* __restrict__ pixel_idx, unsigned long long seed, const int* __restrict__ counter,
+                   const float* __restrict__ images, const float* __restrict__ masks, const double* __restrict__ kinv9,
+                   const double* __restrict__ rot9, const float* __restrict__ camloc_all, float* __restrict__ raydir,
+                   float* __restrict__ camloc, float* __restrict__ color_gt, float* __restrict__ obj_mask,
+                   int* __restrict__ pixel_out) {
+  const unsigned long long c = counter ? (unsigned long long)__ldg(counter) : 0ull;
+  const unsigned long long key = mix64(seed * 0x9e3779b97f4a7c15ull + c + 0x2545f4914f6cdd1dull);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * R; i += gridDim.x * blockDim.x) {
+    const int b = i / R, v = __ldg(view_ids + b);
+    long long p;
+    if (pixel_idx) p = __ldg(pixel_idx + i);
+    else p = (long long)(mix64(key + 0x9e3779b97f4a7c15ull * (unsigned long long)(i + 1)) % (unsigned long long)n_pixels);
+    if (pixel_out) pixel_out[i] = (int)p;
+    const double x = (double)(p % W), y = (double)(p / W);
+    const double* kinv = kinv9 + 9 * v;
+    const double* rot = rot9 + 9 * v;
+    double cam[3], w[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) cam[r] = kinv[3 * r] * x + kinv[3 * r + 1] * y + kinv[3 * r + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) w[r] = rot[3 * r] * cam[0] + rot[3 * r + 1] * cam[1] + rot[3 * r + 2] * cam[2];
+    const double inv = 1.0 / sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const float* px = images + ((long long)v * n_pixels + p) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      raydir[3 * i + k] = (float)(w[k] * inv);
+      color_gt[3 * i + k] = __ldg(px + k);
+    }
+    if (obj_mask) obj_mask[i] = masks ? __ldg(masks + (long long)v * n_pixels + p) : 1.f;
+    if (i % R == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) camloc[3 * b + k] = __ldg(camloc_all + 3 * v + k);
+    }
+  }
+}
+
 // lattice of extract_by_mc.compute_pts_vol (python/extract_by_mc.py:47-73): np.linspace(-r, r, G) on every axis, x the
 // slowest axis; point i of the batch lies on x-plane ix0 + (i / G^2) * ix_stride
 __global__ void __launch_bounds__(NDJIR_BLOCK)
@@ -100,6 +142,20 @@ int ndjir_generate_rays(int n_rays, int W, long long n_pixels, long long pixel0,
   if (n_rays < 0 || W <= 0 || n_pixels <= 0 || !kinv9_dev || !rot9_dev || !raydir) return NDJIR_ERR_ARG;
   inference::generate_rays_kernel<<<grid_for(n_rays), NDJIR_BLOCK, 0, stream>>>(n_rays, W, n_pixels, pixel0, chunk_dev,
                                                                                kinv9_dev, rot9_dev, raydir);
+  NDJIR_RETURN_LAST_ERROR();
+}
+
+int ndjir_train_batch(int B, int R, int W, long long n_pixels, const int* view_ids, const int* pixel_idx, long long seed,
+                      const int* counter_dev, const float* images, const float* masks, const double* kinv9,
+                      const double* rot9, const float* camloc_all, float* raydir, float* camloc, float* color_gt,
+                      float* obj_mask, int* pixel_out, cudaStream_t stream) {
+  if (B == 0 || R == 0) return NDJIR_OK;
+  if (B < 0 || R < 0 || W <= 0 || n_pixels <= 0 || n_pixels > 0x7fffffffll || !view_ids || !images || !kinv9 || !rot9 ||
+      !camloc_all || !raydir || !camloc || !color_gt)
+    return NDJIR_ERR_ARG;
+  inference::train_batch_kernel<<<grid_for((long long)B * R), NDJIR_BLOCK, 0, stream>>>(
+      B, R, W, n_pixels, view_ids, pixel_idx, (unsigned long long)seed, counter_dev, images, masks, kinv9, rot9, camloc_all,
+      raydir, camloc, color_gt, obj_mask, pixel_out);
   NDJIR_RETURN_LAST_ERROR();
 }
 

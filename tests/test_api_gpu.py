@@ -285,3 +285,59 @@ def test_inference_mode_renders_the_same_pixels():
         if k == "attpix":          # column layout: only the rendered material attributes, not the prior terms
             continue
         assert torch.equal(a, b), k
+
+
+def test_device_train_batch_matches_the_host_data_source():
+    """ndjir_train_batch / ndjir_b200.dataset.DeviceRaySource against the host path of the reference restated in numpy
+    (python/dataset.py:33-55, 180-189: permutation then randint from RandomState(313), colour = image[pixel_idx];
+    python/train.py:126-130 -> helper.generate_raydir_camloc in float64): same views, same pixels, colours and masks
+    bit-exact, rays to float32 rounding - over three epochs' worth of batches, batches straddling an epoch end included.
+    With device_rng the pixels are drawn on the device: in range, different every step, and everything else consistent
+    with the pixels reported."""
+    from ndjir_b200 import scene
+    from ndjir_b200.dataset import DeviceRaySource
+    n, W, H, R, B = 5, 40, 30, 64, 2
+    poses, intr, _ = scene.make_cameras(n, W=W, H=H, focal=55.0)
+    g = np.random.RandomState(3)
+    images = g.rand(n, H, W, 3).astype(np.float32)
+    masks = (g.rand(n, H, W, 1) > 0.5).astype(np.float32)
+    src = DeviceRaySource(images, masks, intr, poses, R, shuffle=True)
+    ref = np.random.RandomState(313)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    xy_all = np.stack([xs.reshape(-1), ys.reshape(-1)], axis=-1)            # dataset.py:158-162
+    order, pix, pos = None, None, n
+    for step in range(8):
+        views = []
+        for _ in range(B):
+            if pos >= n:
+                order, pix, pos = ref.permutation(n), ref.randint(0, H * W, (n, R)), 0
+            views.append(int(order[pos])); pos += 1
+        out = src.next(B)
+        torch.cuda.synchronize()
+        assert out["views"] == views
+        idx = np.stack([pix[v] for v in views])
+        want_rays, want_cam = scene.generate_raydir_camloc(poses[views], intr[views], xy_all[idx].astype(np.float64))
+        assert np.array_equal(out["pixels"].cpu().numpy(), idx)
+        assert np.array_equal(out["color_gt"].cpu().numpy(), np.stack([images[v].reshape(-1, 3)[pix[v]] for v in views]))
+        assert np.array_equal(out["obj_mask"].cpu().numpy(), np.stack([masks[v].reshape(-1, 1)[pix[v]] for v in views]))
+        np.testing.assert_allclose(out["raydir"].cpu().numpy(), want_rays, atol=1e-7)
+        assert np.array_equal(out["camloc"].cpu().numpy(), want_cam)
+    dsrc = DeviceRaySource(images, None, intr, poses, R, shuffle=False, device_rng=True)
+    seen = []
+    for step in range(3):
+        out = dsrc.next(B)
+        torch.cuda.synchronize()
+        p = out["pixels"].cpu().numpy()
+        assert p.min() >= 0 and p.max() < H * W and len(np.unique(p)) > R
+        seen.append(p.copy())
+        views = out["views"]
+        want_rays, _ = scene.generate_raydir_camloc(poses[views], intr[views], xy_all[p].astype(np.float64))
+        np.testing.assert_allclose(out["raydir"].cpu().numpy(), want_rays, atol=1e-7)
+        assert np.array_equal(out["color_gt"].cpu().numpy(), np.stack([images[v].reshape(-1, 3)[p[i]] for i, v in enumerate(views)]))
+        assert float(out["obj_mask"].min()) == 1.0
+    assert not np.array_equal(seen[0], seen[1]) and not np.array_equal(seen[1], seen[2])
+    big = DeviceRaySource(images, None, intr, poses, 1 << 16, shuffle=False, device_rng=True).next(1)["pixels"]
+    hist = np.bincount(big.cpu().numpy().reshape(-1), minlength=H * W)
+    assert hist.min() > 0 and abs(hist.mean() - (1 << 16) / (H * W)) < 1e-9 and hist.std() < 3 * np.sqrt(hist.mean())
+    with pytest.raises(NotImplementedError):
+        DeviceRaySource(images, None, intr, poses, R, patch_ray_sampling=True)
