@@ -471,6 +471,66 @@ def test_mask_loss_term_matches_oracle(mlp_path):
     rep.finish()
 
 
+def test_sphere_bounds_sampling_and_step_match_oracle():
+    """renderer.t_near_far_method: intersect_with_r_sphere (sampler.py:84-91; ndjir_ray_sphere_intersection inside
+    ndjir_sample_points_fwd) at cos_anneal_ratio 1: hit mask exact and sample distances against the oracle (pinned on the
+    reference's own sampler.py for this mode by tests/golden/render_small_sphere_bounds.npz), then losses and every
+    gradient of a step on the oracle's samples."""
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup("default", shape="small")
+    conf.renderer.t_near_far_method = "intersect_with_r_sphere"
+    rep = Report("train_sphere_bounds")
+    samples = CR.sample_points(model, camloc, raydir, rnd["stratified"], rnd["background"])
+    args = [dev(camloc), dev(raydir), dev(rnd["stratified"]), dev(rnd["background"])]
+    for _ in range(2):                                           # second pass: settled delayed scales
+        ms = torch.zeros(1, device="cuda")
+        own = eng.sample_points(*args, mask_sum=ms)
+    torch.cuda.synchronize()
+    want_mask = samples[4].numpy().reshape(-1)
+    assert np.array_equal(own[4].cpu().numpy().reshape(-1), want_mask) and 0 < want_mask.sum() < want_mask.size
+    assert float(ms) == float(want_mask.sum())
+    hit = want_mask.reshape(-1) > 0
+    t_own = own[1].cpu().numpy().reshape(hit.size, -1)[hit]
+    t_want = samples[1].numpy().reshape(hit.size, -1)[hit]
+    close = (np.abs(t_own - t_want) <= 1e-4 * np.abs(t_want).max()).mean()      # (a CDF decision may flip in float32)
+    assert close >= 0.99, close
+    rep.check("t_bg", own[3].cpu().numpy().reshape(hit.size, -1)[hit], samples[3].numpy().reshape(hit.size, -1)[hit], 1e-5)
+    samples32 = [dev(s.numpy()) for s in samples]
+    drnd = {k: dev(v) for k, v in rnd.items()}
+    losses = eng.train_step(dev(camloc), dev(raydir), dev(color_gt), drnd, cos_anneal_ratio=1.0, samples=samples32,
+                            keep=True)
+    torch.cuda.synchronize()
+    d = eng.debug
+    B, R, N, Nb, M = d["dims"]
+    NR = B * R
+    fixed = (d["dirs_u"][:NR * M].reshape(B, R, M, 3).cpu().numpy(), d["dirs_s"][:NR * M].reshape(B, R, M, 3).cpu().numpy())
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        m = model if dt == torch.float64 else CR.Model(conf, P, dtype=torch.float32)
+        smp = [torch.as_tensor(s.cpu().numpy(), dtype=dt) for s in samples32]
+        ol, res, _ = CR.total_loss(m, camloc, raydir, color_gt, 1.0, rnd, return_all=True, samples=smp, fixed_dirs=fixed)
+        params = m.parameters()
+        for p in params.values():
+            p.grad = None
+        ol["loss"].backward()
+        out[dt] = (ol, params)
+    ol, params = out[torch.float64]
+    for i, k in ((0, "loss"), (1, "loss_rgb"), (2, "loss_eikonal")):
+        want, got = float(ol[k].detach()), float(losses[i])
+        e = abs(got - want) / abs(want)
+        rep.rows.append(dict(what=f"loss.{k}", err=e, tol=5e-5, ok=bool(e <= 5e-5)))
+        if e > 5e-5:
+            rep.bad.append(f"loss.{k}: got {got} want {want}")
+    ours = eng.params.export_reference("grad")
+    for k, p in params.items():
+        want = p.grad.detach().numpy() if p.grad is not None else np.zeros(tuple(p.shape))
+        if np.abs(want).max() == 0 and np.abs(ours[k]).max() == 0:
+            continue
+        p32 = out[torch.float32][1][k]
+        w32 = p32.grad.detach().numpy() if p32.grad is not None else np.zeros(tuple(p.shape))
+        rep.check(f"grad.{k}", ours[k], want, 1e-4, w32, l2_tol=1e-4)
+    rep.finish()
+
+
 def test_full_step_with_own_sampling_is_close():
     """End to end (own sample placement): the loss agrees with the oracle's end-to-end loss; placement differs only
     by fp32 rounding of the SDF, which moves samples continuously."""
