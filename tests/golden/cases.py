@@ -8,6 +8,7 @@ path on the same inputs).  Parameters and inputs are rebuilt from seeds, so only
   full_default   default.yaml widths (256 / 128, skip 213 + 43), voxel 32^3 x 4, 1 view x 8 rays; large gradient
                  tensors are stored as norms + sampled entries (sampled_view)
   small_default_mask   small_default with train.mask_weight = 0.5 and a seeded object mask (obj_mask_of)
+  small_default_l2     small_default with train.rgb_loss = l2
   small_sphere_bounds  small_default with the ray bounds taken from the bounding sphere, cos_anneal_ratio 1
 """
 import numpy as np
@@ -24,6 +25,8 @@ CASES = {
     "small_default_mask": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.6, G=16, mask_weight=0.5),
     # ray bounds from the sphere of radius bounding_sphere_radius (renderer.t_near_far_method: intersect_with_r_sphere,
     # sampler.py:84-91) instead of the box, at the annealing ratio images are rendered with
+    # squared-error colour loss (train.rgb_loss: l2, loss.py:60-62; l1 in every shipped config)
+    "small_default_l2": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.2, G=16, train={"rgb_loss": "l2"}),
     "small_sphere_bounds": dict(kind="default", small=True, B=2, R=4, cos_anneal=1.0, G=16,
                                 renderer={"t_near_far_method": "intersect_with_r_sphere"}),
 }
@@ -40,6 +43,7 @@ def case_conf(name):
             photogrammetric_light_network={"feature_size": 32}, roughness_network={"feature_size": 32},
             specular_reflectance_network={"feature_size": 32},
             background_network={"feature_size0": 32, "feature_size1": 32})
+    over["train"].update(c.get("train", {}))
     if "renderer" in c:
         over["renderer"] = dict(c["renderer"])
     if c["G"] is not None:

@@ -471,14 +471,23 @@ def test_mask_loss_term_matches_oracle(mlp_path):
     rep.finish()
 
 
-def test_sphere_bounds_sampling_and_step_match_oracle():
-    """renderer.t_near_far_method: intersect_with_r_sphere (sampler.py:84-91; ndjir_ray_sphere_intersection inside
-    ndjir_sample_points_fwd) at cos_anneal_ratio 1: hit mask exact and sample distances against the oracle (pinned on the
-    reference's own sampler.py for this mode by tests/golden/render_small_sphere_bounds.npz), then losses and every
-    gradient of a step on the oracle's samples."""
+@pytest.mark.parametrize("variant", ["sphere_bounds", "rgb_l2"])
+def test_non_default_branches_sampling_and_step_match_oracle(variant):
+    """Branches no BASELINE config takes, each pinned on the reference's own Python by a golden case
+    (tests/golden/render_small_sphere_bounds.npz, render_small_default_l2.npz):
+      sphere_bounds  renderer.t_near_far_method: intersect_with_r_sphere (sampler.py:84-91; ndjir_ray_sphere_intersection
+                     inside ndjir_sample_points_fwd) at cos_anneal_ratio 1
+      rgb_l2         train.rgb_loss: l2 (loss.py:60-62)
+    Hit mask exact and sample distances against the oracle, then losses and every gradient of a step on the oracle's
+    samples."""
     conf, P, camloc, raydir, color_gt, rnd, eng, model = setup("default", shape="small")
-    conf.renderer.t_near_far_method = "intersect_with_r_sphere"
-    rep = Report("train_sphere_bounds")
+    if variant == "sphere_bounds":
+        conf.renderer.t_near_far_method = "intersect_with_r_sphere"
+        ratio = 1.0
+    else:
+        conf.train.rgb_loss = "l2"
+        ratio = 0.2
+    rep = Report(f"train_{variant}")
     samples = CR.sample_points(model, camloc, raydir, rnd["stratified"], rnd["background"])
     args = [dev(camloc), dev(raydir), dev(rnd["stratified"]), dev(rnd["background"])]
     for _ in range(2):                                           # second pass: settled delayed scales
@@ -496,7 +505,7 @@ def test_sphere_bounds_sampling_and_step_match_oracle():
     rep.check("t_bg", own[3].cpu().numpy().reshape(hit.size, -1)[hit], samples[3].numpy().reshape(hit.size, -1)[hit], 1e-5)
     samples32 = [dev(s.numpy()) for s in samples]
     drnd = {k: dev(v) for k, v in rnd.items()}
-    losses = eng.train_step(dev(camloc), dev(raydir), dev(color_gt), drnd, cos_anneal_ratio=1.0, samples=samples32,
+    losses = eng.train_step(dev(camloc), dev(raydir), dev(color_gt), drnd, cos_anneal_ratio=ratio, samples=samples32,
                             keep=True)
     torch.cuda.synchronize()
     d = eng.debug
@@ -507,7 +516,7 @@ def test_sphere_bounds_sampling_and_step_match_oracle():
     for dt in (torch.float64, torch.float32):
         m = model if dt == torch.float64 else CR.Model(conf, P, dtype=torch.float32)
         smp = [torch.as_tensor(s.cpu().numpy(), dtype=dt) for s in samples32]
-        ol, res, _ = CR.total_loss(m, camloc, raydir, color_gt, 1.0, rnd, return_all=True, samples=smp, fixed_dirs=fixed)
+        ol, res, _ = CR.total_loss(m, camloc, raydir, color_gt, ratio, rnd, return_all=True, samples=smp, fixed_dirs=fixed)
         params = m.parameters()
         for p in params.values():
             p.grad = None
