@@ -878,14 +878,15 @@ __global__ void finalize_losses_kernel(float* __restrict__ losses, const float* 
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float idn = 1.f / (__ldg(mask_sum) * (float)N + 1e-5f);
   if (inv_denorm_out) { *inv_denorm_out = idn; return; }
+  // a term whose weight is not > 0 is never built by the reference and reads 0.0 in its dict (loss.py:70-165)
   losses[NDJIR_LOSS_RGB] *= inv_rays;
-  losses[NDJIR_LOSS_EIKONAL] *= idn;
-  losses[NDJIR_LOSS_TV] *= idn;
-  losses[NDJIR_LOSS_PRIOR_BASE_COLOR] *= idn;
-  losses[NDJIR_LOSS_PRIOR_ROUGHNESS] *= idn;
-  losses[NDJIR_LOSS_REG_STD_ROUGHNESS] *= idn;
-  losses[NDJIR_LOSS_PRIOR_SPECULAR] *= idn;
-  losses[NDJIR_LOSS_REG_STD_SPECULAR] *= idn;
+  losses[NDJIR_LOSS_EIKONAL] *= w_eik > 0.f ? idn : 0.f;
+  losses[NDJIR_LOSS_TV] *= w_tv > 0.f ? idn : 0.f;
+  losses[NDJIR_LOSS_PRIOR_BASE_COLOR] *= w_bc > 0.f ? idn : 0.f;
+  losses[NDJIR_LOSS_PRIOR_ROUGHNESS] *= w_ro > 0.f ? idn : 0.f;
+  losses[NDJIR_LOSS_REG_STD_ROUGHNESS] *= w_ro > 0.f ? idn : 0.f;
+  losses[NDJIR_LOSS_PRIOR_SPECULAR] *= w_sp > 0.f ? idn : 0.f;
+  losses[NDJIR_LOSS_REG_STD_SPECULAR] *= w_sp > 0.f ? idn : 0.f;
   losses[NDJIR_LOSS_TOTAL] = losses[NDJIR_LOSS_RGB] + w_eik * losses[NDJIR_LOSS_EIKONAL] +
                              w_tv * losses[NDJIR_LOSS_TV] + w_bc * losses[NDJIR_LOSS_PRIOR_BASE_COLOR] +
                              w_ro * (losses[NDJIR_LOSS_PRIOR_ROUGHNESS] + losses[NDJIR_LOSS_REG_STD_ROUGHNESS]) +

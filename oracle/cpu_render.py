@@ -548,6 +548,13 @@ def total_loss(model, camloc, raydir, color_gt, cos_anneal_ratio, rnd, return_al
             + tr.specular_reflectance_prior_weight * (losses["prior_specular_reflectance"]
                                                       + losses["reg_std_specular_reflectance"]))
     losses["loss"] = loss
+    # a term whose weight is not > 0 is never built by the reference and reads 0.0 in its dict (loss.py:70-165)
+    for w, keys in ((tr.eikonal_weight, ("loss_eikonal",)), (tr.base_color_prior_weight, ("prior_base_color",)),
+                    (tr.roughness_prior_weight, ("prior_roughness", "reg_std_roughness")),
+                    (tr.specular_reflectance_prior_weight, ("prior_specular_reflectance", "reg_std_specular_reflectance"))):
+        if not w > 0.0:
+            for k in keys:
+                losses[k] = zero
     if return_all:
         return losses, res, dict(x_fg=x_fg, t_fg=t_fg, x_bg=x_bg, t_bg=t_bg, mask=mask)
     return losses

@@ -9,6 +9,7 @@ path on the same inputs).  Parameters and inputs are rebuilt from seeds, so only
                  tensors are stored as norms + sampled entries (sampled_view)
   small_default_mask   small_default with train.mask_weight = 0.5 and a seeded object mask (obj_mask_of)
   small_default_l2     small_default with train.rgb_loss = l2
+  small_spps008, small_pel4, small_terms_off   the shipped ablation configs that change shapes / switch terms off
   small_sphere_bounds  small_default with the ray bounds taken from the bounding sphere, cos_anneal_ratio 1
 """
 import numpy as np
@@ -27,6 +28,16 @@ CASES = {
     # sampler.py:84-91) instead of the box, at the annealing ratio images are rendered with
     # squared-error colour loss (train.rgb_loss: l2, loss.py:60-62; l1 in every shipped config)
     "small_default_l2": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.2, G=16, train={"rgb_loss": "l2"}),
+    # shipped ablation configs: config/no_prior_varying_spps008.yaml (n_thetas 2 -> 8 light directions, no roughness /
+    # specular priors), config/varying_pel4.yaml (4 encoding bands for the environment-light and soft-visibility
+    # directions), config/varying_tv_weights0.0.yaml + varying_color_prior_weights0.00.yaml (terms switched off)
+    "small_spps008": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16, renderer={"n_thetas": 2},
+                          train={"roughness_prior_weight": 0.0, "specular_reflectance_prior_weight": 0.0}),
+    "small_pel4": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
+                       extra={"environment_light_network": {"pe_bands": 4},
+                              "soft_visibility_light_network": {"pe_bands": 4}}),
+    "small_terms_off": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
+                            train={"tv_weight": 0.0, "base_color_prior_weight": 0.0}),
     "small_sphere_bounds": dict(kind="default", small=True, B=2, R=4, cos_anneal=1.0, G=16,
                                 renderer={"t_near_far_method": "intersect_with_r_sphere"}),
 }
@@ -44,6 +55,8 @@ def case_conf(name):
             specular_reflectance_network={"feature_size": 32},
             background_network={"feature_size0": 32, "feature_size1": 32})
     over["train"].update(c.get("train", {}))
+    for sec, kv in c.get("extra", {}).items():
+        over.setdefault(sec, {}).update(kv)
     if "renderer" in c:
         over["renderer"] = dict(c["renderer"])
     if c["G"] is not None:

@@ -47,6 +47,8 @@ def small_conf(kind="default", **over):
         base["geometric_network"]["voxel"] = {"grid_size": 32, "feature_size": 2}
     if kind == "no_voxel":
         base["geometric_network"]["voxel"] = {}
+    for sec, kv in over.items():
+        base.setdefault(sec, {}).update(kv)
     conf = make_conf(kind, **base)
     return conf
 
@@ -114,9 +116,9 @@ class Report:
         assert not self.bad, "\n".join(self.bad)
 
 
-def setup(kind, seed=0, miss=True, grid_std=0.05, shape="small", mlp="h16", mask_weight=0.0):
+def setup(kind, seed=0, miss=True, grid_std=0.05, shape="small", mlp="h16", mask_weight=0.0, over=None):
     from ndjir_b200.engine import Engine
-    conf = small_conf(kind) if shape == "small" else full_conf(kind)
+    conf = small_conf(kind, **(over or {})) if shape == "small" else full_conf(kind)
     conf.train.mask_weight = mask_weight
     # A scene WITH a surface: the geometric initialisation's sphere (radius 0.6 here) stays intact under a small
     # perturbation of the SDF network, and every second ray is aimed at it.  (Perturbing the SDF network as much as the
@@ -471,22 +473,35 @@ def test_mask_loss_term_matches_oracle(mlp_path):
     rep.finish()
 
 
-@pytest.mark.parametrize("variant", ["sphere_bounds", "rgb_l2"])
+VARIANTS = {
+    "sphere_bounds": {},
+    "rgb_l2": {},
+    # config/varying_tv_weights0.0.yaml, varying_color_prior_weights0.00.yaml, no_prior_varying_spps*.yaml
+    "terms_off": dict(train={"tv_weight": 0.0, "base_color_prior_weight": 0.0, "roughness_prior_weight": 0.0,
+                             "specular_reflectance_prior_weight": 0.0}),
+    # config/varying_pel4.yaml
+    "pel4": dict(environment_light_network={"pe_bands": 4}, soft_visibility_light_network={"pe_bands": 4}),
+}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
 def test_non_default_branches_sampling_and_step_match_oracle(variant):
     """Branches no BASELINE config takes, each pinned on the reference's own Python by a golden case
     (tests/golden/render_small_sphere_bounds.npz, render_small_default_l2.npz):
       sphere_bounds  renderer.t_near_far_method: intersect_with_r_sphere (sampler.py:84-91; ndjir_ray_sphere_intersection
                      inside ndjir_sample_points_fwd) at cos_anneal_ratio 1
       rgb_l2         train.rgb_loss: l2 (loss.py:60-62)
+      terms_off      TV, base-colour, roughness and specular prior weights 0: the terms read 0.0 like the reference's dict
+      pel4           4 encoding bands for the light directions (environment light, soft visibility)
     Hit mask exact and sample distances against the oracle, then losses and every gradient of a step on the oracle's
     samples."""
-    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup("default", shape="small")
+    conf, P, camloc, raydir, color_gt, rnd, eng, model = setup("default", shape="small", over=VARIANTS[variant])
+    ratio = 0.2
     if variant == "sphere_bounds":
         conf.renderer.t_near_far_method = "intersect_with_r_sphere"
         ratio = 1.0
-    else:
+    elif variant == "rgb_l2":
         conf.train.rgb_loss = "l2"
-        ratio = 0.2
     rep = Report(f"train_{variant}")
     samples = CR.sample_points(model, camloc, raydir, rnd["stratified"], rnd["background"])
     args = [dev(camloc), dev(raydir), dev(rnd["stratified"]), dev(rnd["background"])]
@@ -523,12 +538,19 @@ def test_non_default_branches_sampling_and_step_match_oracle(variant):
         ol["loss"].backward()
         out[dt] = (ol, params)
     ol, params = out[torch.float64]
-    for i, k in ((0, "loss"), (1, "loss_rgb"), (2, "loss_eikonal")):
+    names = ("loss", "loss_rgb", "loss_eikonal", "loss_tv", "loss_mask", "prior_base_color", "prior_roughness",
+             "prior_specular_reflectance", "reg_std_roughness", "reg_std_specular_reflectance")
+    for i, k in enumerate(names):
         want, got = float(ol[k].detach()), float(losses[i])
+        if want == 0.0:
+            assert got == 0.0, (k, got)
+            continue
         e = abs(got - want) / abs(want)
         rep.rows.append(dict(what=f"loss.{k}", err=e, tol=5e-5, ok=bool(e <= 5e-5)))
         if e > 5e-5:
             rep.bad.append(f"loss.{k}: got {got} want {want}")
+    if variant == "terms_off":
+        assert all(float(ol[k].detach()) == 0.0 for k in names[3:])
     ours = eng.params.export_reference("grad")
     for k, p in params.items():
         want = p.grad.detach().numpy() if p.grad is not None else np.zeros(tuple(p.shape))
