@@ -93,8 +93,9 @@ class ParamStore:
         self.nets["bc"] = head("bc", [("x", 3), ("f", Df)], ["f", "x"])
         for n in ("ii", "ro", "sp"):
             self.nets[n] = head(n, [("x", 3), ("f", Df), ("n", 3)], ["f", "x", "n"])
-        self.nets["pl"] = head("pl", [("x", 3), ("pe", pe_dim(3, pl.pe_bands)), ("f", Df), ("n", 3), ("inv", 1)],
-                               ["f", "x", "n", "pe", "inv"])
+        inv = [("inv", 1)] if pl.use_inverse_distance else []          # network.py:410 (config/no_inv_distance_square.yaml)
+        self.nets["pl"] = head("pl", [("x", 3), ("pe", pe_dim(3, pl.pe_bands)), ("f", Df), ("n", 3)] + inv,
+                               ["f", "x", "n", "pe"] + [n for n, _ in inv])
         self.nets["sv"] = head("sv", [("x", 3), ("pe", pe_dim(3, sv.pe_bands)), ("f", Df), ("n", 3)],
                                ["f", "x", "n", "pe"])
         self.nets["el"] = [Layer(di, do) for (di, do) in dims["el"]]
@@ -361,8 +362,7 @@ class Engine:
              "soft_visibility_light_network head")
         need(ii.act_last == "sigmoid" and ii.use_me and not ii.use_me_on_specular and ii.channels == 1,
              "implicit_illumination_network head")
-        need(conf.photogrammetric_light_network.use_me and conf.photogrammetric_light_network.use_inverse_distance,
-             "photogrammetric_light_network")
+        need(conf.photogrammetric_light_network.use_me, "photogrammetric_light_network.use_me")
         need(not conf.specular_reflectance_network.fixme, "specular_reflectance_network.fixme")
         need(conf.train.rgb_loss in ("l1", "l2"), "train.rgb_loss l1 / l2")
         self.cskip = 1.0 / math.sqrt(2.0) if g.use_inv_square else 1.0
@@ -1277,14 +1277,16 @@ class Engine:
         acts["sp"] = self.mlp_forward("sp", "sp", O, P, [(RAWm, 6)])
         plc = conf.photogrammetric_light_network
         npl = pe_dim(3, plc.pe_bands)
-        Xpl = self.mat("Xpl", P, Df + 6 + npl + 1, "a", slot="O")      # [O | PE(view) | 1/d^2], same scale as O
+        use_inv = bool(plc.use_inverse_distance)
+        Xpl = self.mat("Xpl", P, Df + 6 + npl + int(use_inv), "a", slot="O")      # [O | PE(view) | 1/d^2], same scale as O
         self.copy_cols(Xpl, O, Df + 6, P)
         vpe_pl = self.buf("vpe_pl", NR, r4(npl))
         self.call("ndjir_positional_encoding", NR, 3, plc.pe_bands, P_(view), 3, 1, P_(vpe_pl), vpe_pl.shape[1])
         self.fill_cols(Xpl, Df + 6, P_(vpe_pl), vpe_pl.shape[1], npl, P, rep=N)
-        invd = self.buf("inv_sq_dist", P, 1)
-        self.call("ndjir_inv_sq_dist", P, R * N, P_(x_fg), P_(camloc), P_(invd), 1)
-        self.fill_cols(Xpl, Df + 6 + npl, P_(invd), 1, 1, P)
+        if use_inv:
+            invd = self.buf("inv_sq_dist", P, 1)
+            self.call("ndjir_inv_sq_dist", P, R * N, P_(x_fg), P_(camloc), P_(invd), 1)
+            self.fill_cols(Xpl, Df + 6 + npl, P_(invd), 1, 1, P)
         acts["pl"] = self.mlp_forward("pl", "pl", Xpl, P, [(RAWm, 12)])
         # ---------------- perturbed colour branch (renderer.py:187-193) ----------------
         # It only feeds the base-colour prior of the loss: image rendering (inference=True, forward only) skips the

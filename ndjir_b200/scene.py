@@ -57,7 +57,7 @@ def network_dims(conf):
         "el": head(el, pe_dim(3, el.pe_bands), el.channels),
         "sv": head(sv, 3 + pe_dim(3, sv.pe_bands) + Df + 3, sv.channels),
         "ii": head(ii, 3 + Df + 3, ii.channels),
-        "pl": head(pl, 3 + pe_dim(3, pl.pe_bands) + Df + 3 + 1, pl.channels),
+        "pl": head(pl, 3 + pe_dim(3, pl.pe_bands) + Df + 3 + (1 if pl.use_inverse_distance else 0), pl.channels),
         "ro": head(ro, 3 + Df + 3, 2),
         "sp": head(sp, 3 + Df + 3, 2 * sp.channels),
     }

@@ -245,7 +245,8 @@ class Model:
         view = view.expand(x.shape)
         dist2 = ((x - camloc) ** 2).sum(-1, keepdim=True)
         inv = 1.0 / (dist2 + 1e-5)
-        h = torch.cat([x, positional_encoding(view, c.pe_bands), feature, normal, inv], dim=-1)
+        parts = [x, positional_encoding(view, c.pe_bands), feature, normal]
+        h = torch.cat(parts + ([inv] if c.use_inverse_distance else []), dim=-1)                # network.py:410
         return torch.sigmoid(self.pl_gain * mlp(h, self.nets["pl"]))
 
     def roughness_network(self, x, feature, normal):

@@ -38,6 +38,9 @@ CASES = {
                               "soft_visibility_light_network": {"pe_bands": 4}}),
     "small_terms_off": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
                             train={"tv_weight": 0.0, "base_color_prior_weight": 0.0}),
+    # config/no_inv_distance_square.yaml: the photogrammetric light network without its 1 / d^2 input (network.py:410)
+    "small_no_inv_dist": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
+                              extra={"photogrammetric_light_network": {"use_inverse_distance": False}}),
     "small_sphere_bounds": dict(kind="default", small=True, B=2, R=4, cos_anneal=1.0, G=16,
                                 renderer={"t_near_far_method": "intersect_with_r_sphere"}),
 }

@@ -479,6 +479,8 @@ VARIANTS = {
     # config/varying_tv_weights0.0.yaml, varying_color_prior_weights0.00.yaml, no_prior_varying_spps*.yaml
     "terms_off": dict(train={"tv_weight": 0.0, "base_color_prior_weight": 0.0, "roughness_prior_weight": 0.0,
                              "specular_reflectance_prior_weight": 0.0}),
+    # config/no_inv_distance_square.yaml
+    "no_inv_dist": dict(photogrammetric_light_network={"use_inverse_distance": False}),
     # config/varying_pel4.yaml
     "pel4": dict(environment_light_network={"pe_bands": 4}, soft_visibility_light_network={"pe_bands": 4}),
 }
@@ -493,6 +495,7 @@ def test_non_default_branches_sampling_and_step_match_oracle(variant):
       rgb_l2         train.rgb_loss: l2 (loss.py:60-62)
       terms_off      TV, base-colour, roughness and specular prior weights 0: the terms read 0.0 like the reference's dict
       pel4           4 encoding bands for the light directions (environment light, soft visibility)
+      no_inv_dist    photogrammetric light network without its 1 / d^2 input (network.py:410)
     Hit mask exact and sample distances against the oracle, then losses and every gradient of a step on the oracle's
     samples."""
     conf, P, camloc, raydir, color_gt, rnd, eng, model = setup("default", shape="small", over=VARIANTS[variant])
