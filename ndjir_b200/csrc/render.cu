@@ -403,6 +403,7 @@ struct AttrCfg {
   float rough_lb, rough_prior, spec_prior, spec_scale, pl_gain;
   float w_eik, w_bc, w_ro, w_sp;   // loss weights
   int bc_sym;
+  int entangle;                    // diffuse_brdf.entangle (renderer.py:166-173): attribute 6..8 = bc * pl, else bc
 };
 
 __device__ __forceinline__ float block_sum_to(float v, float* dst, float scale) {
@@ -437,7 +438,8 @@ attrs_fwd_kernel(long long P, int N, const float* __restrict__ raw, float* __res
     float pl = sigmoidf_(cfg.pl_gain * __ldg(rw + 12));
     float* a = att + p * 12;
     a[0] = ii; a[1] = rough; a[2] = spec[0]; a[3] = spec[1]; a[4] = spec[2]; a[5] = pl;
-    a[6] = bc[0] * pl; a[7] = bc[1] * pl; a[8] = bc[2] * pl; a[9] = 0.f; a[10] = 0.f; a[11] = 0.f;
+    const float plw = cfg.entangle ? pl : 1.f;
+    a[6] = bc[0] * plw; a[7] = bc[1] * plw; a[8] = bc[2] * plw; a[9] = 0.f; a[10] = 0.f; a[11] = 0.f;
     const float* nn = nrm + p * ld_n;
     float nx = __ldg(nn), ny = __ldg(nn + 1), nz = __ldg(nn + 2);
     float gn = sqrtf(nx * nx + ny * ny + nz * nz);
@@ -484,8 +486,8 @@ attrs_bwd_kernel(long long P, int N, const float* __restrict__ raw, const float*
       float dbcpl = __ldg(da + 6 + k);
       float sgn = (b > bp) ? 1.f : ((b < bp) ? -1.f : 0.f);
       float gprior = cfg.w_bc * sgn * m * idn;
-      float db = dbcpl * pl + (cfg.bc_sym ? gprior : 0.f);
-      dpl += dbcpl * b;
+      float db = dbcpl * (cfg.entangle ? pl : 1.f) + (cfg.bc_sym ? gprior : 0.f);
+      if (cfg.entangle) dpl += dbcpl * b;
       dr[k] = db * b * (1.f - b);
       dr[13 + k] = -gprior * bp * (1.f - bp);
     }
@@ -569,7 +571,26 @@ struct ShadeCfg {
   float eps_dot, spec_weight, inv_rays;   // inv_rays = 1 / (B*R over all ranks)
   const float* ray_weight;                // per-ray weight of the colour loss (loss.py:63-65), or nullptr = 1
   int entangle, l2;
+  int uniform;                            // specular_brdf.sampling: uniform -> sBRDF = pi D V F (specular_brdf.py:104-108)
 };
+
+// the factor of the specular lobe next to V1(nol) V1(nov) F: 4 voh / noh with importance-sampled directions,
+// pi D = pi a2 / (pi (noh^2 (a2 - 1) + 1)^2 + 1e-6) with uniform ones (specular_brdf.py:75-79, 100-108)
+__device__ __forceinline__ float lobe_factor(bool uniform, float noh, float voh, float a2, float* d_noh, float* d_a2) {
+  if (!uniform) {
+    const float w = 4.f * voh / noh;
+    *d_noh = -w / noh;
+    *d_a2 = 0.f;
+    return w;
+  }
+  const float PI = 3.14159265358979323846f;
+  const float q = noh * noh * (a2 - 1.f) + 1.f;
+  const float den = PI * q * q + 1e-6f;
+  const float w = PI * a2 / den;
+  *d_noh = -w * (4.f * PI * q * noh * (a2 - 1.f)) / den;
+  *d_a2 = PI / den - w * (2.f * PI * q * noh * noh) / den;
+  return w;
+}
 
 struct DirTerms {   // everything the specular lobe needs for one direction
   float nol, nov, noh, voh, m, v1l, v1v, sql, sqv, fr;   // fr = (1 - voh)^5
@@ -639,7 +660,8 @@ shade_kernel(int NR, int M, const float* __restrict__ nhat, const float* __restr
     float env_s = softplus1(__ldg(el_raw + (row_s + j) * ld_el));
     float vis_s = sigmoidf_(__ldg(sv_raw + (row_s + j) * ld_sv));
     DirTerms t = spec_terms(nx, ny, nz, vx, vy, vz, sx, sy, sz, a2, cfg.eps_dot);
-    float G = t.v1l * t.v1v * (4.f * t.voh / t.noh) * t.m;
+    float w_noh, w_a2;
+    float G = t.v1l * t.v1v * lobe_factor(cfg.uniform, t.noh, t.voh, a2, &w_noh, &w_a2) * t.m;
     float K = G * vis_s * env_s * t.nol;
 #pragma unroll
     for (int k = 0; k < 3; ++k) S[k] += K * (F0[k] + (1.f - F0[k]) * t.fr);
@@ -699,7 +721,9 @@ shade_kernel(int NR, int M, const float* __restrict__ nhat, const float* __restr
     float er_s = __ldg(el_raw + (row_s + j) * ld_el), sr_s = __ldg(sv_raw + (row_s + j) * ld_sv);
     float env_s = softplus1(er_s), vis_s = sigmoidf_(sr_s);
     DirTerms t = spec_terms(nx, ny, nz, vx, vy, vz, sx, sy, sz, a2, cfg.eps_dot);
-    float G = t.v1l * t.v1v * (4.f * t.voh / t.noh) * t.m;
+    float w_noh, w_a2;
+    const float W = lobe_factor(cfg.uniform, t.noh, t.voh, a2, &w_noh, &w_a2);
+    float G = t.v1l * t.v1v * W * t.m;
     float q = 0.f;   // dL/dK
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -711,10 +735,12 @@ shade_kernel(int NR, int M, const float* __restrict__ nhat, const float* __restr
     d_sv_raw[(row_s + j) * ld_sv] = q * G * env_s * t.nol * vis_s * (1.f - vis_s);
     float dG = q * vis_s * env_s * t.nol;
     float dnol = q * G * vis_s * env_s;
-    // G = v1l * v1v * 4 voh / noh * m
-    float dv1l = dG * t.v1v * (4.f * t.voh / t.noh) * t.m;
-    float dv1v = dG * t.v1l * (4.f * t.voh / t.noh) * t.m;
-    float dnoh = -dG * G / t.noh;
+    // G = v1l * v1v * W(noh, a2) * m
+    float dv1l = dG * t.v1v * W * t.m;
+    float dv1v = dG * t.v1l * W * t.m;
+    const float dW = dG * t.v1l * t.v1v * t.m;
+    float dnoh = dW * w_noh;
+    da2 += dW * w_a2;
     // V1(u) = 1/(u + sqrt(a2 + (1-a2) u^2) + eps)
     dnol += dv1l * (-t.v1l * t.v1l) * (1.f + (1.f - a2) * t.nol / t.sql);
     float dnov = dv1v * (-t.v1v * t.v1v) * (1.f + (1.f - a2) * t.nov / t.sqv);
@@ -1077,7 +1103,9 @@ int ndjir_volume_render_backward(int n_rays, int N, int C, const float* w, long 
 static AttrCfg make_attr_cfg(const float* c) {
   AttrCfg a;
   a.rough_lb = c[0]; a.rough_prior = c[1]; a.spec_prior = c[2]; a.spec_scale = c[3]; a.pl_gain = c[4];
-  a.w_eik = c[5]; a.w_bc = c[6]; a.w_ro = c[7]; a.w_sp = c[8]; a.bc_sym = c[9] != 0.f;
+  a.w_eik = c[5]; a.w_bc = c[6]; a.w_ro = c[7]; a.w_sp = c[8];
+  const int flags = (int)c[9];       // bit 0: base_color_prior_sym_backward, bit 1: diffuse_brdf.entangle is FALSE
+  a.bc_sym = flags & 1; a.entangle = !(flags & 2);
   return a;
 }
 
@@ -1123,7 +1151,9 @@ int ndjir_pixel_normal_backward(int n_rays, const float* npix, long long ld, flo
 
 static ShadeCfg make_shade_cfg(const float* c, const float* ray_weight = nullptr) {
   ShadeCfg s;
-  s.eps_dot = c[0]; s.spec_weight = c[1]; s.inv_rays = c[2]; s.entangle = c[3] != 0.f; s.l2 = c[4] != 0.f;
+  s.eps_dot = c[0]; s.spec_weight = c[1]; s.inv_rays = c[2]; s.l2 = c[4] != 0.f;
+  const int flags = (int)c[3];       // bit 0: diffuse_brdf.entangle, bit 1: specular_brdf.sampling is uniform
+  s.entangle = flags & 1; s.uniform = (flags >> 1) & 1;
   s.ray_weight = ray_weight;
   return s;
 }

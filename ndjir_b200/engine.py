@@ -350,10 +350,9 @@ class Engine:
                 raise NotImplementedError(f"ndjir_b200 implements the default.yaml branch only: {what}")
         need(len(g.skip_layers) <= 1 and g.geometric_init and not g.voxel.use_ste and g.act == "softplus",
              "geometric_network (one skip layer, geometric_init, no STE, softplus)")
-        need(conf.diffuse_brdf.entangle, "diffuse_brdf.entangle")
         sb = conf.specular_brdf
-        need(sb.model == "filament" and sb.remap and sb.sampling == "importance" and not sb.use_split_sum,
-             "specular_brdf (filament, remap, importance sampling, no split sum)")
+        need(sb.model == "filament" and sb.remap and sb.sampling in ("importance", "uniform") and not sb.use_split_sum,
+             "specular_brdf (filament, remap, importance / uniform sampling, no split sum)")
         need(conf.background_modeling, "background_modeling")
         need(not conf.use_wn, "use_wn")
         el, sv, ii = conf.environment_light_network, conf.soft_visibility_light_network, conf.implicit_illumination_network
@@ -1308,7 +1307,8 @@ class Engine:
         # (upper_bound_scale only enters the other branch, :506, which __init__ rejects)
         cfg10 = [ro_c.lower_bound, ro_c.prior_value, sp_c.prior_value, 0.16, ps.pl_gain,
                  tr.eikonal_weight, tr.base_color_prior_weight, tr.roughness_prior_weight,
-                 tr.specular_reflectance_prior_weight, float(tr.base_color_prior_sym_backward)]
+                 tr.specular_reflectance_prior_weight,
+                 float(int(bool(tr.base_color_prior_sym_backward)) + (0 if conf.diffuse_brdf.entangle else 2))]
         ATT = self.buf("ATT", P, 12)
         self.call("ndjir_sample_attributes_forward", P, N, P_(RAW), P_(ATT), P_(nrm), 3, P_(maskv), cfg10, P_(losses))
         # mask loss (loss.py:108-116): obj_mask_pred = sum_i alpha_i T_i (renderer.py:183-185) is the volume-rendering
@@ -1329,8 +1329,12 @@ class Engine:
                   P_(rnd["diffuse_cdf_phi"]), NR, M, nt, 2 * nt, 0.0)
         rho = self.buf("rho_pix", NR, 1)
         self.copy2d(NR, 1, P_(rho), 1, P_(attpix, 1), 12)
-        self.call("ndjir_sample_importance_directions", NR * M, P_(dirs_s), P_(nhat), P_(rnd["specular_cdf_the"]),
-                  P_(rnd["specular_cdf_phi"]), P_(rho), NR, M, nt, 2 * nt, 0.0)
+        if conf.specular_brdf.sampling == "importance":
+            self.call("ndjir_sample_importance_directions", NR * M, P_(dirs_s), P_(nhat), P_(rnd["specular_cdf_the"]),
+                      P_(rnd["specular_cdf_phi"]), P_(rho), NR, M, nt, 2 * nt, 0.0)
+        else:       # renderer.py:137-140 (config/uniform_sampling_on_sepcular.yaml)
+            self.call("ndjir_sample_uniform_directions", NR * M, P_(dirs_s), P_(nhat), P_(rnd["specular_cdf_the"]),
+                      P_(rnd["specular_cdf_phi"]), NR, M, nt, 2 * nt, 0.0)
         elc, svc = conf.environment_light_network, conf.soft_visibility_light_network
         rows_d = NR * 2 * M
         nel = pe_dim(3, elc.pe_bands)
@@ -1352,7 +1356,9 @@ class Engine:
         svraw = self.buf("sv_raw", rows_d, 4)
         acts["sv"] = self.mlp_forward("sv", "sv", Xsv, rows_d, [(Mat(f=svraw), 0)])
         # ---------------- shading + colour loss ----------------
-        cfg5 = [r.eps_dot, conf.specular_brdf.weight, inv_rays, 1.0, 0.0 if tr.rgb_loss == "l1" else 1.0]
+        cfg5 = [r.eps_dot, conf.specular_brdf.weight, inv_rays,
+                float(int(bool(conf.diffuse_brdf.entangle)) + (2 if conf.specular_brdf.sampling == "uniform" else 0)),
+                0.0 if tr.rgb_loss == "l1" else 1.0]
         color = self.buf("color", NR, 3)
         ray_w = None
         if mask_term:     # loss.py:63-65: the colour loss over the object's rays only, / (sum(obj_mask) + 1e-5)

@@ -41,6 +41,12 @@ CASES = {
     # config/no_inv_distance_square.yaml: the photogrammetric light network without its 1 / d^2 input (network.py:410)
     "small_no_inv_dist": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
                               extra={"photogrammetric_light_network": {"use_inverse_distance": False}}),
+    # config/disentangle_diffuse.yaml: colour = VR(pl) (VR(bc) diffuse + specular)  (renderer.py:170-173)
+    "small_disentangle": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
+                              extra={"diffuse_brdf": {"entangle": False}}),
+    # config/uniform_sampling_on_sepcular.yaml: uniform specular directions, sBRDF = pi D V F (specular_brdf.py:104-108)
+    "small_uniform_specular": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
+                                   extra={"specular_brdf": {"sampling": "uniform"}}),
     "small_sphere_bounds": dict(kind="default", small=True, B=2, R=4, cos_anneal=1.0, G=16,
                                 renderer={"t_near_far_method": "intersect_with_r_sphere"}),
 }

@@ -481,6 +481,10 @@ VARIANTS = {
                              "specular_reflectance_prior_weight": 0.0}),
     # config/no_inv_distance_square.yaml
     "no_inv_dist": dict(photogrammetric_light_network={"use_inverse_distance": False}),
+    # config/disentangle_diffuse.yaml
+    "disentangle": dict(diffuse_brdf={"entangle": False}),
+    # config/uniform_sampling_on_sepcular.yaml
+    "uniform_specular": dict(specular_brdf={"sampling": "uniform"}),
     # config/varying_pel4.yaml
     "pel4": dict(environment_light_network={"pe_bands": 4}, soft_visibility_light_network={"pe_bands": 4}),
 }
@@ -496,6 +500,8 @@ def test_non_default_branches_sampling_and_step_match_oracle(variant):
       terms_off      TV, base-colour, roughness and specular prior weights 0: the terms read 0.0 like the reference's dict
       pel4           4 encoding bands for the light directions (environment light, soft visibility)
       no_inv_dist    photogrammetric light network without its 1 / d^2 input (network.py:410)
+      uniform_specular  specular_brdf.sampling: uniform (uniform directions, sBRDF = pi D V F, specular_brdf.py:104-108)
+      disentangle    diffuse_brdf.entangle: false, colour = VR(pl) (VR(bc) diffuse + specular) (renderer.py:170-173)
     Hit mask exact and sample distances against the oracle, then losses and every gradient of a step on the oracle's
     samples."""
     conf, P, camloc, raydir, color_gt, rnd, eng, model = setup("default", shape="small", over=VARIANTS[variant])
