@@ -500,7 +500,8 @@ int ndjir_render_segment_backward(int n_rays, int N, int Nb, int C, int C2, cons
  *      raw (P,16): bc 0:3 | ii 3 | ro 4:6 | sp 6:12 | pl 12 | bc_ptb 13:16;  att (P,12): ii | rough | spec(3) |
  *      pl | bc*pl(3) | pad.  cfg10 (HOST): rough_lb, rough_prior, spec_prior, spec_scale, pl_gain, w_eik, w_bc,
  *      w_ro, w_sp, flags (bit 0: base_color_prior_sym_backward; bit 1: diffuse_brdf.entangle is FALSE, att 6:9 then
- *      holds bc instead of bc*pl, renderer.py:166-173) ---- */
+ *      holds bc instead of bc*pl, renderer.py:166-173; bit 2: implicit illumination switched off, att 0 = 0,
+ *      network.py:308-309; bit 3: photogrammetric light switched off, pl = 1, renderer.py:174-176) ---- */
 int ndjir_sample_attributes_forward(long long n_points, int N, const float* raw, float* att, const float* normal,
                                     long long ld_n, const float* mask, const float* cfg10, float* losses,
                                     cudaStream_t stream);
@@ -511,7 +512,8 @@ int ndjir_sample_attributes_backward(long long n_points, int N, const float* raw
 
 /* ---- per-ray shading + colour loss (python/renderer.py:88-180, python/specular_brdf.py:40-118).
  *      cfg5 (HOST): eps_dot, specular weight, 1/(B*R over all ranks), flags (bit 0: diffuse_brdf.entangle, bit 1:
- *      specular_brdf.sampling is uniform: sBRDF = pi D V F, specular_brdf.py:104-108, instead of V F 4 voh / noh), l2 ---- */
+ *      specular_brdf.sampling is uniform: sBRDF = pi D V F, specular_brdf.py:104-108, instead of V F 4 voh / noh;
+ *      bit 2: photogrammetric light switched off: colour = VR(bc) + specular, renderer.py:174-176), l2 ---- */
 int ndjir_pixel_normal_forward(int n_rays, const float* npix, long long ld, float eps, float* nhat,
                                cudaStream_t stream);
 int ndjir_pixel_normal_backward(int n_rays, const float* npix, long long ld, float eps, const float* dnhat,

@@ -404,6 +404,7 @@ struct AttrCfg {
   float w_eik, w_bc, w_ro, w_sp;   // loss weights
   int bc_sym;
   int entangle;                    // diffuse_brdf.entangle (renderer.py:166-173): attribute 6..8 = bc * pl, else bc
+  int no_ii, no_pl;                // network switched off: ii = 0 (network.py:308-309) / pl unused (renderer.py:174-176)
 };
 
 __device__ __forceinline__ float block_sum_to(float v, float* dst, float scale) {
@@ -424,7 +425,7 @@ attrs_fwd_kernel(long long P, int N, const float* __restrict__ raw, float* __res
     float bc[3], bcp[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { bc[k] = sigmoidf_(__ldg(rw + k)); bcp[k] = sigmoidf_(__ldg(rw + 13 + k)); }
-    float ii = sigmoidf_(__ldg(rw + 3));
+    float ii = cfg.no_ii ? 0.f : sigmoidf_(__ldg(rw + 3));
     float sr = sigmoidf_(__ldg(rw + 4));
     float rough = fminf(fmaxf(sr * sr, cfg.rough_lb), 1.f);
     float std_r = softplus1(__ldg(rw + 5));
@@ -435,7 +436,7 @@ attrs_fwd_kernel(long long P, int N, const float* __restrict__ raw, float* __res
       spec[k] = cfg.spec_scale * s * s;
       std_s[k] = softplus1(__ldg(rw + 9 + k));
     }
-    float pl = sigmoidf_(cfg.pl_gain * __ldg(rw + 12));
+    float pl = cfg.no_pl ? 1.f : sigmoidf_(cfg.pl_gain * __ldg(rw + 12));
     float* a = att + p * 12;
     a[0] = ii; a[1] = rough; a[2] = spec[0]; a[3] = spec[1]; a[4] = spec[2]; a[5] = pl;
     const float plw = cfg.entangle ? pl : 1.f;
@@ -476,8 +477,7 @@ attrs_bwd_kernel(long long P, int N, const float* __restrict__ raw, const float*
     const float* da = datt + p * 12;
     float* dr = draw + p * 16;
     float m = __ldg(mask + p / N);
-    float plr = __ldg(rw + 12);
-    float pl = sigmoidf_(cfg.pl_gain * plr);
+    float pl = cfg.no_pl ? 1.f : sigmoidf_(cfg.pl_gain * __ldg(rw + 12));
     float dpl = __ldg(da + 5);
     // base colour (both sides of the prior receive gradient when bc_sym, loss.py:107-121)
 #pragma unroll
@@ -491,9 +491,9 @@ attrs_bwd_kernel(long long P, int N, const float* __restrict__ raw, const float*
       dr[k] = db * b * (1.f - b);
       dr[13 + k] = -gprior * bp * (1.f - bp);
     }
-    dr[12] = dpl * pl * (1.f - pl) * cfg.pl_gain;
+    dr[12] = cfg.no_pl ? 0.f : dpl * pl * (1.f - pl) * cfg.pl_gain;
     // implicit illumination
-    float ii = sigmoidf_(__ldg(rw + 3));
+    float ii = cfg.no_ii ? 0.f : sigmoidf_(__ldg(rw + 3));
     dr[3] = __ldg(da + 0) * ii * (1.f - ii);
     // roughness
     {
@@ -572,6 +572,7 @@ struct ShadeCfg {
   const float* ray_weight;                // per-ray weight of the colour loss (loss.py:63-65), or nullptr = 1
   int entangle, l2;
   int uniform;                            // specular_brdf.sampling: uniform -> sBRDF = pi D V F (specular_brdf.py:104-108)
+  int no_pl;                              // photogrammetric light off: colour = VR(bc) + specular (renderer.py:174-176)
 };
 
 // the factor of the specular lobe next to V1(nol) V1(nov) F: 4 voh / noh with importance-sampled directions,
@@ -676,7 +677,7 @@ shade_kernel(int NR, int M, const float* __restrict__ nhat, const float* __restr
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     // entangle (renderer.py:159-170): VR(bc*pl)*D + VR(pl)*S ; else VR(pl)*(VR(bc)*D + S) [BCPL then holds VR(bc)]
-    col[k] = cfg.entangle ? BCPL[k] * DL + PL * S[k] : PL * (BCPL[k] * DL + S[k]);
+    col[k] = cfg.no_pl ? BCPL[k] + S[k] : (cfg.entangle ? BCPL[k] * DL + PL * S[k] : PL * (BCPL[k] * DL + S[k]));
     col[k] += __ldg(colbg + r * 3 + k);
     float diff = col[k] - __ldg(color_gt + r * 3 + k);
     const float wr = cfg.ray_weight ? __ldg(cfg.ray_weight + r) : 1.f;
@@ -694,7 +695,9 @@ shade_kernel(int NR, int M, const float* __restrict__ nhat, const float* __restr
   float dDL = 0.f, dPL = 0.f, dS[3], dBCPL[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    if (cfg.entangle) {
+    if (cfg.no_pl) {
+      dBCPL[k] = dc[k]; dS[k] = dc[k];
+    } else if (cfg.entangle) {
       dBCPL[k] = dc[k] * DL; dDL += dc[k] * BCPL[k]; dPL += dc[k] * S[k]; dS[k] = dc[k] * PL;
     } else {
       dBCPL[k] = dc[k] * PL * DL; dDL += dc[k] * PL * BCPL[k]; dPL += dc[k] * (BCPL[k] * DL + S[k]); dS[k] = dc[k] * PL;
@@ -1105,7 +1108,8 @@ static AttrCfg make_attr_cfg(const float* c) {
   a.rough_lb = c[0]; a.rough_prior = c[1]; a.spec_prior = c[2]; a.spec_scale = c[3]; a.pl_gain = c[4];
   a.w_eik = c[5]; a.w_bc = c[6]; a.w_ro = c[7]; a.w_sp = c[8];
   const int flags = (int)c[9];       // bit 0: base_color_prior_sym_backward, bit 1: diffuse_brdf.entangle is FALSE
-  a.bc_sym = flags & 1; a.entangle = !(flags & 2);
+  a.bc_sym = flags & 1; a.entangle = !(flags & 2);      // bit 2 / 3: implicit illumination / photogrammetric light off
+  a.no_ii = (flags >> 2) & 1; a.no_pl = (flags >> 3) & 1;
   return a;
 }
 
@@ -1153,7 +1157,7 @@ static ShadeCfg make_shade_cfg(const float* c, const float* ray_weight = nullptr
   ShadeCfg s;
   s.eps_dot = c[0]; s.spec_weight = c[1]; s.inv_rays = c[2]; s.l2 = c[4] != 0.f;
   const int flags = (int)c[3];       // bit 0: diffuse_brdf.entangle, bit 1: specular_brdf.sampling is uniform
-  s.entangle = flags & 1; s.uniform = (flags >> 1) & 1;
+  s.entangle = flags & 1; s.uniform = (flags >> 1) & 1; s.no_pl = (flags >> 2) & 1;
   s.ray_weight = ray_weight;
   return s;
 }

@@ -359,9 +359,11 @@ class Engine:
         need(el.act_last == "softplus" and el.upper_bound <= 0 and el.channels == 1, "environment_light_network head")
         need(sv.act_last == "sigmoid" and sv.channels == 1 and sv.use_geometric_feature and sv.use_normal,
              "soft_visibility_light_network head")
-        need(ii.act_last == "sigmoid" and ii.use_me and not ii.use_me_on_specular and ii.channels == 1,
+        need(ii.act_last == "sigmoid" and not (ii.use_me and ii.use_me_on_specular) and ii.channels == 1,
              "implicit_illumination_network head")
-        need(conf.photogrammetric_light_network.use_me, "photogrammetric_light_network.use_me")
+        # networks the configuration switches off (config/no_implicit_illumination.yaml, no_lightp.yaml): their parameters
+        # stay in the store (zero gradient, left out of parameter files like the reference, scene.active_nets)
+        self.use_ii, self.use_pl = bool(ii.use_me), bool(conf.photogrammetric_light_network.use_me)
         need(not conf.specular_reflectance_network.fixme, "specular_reflectance_network.fixme")
         need(conf.train.rgb_loss in ("l1", "l2"), "train.rgb_loss l1 / l2")
         self.cskip = 1.0 / math.sqrt(2.0) if g.use_inv_square else 1.0
@@ -1271,22 +1273,25 @@ class Engine:
         RAWm = Mat(f=RAW)
         acts = {}
         acts["bc"] = self.mlp_forward("bc", "bc", O, P, [(RAWm, 0)])
-        acts["ii"] = self.mlp_forward("ii", "ii", O, P, [(RAWm, 3)])
+        if self.use_ii:
+            acts["ii"] = self.mlp_forward("ii", "ii", O, P, [(RAWm, 3)])
         acts["ro"] = self.mlp_forward("ro", "ro", O, P, [(RAWm, 4)])
         acts["sp"] = self.mlp_forward("sp", "sp", O, P, [(RAWm, 6)])
-        plc = conf.photogrammetric_light_network
-        npl = pe_dim(3, plc.pe_bands)
-        use_inv = bool(plc.use_inverse_distance)
-        Xpl = self.mat("Xpl", P, Df + 6 + npl + int(use_inv), "a", slot="O")      # [O | PE(view) | 1/d^2], same scale as O
-        self.copy_cols(Xpl, O, Df + 6, P)
-        vpe_pl = self.buf("vpe_pl", NR, r4(npl))
-        self.call("ndjir_positional_encoding", NR, 3, plc.pe_bands, P_(view), 3, 1, P_(vpe_pl), vpe_pl.shape[1])
-        self.fill_cols(Xpl, Df + 6, P_(vpe_pl), vpe_pl.shape[1], npl, P, rep=N)
-        if use_inv:
-            invd = self.buf("inv_sq_dist", P, 1)
-            self.call("ndjir_inv_sq_dist", P, R * N, P_(x_fg), P_(camloc), P_(invd), 1)
-            self.fill_cols(Xpl, Df + 6 + npl, P_(invd), 1, 1, P)
-        acts["pl"] = self.mlp_forward("pl", "pl", Xpl, P, [(RAWm, 12)])
+        Xpl = None
+        if self.use_pl:
+            plc = conf.photogrammetric_light_network
+            npl = pe_dim(3, plc.pe_bands)
+            use_inv = bool(plc.use_inverse_distance)
+            Xpl = self.mat("Xpl", P, Df + 6 + npl + int(use_inv), "a", slot="O")      # [O | PE(view) | 1/d^2], same scale as O
+            self.copy_cols(Xpl, O, Df + 6, P)
+            vpe_pl = self.buf("vpe_pl", NR, r4(npl))
+            self.call("ndjir_positional_encoding", NR, 3, plc.pe_bands, P_(view), 3, 1, P_(vpe_pl), vpe_pl.shape[1])
+            self.fill_cols(Xpl, Df + 6, P_(vpe_pl), vpe_pl.shape[1], npl, P, rep=N)
+            if use_inv:
+                invd = self.buf("inv_sq_dist", P, 1)
+                self.call("ndjir_inv_sq_dist", P, R * N, P_(x_fg), P_(camloc), P_(invd), 1)
+                self.fill_cols(Xpl, Df + 6 + npl, P_(invd), 1, 1, P)
+            acts["pl"] = self.mlp_forward("pl", "pl", Xpl, P, [(RAWm, 12)])
         # ---------------- perturbed colour branch (renderer.py:187-193) ----------------
         # It only feeds the base-colour prior of the loss: image rendering (inference=True, forward only) skips the
         # second geometric-network evaluation and reads a zero base colour there.
@@ -1308,7 +1313,8 @@ class Engine:
         cfg10 = [ro_c.lower_bound, ro_c.prior_value, sp_c.prior_value, 0.16, ps.pl_gain,
                  tr.eikonal_weight, tr.base_color_prior_weight, tr.roughness_prior_weight,
                  tr.specular_reflectance_prior_weight,
-                 float(int(bool(tr.base_color_prior_sym_backward)) + (0 if conf.diffuse_brdf.entangle else 2))]
+                 float(int(bool(tr.base_color_prior_sym_backward)) + (0 if conf.diffuse_brdf.entangle else 2)
+                       + (0 if self.use_ii else 4) + (0 if self.use_pl else 8))]
         ATT = self.buf("ATT", P, 12)
         self.call("ndjir_sample_attributes_forward", P, N, P_(RAW), P_(ATT), P_(nrm), 3, P_(maskv), cfg10, P_(losses))
         # mask loss (loss.py:108-116): obj_mask_pred = sum_i alpha_i T_i (renderer.py:183-185) is the volume-rendering
@@ -1357,7 +1363,8 @@ class Engine:
         acts["sv"] = self.mlp_forward("sv", "sv", Xsv, rows_d, [(Mat(f=svraw), 0)])
         # ---------------- shading + colour loss ----------------
         cfg5 = [r.eps_dot, conf.specular_brdf.weight, inv_rays,
-                float(int(bool(conf.diffuse_brdf.entangle)) + (2 if conf.specular_brdf.sampling == "uniform" else 0)),
+                float(int(bool(conf.diffuse_brdf.entangle)) + (2 if conf.specular_brdf.sampling == "uniform" else 0)
+                      + (0 if self.use_pl else 4)),
                 0.0 if tr.rgb_loss == "l1" else 1.0]
         color = self.buf("color", NR, 3)
         ray_w = None
@@ -1446,8 +1453,10 @@ class Engine:
                   P_(dRAW), dO.fptr(Df + 3), LDO)
         self.mlp_backward("bc", "bc", O, P, acts["bc"], [(dRAWm, 0)], dX=dO, accum_dx=True, dx_cols=Df + 3)
         for name, col in (("ii", 3), ("ro", 4), ("sp", 6)):
-            self.mlp_backward(name, name, O, P, acts[name], [(dRAWm, col)], dX=dO, accum_dx=True, dx_cols=Df + 6)
-        self.mlp_backward("pl", "pl", Xpl, P, acts["pl"], [(dRAWm, 12)], dX=dO, accum_dx=True, dx_cols=Df + 6)
+            if name in acts:
+                self.mlp_backward(name, name, O, P, acts[name], [(dRAWm, col)], dX=dO, accum_dx=True, dx_cols=Df + 6)
+        if self.use_pl:
+            self.mlp_backward("pl", "pl", Xpl, P, acts["pl"], [(dRAWm, 12)], dX=dO, accum_dx=True, dx_cols=Df + 6)
         # background networks
         dXbg1 = self.mat("dXbg1", rows_bg, Dfb, "a", grad=True)
         self.mlp_backward("bg1", "bg1", Xbg1, rows_bg, acts_bg1, [(Mat(f=d_bgraw), 0)], dX=dXbg1, dx_cols=Dfb)

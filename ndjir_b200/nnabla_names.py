@@ -14,7 +14,9 @@ The names follow the scopes opened in the reference's python/network.py:
 tests/golden/make_golden.py executes the reference's network.py against a parameter registry filled through this
 table: a name the reference asks for that the table does not produce fails the golden generation.
 """
-from .scene import NET_ORDER, network_dims
+import numpy as np
+
+from .scene import NET_ORDER, active_nets, network_dims
 
 SCOPES = {
     "geo": "geometric-network", "bc": "base-color-network", "el": "environment-light-network",
@@ -42,7 +44,7 @@ def parameter_names(conf):
     ("grid", part)."""
     dims = network_dims(conf)
     out = []
-    for net in NET_ORDER:
+    for net in active_nets(conf):          # (networks the configuration switches off own no parameters)
         n = len(dims[net])
         for l in range(n):
             base = f"{SCOPES[net]}/{layer_scope(conf, net, l, n)}/affine"
@@ -79,6 +81,10 @@ def from_nnabla(conf, params):
     """{nnabla name: array} -> the dictionary layout ParamStore.load_reference takes.  Missing names raise KeyError."""
     dims = network_dims(conf)
     P = {net: [[None, None] for _ in dims[net]] for net in NET_ORDER}
+    for net in set(NET_ORDER) - set(active_nets(conf)):      # switched off: no entries in the file, zeros in the store
+        P[net] = [[np.zeros((di, do), np.float32), np.zeros(do, np.float32)] for di, do in dims[net]]
+    if "pl" not in active_nets(conf):
+        P["pl_gain"] = np.asarray([conf.train.sigmoid_gain_lv_start], np.float32)
     P["grid"] = {}
     for name, key in parameter_names(conf):
         if key[0] == "grid":

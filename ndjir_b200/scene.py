@@ -78,6 +78,18 @@ def network_dims(conf):
 NET_ORDER = ["geo", "bc", "el", "sv", "ii", "pl", "ro", "sp", "bg0", "bg1"]
 
 
+def active_nets(conf):
+    """The networks the reference actually creates: implicit_illumination_network returns a constant 0 without touching a
+    parameter when use_me is false (network.py:308-309, config/no_implicit_illumination.yaml) and the photogrammetric
+    light network is never called (renderer.py:161, config/no_lightp.yaml)."""
+    off = set()
+    if not conf.implicit_illumination_network.use_me:
+        off.add("ii")
+    if not conf.photogrammetric_light_network.use_me:
+        off.add("pl")
+    return [n for n in NET_ORDER if n not in off]
+
+
 def init_params(conf, seed=313, grid_std=1e-3, dtype=f32):
     """Returns {"geo": [(W,b),...], ..., "geo_gain": (1,), "pl_gain": (1,), "grid": {...}} as numpy arrays.
     W has shape (in, out) like nnabla's affine (x @ W + b)."""

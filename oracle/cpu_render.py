@@ -177,7 +177,14 @@ class Model:
 
     def parameters(self):
         out = {}
+        off = set()      # networks the configuration switches off are never created by the reference (network.py:308-309,
+        if not self.conf.implicit_illumination_network.use_me:                                   # renderer.py:161)
+            off.add("ii")
+        if not self.conf.photogrammetric_light_network.use_me:
+            off.add("pl")
         for k, layers in self.nets.items():
+            if k in off:
+                continue
             for i, (W, b) in enumerate(layers):
                 out[f"{k}.W{i}"], out[f"{k}.b{i}"] = W, b
         out["geo_gain"] = self.geo_gain
@@ -452,7 +459,10 @@ def pb_render(model, x_fg, t_fg, x_bg, t_bg, camloc, raydir, mask, cos_anneal_ra
                                        rnd["diffuse_cdf_phi"]), dt)
     env = model.environment_light_network(dirs_u)
     vis = model.soft_visibility_light_network(x_pix, dirs_u, f_pix, n_b)
-    ii = model.implicit_illumination_network(x_fg, feat, grad_x)
+    if conf.implicit_illumination_network.use_me:
+        ii = model.implicit_illumination_network(x_fg, feat, grad_x)
+    else:                                                   # network.py:308-309: a constant 0, no parameters
+        ii = torch.zeros(x_fg.shape[:-1] + (1,), dtype=dt)
     ii_pix = VR(ii)
     cosd, _ = dot_clamped(n_b, dirs_u, 1e-8)                                   # specular_brdf.dot default eps
     env_diffuse = (vis * env * cosd).mean(dim=2)
@@ -474,12 +484,16 @@ def pb_render(model, x_fg, t_fg, x_bg, t_bg, camloc, raydir, mask, cos_anneal_ra
     env_s = model.environment_light_network(dirs_s)
     vis_s = model.soft_visibility_light_network(x_pix, dirs_s, f_pix, n_b)
     spec_color = (sBRDF * vis_s * env_s * cos_s).mean(dim=2) * conf.specular_brdf.weight
-    pl = model.photogrammetric_light_network(x_fg, camloc, view_dir, feat, grad_x)
-    pl_pix = VR(pl)
-    if conf.diffuse_brdf.entangle:
-        color_fg = VR(base_color * pl) * diffuse_light + pl_pix * spec_color
-    else:
-        color_fg = pl_pix * (VR(base_color) * diffuse_light + spec_color)
+    if conf.photogrammetric_light_network.use_me:
+        pl = model.photogrammetric_light_network(x_fg, camloc, view_dir, feat, grad_x)
+        pl_pix = VR(pl)
+        if conf.diffuse_brdf.entangle:
+            color_fg = VR(base_color * pl) * diffuse_light + pl_pix * spec_color
+        else:
+            color_fg = pl_pix * (VR(base_color) * diffuse_light + spec_color)
+    else:                                                   # renderer.py:174-176 (sic: no diffuse-light factor)
+        pl = torch.ones(x_fg.shape[:-1] + (1,), dtype=dt)
+        color_fg = VR(base_color) + spec_color
     color = color_fg + VR(color_bg, w_bg)
     # colour perturbation branch (renderer.py:187-193)
     G = conf.geometric_network.voxel.grid_size

@@ -47,6 +47,12 @@ CASES = {
     # config/uniform_sampling_on_sepcular.yaml: uniform specular directions, sBRDF = pi D V F (specular_brdf.py:104-108)
     "small_uniform_specular": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
                                    extra={"specular_brdf": {"sampling": "uniform"}}),
+    # config/no_implicit_illumination.yaml (network.py:308-309) and config/no_lightp.yaml (renderer.py:161, 174-176): the
+    # network is never created, its parameters do not exist
+    "small_no_ii": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
+                        extra={"implicit_illumination_network": {"use_me": False}}),
+    "small_no_lightp": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
+                            extra={"photogrammetric_light_network": {"use_me": False}}),
     "small_sphere_bounds": dict(kind="default", small=True, B=2, R=4, cos_anneal=1.0, G=16,
                                 renderer={"t_near_far_method": "intersect_with_r_sphere"}),
 }
