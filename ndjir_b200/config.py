@@ -96,3 +96,75 @@ def grid_channels(conf):
     if v.type == "triplaneline":
         return 2 * 3 * v.feature_size
     raise ValueError(f"voxel.type {v.type!r} is not supported by the B200 path")
+
+
+def _set_path(d, dotted, value):
+    keys = dotted.split(".")
+    for k in keys[:-1]:
+        d = d.setdefault(k, {})
+    d[keys[-1]] = value
+
+
+_SCI = None
+
+
+def _coerce(v):
+    """PyYAML follows YAML 1.1, where `1e-8` (no dot) is a STRING; OmegaConf, which the reference loads its files
+    with, reads it as a float (config/default.yaml: eps_dot, eps_normal, the prior weights)."""
+    global _SCI
+    if _SCI is None:
+        import re
+        _SCI = re.compile(r"^[-+]?(\d+\.?\d*|\.\d+)[eE][-+]?\d+$")
+    if isinstance(v, dict):
+        return {k: _coerce(x) for k, x in v.items()}
+    if isinstance(v, list):
+        return [_coerce(x) for x in v]
+    if isinstance(v, str) and _SCI.match(v.strip()):
+        return float(v)
+    return v
+
+
+def load_conf(path, overrides=()):
+    """One of the reference's `config/*.yaml` files (or a user's copy) -> the configuration object of this package,
+    with command-line overrides in the `section.key=value` form train.py hands to hydra (python/train.py:168-179:
+    `--config-name <name> key=value ...`).  Keys the hot path does not read (data_path, valid.*, extraction.* ...) are
+    kept as they are; keys missing from the file fall back to default.yaml's values."""
+    import yaml
+    with open(path) as f:
+        user = _coerce(yaml.safe_load(f) or {})
+    d = copy.deepcopy(DEFAULT)
+    _merge(d, user)
+    for item in overrides:
+        key, sep, val = item.partition("=")
+        if not sep:
+            raise ValueError(f"override {item!r} is not of the form section.key=value")
+        _set_path(d, key.strip(), _coerce(yaml.safe_load(val)))
+    return _ns(d)
+
+
+def check_supported(conf):
+    """Raises NotImplementedError naming the key when the configuration takes a branch the CUDA path does not have
+    (it never falls back to default.yaml's behaviour silently).  Engine.__init__ calls this; it needs no GPU."""
+    def need(ok, what):
+        if not ok:
+            raise NotImplementedError(f"ndjir_b200 does not implement this branch of the reference: {what}")
+    g = conf.geometric_network
+    need(g.voxel.type in ("none", "voxel", "triplaneline"),
+         f"geometric_network.voxel.type {g.voxel.type!r} (none / voxel / triplaneline)")
+    need(len(g.skip_layers) <= 1 and g.geometric_init and not g.voxel.use_ste and g.act == "softplus",
+         "geometric_network (one skip layer, geometric_init, no STE, softplus)")
+    sb = conf.specular_brdf
+    need(sb.model == "filament" and sb.remap and sb.sampling in ("importance", "uniform") and not sb.use_split_sum,
+         "specular_brdf (filament, remap, importance / uniform sampling, no split sum)")
+    need(conf.background_modeling, "background_modeling")
+    need(not conf.use_wn, "use_wn")
+    el, sv, ii = conf.environment_light_network, conf.soft_visibility_light_network, conf.implicit_illumination_network
+    need(el.act_last == "softplus" and el.upper_bound <= 0 and el.channels == 1, "environment_light_network head")
+    need(sv.act_last == "sigmoid" and sv.channels == 1 and sv.use_geometric_feature and sv.use_normal,
+         "soft_visibility_light_network head")
+    need(ii.act_last == "sigmoid" and not (ii.use_me and ii.use_me_on_specular) and ii.channels == 1,
+         "implicit_illumination_network head")
+    need(not conf.specular_reflectance_network.fixme, "specular_reflectance_network.fixme")
+    need(conf.train.rgb_loss in ("l1", "l2"), "train.rgb_loss l1 / l2")
+    need(conf.renderer.t_near_far_method in ("intersect_with_aabb", "intersect_with_r_sphere"),
+         f"renderer.t_near_far_method {conf.renderer.t_near_far_method!r}")

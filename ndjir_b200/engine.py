@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from . import h16
 from .h16 import HMat
-from .config import grid_channels
+from .config import check_supported, grid_channels
 from .parallel import allgather_rows, allreduce_gradients, allreduce_mask_sum
 from .scene import network_dims, pe_dim, NET_ORDER
 
@@ -335,6 +335,9 @@ class Engine:
         # tables above 256 MB (the 2 GiB voxel grid), dense for small ones
         self.grid_exchange = grid_exchange
         self._gather_cache = {}
+        # a configuration that takes a branch the kernels do not have must fail here instead of silently rendering
+        # default.yaml's (config.check_supported names the key)
+        check_supported(conf)
         g = conf.geometric_network
         self.Df = g.feature_size
         self.Dg = grid_channels(conf)
@@ -343,29 +346,10 @@ class Engine:
         self.ld0 = r4(self.din)
         self.LDO = r4(self.Df + 6)
         self.skip = g.skip_layers[0] if len(g.skip_layers) else -1
-        # every configuration key the kernels hard-code: a config outside BASELINE's three (e.g. the reference's ue4.yaml)
-        # must fail here instead of silently rendering default.yaml's branches
-        def need(ok, what):
-            if not ok:
-                raise NotImplementedError(f"ndjir_b200 implements the default.yaml branch only: {what}")
-        need(len(g.skip_layers) <= 1 and g.geometric_init and not g.voxel.use_ste and g.act == "softplus",
-             "geometric_network (one skip layer, geometric_init, no STE, softplus)")
-        sb = conf.specular_brdf
-        need(sb.model == "filament" and sb.remap and sb.sampling in ("importance", "uniform") and not sb.use_split_sum,
-             "specular_brdf (filament, remap, importance / uniform sampling, no split sum)")
-        need(conf.background_modeling, "background_modeling")
-        need(not conf.use_wn, "use_wn")
-        el, sv, ii = conf.environment_light_network, conf.soft_visibility_light_network, conf.implicit_illumination_network
-        need(el.act_last == "softplus" and el.upper_bound <= 0 and el.channels == 1, "environment_light_network head")
-        need(sv.act_last == "sigmoid" and sv.channels == 1 and sv.use_geometric_feature and sv.use_normal,
-             "soft_visibility_light_network head")
-        need(ii.act_last == "sigmoid" and not (ii.use_me and ii.use_me_on_specular) and ii.channels == 1,
-             "implicit_illumination_network head")
+        ii = conf.implicit_illumination_network
         # networks the configuration switches off (config/no_implicit_illumination.yaml, no_lightp.yaml): their parameters
         # stay in the store (zero gradient, left out of parameter files like the reference, scene.active_nets)
         self.use_ii, self.use_pl = bool(ii.use_me), bool(conf.photogrammetric_light_network.use_me)
-        need(not conf.specular_reflectance_network.fixme, "specular_reflectance_network.fixme")
-        need(conf.train.rgb_loss in ("l1", "l2"), "train.rgb_loss l1 / l2")
         self.cskip = 1.0 / math.sqrt(2.0) if g.use_inv_square else 1.0
         self._bufs = {}
         self._graphs = {}
