@@ -735,6 +735,8 @@ typedef struct ndjir_geo_net {
   const float* grid1;     /* triline table */
   int precise;            /* accumulation order of the forward products (ndjir_gemm_h_desc.precise) */
   ndjir_mlp_layer feat;   /* feature block of the output layer (N = feature_size); used by ndjir_geo_forward only */
+  int use_ste;            /* geometric_network.voxel.use_ste: the normal (ndjir_geo_normal) does not differentiate the
+                             grid features with respect to the point (voxel_feature.py:390-391) */
 } ndjir_geo_net;
 
 /* caller-owned scratch of one network evaluation over up to `rows` points */

@@ -151,8 +151,8 @@ def check_supported(conf):
     g = conf.geometric_network
     need(g.voxel.type in ("none", "voxel", "triplaneline"),
          f"geometric_network.voxel.type {g.voxel.type!r} (none / voxel / triplaneline)")
-    need(len(g.skip_layers) <= 1 and g.geometric_init and not g.voxel.use_ste and g.act == "softplus",
-         "geometric_network (one skip layer, geometric_init, no STE, softplus)")
+    need(len(g.skip_layers) <= 1 and g.geometric_init and g.act == "softplus",
+         "geometric_network (one skip layer, geometric_init, softplus)")
     sb = conf.specular_brdf
     need(sb.model == "filament" and sb.remap and sb.sampling in ("importance", "uniform") and not sb.use_split_sum,
          "specular_brdf (filament, remap, importance / uniform sampling, no split sum)")

@@ -205,6 +205,7 @@ extern "C" int ndjir_geo_normal(const ndjir_geo_net* net, long long rows, const 
   }
   NDJIR_TRY(ndjir_positional_encoding_grad_input(rows, 3, net->pe_bands, fwd->enc, fwd->ld_enc, ws->g_in, fwd->ld_enc, normal,
                                                  ld_n, 0, st));
+  if (net->use_ste) return NDJIR_OK;      // straight-through: no d(grid feature) / d(point) in the normal
   const float mn[3] = {-1.f, -1.f, -1.f}, mx[3] = {1.f, 1.f, 1.f};
   const int G = net->grid_size, D = net->grid_channels;
   if (net->grid_kind == 1) {

@@ -741,7 +741,7 @@ class Engine:
         g = self.conf.geometric_network
         self.call("ndjir_positional_encoding_grad_input", rows, 3, g.pe_bands, A[0].fptr(), self.ld0, Gin.fptr(),
                   self.ld0, P_(nrm), 3, 0)
-        for part, width, off in self._grid_parts():
+        for part, width, off in ([] if g.voxel.use_ste else self._grid_parts()):     # (use_ste: voxel_feature.py:390-391)
             tmp = self.buf(f"gg_{part}", rows, width)
             self.copy2d(rows, width, P_(tmp), width, Gin.fptr(self.npe + off), self.ld0)
             self._grid_call("grad_query", part, rows, P_(nrm), P_(tmp), P_(x), P_(self.params.grid[part]))
@@ -757,7 +757,7 @@ class Engine:
         Gh0 = self.mat(f"{tag}_Gh0", rows, self.din, "fa", zero=True, grad=True)
         self.call("ndjir_positional_encoding_grad_input_adjoint", rows, 3, g.pe_bands, A[0].fptr(), self.ld0, P_(nbar), 3,
                   Gh0.fptr(), self.ld0)
-        for part, width, off in self._grid_parts():
+        for part, width, off in ([] if g.voxel.use_ste else self._grid_parts()):     # (use_ste: no grid terms in the normal)
             tmp = self.buf(f"gg_{part}", rows, width)       # g_in grid columns (dense)
             self.copy2d(rows, width, P_(tmp), width, Gin.fptr(self.npe + off), self.ld0)
             tmp2 = self.buf(f"ggo_{part}", rows, width)
@@ -1006,6 +1006,7 @@ class Engine:
         d.grid0 = ps.grid["voxel"].data_ptr() if d.grid_kind == 1 else (ps.grid["triplane"].data_ptr() if d.grid_kind == 2 else None)
         d.grid1 = ps.grid["triline"].data_ptr() if d.grid_kind == 2 else None
         d.precise = int(self.precise_fwd)
+        d.use_ste = int(bool(v.use_ste))
         return d
 
     def _sample_points_c(self, camloc, raydir, stratified_sample, background_sample, mask_sum):

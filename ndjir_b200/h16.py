@@ -56,7 +56,8 @@ class GeoNet(ctypes.Structure):
     _fields_ = [("n_hidden", ctypes.c_int), ("hidden", MlpLayer * MAX_MLP_LAYERS), ("sdf", MlpLayer),
                 ("skip_layer", ctypes.c_int), ("skip_scale", ctypes.c_float), ("pe_bands", ctypes.c_int),
                 ("grid_kind", ctypes.c_int), ("grid_size", ctypes.c_int), ("grid_channels", ctypes.c_int),
-                ("grid0", ctypes.c_void_p), ("grid1", ctypes.c_void_p), ("precise", ctypes.c_int), ("feat", MlpLayer)]
+                ("grid0", ctypes.c_void_p), ("grid1", ctypes.c_void_p), ("precise", ctypes.c_int), ("feat", MlpLayer),
+                ("use_ste", ctypes.c_int)]
 
 
 class GeoScratch(ctypes.Structure):

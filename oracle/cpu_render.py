@@ -198,6 +198,8 @@ class Model:
         r = self.conf.renderer.bounding_sphere_radius
         if v.type == "none":
             return None
+        if v.use_ste:      # voxel_feature.py:390-391 (and the triplane / triline twins): the backward registered for nn.grad
+            x = x.detach()  # returns no gradient for the query - the normal does not see the grid features
         if v.type == "voxel":
             return voxel_query_torch(x, self.grid["voxel"], 1.0)   # PF defaults min=-1,max=1 (voxel_feature.py:147-148)
         if v.type == "triplaneline":

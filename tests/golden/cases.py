@@ -53,6 +53,9 @@ CASES = {
                         extra={"implicit_illumination_network": {"use_me": False}}),
     "small_no_lightp": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16,
                             extra={"photogrammetric_light_network": {"use_me": False}}),
+    # config/ste.yaml: geometric_network.voxel.use_ste, the normal does not differentiate the grid features
+    "small_ste": dict(kind="default", small=True, B=2, R=4, cos_anneal=0.5, G=16, ste=True),
+    "small_ste_triplaneline": dict(kind="triplaneline", small=True, B=2, R=4, cos_anneal=0.5, G=32, ste=True),
     "small_sphere_bounds": dict(kind="default", small=True, B=2, R=4, cos_anneal=1.0, G=16,
                                 renderer={"t_near_far_method": "intersect_with_r_sphere"}),
 }
@@ -78,6 +81,8 @@ def case_conf(name):
         vox = {"grid_size": c["G"]}
         if c["kind"] == "triplaneline":
             vox["feature_size"] = 2
+        if c.get("ste"):
+            vox["use_ste"] = True
         over.setdefault("geometric_network", {})["voxel"] = vox
     return make_conf(c["kind"], **over)
 

@@ -291,10 +291,11 @@ def _install_native(F, PF):
     def pf_grid(scope, fn, shape_of):
         def q(x, G, feature_size, min_=[-1, -1, -1], max_=[1, 1, 1], use_ste=False, f_init=None, fix_parameters=False,
               rng=None):
-            assert not use_ste
             with parameter_scope(scope):
                 Fp = get_parameter_or_create("F", shape_of(G, feature_size), f_init, True, not fix_parameters)
-            return W_(fn(x, Fp, 1.0))
+            # use_ste: the backward the wrapper registers for nn.grad returns (None, None) (voxel_feature.py:383-391,
+            # triplane_feature.py / triline_feature.py alike): no gradient reaches the query
+            return W_(fn(x.detach() if use_ste else x, Fp, 1.0))
         return q
     PF.query_on_voxel = pf_grid("voxel_feature", CR.voxel_query_torch,
                                 lambda G, D: tuple([G] * 3 if isinstance(G, int) else G) + (D,))

@@ -35,7 +35,7 @@ def test_load_conf_merges_file_defaults_and_overrides(tmp_path):
 
 
 @pytest.mark.parametrize("over,key", [
-    (dict(geometric_network={"voxel": {"use_ste": True}}), "STE"),
+    (dict(geometric_network={"geometric_init": False}), "geometric_network"),
     (dict(specular_brdf={"model": "ue4", "remap": False}), "specular_brdf"),
     (dict(geometric_network={"voxel": {"type": "lanczos_voxel"}}), "lanczos_voxel"),
     (dict(use_wn=True), "use_wn"),
@@ -84,7 +84,7 @@ def test_builtin_defaults_equal_the_reference_files():
 
 @needs_reference
 def test_every_shipped_config_is_supported_or_rejected_by_name():
-    rejected = {"custom.yaml": "lanczos_voxel", "ste.yaml": "STE", "ue4.yaml": "specular_brdf"}
+    rejected = {"custom.yaml": "lanczos_voxel", "ue4.yaml": "specular_brdf"}
     files = sorted(glob.glob(os.path.join(REF_CONFIG, "*.yaml")))
     assert len(files) >= 23
     for f in files:

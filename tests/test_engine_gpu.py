@@ -505,6 +505,8 @@ VARIANTS = {
     # config/no_implicit_illumination.yaml, config/no_lightp.yaml: the network is never created
     "no_ii": dict(implicit_illumination_network={"use_me": False}),
     "no_lightp": dict(photogrammetric_light_network={"use_me": False}),
+    # config/ste.yaml
+    "ste": dict(geometric_network={"voxel": {"grid_size": 16, "use_ste": True}}),
     # config/varying_pel4.yaml
     "pel4": dict(environment_light_network={"pe_bands": 4}, soft_visibility_light_network={"pe_bands": 4}),
 }
@@ -523,6 +525,7 @@ def test_non_default_branches_sampling_and_step_match_oracle(variant):
       uniform_specular  specular_brdf.sampling: uniform (uniform directions, sBRDF = pi D V F, specular_brdf.py:104-108)
       no_ii          implicit illumination off: a constant 0 and no parameters (network.py:308-309)
       no_lightp      photogrammetric light off: colour = VR(bc) + specular, no parameters (renderer.py:161, 174-176)
+      ste            geometric_network.voxel.use_ste: the normal ignores d(grid feature)/d(point) (voxel_feature.py:390-391)
       disentangle    diffuse_brdf.entangle: false, colour = VR(pl) (VR(bc) diffuse + specular) (renderer.py:170-173)
     Hit mask exact and sample distances against the oracle, then losses and every gradient of a step on the oracle's
     samples."""
