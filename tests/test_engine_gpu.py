@@ -259,11 +259,11 @@ def test_backward_sweeps_as_c_abi_calls_equal_the_sequenced_path(kind, shape):
         runs.append((losses.clone(), eng.params.export_reference("grad")))
     eng.fused_sampler = True
     (l_seq, g_seq), (l_c, g_c) = runs[2], runs[3]
-    assert torch.allclose(l_seq, l_c, rtol=2e-6, atol=0)      # (the loss sums are atomic too)
+    assert torch.allclose(l_seq, l_c, rtol=1e-5, atol=0)      # (the loss sums are atomic too)
     for k in g_seq:
         scale = max(np.abs(g_seq[k]).max(), 1e-30)
         d_paths = np.abs(g_seq[k] - g_c[k]).max() / scale
-        assert d_paths <= 2e-6, (k, d_paths)
+        assert d_paths <= 1e-5, (k, d_paths)      # (atomic summation order; a wrong product shows up at >= 1e-3)
     assert any(np.abs(v).max() > 0 for v in g_c.values())
 
 
