@@ -235,3 +235,32 @@ def test_parameter_file_round_trip_under_reference_names(kind, tmp_path):
     assert np.array_equal(ps2.data.numpy(), ps.data.numpy()) and ps2.pl_gain == 3.25
     for k in ps.grid:
         assert np.array_equal(ps2.grid[k].numpy(), ps.grid[k].numpy())
+
+
+@pytest.mark.parametrize("off,scope", [("implicit_illumination_network", "implicit-illumination-network"),
+                                       ("photogrammetric_light_network", "photogrammetric-light-network")])
+def test_parameter_file_of_a_config_that_switches_a_network_off(off, scope, tmp_path):
+    """config/no_implicit_illumination.yaml / no_lightp.yaml: the reference never creates the network, so its parameter
+    file has no entry under that scope (network.py:308-309, renderer.py:161).  Ours writes the same set of names and
+    reads such a file back: the active networks bit for bit, the unused block of the flat store zero."""
+    conf = make_conf("default", geometric_network={"feature_size": 128, "voxel": {"grid_size": 8}}, **{off: {"use_me": False}})
+    full = make_conf("default", geometric_network={"feature_size": 128, "voxel": {"grid_size": 8}})
+    P = scene.init_params(conf, seed=5)
+    ps = ParamStore(conf, "cpu")
+    ps.load_reference(P)
+    path = str(tmp_path / "param.h5")
+    ps.save_parameters(path)
+    params, _ = h5lite.load_parameters(path)
+    names_full = [n for n, _ in nnabla_names.parameter_names(full)]
+    assert not [n for n in params if n.startswith(scope + "/")]
+    assert list(params) == [n for n in names_full if not n.startswith(scope + "/")]
+    ps2 = ParamStore(conf, "cpu")
+    ps2.load_parameters(path)
+    net = {"implicit_illumination_network": "ii", "photogrammetric_light_network": "pl"}[off]
+    a, b = ps.reference_dict(), ps2.reference_dict()
+    for name in scene.NET_ORDER:
+        for (W1, b1), (W2, b2) in zip(a[name], b[name]):
+            if name == net:
+                assert not W2.any() and not b2.any()
+            else:
+                assert np.array_equal(W1, W2) and np.array_equal(b1, b2), name
